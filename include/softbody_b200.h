@@ -1,0 +1,191 @@
+/*
+ * softbody_b200.h -- C ABI of libsoftbody_b200.so, the B200-native replacement for
+ * the per-timestep inner loop of a Unity soft-body solver component.
+ *
+ * WHAT EACH ENTRY POINT REPLACES.  The reference mount contains only
+ * /root/reference/README.md:1 ("# SoftbodyUnity"); the C# solver component this
+ * library is meant to sit behind is NOT IN MOUNT, so no
+ * reference file:line can be cited for any entry point.  The surface below is the
+ * one BASELINE.json:5 describes: "the reference's solver component API (its
+ * MonoBehaviour-facing Step/parameters: stiffness, damping, substeps,
+ * iterations)".  Mapping to the (hypothetical) managed component:
+ *
+ *   MonoBehaviour.Start()        -> sb_create        (mesh ingest, colouring, tiling, upload)
+ *   inspector fields             -> sb_params / sb_set_params
+ *   FixedUpdate() { Step(dt); }  -> sb_step          (predict, project, collide, velocity, normals)
+ *   LateUpdate() mesh write-back -> sb_read_positions / sb_read_normals / sb_read_surface
+ *   OnDestroy()                  -> sb_destroy
+ *
+ * Conventions: cdecl, plain pointers and sizes, all structs are blittable
+ * (4-byte scalars and 8-byte pointers only, natural alignment, no packing
+ * pragmas).  Every function returns SB_OK (0) or a negative sb_status; no C++
+ * exception crosses this boundary.  The library owns all device memory; the
+ * caller owns every host buffer and the library keeps no host pointer after a
+ * call returns.  One handle is used by one thread at a time.  There is NO CPU
+ * fallback: without a CUDA device sb_create fails with SB_E_CUDA.
+ */
+#ifndef SOFTBODY_B200_H
+#define SOFTBODY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_ABI_VERSION 1u
+
+typedef struct sb_solver *sb_handle;
+
+typedef enum sb_status {
+  SB_OK = 0,
+  SB_E_ARG = -1,   /* null pointer, bad size, index out of range, degenerate mesh */
+  SB_E_CUDA = -2,  /* CUDA runtime error (message via sb_last_error) */
+  SB_E_NCCL = -3,  /* reserved for the multi-GPU halo exchange */
+  SB_E_NAN = -4,   /* non-finite state detected */
+  SB_E_STATE = -5, /* call not valid in the current state (e.g. destroyed handle) */
+  SB_E_NOMEM = -6
+} sb_status;
+
+/* sb_params.flags */
+#define SB_FLAG_NO_GROUND 1  /* disable the ground plane */
+#define SB_FLAG_FAST_MATH 2  /* rsqrt/rcp approximations in the projection kernels
+                                (default is IEEE sqrt/div, bit-identical to the CPU oracle) */
+#define SB_FLAG_NO_GRAPH 4   /* launch kernels one by one instead of one CUDA graph per frame */
+#define SB_FLAG_NO_NORMALS 8 /* skip the per-frame normal recompute */
+
+/*
+ * Solver parameters (the inspector fields).  Names per BASELINE.json:5; units,
+ * defaults and the stiffness->compliance mapping are [SPEC]:
+ *   compliance = 1/stiffness for finite stiffness > 0, 0 for +INFINITY,
+ *   and stiffness <= 0 switches that constraint family off.
+ */
+typedef struct sb_params {
+  float dt;                 /* frame step in seconds, used when sb_step is given dt <= 0 */
+  int32_t substeps;         /* >= 1 */
+  int32_t iterations;       /* constraint sweeps per substep, >= 0 */
+  float stiffness_distance; /* edge (spring) constraints */
+  float stiffness_volume;   /* tet-volume constraints */
+  float damping;            /* 1/s: v *= max(0, 1 - h*damping) after each substep */
+  float friction;           /* 0..1: share of tangential motion removed on ground contact */
+  float gravity[3];
+  float ground_y;
+  int32_t flags;
+} sb_params; /* 48 bytes */
+
+/* Mesh and build options, read only during sb_create. */
+typedef struct sb_mesh_desc {
+  const float *pos_xyz;     /* n_verts * 3, rest pose */
+  const int32_t *tets;      /* n_tets * 4 vertex ids */
+  const int32_t *surf_tris; /* n_tris * 3 vertex ids, may be NULL when n_tris == 0 */
+  const float *inv_mass;    /* n_verts, or NULL: lumped from density; 0 pins a vertex */
+  void *stream;             /* cudaStream_t to run on, or NULL: the library creates one */
+  uint32_t n_verts;
+  uint32_t n_tets;
+  uint32_t n_tris;
+  float density;            /* kg/m^3, used when inv_mass == NULL */
+  int32_t device;           /* CUDA device ordinal */
+  int32_t tile_cap;         /* max vertices per shared-memory tile; 0 = auto */
+  int32_t max_tile_passes;  /* -1 = auto; 0 = global colour batches only */
+  int32_t block_threads;    /* threads per tile CTA (256, 512 or 1024); 0 = auto */
+  int32_t later_tile_cap;   /* max vertices per tile in passes after the first; 0 = auto */
+  int32_t host_threads;     /* threads for the host-side build; 0 = auto */
+  int32_t reserved[6];      /* must be 0 */
+} sb_mesh_desc; /* 104 bytes */
+
+/* Sizes and build statistics, for logs, benches and the byte model. */
+typedef struct sb_info {
+  uint32_t n_verts, n_edges, n_tets, n_tris;
+  uint32_t n_surface_verts;
+  uint32_t n_tile_passes;        /* shared-memory tile passes per iteration */
+  uint32_t n_global_batches;     /* leftover global colour batches per iteration */
+  uint32_t n_batches;            /* independent sets per iteration in the exported schedule */
+  uint32_t tiles_in_pass[8];
+  uint32_t max_colours_in_pass[8];
+  uint64_t constraints_in_pass[8];
+  uint64_t constraints_global;
+  uint32_t tile_cap;
+  uint32_t block_threads;
+  uint32_t smem_bytes;
+  uint32_t launches_per_frame;   /* kernel launches inside one sb_step at current params */
+  uint64_t device_bytes;         /* device memory held by the handle */
+  double build_seconds;          /* host time spent in sb_create */
+} sb_info;
+
+/* Layout guard for managed mirrors: writes the ABI version and struct sizes. */
+int sb_abi_check(uint32_t *version, uint32_t *sizeof_params, uint32_t *sizeof_desc, uint32_t *sizeof_info);
+
+void sb_default_params(sb_params *out);
+
+int sb_create(const sb_mesh_desc *mesh, const sb_params *params, sb_handle *out);
+/*
+ * Host-only handle: topology, tiling, colouring and schedule, no CUDA call.  The
+ * sb_get_info / sb_get_topology / sb_get_schedule / sb_get_tiles / sb_surface_vertices
+ * queries work on it; everything that needs the device returns SB_E_STATE.
+ */
+int sb_plan(const sb_mesh_desc *mesh, const sb_params *params, sb_handle *out);
+int sb_destroy(sb_handle h);
+
+int sb_set_params(sb_handle h, const sb_params *params);
+int sb_get_params(sb_handle h, sb_params *out);
+
+/* Analytic sphere colliders, n * (cx, cy, cz, r); n <= 16; n == 0 clears. */
+int sb_set_colliders(sb_handle h, const float *spheres_xyzr, uint32_t n);
+
+/*
+ * Advance one frame of `dt` seconds (dt <= 0: params.dt): substeps x (predict,
+ * iterations x projection sweep, ground/collider response, velocity update), then
+ * the surface normals.  Asynchronous: returns after the work is enqueued.
+ */
+int sb_step(sb_handle h, float dt);
+int sb_synchronize(sb_handle h);
+
+/* All vertices, caller's numbering, tightly packed xyz.  Synchronises. */
+int sb_read_positions(sb_handle h, float *dst_xyz, uint32_t n_verts);
+int sb_read_normals(sb_handle h, float *dst_xyz, uint32_t n_verts);
+/* Surface vertices only (ascending vertex id of those on surf_tris). */
+int sb_surface_vertices(sb_handle h, int32_t *ids, uint32_t capacity, uint32_t *n_surface);
+int sb_read_surface(sb_handle h, float *dst_pos_xyz, float *dst_nrm_xyz, uint32_t n_surface);
+
+/* Full state as float4 arrays in the caller's numbering: x4 = (x,y,z,inv_mass), v4 = (vx,vy,vz,0). */
+int sb_get_state(sb_handle h, float *x4, float *v4, uint32_t n_verts);
+int sb_set_state(sb_handle h, const float *x4, const float *v4, uint32_t n_verts);
+
+/* Same 16 doubles as the oracle's diagnostics (energy, volume, momenta, strain, NaN count, min y). */
+int sb_diagnostics(sb_handle h, double *out16);
+
+int sb_get_info(sb_handle h, sb_info *out);
+
+/* Derived topology in the caller's numbering (any pointer may be NULL). */
+int sb_get_topology(sb_handle h, int32_t *edges_2E, float *rest_len_E, float *rest_vol6_T, float *inv_mass_V);
+
+/*
+ * The Gauss-Seidel processing order of one iteration, equivalent to what the
+ * kernels do: entry >= 0 is an edge id, entry < 0 a tet id in the low 31 bits;
+ * batch_off (n_batches + 1) delimits vertex-disjoint runs.  Call with NULL
+ * arrays to get the sizes.  This is what a CPU solver must replay to be compared
+ * ("re-run under the same colour ordering", BASELINE.json:5).
+ */
+int sb_get_schedule(sb_handle h, int64_t *n_order, int32_t *order, int32_t *n_batches, int64_t *batch_off);
+
+/* For tile pass `pass`: per caller vertex, the tile that stages it, or -1 (tile_of may be NULL). */
+int sb_get_tiles(sb_handle h, uint32_t pass, int32_t *tile_of, uint32_t *n_tiles);
+
+/*
+ * Device-timed runs for benches: enqueue n_frames frames on the solver stream
+ * between two CUDA events and return the elapsed milliseconds.
+ */
+int sb_time_frames(sb_handle h, int32_t n_frames, float dt, float *elapsed_ms);
+/*
+ * Time `reps` back-to-back launches of one kernel of the path in isolation
+ * (which: 0 predict, 1 finish, 2 normals, 16+p tile pass p, 32 all global batches).
+ * The state is saved and restored around the run.
+ */
+int sb_time_kernel(sb_handle h, int32_t which, int32_t reps, float *avg_ms);
+
+const char *sb_last_error(sb_handle h); /* h may be NULL: last sb_create failure on this thread */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOFTBODY_B200_H */

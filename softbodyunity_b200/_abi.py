@@ -1,0 +1,130 @@
+"""ctypes binding of include/softbody_b200.h (the same calls a C# P/Invoke shim makes).
+
+The product path has no CPU fallback: if libsoftbody_b200.so is missing or a device
+call fails, this module raises.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+SB_OK, SB_E_ARG, SB_E_CUDA, SB_E_NCCL, SB_E_NAN, SB_E_STATE, SB_E_NOMEM = 0, -1, -2, -3, -4, -5, -6
+FLAG_NO_GROUND, FLAG_FAST_MATH, FLAG_NO_GRAPH, FLAG_NO_NORMALS = 1, 2, 4, 8
+ABI_VERSION = 1
+
+EXPORTS = [
+    "sb_abi_check", "sb_default_params", "sb_create", "sb_plan", "sb_destroy", "sb_set_params",
+    "sb_get_params", "sb_set_colliders", "sb_step", "sb_synchronize", "sb_read_positions",
+    "sb_read_normals", "sb_surface_vertices", "sb_read_surface", "sb_get_state", "sb_set_state",
+    "sb_diagnostics", "sb_get_info", "sb_get_topology", "sb_get_schedule", "sb_get_tiles",
+    "sb_time_frames", "sb_time_kernel", "sb_last_error",
+]
+
+
+class SbParams(C.Structure):
+    _fields_ = [
+        ("dt", C.c_float), ("substeps", C.c_int32), ("iterations", C.c_int32),
+        ("stiffness_distance", C.c_float), ("stiffness_volume", C.c_float),
+        ("damping", C.c_float), ("friction", C.c_float), ("gravity", C.c_float * 3),
+        ("ground_y", C.c_float), ("flags", C.c_int32),
+    ]
+
+
+class SbMeshDesc(C.Structure):
+    _fields_ = [
+        ("pos_xyz", C.c_void_p), ("tets", C.c_void_p), ("surf_tris", C.c_void_p),
+        ("inv_mass", C.c_void_p), ("stream", C.c_void_p),
+        ("n_verts", C.c_uint32), ("n_tets", C.c_uint32), ("n_tris", C.c_uint32),
+        ("density", C.c_float), ("device", C.c_int32), ("tile_cap", C.c_int32),
+        ("max_tile_passes", C.c_int32), ("block_threads", C.c_int32),
+        ("later_tile_cap", C.c_int32), ("host_threads", C.c_int32), ("reserved", C.c_int32 * 6),
+    ]
+
+
+class SbInfo(C.Structure):
+    _fields_ = [
+        ("n_verts", C.c_uint32), ("n_edges", C.c_uint32), ("n_tets", C.c_uint32), ("n_tris", C.c_uint32),
+        ("n_surface_verts", C.c_uint32), ("n_tile_passes", C.c_uint32),
+        ("n_global_batches", C.c_uint32), ("n_batches", C.c_uint32),
+        ("tiles_in_pass", C.c_uint32 * 8), ("max_colours_in_pass", C.c_uint32 * 8),
+        ("constraints_in_pass", C.c_uint64 * 8), ("constraints_global", C.c_uint64),
+        ("tile_cap", C.c_uint32), ("block_threads", C.c_uint32), ("smem_bytes", C.c_uint32),
+        ("launches_per_frame", C.c_uint32), ("device_bytes", C.c_uint64), ("build_seconds", C.c_double),
+    ]
+
+    def as_dict(self):
+        d = {}
+        for name, _ in self._fields_:
+            val = getattr(self, name)
+            d[name] = list(val) if hasattr(val, "__len__") else val
+        return d
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Loads (building first if the sources are newer) libsoftbody_b200.so."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if _build.stale():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this box: a prebuilt library is still fine
+            if not os.path.exists(path):
+                raise RuntimeError(f"libsoftbody_b200.so is missing and could not be built: {e}") from e
+    lib = C.CDLL(path)
+    vp, i32, u32, f32 = C.c_void_p, C.c_int32, C.c_uint32, C.c_float
+    P = C.POINTER
+    sig = {
+        "sb_abi_check": (C.c_int, [P(u32), P(u32), P(u32), P(u32)]),
+        "sb_default_params": (None, [P(SbParams)]),
+        "sb_create": (C.c_int, [P(SbMeshDesc), P(SbParams), P(vp)]),
+        "sb_plan": (C.c_int, [P(SbMeshDesc), P(SbParams), P(vp)]),
+        "sb_destroy": (C.c_int, [vp]),
+        "sb_set_params": (C.c_int, [vp, P(SbParams)]),
+        "sb_get_params": (C.c_int, [vp, P(SbParams)]),
+        "sb_set_colliders": (C.c_int, [vp, vp, u32]),
+        "sb_step": (C.c_int, [vp, f32]),
+        "sb_synchronize": (C.c_int, [vp]),
+        "sb_read_positions": (C.c_int, [vp, vp, u32]),
+        "sb_read_normals": (C.c_int, [vp, vp, u32]),
+        "sb_surface_vertices": (C.c_int, [vp, vp, u32, P(u32)]),
+        "sb_read_surface": (C.c_int, [vp, vp, vp, u32]),
+        "sb_get_state": (C.c_int, [vp, vp, vp, u32]),
+        "sb_set_state": (C.c_int, [vp, vp, vp, u32]),
+        "sb_diagnostics": (C.c_int, [vp, vp]),
+        "sb_get_info": (C.c_int, [vp, P(SbInfo)]),
+        "sb_get_topology": (C.c_int, [vp, vp, vp, vp, vp]),
+        "sb_get_schedule": (C.c_int, [vp, P(C.c_int64), vp, P(i32), vp]),
+        "sb_get_tiles": (C.c_int, [vp, u32, vp, P(u32)]),
+        "sb_time_frames": (C.c_int, [vp, i32, f32, P(f32)]),
+        "sb_time_kernel": (C.c_int, [vp, i32, i32, P(f32)]),
+        "sb_last_error": (C.c_char_p, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    ver, sp, sd, si = u32(), u32(), u32(), u32()
+    lib.sb_abi_check(C.byref(ver), C.byref(sp), C.byref(sd), C.byref(si))
+    if (ver.value, sp.value, sd.value, si.value) != (ABI_VERSION, C.sizeof(SbParams), C.sizeof(SbMeshDesc), C.sizeof(SbInfo)):
+        raise RuntimeError(
+            f"ABI mismatch: library v{ver.value} params={sp.value} desc={sd.value} info={si.value}; "
+            f"binding v{ABI_VERSION} params={C.sizeof(SbParams)} desc={C.sizeof(SbMeshDesc)} info={C.sizeof(SbInfo)}")
+    _lib = lib
+    return lib
+
+
+class SbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"softbody_b200 error {code}: {msg}")
+        self.code = code

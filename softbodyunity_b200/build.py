@@ -1,0 +1,45 @@
+"""Builds libsoftbody_b200.so in-tree with nvcc for sm_100a (no JIT cache: the
+built file travels to the GPU box with the repo snapshot)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libsoftbody_b200.so")
+SOURCES = ["solver.cu", "plan.cpp"]
+DEPS = SOURCES + ["kernels.cuh", "plan.h", os.path.join("..", "..", "include", "softbody_b200.h")]
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+# -ffp-contract=off: host code (rest values, step constants) must round exactly like
+# the arithmetic contract says; device code uses explicit rounding intrinsics.
+HOST_FLAGS = "-fPIC,-ffp-contract=off,-march=x86-64-v3,-O2,-Wall,-pthread"
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-ccbin", "/usr/bin/g++", "-Xcompiler", HOST_FLAGS, "-shared", "-cudart", "static",
+]
+
+
+def stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not stale():
+        return LIB
+    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building libsoftbody_b200.so")
+    if verbose:
+        sys.stderr.write(r.stdout + r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,757 @@
+// plan.cpp -- see plan.h.  Compiled with -ffp-contract=off: the rest values use the
+// same operation order as the kernels (explicit fmaf only).
+#include "plan.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <numeric>
+#include <thread>
+
+namespace sb {
+
+namespace {
+
+int resolve_threads(int t) {
+  if (t > 0) return t;
+  unsigned hc = std::thread::hardware_concurrency();
+  return hc ? (int)std::min(hc, 32u) : 4;
+}
+
+// Dynamic-chunk parallel loop over [0, n).
+template <class F>
+void parallel_for(size_t n, int threads, size_t chunk, F fn) {
+  if (threads <= 1 || n <= chunk) {
+    for (size_t i = 0; i < n; i++) fn(i, 0);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> pool;
+  int nt = (int)std::min<size_t>((size_t)threads, (n + chunk - 1) / chunk);
+  for (int w = 0; w < nt; w++)
+    pool.emplace_back([&, w]() {
+      for (;;) {
+        size_t lo = next.fetch_add(chunk);
+        if (lo >= n) break;
+        size_t hi = std::min(n, lo + chunk);
+        for (size_t i = lo; i < hi; i++) fn(i, w);
+      }
+    });
+  for (auto &t : pool) t.join();
+}
+
+inline uint32_t f2u(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  return u;
+}
+
+// ---- canonical topology ------------------------------------------------------
+
+std::string build_edges(Plan &P, int threads) {
+  static const int pr[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+  const uint32_t V = P.V, T = P.T;
+  std::vector<uint64_t> off((size_t)V + 1, 0);
+  for (uint32_t t = 0; t < T; t++) {
+    const int32_t *q = &P.tets[4 * (size_t)t];
+    for (int j = 0; j < 4; j++)
+      if (q[j] < 0 || (uint32_t)q[j] >= V) return "tet vertex index out of range";
+    for (int k = 0; k < 6; k++) {
+      int32_t a = q[pr[k][0]], b = q[pr[k][1]];
+      if (a == b) return "tet with a repeated vertex";
+      off[(size_t)std::min(a, b) + 1]++;
+    }
+  }
+  for (uint32_t v = 0; v < V; v++) off[v + 1] += off[v];
+  std::vector<int32_t> nb(off[V]);
+  {
+    std::vector<uint64_t> cur(off.begin(), off.end() - 1);
+    for (uint32_t t = 0; t < T; t++) {
+      const int32_t *q = &P.tets[4 * (size_t)t];
+      for (int k = 0; k < 6; k++) {
+        int32_t a = q[pr[k][0]], b = q[pr[k][1]];
+        if (a > b) std::swap(a, b);
+        nb[cur[a]++] = b;
+      }
+    }
+  }
+  std::vector<uint32_t> ucnt(V);
+  parallel_for(V, threads, 16384, [&](size_t v, int) {
+    auto lo = nb.begin() + off[v], hi = nb.begin() + off[v + 1];
+    std::sort(lo, hi);
+    ucnt[v] = (uint32_t)(std::unique(lo, hi) - lo);
+  });
+  std::vector<uint64_t> eoff((size_t)V + 1, 0);
+  for (uint32_t v = 0; v < V; v++) eoff[v + 1] = eoff[v] + ucnt[v];
+  if (eoff[V] >= 0x7fffffffull) return "too many edges";
+  P.E = (uint32_t)eoff[V];
+  P.edges.resize(2 * (size_t)P.E);
+  parallel_for(V, threads, 16384, [&](size_t v, int) {
+    for (uint32_t k = 0; k < ucnt[v]; k++) {
+      P.edges[2 * (eoff[v] + k)] = (int32_t)v;
+      P.edges[2 * (eoff[v] + k) + 1] = nb[off[v] + k];
+    }
+  });
+  return "";
+}
+
+void lumped_inv_mass(Plan &P, float density) {
+  // m_i = sum over tets (ascending) of (density * |det|/6) * 0.25, in double.
+  std::vector<double> m(P.V, 0.0);
+  for (uint32_t t = 0; t < P.T; t++) {
+    const int32_t *q = &P.tets[4 * (size_t)t];
+    double p[4][3];
+    for (int j = 0; j < 4; j++)
+      for (int k = 0; k < 3; k++) p[j][k] = (double)P.pos[3 * (size_t)q[j] + k];
+    double e1[3], e2[3], e3[3];
+    for (int k = 0; k < 3; k++) {
+      e1[k] = p[1][k] - p[0][k];
+      e2[k] = p[2][k] - p[0][k];
+      e3[k] = p[3][k] - p[0][k];
+    }
+    double cx = e2[1] * e3[2] - e2[2] * e3[1];
+    double cy = e2[2] * e3[0] - e2[0] * e3[2];
+    double cz = e2[0] * e3[1] - e2[1] * e3[0];
+    double det = e1[0] * cx + e1[1] * cy + e1[2] * cz;
+    double share = ((double)density * (std::fabs(det) / 6.0)) * 0.25;
+    for (int j = 0; j < 4; j++) m[q[j]] += share;
+  }
+  P.inv_mass.resize(P.V);
+  for (uint32_t i = 0; i < P.V; i++) P.inv_mass[i] = m[i] > 0 ? (float)(1.0 / m[i]) : 0.0f;
+}
+
+inline void cross_c(float *o, const float *a, const float *b) {
+  o[0] = std::fmaf(a[1], b[2], -(a[2] * b[1]));
+  o[1] = std::fmaf(a[2], b[0], -(a[0] * b[2]));
+  o[2] = std::fmaf(a[0], b[1], -(a[1] * b[0]));
+}
+
+void rest_values(Plan &P, int threads) {
+  P.rest_len.resize(P.E);
+  P.rest_vol6.resize(P.T);
+  parallel_for(P.E, threads, 65536, [&](size_t e, int) {
+    const float *a = &P.pos[3 * (size_t)P.edges[2 * e]], *b = &P.pos[3 * (size_t)P.edges[2 * e + 1]];
+    float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+    P.rest_len[e] = std::sqrt(std::fmaf(dz, dz, std::fmaf(dy, dy, dx * dx)));
+  });
+  parallel_for(P.T, threads, 65536, [&](size_t t, int) {
+    const int32_t *q = &P.tets[4 * t];
+    const float *p0 = &P.pos[3 * (size_t)q[0]], *p1 = &P.pos[3 * (size_t)q[1]];
+    const float *p2 = &P.pos[3 * (size_t)q[2]], *p3 = &P.pos[3 * (size_t)q[3]];
+    float e1[3], e2[3], e3[3], G1[3];
+    for (int k = 0; k < 3; k++) {
+      e1[k] = p1[k] - p0[k];
+      e2[k] = p2[k] - p0[k];
+      e3[k] = p3[k] - p0[k];
+    }
+    cross_c(G1, e2, e3);
+    P.rest_vol6[t] = std::fmaf(e1[2], G1[2], std::fmaf(e1[1], G1[1], e1[0] * G1[0]));
+  });
+}
+
+std::string build_surface(Plan &P) {
+  const uint32_t V = P.V, F = P.F;
+  std::vector<uint32_t> cnt((size_t)V + 1, 0);
+  for (size_t i = 0; i < 3 * (size_t)F; i++) {
+    if (P.tris[i] < 0 || (uint32_t)P.tris[i] >= V) return "surface triangle index out of range";
+    cnt[P.tris[i]]++;
+  }
+  std::vector<int32_t> sidx(V, -1);
+  P.surf_ids.clear();
+  for (uint32_t v = 0; v < V; v++)
+    if (cnt[v]) {
+      sidx[v] = (int32_t)P.surf_ids.size();
+      P.surf_ids.push_back((int32_t)v);
+    }
+  size_t ns = P.surf_ids.size();
+  P.surf_tri_off.assign(ns + 1, 0);
+  for (size_t s = 0; s < ns; s++) P.surf_tri_off[s + 1] = P.surf_tri_off[s] + cnt[P.surf_ids[s]];
+  P.surf_tri_ids.resize(P.surf_tri_off[ns]);
+  std::vector<uint32_t> cur(P.surf_tri_off.begin(), P.surf_tri_off.end() - 1);
+  for (uint32_t f = 0; f < F; f++)
+    for (int j = 0; j < 3; j++) {
+      int32_t s = sidx[P.tris[3 * (size_t)f + j]];
+      // a triangle listing the same vertex twice contributes twice, like the sequential sum does
+      P.surf_tri_ids[cur[s]++] = f;
+    }
+  return "";
+}
+
+// ---- vertex tiling -----------------------------------------------------------
+
+struct Uf {
+  std::vector<uint32_t> p;
+  explicit Uf(uint32_t n) : p(n) { std::iota(p.begin(), p.end(), 0u); }
+  uint32_t find(uint32_t x) {
+    while (p[x] != x) {
+      p[x] = p[p[x]];
+      x = p[x];
+    }
+    return x;
+  }
+  void unite(uint32_t a, uint32_t b) {
+    a = find(a);
+    b = find(b);
+    if (a != b) p[std::max(a, b)] = std::min(a, b); // root = smallest id of the component
+  }
+};
+
+// Recursive coordinate bisection of idx[lo,hi) into K parts of near-equal size
+// along the longest axis; appends the part boundaries (as end offsets) to `ends`.
+void rcb(std::vector<uint32_t> &idx, size_t lo, size_t hi, uint32_t K, const float *pos3,
+         std::vector<size_t> &ends) {
+  if (K <= 1 || hi - lo <= 1) {
+    ends.push_back(hi);
+    return;
+  }
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (size_t i = lo; i < hi; i++)
+    for (int k = 0; k < 3; k++) {
+      float c = pos3[3 * (size_t)idx[i] + k];
+      mn[k] = std::min(mn[k], c);
+      mx[k] = std::max(mx[k], c);
+    }
+  int ax = 0;
+  for (int k = 1; k < 3; k++)
+    if (mx[k] - mn[k] > mx[ax] - mn[ax]) ax = k;
+  uint32_t KL = K / 2;
+  size_t nL = (size_t)(((unsigned __int128)(hi - lo) * KL + K / 2) / K);
+  nL = std::min(std::max<size_t>(nL, 1), hi - lo - 1);
+  auto cmp = [&](uint32_t a, uint32_t b) {
+    float ca = pos3[3 * (size_t)a + ax], cb = pos3[3 * (size_t)b + ax];
+    return ca < cb || (ca == cb && a < b);
+  };
+  std::nth_element(idx.begin() + lo, idx.begin() + lo + nL, idx.begin() + hi, cmp);
+  rcb(idx, lo, lo + nL, KL, pos3, ends);
+  rcb(idx, lo + nL, hi, K - KL, pos3, ends);
+}
+
+// First-level tiling in the caller's numbering.  Fills P.perm / P.inv and returns
+// the tile boundaries in device numbering.
+std::vector<uint32_t> tile_vertices(Plan &P, uint32_t cap, int n_sm) {
+  const uint32_t V = P.V;
+  Uf uf(V);
+  for (uint32_t t = 0; t < P.T; t++) {
+    const int32_t *q = &P.tets[4 * (size_t)t];
+    uf.unite(q[0], q[1]);
+    uf.unite(q[0], q[2]);
+    uf.unite(q[0], q[3]);
+  }
+  // components in order of their smallest vertex id
+  std::vector<uint32_t> root(V), csize(V, 0);
+  for (uint32_t v = 0; v < V; v++) {
+    root[v] = uf.find(v);
+    csize[root[v]]++;
+  }
+  std::vector<uint64_t> coff((size_t)V + 1, 0);
+  for (uint32_t v = 0; v < V; v++) coff[v + 1] = coff[v] + (root[v] == v ? csize[v] : 0);
+  std::vector<uint32_t> members(V);
+  {
+    std::vector<uint64_t> cur(coff.begin(), coff.end() - 1);
+    for (uint32_t v = 0; v < V; v++) members[cur[root[v]]++] = v; // ascending within a component
+  }
+  std::vector<uint32_t> tile_end; // ends in `members` order (which becomes the device order)
+  size_t open_lo = 0, open_n = 0;
+  auto flush = [&]() {
+    if (open_n) tile_end.push_back((uint32_t)(open_lo + open_n));
+    open_n = 0;
+  };
+  for (uint32_t r = 0; r < V; r++) {
+    if (root[r] != r) continue;
+    size_t lo = coff[r], n = csize[r];
+    if (n <= cap) {
+      if (open_n + n > cap) flush();
+      if (!open_n) open_lo = lo;
+      open_n += n;
+    } else {
+      flush();
+      uint32_t K = (uint32_t)((n + cap - 1) / cap);
+      if (K > (uint32_t)n_sm) K = ((K + n_sm - 1) / n_sm) * n_sm; // whole waves
+      while ((n + K - 1) / K > cap) K++;
+      std::vector<size_t> ends;
+      rcb(members, lo, lo + n, K, P.pos.data(), ends);
+      size_t prev = lo;
+      for (size_t e : ends) {
+        std::sort(members.begin() + prev, members.begin() + e);
+        tile_end.push_back((uint32_t)e);
+        prev = e;
+      }
+    }
+  }
+  flush();
+  P.perm = members;
+  P.inv.resize(V);
+  for (uint32_t d = 0; d < V; d++) P.inv[P.perm[d]] = d;
+  std::vector<uint32_t> off;
+  off.push_back(0);
+  for (uint32_t e : tile_end) off.push_back(e);
+  return off;
+}
+
+// ---- tile passes -------------------------------------------------------------
+
+struct Mask128 {
+  uint64_t lo = 0, hi = 0;
+};
+
+inline int first_free(const Mask128 &m) {
+  if (~m.lo) return __builtin_ctzll(~m.lo);
+  if (~m.hi) return 64 + __builtin_ctzll(~m.hi);
+  return -1;
+}
+inline void set_bit(Mask128 &m, int c) {
+  if (c < 64) m.lo |= 1ull << c;
+  else m.hi |= 1ull << (c - 64);
+}
+
+struct TileOut {
+  std::vector<uint32_t> verts; // device ids (non-contiguous passes)
+  uint32_t n_ecol = 0, n_tcol = 0, n_verts = 0;
+  std::vector<U2> ctab, erec, tidx;
+  std::vector<float> trest;
+  std::vector<int32_t> erec_id, trec_id;
+  std::string err;
+};
+
+struct DevTopo {
+  std::vector<int32_t> edges; // 2E device ids, roles (a,b) as in the canonical list
+  std::vector<int32_t> tets;  // 4T device ids, roles as given
+};
+
+inline int ent_verts(const DevTopo &D, int32_t ent, int32_t *vs) {
+  if (ent >= 0) {
+    vs[0] = D.edges[2 * (size_t)ent];
+    vs[1] = D.edges[2 * (size_t)ent + 1];
+    return 2;
+  }
+  const int32_t *q = &D.tets[4 * (size_t)(ent & 0x7fffffff)];
+  vs[0] = q[0]; vs[1] = q[1]; vs[2] = q[2]; vs[3] = q[3];
+  return 4;
+}
+
+// Builds one pass.  part[v] = tile of device vertex v or -1.  Constraints of
+// `in` whose vertices all lie in one tile are consumed; the rest go to `out`.
+std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_t> &part, uint32_t n_tiles,
+                       const std::vector<uint32_t> *contig_off, const std::vector<int32_t> &in,
+                       std::vector<int32_t> &out, TilePass &TP, int threads) {
+  // 1. classify and bucket by tile (stable)
+  std::vector<uint64_t> toff((size_t)n_tiles + 1, 0);
+  std::vector<int32_t> owner(in.size());
+  parallel_for(in.size(), threads, 1 << 16, [&](size_t i, int) {
+    int32_t vs[4];
+    int n = ent_verts(D, in[i], vs);
+    int32_t p = part[vs[0]];
+    for (int k = 1; k < n; k++)
+      if (part[vs[k]] != p) p = -1;
+    owner[i] = p;
+  });
+  out.clear();
+  for (size_t i = 0; i < in.size(); i++) {
+    if (owner[i] >= 0) toff[(size_t)owner[i] + 1]++;
+    else out.push_back(in[i]);
+  }
+  for (uint32_t t = 0; t < n_tiles; t++) toff[t + 1] += toff[t];
+  std::vector<int32_t> tent(toff[n_tiles]);
+  {
+    std::vector<uint64_t> cur(toff.begin(), toff.end() - 1);
+    for (size_t i = 0; i < in.size(); i++)
+      if (owner[i] >= 0) tent[cur[owner[i]]++] = in[i];
+  }
+  owner.clear();
+  owner.shrink_to_fit();
+
+  // 2. per tile: local numbering, greedy colouring, records
+  std::vector<TileOut> outs(n_tiles);
+  int nt = std::max(1, threads);
+  std::vector<std::vector<uint32_t>> loc_scratch(nt);
+  parallel_for(n_tiles, threads, 1, [&](size_t t, int w) {
+    TileOut &O = outs[t];
+    const int32_t *ents = tent.data() + toff[t];
+    size_t ne = toff[t + 1] - toff[t];
+    uint32_t base = 0, nv = 0;
+    std::vector<uint32_t> &loc = loc_scratch[w];
+    if (contig_off) {
+      base = (*contig_off)[t];
+      nv = (*contig_off)[t + 1] - base;
+    } else {
+      if (loc.size() != P.V) loc.assign(P.V, 0xffffffffu);
+      for (size_t i = 0; i < ne; i++) {
+        int32_t vs[4];
+        int n = ent_verts(D, ents[i], vs);
+        for (int k = 0; k < n; k++)
+          if (loc[vs[k]] == 0xffffffffu) {
+            loc[vs[k]] = 0;
+            O.verts.push_back((uint32_t)vs[k]);
+          }
+      }
+      std::sort(O.verts.begin(), O.verts.end());
+      nv = (uint32_t)O.verts.size();
+      for (uint32_t k = 0; k < nv; k++) loc[O.verts[k]] = k;
+    }
+    O.n_verts = nv;
+    if (nv > 65536) {
+      O.err = "tile exceeds 65536 vertices";
+      return;
+    }
+    auto local = [&](int32_t v) -> uint32_t { return contig_off ? (uint32_t)v - base : loc[v]; };
+    std::vector<Mask128> me(nv), mt(nv);
+    std::vector<uint8_t> col(ne);
+    std::vector<uint32_t> ecount, tcount;
+    for (size_t i = 0; i < ne; i++) {
+      int32_t vs[4];
+      int n = ent_verts(D, ents[i], vs);
+      bool tet = ents[i] < 0;
+      std::vector<Mask128> &M = tet ? mt : me;
+      Mask128 u;
+      for (int k = 0; k < n; k++) {
+        const Mask128 &m = M[local(vs[k])];
+        u.lo |= m.lo;
+        u.hi |= m.hi;
+      }
+      int c = first_free(u);
+      if (c < 0) {
+        O.err = "vertex valence needs more than 128 colours";
+        return;
+      }
+      for (int k = 0; k < n; k++) set_bit(M[local(vs[k])], c);
+      col[i] = (uint8_t)c;
+      std::vector<uint32_t> &cnt = tet ? tcount : ecount;
+      if ((size_t)c >= cnt.size()) cnt.resize(c + 1, 0);
+      cnt[c]++;
+    }
+    O.n_ecol = (uint32_t)ecount.size();
+    O.n_tcol = (uint32_t)tcount.size();
+    std::vector<uint32_t> eoff(O.n_ecol + 1, 0), tof(O.n_tcol + 1, 0);
+    for (uint32_t c = 0; c < O.n_ecol; c++) eoff[c + 1] = eoff[c] + ecount[c];
+    for (uint32_t c = 0; c < O.n_tcol; c++) tof[c + 1] = tof[c] + tcount[c];
+    O.erec.resize(eoff[O.n_ecol]);
+    O.erec_id.resize(eoff[O.n_ecol]);
+    O.tidx.resize(tof[O.n_tcol]);
+    O.trest.resize(tof[O.n_tcol]);
+    O.trec_id.resize(tof[O.n_tcol]);
+    for (uint32_t c = 0; c < O.n_ecol; c++) O.ctab.push_back({eoff[c], ecount[c]});
+    for (uint32_t c = 0; c < O.n_tcol; c++) O.ctab.push_back({tof[c], tcount[c]});
+    std::vector<uint32_t> ecur(eoff.begin(), eoff.end() - 1), tcur(tof.begin(), tof.end() - 1);
+    for (size_t i = 0; i < ne; i++) {
+      int32_t vs[4];
+      ent_verts(D, ents[i], vs);
+      if (ents[i] >= 0) {
+        uint32_t k = ecur[col[i]]++;
+        O.erec[k] = {local(vs[0]) | (local(vs[1]) << 16), f2u(P.rest_len[ents[i]])};
+        O.erec_id[k] = ents[i];
+      } else {
+        int32_t id = ents[i] & 0x7fffffff;
+        uint32_t k = tcur[col[i]]++;
+        O.tidx[k] = {local(vs[0]) | (local(vs[1]) << 16), local(vs[2]) | (local(vs[3]) << 16)};
+        O.trest[k] = P.rest_vol6[id];
+        O.trec_id[k] = id;
+      }
+    }
+    if (!contig_off)
+      for (uint32_t v : O.verts) loc[v] = 0xffffffffu;
+  });
+
+  // 3. concatenate
+  TP = TilePass();
+  TP.contiguous = contig_off != nullptr;
+  TP.vert_off.push_back(0);
+  TP.ctab_off.push_back(0);
+  size_t ne = 0, ntt = 0, nv = 0;
+  for (auto &O : outs) {
+    if (!O.err.empty()) return O.err;
+    ne += O.erec.size();
+    ntt += O.tidx.size();
+    nv += O.verts.size();
+  }
+  TP.erec.reserve(ne);
+  TP.erec_id.reserve(ne);
+  TP.tidx.reserve(ntt);
+  TP.trest.reserve(ntt);
+  TP.trec_id.reserve(ntt);
+  TP.tile_verts.reserve(nv);
+  for (uint32_t t = 0; t < n_tiles; t++) {
+    TileOut &O = outs[t];
+    uint32_t eb = (uint32_t)TP.erec.size(), tb = (uint32_t)TP.tidx.size();
+    for (uint32_t c = 0; c < O.n_ecol; c++) TP.ctab.push_back({O.ctab[c].x + eb, O.ctab[c].y});
+    for (uint32_t c = 0; c < O.n_tcol; c++) TP.ctab.push_back({O.ctab[O.n_ecol + c].x + tb, O.ctab[O.n_ecol + c].y});
+    TP.n_ecol.push_back(O.n_ecol);
+    TP.ctab_off.push_back((uint32_t)TP.ctab.size());
+    TP.erec.insert(TP.erec.end(), O.erec.begin(), O.erec.end());
+    TP.erec_id.insert(TP.erec_id.end(), O.erec_id.begin(), O.erec_id.end());
+    TP.tidx.insert(TP.tidx.end(), O.tidx.begin(), O.tidx.end());
+    TP.trest.insert(TP.trest.end(), O.trest.begin(), O.trest.end());
+    TP.trec_id.insert(TP.trec_id.end(), O.trec_id.begin(), O.trec_id.end());
+    if (TP.contiguous) {
+      TP.vert_off.push_back((*contig_off)[t + 1]);
+    } else {
+      TP.tile_verts.insert(TP.tile_verts.end(), O.verts.begin(), O.verts.end());
+      TP.vert_off.push_back((uint32_t)TP.tile_verts.size());
+    }
+    TP.max_ecol = std::max(TP.max_ecol, O.n_ecol);
+    TP.max_tcol = std::max(TP.max_tcol, O.n_tcol);
+    TP.max_tile_verts = std::max(TP.max_tile_verts, O.n_verts);
+    O = TileOut();
+  }
+  if (TP.contiguous) TP.vert_off[0] = (*contig_off)[0];
+  return "";
+}
+
+// Next-level parts for the vertices of the cut constraints `cut`: a vertex joins
+// the group keyed by the unordered pair {its part, the other part it shares most
+// cut constraints with}; groups are packed (in key order) into tiles of <= cap.
+uint32_t next_parts(const Plan &P, const DevTopo &D, const std::vector<int32_t> &cut, std::vector<int32_t> &part,
+                    uint32_t cap, const std::vector<float> &dev_pos) {
+  std::vector<uint64_t> votes;
+  votes.reserve(cut.size() * 4);
+  for (int32_t ent : cut) {
+    int32_t vs[4];
+    int n = ent_verts(D, ent, vs);
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++)
+        if (part[vs[j]] != part[vs[i]]) votes.push_back(((uint64_t)(uint32_t)vs[i] << 32) | (uint32_t)part[vs[j]]);
+  }
+  std::sort(votes.begin(), votes.end());
+  struct KV {
+    uint64_t key;
+    uint32_t v;
+  };
+  std::vector<KV> kv;
+  for (size_t i = 0; i < votes.size();) {
+    uint32_t v = (uint32_t)(votes[i] >> 32);
+    uint32_t best_q = 0, best_n = 0;
+    while (i < votes.size() && (uint32_t)(votes[i] >> 32) == v) {
+      uint32_t q = (uint32_t)votes[i];
+      size_t j = i;
+      while (j < votes.size() && votes[j] == votes[i]) j++;
+      if ((uint32_t)(j - i) > best_n) {
+        best_n = (uint32_t)(j - i);
+        best_q = q;
+      }
+      i = j;
+    }
+    uint32_t p = (uint32_t)part[v];
+    kv.push_back({((uint64_t)std::min(p, best_q) << 32) | std::max(p, best_q), v});
+  }
+  votes.clear();
+  votes.shrink_to_fit();
+  std::sort(kv.begin(), kv.end(), [](const KV &a, const KV &b) { return a.key < b.key || (a.key == b.key && a.v < b.v); });
+  std::fill(part.begin(), part.end(), -1);
+  uint32_t n_tiles = 0, open = 0;
+  for (size_t i = 0; i < kv.size();) {
+    size_t j = i;
+    while (j < kv.size() && kv[j].key == kv[i].key) j++;
+    uint32_t n = (uint32_t)(j - i);
+    if (n > cap) {
+      if (open) { n_tiles++; open = 0; }
+      std::vector<uint32_t> idx(n);
+      for (uint32_t k = 0; k < n; k++) idx[k] = kv[i + k].v;
+      std::vector<size_t> ends;
+      rcb(idx, 0, n, (n + cap - 1) / cap, dev_pos.data(), ends);
+      size_t prev = 0;
+      for (size_t e : ends) {
+        for (size_t k = prev; k < e; k++) part[idx[k]] = (int32_t)n_tiles;
+        n_tiles++;
+        prev = e;
+      }
+    } else {
+      if (open + n > cap) { n_tiles++; open = 0; }
+      for (size_t k = i; k < j; k++) part[kv[k].v] = (int32_t)n_tiles;
+      open += n;
+    }
+    i = j;
+  }
+  if (open) n_tiles++;
+  (void)P;
+  return n_tiles;
+}
+
+std::string global_colouring(Plan &P, const DevTopo &D, const std::vector<int32_t> &rest) {
+  if (rest.empty()) return "";
+  std::vector<Mask128> me(P.V), mt(P.V);
+  std::vector<uint8_t> col(rest.size());
+  std::vector<uint32_t> ecount, tcount;
+  for (size_t i = 0; i < rest.size(); i++) {
+    int32_t vs[4];
+    int n = ent_verts(D, rest[i], vs);
+    bool tet = rest[i] < 0;
+    std::vector<Mask128> &M = tet ? mt : me;
+    Mask128 u;
+    for (int k = 0; k < n; k++) {
+      u.lo |= M[vs[k]].lo;
+      u.hi |= M[vs[k]].hi;
+    }
+    int c = first_free(u);
+    if (c < 0) return "vertex valence needs more than 128 colours";
+    for (int k = 0; k < n; k++) set_bit(M[vs[k]], c);
+    col[i] = (uint8_t)c;
+    std::vector<uint32_t> &cnt = tet ? tcount : ecount;
+    if ((size_t)c >= cnt.size()) cnt.resize(c + 1, 0);
+    cnt[c]++;
+  }
+  std::vector<uint32_t> eoff(ecount.size() + 1, 0), tof(tcount.size() + 1, 0);
+  for (size_t c = 0; c < ecount.size(); c++) eoff[c + 1] = eoff[c] + ecount[c];
+  for (size_t c = 0; c < tcount.size(); c++) tof[c + 1] = tof[c] + tcount[c];
+  P.g_edges.resize(eoff.back());
+  P.g_elen.resize(eoff.back());
+  P.g_eid.resize(eoff.back());
+  P.g_tets.resize(tof.back());
+  P.g_trest.resize(tof.back());
+  P.g_tid.resize(tof.back());
+  for (size_t c = 0; c < ecount.size(); c++) P.gbatches.push_back({false, eoff[c], ecount[c]});
+  for (size_t c = 0; c < tcount.size(); c++) P.gbatches.push_back({true, tof[c], tcount[c]});
+  std::vector<uint32_t> ecur(eoff.begin(), eoff.end() - 1), tcur(tof.begin(), tof.end() - 1);
+  for (size_t i = 0; i < rest.size(); i++) {
+    int32_t vs[4];
+    ent_verts(D, rest[i], vs);
+    if (rest[i] >= 0) {
+      uint32_t k = ecur[col[i]]++;
+      P.g_edges[k] = {vs[0], vs[1]};
+      P.g_elen[k] = P.rest_len[rest[i]];
+      P.g_eid[k] = rest[i];
+    } else {
+      int32_t id = rest[i] & 0x7fffffff;
+      uint32_t k = tcur[col[i]]++;
+      P.g_tets[k] = {vs[0], vs[1], vs[2], vs[3]};
+      P.g_trest[k] = P.rest_vol6[id];
+      P.g_tid[k] = id;
+    }
+  }
+  return "";
+}
+
+} // namespace
+
+void Plan::export_schedule(std::vector<int32_t> &order, std::vector<int64_t> &batch_off) const {
+  order.clear();
+  batch_off.clear();
+  batch_off.push_back(0);
+  auto close = [&]() {
+    if ((int64_t)order.size() > batch_off.back()) batch_off.push_back((int64_t)order.size());
+  };
+  for (const TilePass &TP : passes) {
+    uint32_t nt = TP.n_tiles();
+    for (uint32_t c = 0; c < TP.max_ecol; c++) {
+      for (uint32_t t = 0; t < nt; t++)
+        if (c < TP.n_ecol[t]) {
+          U2 r = TP.ctab[TP.ctab_off[t] + c];
+          for (uint32_t k = 0; k < r.y; k++) order.push_back(TP.erec_id[r.x + k]);
+        }
+      close();
+    }
+    for (uint32_t c = 0; c < TP.max_tcol; c++) {
+      for (uint32_t t = 0; t < nt; t++) {
+        uint32_t ntc = TP.ctab_off[t + 1] - TP.ctab_off[t] - TP.n_ecol[t];
+        if (c < ntc) {
+          U2 r = TP.ctab[TP.ctab_off[t] + TP.n_ecol[t] + c];
+          for (uint32_t k = 0; k < r.y; k++) order.push_back((int32_t)(0x80000000u | (uint32_t)TP.trec_id[r.x + k]));
+        }
+      }
+      close();
+    }
+  }
+  for (const GlobalBatch &b : gbatches) {
+    for (uint32_t k = 0; k < b.cnt; k++)
+      order.push_back(b.tet ? (int32_t)(0x80000000u | (uint32_t)g_tid[b.off + k]) : g_eid[b.off + k]);
+    close();
+  }
+}
+
+std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
+  auto t0 = std::chrono::steady_clock::now();
+  if (!in.pos_xyz || in.n_verts == 0) return "no vertices";
+  if (in.n_tets && !in.tets) return "tets is NULL";
+  if (in.n_tris && !in.surf_tris) return "surf_tris is NULL";
+  if (in.n_verts >= 0x7fffffffu || in.n_tets >= 0x7fffffffu) return "mesh too large for 31-bit ids";
+  int threads = resolve_threads(opt.threads);
+  P = Plan();
+  P.V = in.n_verts;
+  P.T = in.n_tets;
+  P.F = in.n_tris;
+  P.pos.assign(in.pos_xyz, in.pos_xyz + 3 * (size_t)P.V);
+  for (float c : P.pos)
+    if (!std::isfinite(c)) return "non-finite rest position";
+  P.tets.assign(in.tets, in.tets + 4 * (size_t)P.T);
+  if (P.F) P.tris.assign(in.surf_tris, in.surf_tris + 3 * (size_t)P.F);
+  std::string err = build_edges(P, threads);
+  if (!err.empty()) return err;
+  if (in.inv_mass) {
+    P.inv_mass.assign(in.inv_mass, in.inv_mass + P.V);
+    for (float w : P.inv_mass)
+      if (!(w >= 0) || !std::isfinite(w)) return "inv_mass must be finite and >= 0";
+  } else {
+    if (!(in.density > 0)) return "density must be > 0 when inv_mass is NULL";
+    lumped_inv_mass(P, in.density);
+  }
+  rest_values(P, threads);
+  err = build_surface(P);
+  if (!err.empty()) return err;
+
+  // ---- tiling ---------------------------------------------------------------
+  uint32_t cap = opt.tile_cap > 0 ? (uint32_t)opt.tile_cap : 6784u;
+  cap = std::min(cap, 65536u);
+  P.tile_cap = cap;
+  int max_passes = opt.max_tile_passes < 0 ? 6 : std::min(opt.max_tile_passes, 8);
+
+  std::vector<uint32_t> tile_off;
+  if (max_passes > 0) {
+    tile_off = tile_vertices(P, cap, opt.n_sm);
+  } else {
+    P.perm.resize(P.V);
+    std::iota(P.perm.begin(), P.perm.end(), 0u);
+    P.inv = P.perm;
+  }
+  DevTopo D;
+  D.edges.resize(2 * (size_t)P.E);
+  D.tets.resize(4 * (size_t)P.T);
+  parallel_for(2 * (size_t)P.E, threads, 1 << 18, [&](size_t i, int) { D.edges[i] = (int32_t)P.inv[P.edges[i]]; });
+  parallel_for(4 * (size_t)P.T, threads, 1 << 18, [&](size_t i, int) { D.tets[i] = (int32_t)P.inv[P.tets[i]]; });
+  std::vector<float> dev_pos(3 * (size_t)P.V);
+  for (uint32_t d = 0; d < P.V; d++)
+    for (int k = 0; k < 3; k++) dev_pos[3 * (size_t)d + k] = P.pos[3 * (size_t)P.perm[d] + k];
+
+  std::vector<int32_t> work((size_t)P.E + P.T), next;
+  for (uint32_t e = 0; e < P.E; e++) work[e] = (int32_t)e;
+  for (uint32_t t = 0; t < P.T; t++) work[(size_t)P.E + t] = (int32_t)(0x80000000u | t);
+
+  if (max_passes > 0) {
+    std::vector<int32_t> part(P.V);
+    uint32_t n_tiles = (uint32_t)tile_off.size() - 1;
+    for (uint32_t t = 0; t < n_tiles; t++)
+      for (uint32_t d = tile_off[t]; d < tile_off[t + 1]; d++) part[d] = (int32_t)t;
+    for (int k = 0; k < max_passes && !work.empty(); k++) {
+      TilePass TP;
+      err = build_pass(P, D, part, n_tiles, k == 0 ? &tile_off : nullptr, work, next, TP, threads);
+      if (!err.empty()) return err;
+      size_t consumed = work.size() - next.size();
+      work.swap(next);
+      if (consumed > 0 || k == 0) P.passes.push_back(std::move(TP));
+      if (work.empty() || k + 1 == max_passes) break;
+      if (consumed == 0 && k > 0) break; // no progress: hand the rest to the global colours
+      // size the next level so it offers about two tiles per SM, within [min_cap, cap]
+      uint32_t lcap = opt.later_cap > 0 ? (uint32_t)opt.later_cap : 0;
+      if (!lcap) {
+        // upper bound on the vertices involved: 4 per cut constraint is too loose, so count
+        std::vector<uint8_t> seen(P.V, 0);
+        size_t nvr = 0;
+        for (int32_t ent : work) {
+          int32_t vs[4];
+          int n = ent_verts(D, ent, vs);
+          for (int j = 0; j < n; j++)
+            if (!seen[vs[j]]) { seen[vs[j]] = 1; nvr++; }
+        }
+        lcap = (uint32_t)std::min<size_t>(cap, std::max<size_t>(2048, (nvr + 2 * opt.n_sm - 1) / (2 * opt.n_sm)));
+      }
+      lcap = std::min(lcap, cap);
+      n_tiles = next_parts(P, D, work, part, lcap, dev_pos);
+    }
+  }
+  err = global_colouring(P, D, work);
+  if (!err.empty()) return err;
+  P.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return "";
+}
+
+} // namespace sb

@@ -1,0 +1,836 @@
+// solver.cu -- device runtime and C ABI of libsoftbody_b200.so (include/softbody_b200.h).
+//
+// Reference: NOT IN MOUNT (/root/reference/README.md:1 is the whole reference); the
+// surface mirrors the solver component BASELINE.json:5 describes (Step + stiffness,
+// damping, substeps, iterations).  No CPU fallback exists: every stage of sb_step is
+// a CUDA kernel from kernels.cuh, replayed as one CUDA graph per frame.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/softbody_b200.h"
+#include "kernels.cuh"
+#include "plan.h"
+
+namespace sb {
+
+struct CudaError {
+  cudaError_t code;
+  const char *what;
+  int line;
+};
+
+#define CK(expr)                                          \
+  do {                                                    \
+    cudaError_t e_ = (expr);                              \
+    if (e_ != cudaSuccess) throw CudaError{e_, #expr, __LINE__}; \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count, uint64_t *tally) {
+    release();
+    n = count;
+    if (count) {
+      CK(cudaMalloc(&p, count * sizeof(T)));
+      if (tally) *tally += count * sizeof(T);
+    }
+  }
+  template <class S>
+  void upload(const std::vector<S> &h, uint64_t *tally) {
+    static_assert(sizeof(S) == sizeof(T), "layout");
+    alloc(h.size(), tally);
+    if (!h.empty()) CK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+struct PassBufs {
+  DevBuf<uint32_t> vert_off, tile_verts, ctab_off, n_ecol;
+  DevBuf<uint2> ctab, erec, tidx;
+  DevBuf<float> trest;
+  PassDev dev{};
+  uint32_t smem = 0;
+};
+
+static const int kDiagBlocks = 592;
+
+} // namespace sb
+
+using namespace sb;
+
+struct sb_solver {
+  Plan plan;
+  sb_params prm{};
+  bool on_device = false;
+  bool destroyed = false;
+  int device = 0;
+  int n_sm = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaStream_t cap_stream = nullptr;
+  uint32_t block_threads = 512;
+  uint64_t dev_bytes = 0;
+  std::string err;
+
+  DevBuf<float4> x, v, xp, nrm, stage_a, stage_b;
+  DevBuf<float> stage_f;
+  DevBuf<uint32_t> inv, surf_slot, surf_tri_off, surf_tri_ids;
+  DevBuf<int32_t> tris_dev;
+  DevBuf<DevParams> dprm;
+  DevParams *hprm = nullptr; // pinned
+  std::vector<PassBufs> passes;
+  DevBuf<int2> g_edges;
+  DevBuf<float> g_elen;
+  DevBuf<int4> g_tets;
+  DevBuf<float> g_trest;
+  // diagnostics (lazy)
+  DevBuf<int2> d_edges;
+  DevBuf<float> d_elen;
+  DevBuf<int4> d_tets;
+  DevBuf<double> d_part;
+  // pinned staging for read-backs
+  float *pin = nullptr;
+  size_t pin_bytes = 0;
+
+  float cur_dt = -1.f;
+  bool prm_dirty = true;
+  float4 spheres[16];
+  int n_spheres = 0;
+  std::map<uint64_t, cudaGraphExec_t> graphs;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  ~sb_solver() { release_device(); }
+
+  void release_device() {
+    if (!on_device) return;
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    for (auto &g : graphs) cudaGraphExecDestroy(g.second);
+    graphs.clear();
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (hprm) cudaFreeHost(hprm);
+    if (pin) cudaFreeHost(pin);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+    hprm = nullptr; pin = nullptr; ev0 = ev1 = nullptr; cap_stream = nullptr; stream = nullptr;
+    on_device = false;
+  }
+
+  bool fast() const { return (prm.flags & SB_FLAG_FAST_MATH) != 0; }
+
+  // ---- upload ---------------------------------------------------------------------
+  void upload(const sb_mesh_desc &m) {
+    device = m.device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    n_sm = prop.multiProcessorCount;
+    on_device = true;
+    if (m.stream) {
+      stream = (cudaStream_t)m.stream;
+    } else {
+      CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+      own_stream = true;
+    }
+    CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    CK(cudaMallocHost(&hprm, sizeof(DevParams)));
+    const uint32_t V = plan.V;
+    x.alloc(V, &dev_bytes);
+    v.alloc(V, &dev_bytes);
+    xp.alloc(V, &dev_bytes);
+    stage_a.alloc(V, &dev_bytes);
+    stage_b.alloc(V, &dev_bytes);
+    stage_f.alloc(3 * (size_t)V, &dev_bytes);
+    dprm.alloc(1, &dev_bytes);
+    inv.upload(plan.inv, &dev_bytes);
+    {
+      std::vector<float4> hx(V), hv(V, make_float4(0, 0, 0, 0));
+      for (uint32_t d = 0; d < V; d++) {
+        uint32_t o = plan.perm[d];
+        hx[d] = make_float4(plan.pos[3 * (size_t)o], plan.pos[3 * (size_t)o + 1], plan.pos[3 * (size_t)o + 2], plan.inv_mass[o]);
+      }
+      CK(cudaMemcpy(x.p, hx.data(), V * sizeof(float4), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(xp.p, hx.data(), V * sizeof(float4), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(v.p, hv.data(), V * sizeof(float4), cudaMemcpyHostToDevice));
+    }
+    // surface
+    {
+      const size_t ns = plan.surf_ids.size();
+      std::vector<uint32_t> slot(ns);
+      for (size_t s = 0; s < ns; s++) slot[s] = plan.inv[plan.surf_ids[s]];
+      surf_slot.upload(slot, &dev_bytes);
+      surf_tri_off.upload(plan.surf_tri_off, &dev_bytes);
+      surf_tri_ids.upload(plan.surf_tri_ids, &dev_bytes);
+      std::vector<int32_t> td(plan.tris.size());
+      for (size_t i = 0; i < td.size(); i++) td[i] = (int32_t)plan.inv[plan.tris[i]];
+      tris_dev.upload(td, &dev_bytes);
+      nrm.alloc(ns ? ns : 1, &dev_bytes);
+      CK(cudaMemset(nrm.p, 0, (ns ? ns : 1) * sizeof(float4)));
+    }
+    // tile passes
+    uint32_t bt = m.block_threads > 0 ? (uint32_t)m.block_threads : 512u;
+    if (bt != 256 && bt != 512 && bt != 1024) throw std::string("block_threads must be 256, 512 or 1024");
+    block_threads = bt;
+    passes.resize(plan.passes.size());
+    for (size_t k = 0; k < plan.passes.size(); k++) {
+      const TilePass &tp = plan.passes[k];
+      PassBufs &pb = passes[k];
+      pb.vert_off.upload(tp.vert_off, &dev_bytes);
+      if (!tp.contiguous) pb.tile_verts.upload(tp.tile_verts, &dev_bytes);
+      pb.ctab_off.upload(tp.ctab_off, &dev_bytes);
+      pb.n_ecol.upload(tp.n_ecol, &dev_bytes);
+      pb.ctab.upload(tp.ctab, &dev_bytes);
+      pb.erec.upload(tp.erec, &dev_bytes);
+      pb.tidx.upload(tp.tidx, &dev_bytes);
+      pb.trest.upload(tp.trest, &dev_bytes);
+      pb.dev = PassDev{pb.vert_off.p, tp.contiguous ? nullptr : pb.tile_verts.p, pb.ctab_off.p, pb.n_ecol.p,
+                       pb.ctab.p, pb.erec.p, pb.tidx.p, pb.trest.p, tp.n_tiles()};
+      pb.smem = tp.max_tile_verts * (uint32_t)sizeof(float4);
+      if (pb.smem > (uint32_t)prop.sharedMemPerBlockOptin) throw std::string("tile_cap exceeds the shared memory of this device");
+    }
+    uint32_t max_smem = 0;
+    for (auto &pb : passes) max_smem = std::max(max_smem, pb.smem);
+    set_smem_attr(max_smem);
+    g_edges.upload(plan.g_edges, &dev_bytes);
+    g_elen.upload(plan.g_elen, &dev_bytes);
+    g_tets.upload(plan.g_tets, &dev_bytes);
+    g_trest.upload(plan.g_trest, &dev_bytes);
+    d_part.alloc((size_t)kDiagBlocks * 16, &dev_bytes);
+    CK(cudaDeviceSynchronize());
+  }
+
+  template <bool FAST, int BT>
+  static void set_attr_one(uint32_t smem) {
+    CK(cudaFuncSetAttribute(k_tile_pass<FAST, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  void set_smem_attr(uint32_t smem) {
+    if (smem <= 48 * 1024) return;
+    set_attr_one<false, 256>(smem); set_attr_one<false, 512>(smem); set_attr_one<false, 1024>(smem);
+    set_attr_one<true, 256>(smem); set_attr_one<true, 512>(smem); set_attr_one<true, 1024>(smem);
+  }
+
+  // ---- parameters -----------------------------------------------------------------
+  void refresh_params(float dt) {
+    if (!prm_dirty && dt == cur_dt) return;
+    DevParams p{};
+    // the oracle's make_consts, in float
+    p.h = dt / (float)prm.substeps;
+    p.inv_h = 1.0f / p.h;
+    const float hh = p.h * p.h;
+    auto compliance = [](float k) -> float {
+      if (std::isinf(k) && k > 0) return 0.0f;
+      if (k > 0) return 1.0f / k;
+      return -1.0f;
+    };
+    const float cd = compliance(prm.stiffness_distance), cv = compliance(prm.stiffness_volume);
+    p.use_d = cd >= 0;
+    p.use_v = cv >= 0;
+    p.a_d = p.use_d ? cd / hh : 0.f;
+    p.a_v36 = p.use_v ? 36.0f * (cv / hh) : 0.f;
+    const float dm = 1.0f - p.h * prm.damping;
+    p.damp = dm > 0 ? dm : 0.f;
+    p.keep = 1.0f - prm.friction;
+    p.gx = prm.gravity[0]; p.gy = prm.gravity[1]; p.gz = prm.gravity[2];
+    p.ground_y = prm.ground_y;
+    p.use_ground = !(prm.flags & SB_FLAG_NO_GROUND);
+    p.n_spheres = n_spheres;
+    for (int s = 0; s < n_spheres; s++) p.spheres[s] = spheres[s];
+    CK(cudaStreamSynchronize(stream)); // hprm may still be in flight from an earlier change
+    *hprm = p;
+    CK(cudaMemcpyAsync(dprm.p, hprm, sizeof(DevParams), cudaMemcpyHostToDevice, stream));
+    cur_dt = dt;
+    prm_dirty = false;
+  }
+
+  // ---- launches -------------------------------------------------------------------
+  int grid_for(size_t n, int bt) const {
+    size_t g = (n + bt - 1) / bt;
+    size_t cap = (size_t)n_sm * 8;
+    return (int)std::max<size_t>(1, std::min(g, cap));
+  }
+
+  template <bool FAST>
+  void launch_tile(const PassBufs &pb, cudaStream_t s) {
+    if (!pb.dev.n_tiles) return;
+    switch (block_threads) {
+      case 256: k_tile_pass<FAST, 256><<<pb.dev.n_tiles, 256, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
+      case 1024: k_tile_pass<FAST, 1024><<<pb.dev.n_tiles, 1024, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
+      default: k_tile_pass<FAST, 512><<<pb.dev.n_tiles, 512, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
+    }
+  }
+  void launch_pass(size_t k, cudaStream_t s) {
+    if (fast()) launch_tile<true>(passes[k], s);
+    else launch_tile<false>(passes[k], s);
+  }
+  void launch_global(cudaStream_t s) {
+    for (const GlobalBatch &b : plan.gbatches) {
+      if (!b.cnt) continue;
+      int g = grid_for(b.cnt, 256);
+      if (b.tet) {
+        if (fast()) k_global_tets<true><<<g, 256, 0, s>>>(g_tets.p + b.off, g_trest.p + b.off, b.cnt, x.p, dprm.p);
+        else k_global_tets<false><<<g, 256, 0, s>>>(g_tets.p + b.off, g_trest.p + b.off, b.cnt, x.p, dprm.p);
+      } else {
+        if (fast()) k_global_edges<true><<<g, 256, 0, s>>>(g_edges.p + b.off, g_elen.p + b.off, b.cnt, x.p, dprm.p);
+        else k_global_edges<false><<<g, 256, 0, s>>>(g_edges.p + b.off, g_elen.p + b.off, b.cnt, x.p, dprm.p);
+      }
+    }
+  }
+  void launch_predict(cudaStream_t s) { k_predict<<<grid_for(plan.V, 256), 256, 0, s>>>(plan.V, x.p, v.p, xp.p, dprm.p); }
+  void launch_finish(cudaStream_t s) { k_finish<<<grid_for(plan.V, 256), 256, 0, s>>>(plan.V, x.p, v.p, xp.p, dprm.p); }
+  void launch_normals(cudaStream_t s) {
+    const uint32_t ns = (uint32_t)plan.surf_ids.size();
+    if (!ns || (prm.flags & SB_FLAG_NO_NORMALS)) return;
+    k_normals<<<grid_for(ns, 256), 256, 0, s>>>(ns, surf_tri_off.p, surf_tri_ids.p, tris_dev.p, x.p, nrm.p);
+  }
+
+  uint32_t launches_per_frame() const {
+    uint32_t per_iter = 0;
+    for (auto &pb : passes) per_iter += pb.dev.n_tiles ? 1 : 0;
+    for (auto &b : plan.gbatches) per_iter += b.cnt ? 1 : 0;
+    uint32_t n = (uint32_t)prm.substeps * (2 + (uint32_t)prm.iterations * per_iter);
+    if (!plan.surf_ids.empty() && !(prm.flags & SB_FLAG_NO_NORMALS)) n++;
+    return n;
+  }
+
+  void enqueue_frame(cudaStream_t s) {
+    for (int ss = 0; ss < prm.substeps; ss++) {
+      launch_predict(s);
+      for (int it = 0; it < prm.iterations; it++) {
+        for (size_t k = 0; k < passes.size(); k++) launch_pass(k, s);
+        launch_global(s);
+      }
+      launch_finish(s);
+    }
+    launch_normals(s);
+    CK(cudaGetLastError());
+  }
+
+  void step(float dt) {
+    CK(cudaSetDevice(device));
+    if (!(dt > 0)) dt = prm.dt;
+    if (!(dt > 0) || !std::isfinite(dt)) throw std::string("dt must be finite and > 0");
+    refresh_params(dt);
+    if (prm.flags & SB_FLAG_NO_GRAPH) {
+      enqueue_frame(stream);
+      return;
+    }
+    const uint64_t key = ((uint64_t)(uint32_t)prm.substeps << 40) | ((uint64_t)(uint32_t)prm.iterations << 16) |
+                         (uint64_t)(prm.flags & 0xffff);
+    auto it = graphs.find(key);
+    if (it == graphs.end()) {
+      cudaGraph_t g = nullptr;
+      CK(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        enqueue_frame(cap_stream);
+      } catch (...) {
+        cudaStreamEndCapture(cap_stream, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+      }
+      CK(cudaStreamEndCapture(cap_stream, &g));
+      cudaGraphExec_t ge = nullptr;
+      cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+      cudaGraphDestroy(g);
+      CK(e);
+      it = graphs.emplace(key, ge).first;
+    }
+    CK(cudaGraphLaunch(it->second, stream));
+  }
+
+  // ---- I/O ------------------------------------------------------------------------
+  float *pinned(size_t bytes) {
+    if (bytes > pin_bytes) {
+      if (pin) cudaFreeHost(pin);
+      pin = nullptr;
+      pin_bytes = 0;
+      CK(cudaMallocHost(&pin, bytes));
+      pin_bytes = bytes;
+    }
+    return pin;
+  }
+  void d2h(void *dst, const void *src, size_t bytes) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
+  void read_positions(float *dst) {
+    CK(cudaSetDevice(device));
+    k_gather_xyz<<<grid_for(plan.V, 256), 256, 0, stream>>>(plan.V, inv.p, x.p, stage_f.p);
+    CK(cudaGetLastError());
+    d2h(dst, stage_f.p, 3 * (size_t)plan.V * sizeof(float));
+  }
+  void read_surface(float *dpos, float *dnrm) {
+    CK(cudaSetDevice(device));
+    const uint32_t ns = (uint32_t)plan.surf_ids.size();
+    if (!ns) return;
+    if (dpos) {
+      k_gather_xyz<<<grid_for(ns, 256), 256, 0, stream>>>(ns, surf_slot.p, x.p, stage_f.p);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(dpos, stage_f.p, 3 * (size_t)ns * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    }
+    if (dnrm) {
+      float *st = stage_f.p + 3 * (size_t)ns; // ns <= V/2 is not guaranteed: use stage_a when tight
+      if (6 * (size_t)ns > 3 * (size_t)plan.V) st = (float *)stage_a.p;
+      k_gather_xyz<<<grid_for(ns, 256), 256, 0, stream>>>(ns, nullptr, nrm.p, st);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(dnrm, st, 3 * (size_t)ns * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    }
+    CK(cudaStreamSynchronize(stream));
+  }
+  void get_state(float *x4, float *v4) {
+    CK(cudaSetDevice(device));
+    const uint32_t V = plan.V;
+    if (x4) k_gather4<<<grid_for(V, 256), 256, 0, stream>>>(V, inv.p, x.p, stage_a.p);
+    if (v4) k_gather4<<<grid_for(V, 256), 256, 0, stream>>>(V, inv.p, v.p, stage_b.p);
+    CK(cudaGetLastError());
+    if (x4) CK(cudaMemcpyAsync(x4, stage_a.p, V * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+    if (v4) CK(cudaMemcpyAsync(v4, stage_b.p, V * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
+  void set_state(const float *x4, const float *v4) {
+    CK(cudaSetDevice(device));
+    const uint32_t V = plan.V;
+    if (x4) {
+      CK(cudaMemcpyAsync(stage_a.p, x4, V * sizeof(float4), cudaMemcpyHostToDevice, stream));
+      k_scatter4<<<grid_for(V, 256), 256, 0, stream>>>(V, inv.p, stage_a.p, x.p);
+    }
+    if (v4) {
+      CK(cudaMemcpyAsync(stage_b.p, v4, V * sizeof(float4), cudaMemcpyHostToDevice, stream));
+      k_scatter4<<<grid_for(V, 256), 256, 0, stream>>>(V, inv.p, stage_b.p, v.p);
+    }
+    CK(cudaGetLastError());
+    // the host buffers belong to the caller again when this returns
+    CK(cudaStreamSynchronize(stream));
+  }
+
+  void diagnostics(double *out) {
+    CK(cudaSetDevice(device));
+    if (!d_edges.p && plan.E) {
+      std::vector<int2> e(plan.E);
+      for (uint32_t k = 0; k < plan.E; k++)
+        e[k] = make_int2((int)plan.inv[plan.edges[2 * (size_t)k]], (int)plan.inv[plan.edges[2 * (size_t)k + 1]]);
+      d_edges.upload(e, &dev_bytes);
+      d_elen.upload(plan.rest_len, &dev_bytes);
+    }
+    if (!d_tets.p && plan.T) {
+      std::vector<int4> q(plan.T);
+      for (uint32_t t = 0; t < plan.T; t++) {
+        const int32_t *s = &plan.tets[4 * (size_t)t];
+        q[t] = make_int4((int)plan.inv[s[0]], (int)plan.inv[s[1]], (int)plan.inv[s[2]], (int)plan.inv[s[3]]);
+      }
+      d_tets.upload(q, &dev_bytes);
+    }
+    if (cur_dt < 0) refresh_params(prm.dt);
+    CK(cudaMemsetAsync(d_part.p, 0, (size_t)kDiagBlocks * 16 * sizeof(double), stream));
+    k_diag_verts<<<kDiagBlocks, 256, 0, stream>>>(plan.V, x.p, v.p, dprm.p, d_part.p);
+    k_diag_tets<<<kDiagBlocks, 256, 0, stream>>>(plan.T, d_tets.p, x.p, d_part.p);
+    k_diag_edges<<<kDiagBlocks, 256, 0, stream>>>(plan.E, d_edges.p, d_elen.p, x.p, d_part.p);
+    CK(cudaGetLastError());
+    std::vector<double> part((size_t)kDiagBlocks * 16);
+    d2h(part.data(), d_part.p, part.size() * sizeof(double));
+    double acc[16] = {0};
+    double maxneg = -INFINITY, smax = 0;
+    for (int b = 0; b < kDiagBlocks; b++) {
+      const double *p = &part[(size_t)b * 16];
+      for (int k = 0; k < 12; k++) acc[k] += p[k];
+      maxneg = std::max(maxneg, p[12]);
+      acc[13] += p[13];
+      smax = std::max(smax, p[14]);
+      acc[15] += p[15];
+    }
+    const double V = plan.V;
+    out[0] = acc[0]; out[1] = acc[1]; out[2] = acc[13];
+    out[3] = acc[2] / V; out[4] = acc[3] / V; out[5] = acc[4] / V;
+    for (int k = 0; k < 6; k++) out[6 + k] = acc[5 + k];
+    out[12] = smax;
+    out[13] = plan.E ? std::sqrt(acc[15] / plan.E) : 0.0;
+    out[14] = acc[11];
+    out[15] = -maxneg;
+  }
+
+  float time_kernel(int which, int reps) {
+    CK(cudaSetDevice(device));
+    if (cur_dt < 0) refresh_params(prm.dt);
+    const size_t nb = plan.V * sizeof(float4);
+    // save state in the staging buffers plus one temporary
+    DevBuf<float4> keep;
+    keep.alloc(plan.V, nullptr);
+    CK(cudaMemcpyAsync(stage_a.p, x.p, nb, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemcpyAsync(stage_b.p, v.p, nb, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemcpyAsync(keep.p, xp.p, nb, cudaMemcpyDeviceToDevice, stream));
+    auto run = [&]() {
+      if (which == 0) launch_predict(stream);
+      else if (which == 1) launch_finish(stream);
+      else if (which == 2) launch_normals(stream);
+      else if (which >= 16 && which < 16 + (int)passes.size()) launch_pass((size_t)(which - 16), stream);
+      else if (which == 32) launch_global(stream);
+      else throw std::string("unknown kernel selector");
+    };
+    run(); // warm-up
+    CK(cudaEventRecord(ev0, stream));
+    for (int r = 0; r < reps; r++) run();
+    CK(cudaEventRecord(ev1, stream));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(x.p, stage_a.p, nb, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemcpyAsync(v.p, stage_b.p, nb, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemcpyAsync(xp.p, keep.p, nb, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    return ms / (float)reps;
+  }
+};
+
+// ---- C ABI -----------------------------------------------------------------------
+
+static thread_local std::string g_create_error;
+
+static std::string validate_params(const sb_params *p) {
+  if (!p) return "params is NULL";
+  if (p->substeps < 1 || p->substeps > 1024) return "substeps must be in [1, 1024]";
+  if (p->iterations < 0 || p->iterations > 4096) return "iterations must be in [0, 4096]";
+  if (!(p->dt > 0) || !std::isfinite(p->dt)) return "dt must be finite and > 0";
+  if (std::isnan(p->stiffness_distance) || std::isnan(p->stiffness_volume)) return "stiffness is NaN";
+  if (!std::isfinite(p->damping) || p->damping < 0) return "damping must be finite and >= 0";
+  if (!(p->friction >= 0 && p->friction <= 1)) return "friction must be in [0, 1]";
+  for (int k = 0; k < 3; k++)
+    if (!std::isfinite(p->gravity[k])) return "gravity must be finite";
+  if (!std::isfinite(p->ground_y)) return "ground_y must be finite";
+  return "";
+}
+
+template <class F>
+static int guarded(sb_handle h, F fn) {
+  std::string &err = h ? h->err : g_create_error;
+  try {
+    return fn();
+  } catch (const CudaError &e) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at solver.cu:%d: %s", (int)e.code, cudaGetErrorString(e.code), e.line, e.what);
+    err = buf;
+    return SB_E_CUDA;
+  } catch (const std::string &s) {
+    err = s;
+    return SB_E_ARG;
+  } catch (const std::bad_alloc &) {
+    err = "out of host memory";
+    return SB_E_NOMEM;
+  } catch (...) {
+    err = "unexpected exception";
+    return SB_E_STATE;
+  }
+}
+
+#define NEED_HANDLE(h)          \
+  if (!(h)) return SB_E_ARG;    \
+  if ((h)->destroyed) return SB_E_STATE
+#define NEED_DEVICE(h)                                   \
+  NEED_HANDLE(h);                                        \
+  if (!(h)->on_device) {                                 \
+    (h)->err = "handle was created by sb_plan (host only)"; \
+    return SB_E_STATE;                                   \
+  }
+
+extern "C" {
+
+int sb_abi_check(uint32_t *version, uint32_t *sizeof_params, uint32_t *sizeof_desc, uint32_t *sizeof_info) {
+  if (version) *version = SB_ABI_VERSION;
+  if (sizeof_params) *sizeof_params = (uint32_t)sizeof(sb_params);
+  if (sizeof_desc) *sizeof_desc = (uint32_t)sizeof(sb_mesh_desc);
+  if (sizeof_info) *sizeof_info = (uint32_t)sizeof(sb_info);
+  return SB_OK;
+}
+
+void sb_default_params(sb_params *p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof *p);
+  p->dt = 1.0f / 60.0f;
+  p->substeps = 10;
+  p->iterations = 10;
+  p->stiffness_distance = INFINITY;
+  p->stiffness_volume = INFINITY;
+  p->damping = 0.f;
+  p->friction = 0.f;
+  p->gravity[1] = -9.81f;
+  p->ground_y = 0.f;
+  p->flags = 0;
+}
+
+static int create_impl(const sb_mesh_desc *mesh, const sb_params *params, sb_handle *out, bool device) {
+  if (!out) return SB_E_ARG;
+  *out = nullptr;
+  g_create_error.clear();
+  if (!mesh) { g_create_error = "mesh is NULL"; return SB_E_ARG; }
+  for (int k = 0; k < 6; k++)
+    if (mesh->reserved[k] != 0) { g_create_error = "reserved fields must be 0"; return SB_E_ARG; }
+  sb_params dp;
+  sb_default_params(&dp);
+  if (params) dp = *params;
+  std::string perr = validate_params(&dp);
+  if (!perr.empty()) { g_create_error = perr; return SB_E_ARG; }
+  sb_solver *s = nullptr;
+  int rc = guarded(nullptr, [&]() -> int {
+    s = new sb_solver();
+    s->prm = dp;
+    MeshInput in{mesh->pos_xyz, mesh->tets, mesh->surf_tris, mesh->inv_mass, mesh->n_verts, mesh->n_tets, mesh->n_tris, mesh->density};
+    PlanOptions opt;
+    opt.tile_cap = mesh->tile_cap;
+    opt.max_tile_passes = mesh->max_tile_passes;
+    opt.later_cap = mesh->later_tile_cap;
+    opt.threads = mesh->host_threads;
+    if (device) {
+      int ndev = 0;
+      CK(cudaGetDeviceCount(&ndev));
+      if (mesh->device < 0 || mesh->device >= ndev) throw std::string("no such CUDA device");
+      cudaDeviceProp prop;
+      CK(cudaGetDeviceProperties(&prop, mesh->device));
+      opt.n_sm = prop.multiProcessorCount;
+    }
+    std::string e = build_plan(in, opt, s->plan);
+    if (!e.empty()) throw e;
+    if (device) {
+      auto t0 = std::chrono::steady_clock::now();
+      s->upload(*mesh);
+      s->plan.build_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return SB_OK;
+  });
+  if (rc != SB_OK) {
+    delete s;
+    return rc;
+  }
+  *out = s;
+  return SB_OK;
+}
+
+int sb_create(const sb_mesh_desc *mesh, const sb_params *params, sb_handle *out) { return create_impl(mesh, params, out, true); }
+
+/* Host-only handle: topology, tiling, colouring and schedule without touching CUDA.
+   sb_get_info / sb_get_topology / sb_get_schedule / sb_surface_vertices work on it. */
+int sb_plan(const sb_mesh_desc *mesh, const sb_params *params, sb_handle *out) { return create_impl(mesh, params, out, false); }
+
+int sb_destroy(sb_handle h) {
+  if (!h) return SB_E_ARG;
+  delete h;
+  return SB_OK;
+}
+
+int sb_set_params(sb_handle h, const sb_params *p) {
+  NEED_HANDLE(h);
+  std::string e = validate_params(p);
+  if (!e.empty()) { h->err = e; return SB_E_ARG; }
+  h->prm = *p;
+  h->prm_dirty = true;
+  return SB_OK;
+}
+
+int sb_get_params(sb_handle h, sb_params *out) {
+  NEED_HANDLE(h);
+  if (!out) return SB_E_ARG;
+  *out = h->prm;
+  return SB_OK;
+}
+
+int sb_set_colliders(sb_handle h, const float *s, uint32_t n) {
+  NEED_HANDLE(h);
+  if (n > 16 || (n && !s)) { h->err = "at most 16 sphere colliders"; return SB_E_ARG; }
+  for (uint32_t k = 0; k < 4 * n; k++)
+    if (!std::isfinite(s[k])) { h->err = "collider is not finite"; return SB_E_ARG; }
+  for (uint32_t k = 0; k < n; k++) h->spheres[k] = make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+  h->n_spheres = (int)n;
+  h->prm_dirty = true;
+  return SB_OK;
+}
+
+int sb_step(sb_handle h, float dt) {
+  NEED_DEVICE(h);
+  return guarded(h, [&]() -> int { h->step(dt); return SB_OK; });
+}
+
+int sb_synchronize(sb_handle h) {
+  NEED_DEVICE(h);
+  return guarded(h, [&]() -> int {
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return SB_OK;
+  });
+}
+
+int sb_read_positions(sb_handle h, float *dst, uint32_t n) {
+  NEED_DEVICE(h);
+  if (!dst || n != h->plan.V) { h->err = "dst is NULL or n_verts mismatch"; return SB_E_ARG; }
+  return guarded(h, [&]() -> int { h->read_positions(dst); return SB_OK; });
+}
+
+int sb_surface_vertices(sb_handle h, int32_t *ids, uint32_t capacity, uint32_t *n_surface) {
+  NEED_HANDLE(h);
+  const uint32_t ns = (uint32_t)h->plan.surf_ids.size();
+  if (n_surface) *n_surface = ns;
+  if (ids) {
+    if (capacity < ns) { h->err = "capacity too small"; return SB_E_ARG; }
+    std::memcpy(ids, h->plan.surf_ids.data(), ns * sizeof(int32_t));
+  }
+  return SB_OK;
+}
+
+int sb_read_surface(sb_handle h, float *dpos, float *dnrm, uint32_t n_surface) {
+  NEED_DEVICE(h);
+  if (n_surface != h->plan.surf_ids.size()) { h->err = "n_surface mismatch"; return SB_E_ARG; }
+  return guarded(h, [&]() -> int { h->read_surface(dpos, dnrm); return SB_OK; });
+}
+
+int sb_read_normals(sb_handle h, float *dst, uint32_t n) {
+  NEED_DEVICE(h);
+  if (!dst || n != h->plan.V) { h->err = "dst is NULL or n_verts mismatch"; return SB_E_ARG; }
+  return guarded(h, [&]() -> int {
+    const size_t ns = h->plan.surf_ids.size();
+    std::memset(dst, 0, 3 * (size_t)n * sizeof(float));
+    if (!ns) return SB_OK;
+    float *tmp = h->pinned(3 * ns * sizeof(float));
+    h->read_surface(nullptr, tmp);
+    for (size_t s = 0; s < ns; s++) std::memcpy(dst + 3 * (size_t)h->plan.surf_ids[s], tmp + 3 * s, 3 * sizeof(float));
+    return SB_OK;
+  });
+}
+
+int sb_get_state(sb_handle h, float *x4, float *v4, uint32_t n) {
+  NEED_DEVICE(h);
+  if (n != h->plan.V) { h->err = "n_verts mismatch"; return SB_E_ARG; }
+  return guarded(h, [&]() -> int { h->get_state(x4, v4); return SB_OK; });
+}
+
+int sb_set_state(sb_handle h, const float *x4, const float *v4, uint32_t n) {
+  NEED_DEVICE(h);
+  if (n != h->plan.V) { h->err = "n_verts mismatch"; return SB_E_ARG; }
+  return guarded(h, [&]() -> int { h->set_state(x4, v4); return SB_OK; });
+}
+
+int sb_diagnostics(sb_handle h, double *out16) {
+  NEED_DEVICE(h);
+  if (!out16) return SB_E_ARG;
+  return guarded(h, [&]() -> int {
+    h->diagnostics(out16);
+    if (out16[14] > 0) { h->err = "non-finite positions"; return SB_E_NAN; }
+    return SB_OK;
+  });
+}
+
+int sb_get_info(sb_handle h, sb_info *o) {
+  NEED_HANDLE(h);
+  if (!o) return SB_E_ARG;
+  std::memset(o, 0, sizeof *o);
+  const Plan &P = h->plan;
+  o->n_verts = P.V; o->n_edges = P.E; o->n_tets = P.T; o->n_tris = P.F;
+  o->n_surface_verts = (uint32_t)P.surf_ids.size();
+  o->n_tile_passes = (uint32_t)P.passes.size();
+  uint32_t nb = 0;
+  for (size_t k = 0; k < P.passes.size(); k++) {
+    nb += P.passes[k].max_ecol + P.passes[k].max_tcol;
+    if (k < 8) {
+      o->tiles_in_pass[k] = P.passes[k].n_tiles();
+      o->max_colours_in_pass[k] = P.passes[k].max_ecol + P.passes[k].max_tcol;
+      o->constraints_in_pass[k] = P.passes[k].erec.size() + P.passes[k].tidx.size();
+    }
+    o->smem_bytes = std::max<uint32_t>(o->smem_bytes, P.passes[k].max_tile_verts * 16u);
+  }
+  o->n_global_batches = (uint32_t)P.gbatches.size();
+  o->n_batches = nb + (uint32_t)P.gbatches.size();
+  o->constraints_global = P.g_edges.size() + P.g_tets.size();
+  o->tile_cap = P.tile_cap;
+  o->block_threads = h->block_threads;
+  o->launches_per_frame = h->on_device ? h->launches_per_frame() : 0;
+  o->device_bytes = h->dev_bytes;
+  o->build_seconds = P.build_seconds;
+  return SB_OK;
+}
+
+int sb_get_topology(sb_handle h, int32_t *edges, float *rest_len, float *rest_vol6, float *inv_mass) {
+  NEED_HANDLE(h);
+  const Plan &P = h->plan;
+  if (edges) std::memcpy(edges, P.edges.data(), P.edges.size() * sizeof(int32_t));
+  if (rest_len) std::memcpy(rest_len, P.rest_len.data(), P.rest_len.size() * sizeof(float));
+  if (rest_vol6) std::memcpy(rest_vol6, P.rest_vol6.data(), P.rest_vol6.size() * sizeof(float));
+  if (inv_mass) std::memcpy(inv_mass, P.inv_mass.data(), P.inv_mass.size() * sizeof(float));
+  return SB_OK;
+}
+
+int sb_get_schedule(sb_handle h, int64_t *n_order, int32_t *order, int32_t *n_batches, int64_t *batch_off) {
+  NEED_HANDLE(h);
+  return guarded(h, [&]() -> int {
+    std::vector<int32_t> ord;
+    std::vector<int64_t> off;
+    h->plan.export_schedule(ord, off);
+    if (n_order) *n_order = (int64_t)ord.size();
+    if (n_batches) *n_batches = (int32_t)off.size() - 1;
+    if (order) std::memcpy(order, ord.data(), ord.size() * sizeof(int32_t));
+    if (batch_off) std::memcpy(batch_off, off.data(), off.size() * sizeof(int64_t));
+    return SB_OK;
+  });
+}
+
+/* Tile membership, for tests of the host plan: for pass p writes, per caller vertex,
+   the tile that stages it (or -1).  tile_of may be NULL to query n_tiles only. */
+int sb_get_tiles(sb_handle h, uint32_t pass, int32_t *tile_of, uint32_t *n_tiles) {
+  NEED_HANDLE(h);
+  const Plan &P = h->plan;
+  if (pass >= P.passes.size()) { h->err = "no such pass"; return SB_E_ARG; }
+  const TilePass &tp = P.passes[pass];
+  if (n_tiles) *n_tiles = tp.n_tiles();
+  if (tile_of) {
+    for (uint32_t i = 0; i < P.V; i++) tile_of[i] = -1;
+    for (uint32_t t = 0; t < tp.n_tiles(); t++)
+      for (uint32_t k = tp.vert_off[t]; k < tp.vert_off[t + 1]; k++) {
+        uint32_t d = tp.contiguous ? k : tp.tile_verts[k];
+        tile_of[P.perm[d]] = (int32_t)t;
+      }
+  }
+  return SB_OK;
+}
+
+int sb_time_frames(sb_handle h, int32_t n_frames, float dt, float *elapsed_ms) {
+  NEED_DEVICE(h);
+  if (n_frames < 1 || !elapsed_ms) return SB_E_ARG;
+  return guarded(h, [&]() -> int {
+    CK(cudaSetDevice(h->device));
+    h->refresh_params(dt > 0 ? dt : h->prm.dt);
+    CK(cudaEventRecord(h->ev0, h->stream));
+    for (int f = 0; f < n_frames; f++) h->step(dt);
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+    return SB_OK;
+  });
+}
+
+int sb_time_kernel(sb_handle h, int32_t which, int32_t reps, float *avg_ms) {
+  NEED_DEVICE(h);
+  if (reps < 1 || !avg_ms) return SB_E_ARG;
+  return guarded(h, [&]() -> int {
+    *avg_ms = h->time_kernel(which, reps);
+    return SB_OK;
+  });
+}
+
+const char *sb_last_error(sb_handle h) {
+  if (!h) return g_create_error.c_str();
+  return h->err.c_str();
+}
+
+} // extern "C"

@@ -1,0 +1,228 @@
+"""Host-side mirror of the soft-body solver component.
+
+Reference: the C# MonoBehaviour is NOT IN MOUNT (/root/reference/README.md:1 is the
+whole reference).  BASELINE.json:5 names its surface: a Step call plus the parameters
+stiffness, damping, substeps, iterations.  `SoftBody` keeps those names; every method
+is a thin call into the C ABI (include/softbody_b200.h), exactly what a P/Invoke shim
+does.  There is no CPU path here.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _abi
+from ._abi import SbError, SbInfo, SbMeshDesc, SbParams
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _buf_ptr(a):
+    """Pointer of a numpy array or a (CPU) torch tensor, without copying."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(a.data_ptr())  # torch tensor
+
+
+def default_params(**over) -> SbParams:
+    p = SbParams()
+    _abi.load().sb_default_params(C.byref(p))
+    for k, v in over.items():
+        if k == "gravity":
+            p.gravity = (C.c_float * 3)(*v)
+        else:
+            setattr(p, k, v)
+    return p
+
+
+class SoftBody:
+    """One soft body (or a batch of independent bodies in one mesh) on one GPU.
+
+    Parameters mirror the component's inspector fields: `stiffness` (edge springs, N/m;
+    inf = rigid), `volume_stiffness`, `damping`, `substeps`, `iterations`.
+    """
+
+    def __init__(self, pos, tets, surf_tris=None, inv_mass=None, *, density=1000.0, device=0,
+                 stiffness=math.inf, volume_stiffness=math.inf, damping=0.0, friction=0.0,
+                 substeps=10, iterations=10, dt=1.0 / 60.0, gravity=(0.0, -9.81, 0.0), ground_y=0.0,
+                 flags=0, tile_cap=0, max_tile_passes=-1, block_threads=0, later_tile_cap=0,
+                 host_threads=0, stream=None, host_only=False):
+        self._lib = _abi.load()
+        self._h = C.c_void_p()
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        tets = np.ascontiguousarray(tets, dtype=np.int32).reshape(-1, 4)
+        tris = None if surf_tris is None else np.ascontiguousarray(surf_tris, dtype=np.int32).reshape(-1, 3)
+        w = None if inv_mass is None else np.ascontiguousarray(inv_mass, dtype=np.float32).reshape(-1)
+        if w is not None and w.shape[0] != pos.shape[0]:
+            raise ValueError("inv_mass must have one entry per vertex")
+        self.n_verts, self.n_tets = pos.shape[0], tets.shape[0]
+        self.n_tris = 0 if tris is None else tris.shape[0]
+        d = SbMeshDesc()
+        d.pos_xyz, d.tets, d.surf_tris, d.inv_mass = _ptr(pos), _ptr(tets), _ptr(tris), _ptr(w)
+        d.stream = C.c_void_p(stream) if stream else None
+        d.n_verts, d.n_tets, d.n_tris = self.n_verts, self.n_tets, self.n_tris
+        d.density, d.device = density, device
+        d.tile_cap, d.max_tile_passes, d.block_threads = tile_cap, max_tile_passes, block_threads
+        d.later_tile_cap, d.host_threads = later_tile_cap, host_threads
+        self._params = default_params(
+            dt=dt, substeps=substeps, iterations=iterations, stiffness_distance=stiffness,
+            stiffness_volume=volume_stiffness, damping=damping, friction=friction, gravity=gravity,
+            ground_y=ground_y, flags=flags)
+        fn = self._lib.sb_plan if host_only else self._lib.sb_create
+        rc = fn(C.byref(d), C.byref(self._params), C.byref(self._h))
+        if rc != 0:
+            raise SbError(rc, self._lib.sb_last_error(None).decode())
+        self.host_only = host_only
+        i = self.info()
+        self.n_edges, self.n_surface = i["n_edges"], i["n_surface_verts"]
+
+    # -- lifecycle ---------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.sb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SbError(rc, self._lib.sb_last_error(self._h).decode())
+
+    # -- parameters (the inspector fields) ----------------------------------------
+    def _push(self):
+        self._ck(self._lib.sb_set_params(self._h, C.byref(self._params)))
+
+    @property
+    def params(self) -> SbParams:
+        return self._params
+
+    def set_params(self, **kw):
+        alias = {"stiffness": "stiffness_distance", "volume_stiffness": "stiffness_volume"}
+        for k, v in kw.items():
+            k = alias.get(k, k)
+            if k == "gravity":
+                self._params.gravity = (C.c_float * 3)(*v)
+            else:
+                if not hasattr(self._params, k):
+                    raise AttributeError(k)
+                setattr(self._params, k, v)
+        self._push()
+
+    stiffness = property(lambda s: s._params.stiffness_distance, lambda s, v: s.set_params(stiffness=v))
+    volume_stiffness = property(lambda s: s._params.stiffness_volume, lambda s, v: s.set_params(volume_stiffness=v))
+    damping = property(lambda s: s._params.damping, lambda s, v: s.set_params(damping=v))
+    substeps = property(lambda s: s._params.substeps, lambda s, v: s.set_params(substeps=v))
+    iterations = property(lambda s: s._params.iterations, lambda s, v: s.set_params(iterations=v))
+
+    def set_colliders(self, spheres_xyzr):
+        s = np.ascontiguousarray(spheres_xyzr, dtype=np.float32).reshape(-1, 4)
+        self._ck(self._lib.sb_set_colliders(self._h, _ptr(s) if len(s) else None, len(s)))
+
+    # -- the hot path ---------------------------------------------------------------
+    def step(self, dt: float = 0.0, frames: int = 1):
+        """FixedUpdate: advance `frames` frames of dt seconds (asynchronous)."""
+        for _ in range(frames):
+            self._ck(self._lib.sb_step(self._h, dt))
+
+    def synchronize(self):
+        self._ck(self._lib.sb_synchronize(self._h))
+
+    # -- write-back -------------------------------------------------------------------
+    def positions(self, out=None):
+        out = np.empty((self.n_verts, 3), np.float32) if out is None else out
+        self._ck(self._lib.sb_read_positions(self._h, _buf_ptr(out), self.n_verts))
+        return out
+
+    def normals(self, out=None):
+        out = np.empty((self.n_verts, 3), np.float32) if out is None else out
+        self._ck(self._lib.sb_read_normals(self._h, _buf_ptr(out), self.n_verts))
+        return out
+
+    def surface_vertices(self):
+        ids = np.empty(self.n_surface, np.int32)
+        n = C.c_uint32()
+        self._ck(self._lib.sb_surface_vertices(self._h, _ptr(ids), self.n_surface, C.byref(n)))
+        return ids
+
+    def read_surface(self, pos_out=None, nrm_out=None):
+        pos_out = np.empty((self.n_surface, 3), np.float32) if pos_out is None else pos_out
+        nrm_out = np.empty((self.n_surface, 3), np.float32) if nrm_out is None else nrm_out
+        self._ck(self._lib.sb_read_surface(self._h, _buf_ptr(pos_out), _buf_ptr(nrm_out), self.n_surface))
+        return pos_out, nrm_out
+
+    def get_state(self, x4=None, v4=None):
+        x4 = np.empty((self.n_verts, 4), np.float32) if x4 is None else x4
+        v4 = np.empty((self.n_verts, 4), np.float32) if v4 is None else v4
+        self._ck(self._lib.sb_get_state(self._h, _buf_ptr(x4), _buf_ptr(v4), self.n_verts))
+        return x4, v4
+
+    def set_state(self, x4=None, v4=None):
+        if isinstance(x4, np.ndarray):
+            x4 = np.ascontiguousarray(x4, np.float32)
+        if isinstance(v4, np.ndarray):
+            v4 = np.ascontiguousarray(v4, np.float32)
+        self._ck(self._lib.sb_set_state(self._h, _buf_ptr(x4), _buf_ptr(v4), self.n_verts))
+
+    def diagnostics(self):
+        out = np.zeros(16, np.float64)
+        rc = self._lib.sb_diagnostics(self._h, _ptr(out))
+        if rc not in (0, _abi.SB_E_NAN):
+            self._ck(rc)
+        return dict(kinetic=out[0], potential=out[1], volume=out[2], centroid=out[3:6].copy(),
+                    momentum=out[6:9].copy(), angular_momentum=out[9:12].copy(), max_strain=out[12],
+                    rms_strain=out[13], nonfinite=int(out[14]), min_y=out[15], raw=out)
+
+    # -- build products ----------------------------------------------------------------
+    def info(self) -> dict:
+        i = SbInfo()
+        self._ck(self._lib.sb_get_info(self._h, C.byref(i)))
+        return i.as_dict()
+
+    def topology(self):
+        i = self.info()
+        edges = np.empty((i["n_edges"], 2), np.int32)
+        rest_len = np.empty(i["n_edges"], np.float32)
+        rest_vol6 = np.empty(i["n_tets"], np.float32)
+        inv_mass = np.empty(i["n_verts"], np.float32)
+        self._ck(self._lib.sb_get_topology(self._h, _ptr(edges), _ptr(rest_len), _ptr(rest_vol6), _ptr(inv_mass)))
+        return edges, rest_len, rest_vol6, inv_mass
+
+    def schedule(self):
+        """(order, batch_off): the Gauss-Seidel order of one iteration (see sb_get_schedule)."""
+        n, nb = C.c_int64(), C.c_int32()
+        self._ck(self._lib.sb_get_schedule(self._h, C.byref(n), None, C.byref(nb), None))
+        order = np.empty(n.value, np.int32)
+        off = np.empty(nb.value + 1, np.int64)
+        self._ck(self._lib.sb_get_schedule(self._h, C.byref(n), _ptr(order), C.byref(nb), _ptr(off)))
+        return order, off
+
+    def tiles(self, p: int):
+        n = C.c_uint32()
+        t = np.empty(self.n_verts, np.int32)
+        self._ck(self._lib.sb_get_tiles(self._h, p, _ptr(t), C.byref(n)))
+        return t, n.value
+
+    # -- device timing -------------------------------------------------------------------
+    def time_frames(self, n_frames: int, dt: float = 0.0) -> float:
+        ms = C.c_float()
+        self._ck(self._lib.sb_time_frames(self._h, n_frames, dt, C.byref(ms)))
+        return ms.value
+
+    def time_kernel(self, which: int, reps: int = 20) -> float:
+        ms = C.c_float()
+        self._ck(self._lib.sb_time_kernel(self._h, which, reps, C.byref(ms)))
+        return ms.value

@@ -1,0 +1,293 @@
+"""Known-answer tests that pin the CPU oracle.
+
+PARITY UNPINNED: the reference mount has no solver, tests or golden vectors
+(/root/reference/README.md:1 is all there is), so the oracle is pinned by closed-form
+answers any correct XPBD distance/volume solver must give, by invariants, and by an
+independently written numpy restatement (tests/np_xpbd.py).
+"""
+import math
+
+import numpy as np
+import pytest
+
+import np_xpbd
+from oracle import xpbd_oracle as orc
+from softbodyunity_b200 import meshgen
+
+TET = np.array([[0, 1, 2, 3]], np.int32)
+TET_POS = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32)
+TET_ENT = np.array([-2147483648], np.int32)  # tet 0
+
+
+def test_free_fall_closed_form():
+    # semi-implicit Euler: y_n = y0 - g h^2 n(n+1)/2 ; v_n = -g h n
+    m = orc.Model(TET_POS + np.float32([0, 100, 0]), TET, inv_mass=np.ones(4, np.float32), dtype=np.float64)
+    p = orc.params(dt=1 / 60, substeps=10, iterations=0, flags=1)
+    y0 = m.x4[:, 1].copy()
+    m.simulate(p, n_frames=6, order=np.zeros(0, np.int32))
+    n, h, g = 60, float(np.float32(1 / 60)) / 10, float(np.float32(9.81))
+    np.testing.assert_allclose(m.x4[:, 1], y0 - g * h * h * n * (n + 1) / 2, rtol=1e-12)
+    np.testing.assert_allclose(m.v4[:, 1], -g * h * n, rtol=1e-9)  # v is re-derived from x - x_prev at y ~ 100
+    assert np.all(m.x4[:, [0, 2]] == TET_POS[:, [0, 2]])
+    # fp32: PBD re-derives v from x - x_prev every substep, so the rounding of x (1 ulp of
+    # the coordinate) is divided by h; near the origin the closed form holds to ~1e-3 of the drop
+    m32 = orc.Model(TET_POS, TET, inv_mass=np.ones(4, np.float32))
+    m32.simulate(p, n_frames=6, order=np.zeros(0, np.int32))
+    drop = g * h * h * n * (n + 1) / 2
+    np.testing.assert_allclose(TET_POS[:, 1] - m32.x4[:, 1], drop, rtol=2e-3)
+
+
+def test_pinned_vertices_do_not_move():
+    w = np.array([0, 1, 1, 1], np.float32)
+    m = orc.Model(TET_POS, TET, inv_mass=w)
+    m.simulate(orc.params(flags=1), n_frames=3)
+    assert np.all(m.x4[0, :3] == TET_POS[0]) and np.all(m.v4[0] == 0)
+    assert m.x4[1, 1] < TET_POS[1, 1]
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-14), (np.float32, 4e-7)])
+def test_distance_projection_two_masses(dtype, tol):
+    # edge (0,1), unequal masses, zero compliance: one projection restores the rest length,
+    # displacements are in ratio w0:w1 along the edge, centre of mass is unchanged.
+    w = np.array([1.0, 3.0, 1.0, 1.0], np.float32)
+    m = orc.Model(TET_POS, TET, inv_mass=w, dtype=dtype)
+    e01 = int(np.where((m.edges == [0, 1]).all(1))[0][0])
+    L0 = float(m.rest_len[e01])
+    m.x4[1, :3] = [1.7, 0.2, -0.1]
+    before = m.x4.copy()
+    m.simulate(orc.params(substeps=1, iterations=1, gravity=(0, 0, 0), flags=1), order=np.array([e01], np.int32))
+    d = m.x4[0, :3] - m.x4[1, :3]
+    assert abs(np.linalg.norm(d) - L0) <= tol * 4
+    dx0, dx1 = m.x4[0, :3] - before[0, :3], m.x4[1, :3] - before[1, :3]
+    np.testing.assert_allclose(np.linalg.norm(dx0) / np.linalg.norm(dx1), 1.0 / 3.0, rtol=1e-5)
+    com_b = before[0, :3] / 1.0 + before[1, :3] / 3.0
+    com_a = m.x4[0, :3] / 1.0 + m.x4[1, :3] / 3.0
+    np.testing.assert_allclose(com_a, com_b, atol=tol * 10)
+    assert np.all(m.x4[2:] == before[2:])
+
+
+def test_distance_compliance_limits():
+    # finite stiffness k: one projection moves the fraction (w)/(w + alpha/h^2) of the way
+    m = orc.Model(TET_POS, TET, inv_mass=np.ones(4, np.float32), dtype=np.float64)
+    e01 = int(np.where((m.edges == [0, 1]).all(1))[0][0])
+    m.x4[1, 0] = 2.0
+    k, dt = 50.0, 0.01
+    m.simulate(orc.params(dt=dt, substeps=1, iterations=1, stiffness_distance=k, gravity=(0, 0, 0), flags=1),
+               order=np.array([e01], np.int32))
+    alpha = float(np.float32(1.0) / np.float32(k)) / float(np.float32(dt)) ** 2
+    expect_gap = 2.0 - (2.0 - 1.0) * 2.0 / (2.0 + alpha)
+    assert abs((m.x4[1, 0] - m.x4[0, 0]) - expect_gap) < 1e-9
+    # stiffness <= 0 disables the family
+    m2 = orc.Model(TET_POS, TET, inv_mass=np.ones(4, np.float32))
+    m2.x4[1, 0] = 2.0
+    m2.simulate(orc.params(substeps=1, iterations=3, stiffness_distance=0.0, stiffness_volume=-1.0, gravity=(0, 0, 0), flags=1))
+    assert m2.x4[1, 0] == 2.0
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 1e-5)])
+def test_volume_projection_single_tet(dtype, tol):
+    w = np.array([1.0, 2.0, 0.5, 1.5], np.float32)
+    m = orc.Model(TET_POS, TET, inv_mass=w, dtype=dtype)
+    V0 = float(m.rest_vol6[0]) / 6
+    assert abs(V0 - 1 / 6) < 1e-7
+    m.x4[3, :3] += np.array([0.003, -0.002, 0.004], dtype)  # small perturbation
+    before = m.x4.copy()
+
+    def volume(x4):
+        p = x4[:, :3].astype(np.float64)
+        return np.dot(p[1] - p[0], np.cross(p[2] - p[0], p[3] - p[0])) / 6
+
+    viol0 = abs(volume(before) - V0) / V0
+    m.simulate(orc.params(substeps=1, iterations=1, stiffness_distance=0, gravity=(0, 0, 0), flags=1), order=TET_ENT)
+    viol1 = abs(volume(m.x4) - V0) / V0
+    assert viol0 > 1e-3
+    assert viol1 < 2 * viol0 ** 2 + tol  # one Newton step: second order in the violation
+    # linear momentum: sum m dx = 0 (gradients sum to zero)
+    dp = (m.x4[:, :3] - before[:, :3]).astype(np.float64) / w[:, None]
+    assert np.abs(dp.sum(0)).max() < tol
+    assert np.abs(dp).max() > 1e-4
+
+
+def test_ground_clamp_and_velocity_update():
+    pos = TET_POS + np.float32([0, 0.001, 0])
+    m = orc.Model(pos, TET, inv_mass=np.ones(4, np.float32))
+    m.v4[:, 0] = 1.0
+    m.v4[:, 1] = -2.0
+    p = orc.params(dt=0.01, substeps=1, iterations=0, gravity=(0, 0, 0), friction=0.25, damping=0.0)
+    m.simulate(p, order=np.zeros(0, np.int32))
+    h = np.float32(0.01)
+    # vertices 0,1,3 start at y=0.001 and move to -0.019 -> clamped, tangential motion scaled by 0.75
+    for i in (0, 1, 3):
+        assert m.x4[i, 1] == 0.0
+        xp = np.float32(pos[i, 0])
+        x_pred = np.float32(np.float32(h * np.float32(1.0)) + xp)  # fma(h, v, x): exact here up to one rounding
+        expect = np.float32(0.75) * np.float32(x_pred - xp) + xp
+        assert abs(m.x4[i, 0] - expect) <= 1e-7
+        assert abs(m.v4[i, 1] - (np.float32(0.0) - pos[i, 1]) / h) < 1e-4
+    # vertex 2 (y = 1.001) stays free
+    assert m.x4[2, 1] > 0.9 and abs(m.v4[2, 1] + 2.0) < 1e-4
+    # damping: v *= max(0, 1 - h*c)
+    m2 = orc.Model(TET_POS + np.float32([0, 10, 0]), TET, inv_mass=np.ones(4, np.float32))
+    m2.v4[:, 0] = 1.0
+    m2.simulate(orc.params(dt=0.01, substeps=1, iterations=0, gravity=(0, 0, 0), damping=5.0), order=np.zeros(0, np.int32))
+    np.testing.assert_allclose(m2.v4[:, 0], 1.0 * (1 - 0.01 * 5.0), rtol=1e-5)
+
+
+def test_sphere_collider_pushes_out():
+    m = orc.Model(TET_POS, TET, inv_mass=np.ones(4, np.float32))
+    sph = np.array([[0.0, 0.0, 0.0, 0.5]], np.float32)
+    m.x4[0, :3] = [0.1, 0.2, 0.2]
+    m.simulate(orc.params(substeps=1, iterations=0, gravity=(0, 0, 0), flags=1), order=np.zeros(0, np.int32), spheres=sph)
+    assert abs(np.linalg.norm(m.x4[0, :3]) - 0.5) < 1e-6
+    np.testing.assert_allclose(m.x4[0, :3] / 0.5, np.array([0.1, 0.2, 0.2]) / 0.3, rtol=1e-5)
+
+
+def test_normals_cube_and_sphere():
+    pos, tets, tris = meshgen.block(5, spacing=0.25, origin=(0, 0, 0), jitter=0.0)
+    m = orc.Model(pos, tets)
+    n = m.normals(tris)
+    ijk = np.rint(pos / 0.25).astype(int)
+    # interior of the +x face: exact (1,0,0); interior vertices: zero
+    face = (ijk[:, 0] == 4) & (ijk[:, 1] > 0) & (ijk[:, 1] < 4) & (ijk[:, 2] > 0) & (ijk[:, 2] < 4)
+    assert np.all(n[face] == np.float32([1, 0, 0]))
+    inner = ((ijk > 0) & (ijk < 4)).all(1)
+    assert np.all(n[inner] == 0)
+    np.testing.assert_allclose(np.linalg.norm(n[~inner], axis=1), 1.0, atol=1e-6)
+    # sphere: normals close to radial (staircase surface: loose bound), all outward
+    ps, ts, fs = meshgen.sphere(22, spacing=0.1, jitter=0.0)
+    ms = orc.Model(ps, ts)
+    ns = ms.normals(fs)
+    on = np.unique(fs)
+    c = ps.mean(0)
+    r = ps[on] - c
+    r /= np.linalg.norm(r, axis=1)[:, None]
+    cosang = (ns[on] * r).sum(1)
+    assert cosang.min() > 0.3 and cosang.mean() > 0.9
+
+
+def _batches_from(order, off):
+    out = []
+    for b in range(len(off) - 1):
+        ids = order[off[b]:off[b + 1]]
+        out.append(("t" if ids[0] < 0 else "e", (ids & 0x7fffffff).astype(np.int64)))
+    return out
+
+
+def _greedy_batches(m):
+    """Plain greedy colouring (test-local), edges then tets."""
+    order, off = [], [0]
+    for kind, cons in (("e", m.edges), ("t", m.tets)):
+        used = [set() for _ in range(m.V)]
+        cols = {}
+        for i, c in enumerate(cons):
+            k = 0
+            while any(k in used[v] for v in c):
+                k += 1
+            for v in c:
+                used[v].add(k)
+            cols.setdefault(k, []).append(i)
+        for k in sorted(cols):
+            ids = np.array(cols[k], np.int64)
+            order.extend((ids | (0x80000000 if kind == "t" else 0)).astype(np.uint32).view(np.int32).tolist()
+                         if kind == "t" else ids.tolist())
+            off.append(len(order))
+    return np.array(order, np.int64).astype(np.int32), np.array(off, np.int64)
+
+
+@pytest.fixture(scope="module")
+def small_case():
+    pos, tets, tris = meshgen.block(5, 4, 4, spacing=0.1, origin=(0, 0.02, 0), jitter=0.1, seed=7)
+    m = orc.Model(pos, tets)
+    order, off = _greedy_batches(m)
+    return pos, tets, order, off
+
+
+def test_oracle_matches_independent_numpy(small_case):
+    pos, tets, order, off = small_case
+    kw = dict(dt=1 / 60, substeps=4, iterations=3, damping=0.2, friction=0.3, gravity=(0.3, -9.81, 0.1), ground_y=0.0)
+    m64 = orc.Model(pos, tets, dtype=np.float64)
+    m64.simulate(orc.params(stiffness_distance=1e6, stiffness_volume=math.inf, **kw), n_frames=5, order=order, batch_off=off)
+    ref = orc.Model(pos, tets, dtype=np.float64)
+    x, v = np_xpbd.simulate(ref.x4[:, :3], ref.v4[:, :3], ref.inv_mass.astype(np.float64), ref.edges,
+                            ref.rest_len, ref.tets, ref.rest_vol6, dt=np.float32(kw["dt"]), substeps=4, iterations=3,
+                            k_d=np.float32(1e6), k_v=np.inf, damping=np.float32(0.2), friction=np.float32(0.3),
+                            gravity=np.float32(kw["gravity"]), ground_y=0.0, use_ground=True,
+                            batches=_batches_from(order, off), n_frames=5)
+    assert m64.x4[:, 1].min() == 0.0  # the case does touch the ground
+    np.testing.assert_allclose(m64.x4[:, :3], x, atol=2e-11)
+    np.testing.assert_allclose(m64.v4[:, :3], v, atol=2e-8)
+    # fp32 oracle stays within 1e-4 relative of the fp64 numpy answer (the tolerance of BASELINE.json:5)
+    m32 = orc.Model(pos, tets)
+    m32.simulate(orc.params(stiffness_distance=1e6, stiffness_volume=math.inf, **kw), n_frames=5, order=order, batch_off=off)
+    scale = np.linalg.norm(x.max(0) - x.min(0))
+    assert np.abs(m32.x4[:, :3] - x).max() / scale < 1e-4
+
+
+def test_batch_permutation_and_threads_are_bitwise_neutral(small_case):
+    pos, tets, order, off = small_case
+    p = orc.params(substeps=3, iterations=4)
+    a = orc.Model(pos, tets)
+    a.simulate(p, n_frames=4, order=order, batch_off=off)
+    rng = np.random.default_rng(3)
+    perm = order.copy()
+    for b in range(len(off) - 1):
+        rng.shuffle(perm[off[b]:off[b + 1]])
+    b_ = orc.Model(pos, tets)
+    b_.simulate(p, n_frames=4, order=perm, batch_off=off)
+    assert np.array_equal(a.x4.view(np.uint32), b_.x4.view(np.uint32))
+    c = orc.Model(pos, tets)
+    c.simulate(p, n_frames=4, order=order, batch_off=off, threads=4)
+    assert np.array_equal(a.x4.view(np.uint32), c.x4.view(np.uint32))
+    assert np.array_equal(a.v4.view(np.uint32), c.v4.view(np.uint32))
+
+
+def test_momentum_conserved_without_gravity_or_ground(small_case):
+    pos, tets, order, off = small_case
+    m = orc.Model(pos, tets, dtype=np.float64)
+    rng = np.random.default_rng(5)
+    m.v4[:, :3] = rng.normal(0, 0.5, (m.V, 3))
+    mass = 1.0 / m.inv_mass.astype(np.float64)
+    p0 = (mass[:, None] * m.v4[:, :3]).sum(0)
+    L0 = (mass[:, None] * np.cross(m.x4[:, :3], m.v4[:, :3])).sum(0)
+    m.simulate(orc.params(substeps=5, iterations=5, gravity=(0, 0, 0), flags=1), n_frames=20, order=order, batch_off=off)
+    p1 = (mass[:, None] * m.v4[:, :3]).sum(0)
+    L1 = (mass[:, None] * np.cross(m.x4[:, :3], m.v4[:, :3])).sum(0)
+    np.testing.assert_allclose(p1, p0, atol=1e-9 * np.abs(mass).sum())
+    # angular momentum: each projection is torque-free, but v = (x - x_prev)/h mixes two
+    # configurations, so PBD keeps L only to O(h): a few percent here, not to rounding
+    assert np.linalg.norm(L1 - L0) < 0.05 * np.linalg.norm(L0)
+
+
+def test_natural_order_and_colour_order_agree_physically(small_case):
+    # different Gauss-Seidel orders are different iterations of the same fixed point:
+    # after settling under gravity the two answers are close, though not bitwise equal
+    pos, tets, order, off = small_case
+    a = orc.Model(pos, tets, dtype=np.float64)
+    b = orc.Model(pos, tets, dtype=np.float64)
+    p = orc.params(substeps=10, iterations=10, damping=2.0)
+    a.simulate(p, n_frames=60)
+    b.simulate(p, n_frames=60, order=order, batch_off=off)
+    assert np.abs(a.x4[:, :3] - b.x4[:, :3]).max() < 5e-3
+    assert not np.array_equal(a.x4, b.x4)
+
+
+def test_diagnostics_known_values():
+    m = orc.Model(TET_POS + np.float32([0, 2, 0]), TET, inv_mass=np.full(4, 0.5, np.float32))
+    m.v4[:, 0] = 3.0
+    d = m.diagnostics()
+    assert abs(d[0] - 4 * 0.5 * 2.0 * 9.0) < 1e-9          # kinetic
+    assert abs(d[2] - 1 / 6) < 1e-7                        # volume
+    np.testing.assert_allclose(d[6:9], [4 * 2.0 * 3.0, 0, 0])  # momentum
+    assert d[12] < 1e-7 and d[14] == 0 and d[15] == 2.0
+    pe = -sum(2.0 * (-float(np.float32(9.81))) * y for y in (2.0, 2.0, 3.0, 2.0))
+    assert abs(d[1] - pe) < 1e-5
+
+
+def test_bad_arguments_are_rejected():
+    m = orc.Model(TET_POS, TET)
+    with pytest.raises(ValueError):
+        m.simulate(orc.params(substeps=0))
+    with pytest.raises(ValueError):
+        m.simulate(orc.params(), order=np.array([99], np.int32))
+    with pytest.raises(ValueError):
+        orc.build_edges(3, TET)

@@ -1,0 +1,218 @@
+"""CPU tests of the boundary and the host planner: the C-ABI library loads and exports
+every symbol the header declares, struct layouts match, and the schedule the planner
+emits is a valid coloured Gauss-Seidel order (each constraint once, every batch
+vertex-disjoint, every tile constraint interior to its tile)."""
+import ctypes as C
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from helpers import INF
+from oracle import xpbd_oracle as orc
+from softbodyunity_b200 import SbError, SoftBody, _abi, meshgen
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _abi.load()
+    hdr = open(os.path.join(ROOT, "include", "softbody_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(sb_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(declared) >= 24
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in the header but not exported"
+    assert sorted(_abi.EXPORTS) == declared
+
+
+def test_struct_layouts_match_the_header():
+    lib = _abi.load()
+    v, a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    assert lib.sb_abi_check(C.byref(v), C.byref(a), C.byref(b), C.byref(c)) == 0
+    assert (v.value, a.value, b.value) == (1, 48, 104)
+    assert c.value == C.sizeof(_abi.SbInfo)
+    assert C.sizeof(orc.OrcParams) == 48  # the oracle takes the same parameter block
+    p = _abi.SbParams()
+    lib.sb_default_params(C.byref(p))
+    assert (p.substeps, p.iterations) == (10, 10) and math.isinf(p.stiffness_distance)
+    assert abs(p.dt - 1 / 60) < 1e-9 and abs(p.gravity[1] + 9.81) < 1e-6
+
+
+def test_no_cpu_fallback_without_a_device():
+    pos, tets, tris = meshgen.block(3)
+    try:
+        import torch
+        has = torch.cuda.is_available()
+    except Exception:
+        has = False
+    if has:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(SbError) as e:
+        SoftBody(pos, tets, tris)
+    assert e.value.code == _abi.SB_E_CUDA
+    sb = SoftBody(pos, tets, tris, host_only=True)
+    with pytest.raises(SbError) as e:
+        sb.step()
+    assert e.value.code == _abi.SB_E_STATE
+    with pytest.raises(SbError):
+        sb.positions()
+
+
+def test_argument_errors():
+    pos, tets, tris = meshgen.block(3)
+    bad = tets.copy()
+    bad[0, 0] = 999
+    for kw in (dict(tets=bad), dict(substeps=0), dict(iterations=-1), dict(dt=0.0), dict(friction=2.0),
+               dict(damping=-1.0), dict(density=0.0), dict(inv_mass=np.full(27, -1, np.float32))):
+        args = dict(pos=pos, tets=tets, surf_tris=tris, host_only=True)
+        args.update(kw)
+        with pytest.raises(SbError) as e:
+            SoftBody(**args)
+        assert e.value.code == _abi.SB_E_ARG, kw
+    rep = tets.copy()
+    rep[0, 1] = rep[0, 0]
+    with pytest.raises(SbError):
+        SoftBody(pos, rep, host_only=True)
+    lib = _abi.load()
+    assert lib.sb_destroy(None) == _abi.SB_E_ARG
+    assert lib.sb_step(None, 0.0) == _abi.SB_E_ARG
+    h = C.c_void_p()
+    assert lib.sb_create(None, None, C.byref(h)) == _abi.SB_E_ARG and b"mesh" in lib.sb_last_error(None)
+
+
+def check_schedule(sb: SoftBody, edges, tets):
+    order, off = sb.schedule()
+    E, T = len(edges), len(tets)
+    kind = order < 0
+    ids = order & 0x7fffffff
+    assert np.array_equal(np.sort(ids[~kind]), np.arange(E)), "every edge exactly once"
+    assert np.array_equal(np.sort(ids[kind]), np.arange(T)), "every tet exactly once"
+    assert off[0] == 0 and off[-1] == len(order) and np.all(np.diff(off) > 0)
+    for b in range(len(off) - 1):
+        k = kind[off[b]:off[b + 1]]
+        assert k.all() or not k.any(), "a batch holds one constraint kind"
+        i = ids[off[b]:off[b + 1]]
+        verts = (tets[i] if k[0] else edges[i]).reshape(-1)
+        assert len(np.unique(verts)) == len(verts), f"batch {b} is not vertex-disjoint"
+    return order, off
+
+
+def check_tiles(sb: SoftBody, edges, tets, order):
+    info = sb.info()
+    n_pass = info["n_tile_passes"]
+    pos_in_order = 0
+    for p in range(n_pass):
+        tile_of, n_tiles = sb.tiles(p)
+        assert n_tiles == info["tiles_in_pass"][p]
+        n_c = info["constraints_in_pass"][p]
+        ents = order[pos_in_order:pos_in_order + n_c]
+        pos_in_order += n_c
+        for ent in ents:
+            vs = tets[ent & 0x7fffffff] if ent < 0 else edges[ent]
+            t = tile_of[vs]
+            assert t[0] >= 0 and (t == t[0]).all(), "tile-pass constraint must be interior to one tile"
+        counts = np.bincount(tile_of[tile_of >= 0], minlength=n_tiles)
+        assert counts.max() <= info["tile_cap"]
+    assert pos_in_order + info["constraints_global"] == len(order)
+
+
+@pytest.mark.parametrize("shape,kw", [
+    ((4, 4, 4), {}),
+    ((9, 8, 7), dict(tile_cap=128)),
+    ((9, 8, 7), dict(tile_cap=128, later_tile_cap=64)),
+    ((12, 12, 12), dict(tile_cap=300, max_tile_passes=2)),
+    ((6, 6, 6), dict(max_tile_passes=0)),
+])
+def test_schedule_is_a_valid_coloured_order(shape, kw):
+    pos, tets, tris = meshgen.block(*shape, spacing=0.1)
+    sb = SoftBody(pos, tets, tris, host_only=True, **kw)
+    edges = sb.topology()[0]
+    order, _ = check_schedule(sb, edges, tets)
+    check_tiles(sb, edges, tets, order)
+    info = sb.info()
+    if kw.get("max_tile_passes") == 0:
+        assert info["n_tile_passes"] == 0 and info["constraints_global"] == len(order)
+    if kw.get("tile_cap") == 128:
+        assert info["n_tile_passes"] >= 2  # the block does not fit one tile: cut constraints get their own passes
+
+
+def test_topology_matches_the_oracles_own_derivation_bitwise():
+    for pos, tets, tris in (meshgen.block(7, 6, 5, spacing=0.03), meshgen.sphere(12, spacing=0.05)):
+        sb = SoftBody(pos, tets, tris, host_only=True, density=850.0)
+        edges, rest_len, rest_vol6, inv_mass = sb.topology()
+        m = orc.Model(pos, tets, density=850.0)
+        assert np.array_equal(edges, m.edges)
+        assert np.array_equal(rest_len.view(np.uint32), m.rest_len.view(np.uint32))
+        assert np.array_equal(rest_vol6.view(np.uint32), m.rest_vol6.view(np.uint32))
+        assert np.array_equal(inv_mass.view(np.uint32), m.inv_mass.view(np.uint32))
+        assert (rest_vol6 > 0).all()
+
+
+def test_block_counts_match_the_closed_forms():
+    n = 14
+    pos, tets, tris = meshgen.block(n)
+    sb = SoftBody(pos, tets, tris, host_only=True)
+    i = sb.info()
+    assert i["n_tets"] == 5 * (n - 1) ** 3
+    assert i["n_edges"] == 3 * n * n * (n - 1) + 3 * n * (n - 1) ** 2
+    assert i["n_tris"] == 12 * (n - 1) ** 2 and i["n_surface_verts"] == n ** 3 - (n - 2) ** 3
+    assert np.array_equal(sb.surface_vertices(), np.unique(tris))
+
+
+def test_independent_bodies_never_share_a_tile_boundary():
+    # config 4 shape: many small bodies; whole bodies are packed into tiles, so nothing is cut
+    pos, tets, tris = meshgen.bodies(12, dims=(5, 5, 4))
+    sb = SoftBody(pos, tets, tris, host_only=True, tile_cap=256)
+    i = sb.info()
+    assert i["n_tile_passes"] == 1 and i["constraints_global"] == 0
+    assert i["tiles_in_pass"][0] == 6  # two 100-vertex bodies per 256-vertex tile
+    check_schedule(sb, sb.topology()[0], tets)
+
+
+def test_plan_is_deterministic_and_thread_count_neutral():
+    pos, tets, tris = meshgen.block(11, 10, 9, spacing=0.1)
+    a = SoftBody(pos, tets, tris, host_only=True, tile_cap=200, host_threads=1)
+    b = SoftBody(pos, tets, tris, host_only=True, tile_cap=200, host_threads=5)
+    assert all(np.array_equal(x, y) for x, y in zip(a.schedule(), b.schedule()))
+
+
+@st.composite
+def random_tet_mesh(draw):
+    """Random small tet soup: points on a jittered lattice, tets from random cells, vertices compacted."""
+    n = draw(st.integers(3, 5))
+    seed = draw(st.integers(0, 2 ** 16))
+    frac = draw(st.floats(0.3, 1.0))
+    rng = np.random.default_rng(seed)
+    pos, tets, _ = meshgen.block(n, n, n, spacing=0.2, jitter=0.15, seed=seed)
+    keep = rng.random(len(tets)) < frac
+    keep[rng.integers(len(tets))] = True
+    tets = tets[keep]
+    used = np.unique(tets)
+    remap = -np.ones(len(pos), np.int64)
+    remap[used] = np.arange(len(used))
+    return pos[used], remap[tets].astype(np.int32), draw(st.sampled_from([16, 40, 4000]))
+
+
+@settings(max_examples=25, deadline=None)
+@given(random_tet_mesh())
+def test_random_meshes_give_valid_schedules(case):
+    pos, tets, cap = case
+    sb = SoftBody(pos, tets, None, host_only=True, tile_cap=cap)
+    edges = sb.topology()[0]
+    order, _ = check_schedule(sb, edges, tets)
+    check_tiles(sb, edges, tets, order)
+
+
+def test_oracle_runs_the_planners_order(tmp_path):
+    # the exported order drives the oracle end to end (the pairing the GPU parity tests use)
+    pos, tets, tris = meshgen.sample_cube(6, centre_height=0.6)
+    sb = SoftBody(pos, tets, tris, host_only=True, tile_cap=100, stiffness=INF)
+    order, off = sb.schedule()
+    m = orc.Model(pos, tets)
+    m.simulate(orc.params(), n_frames=30, order=order, batch_off=off)
+    assert np.isfinite(m.x4).all() and m.x4[:, 1].min() >= 0.0
+    d = m.diagnostics()
+    assert abs(d[2] - 1.0) < 0.02  # volume of the unit cube survives the drop
