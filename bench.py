@@ -69,12 +69,14 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi clocks and throttle reasons, sampled every 100 ms from before the warm-up;
+    only samples whose timestamp falls inside the marked (GPU-busy) window are kept."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t0, self.t1 = index, None, [], None, None
 
     def start(self):
         try:
@@ -85,28 +87,39 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm, mx, reasons = [], None, set()
+        sm, mx, pw, reasons = [], None, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if self.t0 is not None and not (self.t0 <= ts <= (self.t1 or 1e18)):
+                    continue
+                sm.append(float(f[1]))
+                mx = float(f[2])
+                pw.append(float(f[3]))
             except ValueError:
                 continue
-            for nm, val in zip(names, f[3:7]):
+            for nm, val in zip(names, f[4:8]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons)}
 
 
 def cpu_oracle_rate(pos, tets, order, off, substeps, iterations, threads, reps):
@@ -171,6 +184,8 @@ def main():
     ap.add_argument("--tile-cap", type=int, default=0)
     ap.add_argument("--later-tile-cap", type=int, default=0)
     ap.add_argument("--block-threads", type=int, default=0)
+    ap.add_argument("--slot-bytes", type=int, default=0)
+    ap.add_argument("--n-slots", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-breakdown", action="store_true")
     args = ap.parse_args()
@@ -192,11 +207,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()  # nvidia-smi takes a moment to come up; samples are windowed by timestamp
     from softbodyunity_b200 import FLAG_FAST_MATH, SoftBody
     pos, tets, tris, name = workload(args, rank)
     flags = FLAG_FAST_MATH if args.fast_math else 0
     sb = SoftBody(pos, tets, tris, device=local, substeps=args.substeps, iterations=args.iterations, flags=flags,
-                  tile_cap=args.tile_cap, later_tile_cap=args.later_tile_cap, block_threads=args.block_threads)
+                  tile_cap=args.tile_cap, later_tile_cap=args.later_tile_cap, block_threads=args.block_threads,
+                  slot_bytes=args.slot_bytes, n_slots=args.n_slots)
     info = sb.info()
     V, E, T = info["n_verts"], info["n_edges"], info["n_tets"]
     ns = info["n_surface_verts"]
@@ -215,15 +234,19 @@ def main():
         return float(t.item())
 
     # ---- device-resident throughput ---------------------------------------------------
+    clocks.mark_begin()
     sb.step(frames=args.warmup)
     sb.synchronize()
     barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     ms = sb.time_frames(args.steps)
     barrier()
     ms = max_over_ranks(ms)
+    # keep the GPU under the same load until the sampler has seen it (untimed)
+    t_soak = time.time()
+    while time.time() - t_soak < 0.6:
+        sb.step(frames=2)
+        sb.synchronize()
+    clocks.mark_end()
     clk = clocks.stop() if rank == 0 else None
     value = world * V * args.substeps * args.steps / (ms * 1e-3)
 
@@ -261,10 +284,8 @@ def main():
     roof = None
     breakdown = None
     if info["n_tile_passes"] > 0:
-        order, off = sb.schedule()
-        n0 = info["constraints_in_pass"][0]
-        nt0 = int((order[:n0] < 0).sum())
-        ne0 = n0 - nt0
+        ne0 = info["edges_in_pass"][0]
+        nt0 = info["constraints_in_pass"][0] - ne0
         launch_bytes = 12.0 * ne0 + 20.0 * nt0 + 32.0 * V
         k_ms = sb.time_kernel(16, reps=30)
         ach = launch_bytes / (k_ms * 1e-3) / 1e9

@@ -87,10 +87,13 @@ typedef struct sb_mesh_desc {
   int32_t device;           /* CUDA device ordinal */
   int32_t tile_cap;         /* max vertices per shared-memory tile; 0 = auto */
   int32_t max_tile_passes;  /* -1 = auto; 0 = global colour batches only */
-  int32_t block_threads;    /* threads per tile CTA (256, 512 or 1024); 0 = auto */
+  int32_t block_threads;    /* threads per tile CTA (128, 256, 512 or 1024); 0 = auto per pass */
   int32_t later_tile_cap;   /* max vertices per tile in passes after the first; 0 = auto */
   int32_t host_threads;     /* threads for the host-side build; 0 = auto */
-  int32_t reserved[6];      /* must be 0 */
+  int32_t slot_bytes;       /* bytes per shared-memory staging slot of the constraint stream; 0 = auto */
+  int32_t n_slots;          /* staging slots per CTA (2..16); 0 = auto */
+  int32_t tilings;          /* 0 = auto; 1 = hierarchical tile passes only; N >= 2 = N balanced shifted tilings */
+  int32_t reserved[3];      /* must be 0 */
 } sb_mesh_desc; /* 104 bytes */
 
 /* Sizes and build statistics, for logs, benches and the byte model. */
@@ -98,15 +101,18 @@ typedef struct sb_info {
   uint32_t n_verts, n_edges, n_tets, n_tris;
   uint32_t n_surface_verts;
   uint32_t n_tile_passes;        /* shared-memory tile passes per iteration */
+  uint32_t n_tilings;            /* balanced shifted tilings among them (1 = hierarchical only) */
   uint32_t n_global_batches;     /* leftover global colour batches per iteration */
   uint32_t n_batches;            /* independent sets per iteration in the exported schedule */
   uint32_t tiles_in_pass[8];
   uint32_t max_colours_in_pass[8];
   uint64_t constraints_in_pass[8];
+  uint64_t edges_in_pass[8];     /* of which distance constraints */
   uint64_t constraints_global;
   uint32_t tile_cap;
   uint32_t block_threads;
-  uint32_t smem_bytes;
+  uint32_t smem_bytes;           /* dynamic shared memory per tile CTA */
+  uint32_t slot_bytes, n_slots;
   uint32_t launches_per_frame;   /* kernel launches inside one sb_step at current params */
   uint64_t device_bytes;         /* device memory held by the handle */
   double build_seconds;          /* host time spent in sb_create */

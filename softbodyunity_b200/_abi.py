@@ -39,18 +39,21 @@ class SbMeshDesc(C.Structure):
         ("n_verts", C.c_uint32), ("n_tets", C.c_uint32), ("n_tris", C.c_uint32),
         ("density", C.c_float), ("device", C.c_int32), ("tile_cap", C.c_int32),
         ("max_tile_passes", C.c_int32), ("block_threads", C.c_int32),
-        ("later_tile_cap", C.c_int32), ("host_threads", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("later_tile_cap", C.c_int32), ("host_threads", C.c_int32), ("slot_bytes", C.c_int32),
+        ("n_slots", C.c_int32), ("tilings", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
 class SbInfo(C.Structure):
     _fields_ = [
         ("n_verts", C.c_uint32), ("n_edges", C.c_uint32), ("n_tets", C.c_uint32), ("n_tris", C.c_uint32),
-        ("n_surface_verts", C.c_uint32), ("n_tile_passes", C.c_uint32),
+        ("n_surface_verts", C.c_uint32), ("n_tile_passes", C.c_uint32), ("n_tilings", C.c_uint32),
         ("n_global_batches", C.c_uint32), ("n_batches", C.c_uint32),
         ("tiles_in_pass", C.c_uint32 * 8), ("max_colours_in_pass", C.c_uint32 * 8),
-        ("constraints_in_pass", C.c_uint64 * 8), ("constraints_global", C.c_uint64),
+        ("constraints_in_pass", C.c_uint64 * 8), ("edges_in_pass", C.c_uint64 * 8),
+        ("constraints_global", C.c_uint64),
         ("tile_cap", C.c_uint32), ("block_threads", C.c_uint32), ("smem_bytes", C.c_uint32),
+        ("slot_bytes", C.c_uint32), ("n_slots", C.c_uint32),
         ("launches_per_frame", C.c_uint32), ("device_bytes", C.c_uint64), ("build_seconds", C.c_double),
     ]
 

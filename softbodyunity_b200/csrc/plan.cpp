@@ -291,6 +291,79 @@ std::vector<uint32_t> tile_vertices(Plan &P, uint32_t cap, int n_sm) {
   return off;
 }
 
+
+// ---- balanced shifted grid tilings ----------------------------------------------
+//
+// N_T tilings of space by the same box grid, tiling s shifted by s/N_T of a box along
+// every axis.  A constraint (an element spans far less than a quarter box) straddles
+// the planes of at most one tiling per axis, so with 4 tilings it is interior to a
+// tile of at least one; constraints are dealt to the tilings they are interior to so
+// that every pass carries about 1/N_T of the work and 1/N_T of each vertex's colours.
+struct Tiling {
+  std::vector<int32_t> part; // caller numbering -> tile
+  uint32_t n_tiles = 0;
+};
+
+bool grid_tilings(const Plan &P, uint32_t cap, int n_tilings, std::vector<Tiling> &out) {
+  const uint32_t V = P.V;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (uint32_t v = 0; v < V; v++)
+    for (int k = 0; k < 3; k++) {
+      lo[k] = std::min(lo[k], P.pos[3 * (size_t)v + k]);
+      hi[k] = std::max(hi[k], P.pos[3 * (size_t)v + k]);
+    }
+  double ext[3], vol = 1.0;
+  int flat = 0;
+  for (int k = 0; k < 3; k++) {
+    ext[k] = (double)hi[k] - lo[k];
+    if (!(ext[k] > 0)) { ext[k] = 0; flat++; }
+    else vol *= ext[k];
+  }
+  if (flat == 3) return false;
+  // start from the box edge that would hold `cap` vertices at uniform density, then shrink
+  // until no box of any tiling exceeds cap (bounded number of attempts)
+  double w = std::pow((double)cap * vol / V, 1.0 / (3 - flat));
+  std::vector<uint32_t> count;
+  for (int attempt = 0; attempt < 24; attempt++, w *= 0.94) {
+    int n[3];
+    double wa[3];
+    for (int k = 0; k < 3; k++) {
+      n[k] = ext[k] > 0 ? std::max(1, (int)std::ceil(ext[k] / w - 1e-9)) : 1;
+      wa[k] = ext[k] > 0 ? ext[k] / n[k] : 1.0;
+    }
+    if ((double)(n[0] + 1) * (n[1] + 1) * (n[2] + 1) > 64e6) return false;
+    out.assign(n_tilings, Tiling());
+    bool ok = true;
+    for (int s = 0; s < n_tilings && ok; s++) {
+      const int m[3] = {n[0] + (s > 0), n[1] + (s > 0), n[2] + (s > 0)};
+      count.assign((size_t)m[0] * m[1] * m[2], 0u);
+      Tiling &T = out[s];
+      T.part.resize(V);
+      for (uint32_t v = 0; v < V; v++) {
+        int c[3];
+        for (int k = 0; k < 3; k++) {
+          double f = ext[k] > 0 ? ((double)P.pos[3 * (size_t)v + k] - lo[k]) / wa[k] + (double)s / n_tilings : 0.0;
+          c[k] = std::min(m[k] - 1, std::max(0, (int)std::floor(f)));
+        }
+        const uint32_t cell = (uint32_t)c[0] + (uint32_t)m[0] * ((uint32_t)c[1] + (uint32_t)m[1] * (uint32_t)c[2]);
+        T.part[v] = (int32_t)cell;
+        count[cell]++;
+      }
+      // compact the non-empty boxes
+      std::vector<int32_t> remap(count.size(), -1);
+      uint32_t nt = 0;
+      for (size_t c = 0; c < count.size(); c++) {
+        if (count[c] > cap) ok = false;
+        if (count[c]) remap[c] = (int32_t)nt++;
+      }
+      for (uint32_t v = 0; v < V; v++) T.part[v] = remap[T.part[v]];
+      T.n_tiles = nt;
+    }
+    if (ok) return true;
+  }
+  return false;
+}
+
 // ---- tile passes -------------------------------------------------------------
 
 struct Mask128 {
@@ -310,9 +383,11 @@ inline void set_bit(Mask128 &m, int c) {
 struct TileOut {
   std::vector<uint32_t> verts; // device ids (non-contiguous passes)
   uint32_t n_ecol = 0, n_tcol = 0, n_verts = 0;
-  std::vector<U2> ctab, erec, tidx;
-  std::vector<float> trest;
-  std::vector<int32_t> erec_id, trec_id;
+  std::vector<U2> chunks;        // byte offsets relative to this tile's stream
+  std::vector<uint32_t> stream;  // words
+  std::vector<int32_t> ents;     // processing order
+  std::vector<uint32_t> col_cnt; // per colour, edge colours first
+  uint64_t n_edges = 0, n_tets = 0;
   std::string err;
 };
 
@@ -336,7 +411,7 @@ inline int ent_verts(const DevTopo &D, int32_t ent, int32_t *vs) {
 // `in` whose vertices all lie in one tile are consumed; the rest go to `out`.
 std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_t> &part, uint32_t n_tiles,
                        const std::vector<uint32_t> *contig_off, const std::vector<int32_t> &in,
-                       std::vector<int32_t> &out, TilePass &TP, int threads) {
+                       std::vector<int32_t> &out, TilePass &TP, int threads, uint32_t slot_bytes, uint32_t n_slots) {
   // 1. classify and bucket by tile (stable)
   std::vector<uint64_t> toff((size_t)n_tiles + 1, 0);
   std::vector<int32_t> owner(in.size());
@@ -424,32 +499,115 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
     }
     O.n_ecol = (uint32_t)ecount.size();
     O.n_tcol = (uint32_t)tcount.size();
-    std::vector<uint32_t> eoff(O.n_ecol + 1, 0), tof(O.n_tcol + 1, 0);
-    for (uint32_t c = 0; c < O.n_ecol; c++) eoff[c + 1] = eoff[c] + ecount[c];
-    for (uint32_t c = 0; c < O.n_tcol; c++) tof[c + 1] = tof[c] + tcount[c];
-    O.erec.resize(eoff[O.n_ecol]);
-    O.erec_id.resize(eoff[O.n_ecol]);
-    O.tidx.resize(tof[O.n_tcol]);
-    O.trest.resize(tof[O.n_tcol]);
-    O.trec_id.resize(tof[O.n_tcol]);
-    for (uint32_t c = 0; c < O.n_ecol; c++) O.ctab.push_back({eoff[c], ecount[c]});
-    for (uint32_t c = 0; c < O.n_tcol; c++) O.ctab.push_back({tof[c], tcount[c]});
-    std::vector<uint32_t> ecur(eoff.begin(), eoff.end() - 1), tcur(tof.begin(), tof.end() - 1);
-    for (size_t i = 0; i < ne; i++) {
-      int32_t vs[4];
-      ent_verts(D, ents[i], vs);
-      if (ents[i] >= 0) {
-        uint32_t k = ecur[col[i]]++;
-        O.erec[k] = {local(vs[0]) | (local(vs[1]) << 16), f2u(P.rest_len[ents[i]])};
-        O.erec_id[k] = ents[i];
-      } else {
-        int32_t id = ents[i] & 0x7fffffff;
-        uint32_t k = tcur[col[i]]++;
-        O.tidx[k] = {local(vs[0]) | (local(vs[1]) << 16), local(vs[2]) | (local(vs[3]) << 16)};
-        O.trest[k] = P.rest_vol6[id];
-        O.trec_id[k] = id;
+    // bucket by colour (stable): edge colours first, then tet colours
+    const uint32_t ncol = O.n_ecol + O.n_tcol;
+    std::vector<uint32_t> coff(ncol + 1, 0);
+    for (uint32_t c = 0; c < O.n_ecol; c++) coff[c + 1] = coff[c] + ecount[c];
+    for (uint32_t c = 0; c < O.n_tcol; c++) coff[O.n_ecol + c + 1] = coff[O.n_ecol + c] + tcount[c];
+    O.col_cnt.resize(ncol);
+    for (uint32_t c = 0; c < ncol; c++) O.col_cnt[c] = coff[c + 1] - coff[c];
+    O.ents.resize(ne);
+    {
+      std::vector<uint32_t> cur(coff.begin(), coff.end() - 1);
+      for (size_t i = 0; i < ne; i++) O.ents[cur[(ents[i] < 0 ? O.n_ecol : 0) + col[i]]++] = ents[i];
+    }
+    // Within a colour any order is equivalent; pick one where each run of 8 records (the
+    // quarter-warp an LDS.128 serves per wavefront) touches 8 different 16-byte bank groups
+    // (local id mod 8) in every vertex slot.
+    {
+      std::vector<int32_t> tmp;
+      std::vector<uint32_t> bucket[8];
+      for (uint32_t c = 0; c < ncol; c++) {
+        const uint32_t lo = coff[c], n = coff[c + 1] - coff[c];
+        if (n < 16) continue;
+        const int nvs = c >= O.n_ecol ? 4 : 2;
+        for (auto &b : bucket) b.clear();
+        std::vector<uint8_t> res((size_t)n * 4);
+        for (uint32_t k = 0; k < n; k++) {
+          int32_t vs[4];
+          ent_verts(D, O.ents[lo + k], vs);
+          for (int j = 0; j < nvs; j++) res[(size_t)k * 4 + j] = (uint8_t)(local(vs[j]) & 7u);
+          bucket[res[(size_t)k * 4]].push_back(k);
+        }
+        for (auto &b : bucket) std::reverse(b.begin(), b.end()); // pop_back takes ascending ids first
+        tmp.clear();
+        tmp.reserve(n);
+        uint32_t left = n;
+        while (left) {
+          uint8_t used[4] = {0, 0, 0, 0};
+          for (int pos = 0; pos < 8 && left; pos++) {
+            // prefer the bucket whose slot-0 residue is still free in this octet
+            int b = -1;
+            for (int r = 0; r < 8; r++) {
+              const int cand = (pos + r) & 7;
+              if (!bucket[cand].empty() && !(used[0] >> cand & 1)) { b = cand; break; }
+            }
+            if (b < 0) {
+              size_t best = 0;
+              for (int r = 0; r < 8; r++)
+                if (bucket[r].size() > best) { best = bucket[r].size(); b = r; }
+            }
+            std::vector<uint32_t> &B = bucket[b];
+            // among the next few candidates take the one with the fewest conflicts in the other slots
+            size_t pick = B.size() - 1;
+            int pick_conf = 99;
+            for (size_t q = 0; q < 12 && q < B.size(); q++) {
+              const uint32_t k = B[B.size() - 1 - q];
+              int conf = 0;
+              for (int j = 1; j < nvs; j++) conf += used[j] >> res[(size_t)k * 4 + j] & 1;
+              if (conf < pick_conf) { pick_conf = conf; pick = B.size() - 1 - q; if (!conf) break; }
+            }
+            const uint32_t k = B[pick];
+            B.erase(B.begin() + (ptrdiff_t)pick);
+            for (int j = 0; j < nvs; j++) used[j] |= (uint8_t)(1u << res[(size_t)k * 4 + j]);
+            tmp.push_back(O.ents[lo + k]);
+            left--;
+          }
+        }
+        std::copy(tmp.begin(), tmp.end(), O.ents.begin() + lo);
       }
     }
+    // cut every colour into chunks that fit one staging slot
+    const uint32_t max_e = slot_bytes / 8, max_t = (slot_bytes / 12) & ~3u;
+    uint32_t since_barrier = 0;
+    for (uint32_t c = 0; c < ncol; c++) {
+      const bool tet = c >= O.n_ecol;
+      const uint32_t cap_n = tet ? max_t : max_e;
+      for (uint32_t lo = coff[c]; lo < coff[c + 1]; lo += cap_n) {
+        const uint32_t n = std::min(cap_n, coff[c + 1] - lo);
+        const bool last = lo + n == coff[c + 1];
+        since_barrier++;
+        const bool bar = last || since_barrier + 1 >= n_slots;
+        if (bar) since_barrier = 0;
+        const uint32_t word0 = (uint32_t)O.stream.size();
+        O.chunks.push_back({word0 / 4, n | (tet ? 1u << 30 : 0u) | (bar ? 1u << 31 : 0u)});
+        if (!tet) {
+          const uint32_t n2 = (n + 1) & ~1u;
+          O.stream.resize(word0 + 2 * (size_t)n2, 0u);
+          for (uint32_t k = 0; k < n; k++) {
+            int32_t vs[4];
+            const int32_t e = O.ents[lo + k];
+            ent_verts(D, e, vs);
+            O.stream[word0 + 2 * k] = local(vs[0]) | (local(vs[1]) << 16);
+            O.stream[word0 + 2 * k + 1] = f2u(P.rest_len[e]);
+          }
+          O.n_edges += n;
+        } else {
+          const uint32_t n4 = (n + 3) & ~3u;
+          O.stream.resize(word0 + 3 * (size_t)n4, 0u);
+          for (uint32_t k = 0; k < n; k++) {
+            int32_t vs[4];
+            const int32_t e = O.ents[lo + k];
+            ent_verts(D, e, vs);
+            O.stream[word0 + 2 * k] = local(vs[0]) | (local(vs[1]) << 16);
+            O.stream[word0 + 2 * k + 1] = local(vs[2]) | (local(vs[3]) << 16);
+            O.stream[word0 + 2 * n4 + k] = f2u(P.rest_vol6[e & 0x7fffffff]);
+          }
+          O.n_tets += n;
+        }
+      }
+    }
+    if (!O.chunks.empty()) O.chunks.back().y |= 1u << 31;
     if (!contig_off)
       for (uint32_t v : O.verts) loc[v] = 0xffffffffu;
   });
@@ -458,32 +616,31 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
   TP = TilePass();
   TP.contiguous = contig_off != nullptr;
   TP.vert_off.push_back(0);
-  TP.ctab_off.push_back(0);
-  size_t ne = 0, ntt = 0, nv = 0;
+  TP.chunk_off.push_back(0);
+  TP.ent_off.push_back(0);
+  TP.col_off.push_back(0);
+  size_t nw = 0, nen = 0, nv = 0;
   for (auto &O : outs) {
     if (!O.err.empty()) return O.err;
-    ne += O.erec.size();
-    ntt += O.tidx.size();
+    nw += O.stream.size();
+    nen += O.ents.size();
     nv += O.verts.size();
   }
-  TP.erec.reserve(ne);
-  TP.erec_id.reserve(ne);
-  TP.tidx.reserve(ntt);
-  TP.trest.reserve(ntt);
-  TP.trec_id.reserve(ntt);
+  if (nw / 4 >= 0xffffffffull) return "constraint stream of one pass exceeds 64 GiB";
+  TP.stream.reserve(nw);
+  TP.ents.reserve(nen);
   TP.tile_verts.reserve(nv);
   for (uint32_t t = 0; t < n_tiles; t++) {
     TileOut &O = outs[t];
-    uint32_t eb = (uint32_t)TP.erec.size(), tb = (uint32_t)TP.tidx.size();
-    for (uint32_t c = 0; c < O.n_ecol; c++) TP.ctab.push_back({O.ctab[c].x + eb, O.ctab[c].y});
-    for (uint32_t c = 0; c < O.n_tcol; c++) TP.ctab.push_back({O.ctab[O.n_ecol + c].x + tb, O.ctab[O.n_ecol + c].y});
+    const uint32_t base16 = (uint32_t)(TP.stream.size() / 4);
+    for (const U2 &c : O.chunks) TP.chunks.push_back({c.x + base16, c.y});
+    TP.chunk_off.push_back((uint32_t)TP.chunks.size());
+    TP.stream.insert(TP.stream.end(), O.stream.begin(), O.stream.end());
+    TP.ents.insert(TP.ents.end(), O.ents.begin(), O.ents.end());
+    TP.ent_off.push_back(TP.ents.size());
+    TP.col_cnt.insert(TP.col_cnt.end(), O.col_cnt.begin(), O.col_cnt.end());
+    TP.col_off.push_back((uint32_t)TP.col_cnt.size());
     TP.n_ecol.push_back(O.n_ecol);
-    TP.ctab_off.push_back((uint32_t)TP.ctab.size());
-    TP.erec.insert(TP.erec.end(), O.erec.begin(), O.erec.end());
-    TP.erec_id.insert(TP.erec_id.end(), O.erec_id.begin(), O.erec_id.end());
-    TP.tidx.insert(TP.tidx.end(), O.tidx.begin(), O.tidx.end());
-    TP.trest.insert(TP.trest.end(), O.trest.begin(), O.trest.end());
-    TP.trec_id.insert(TP.trec_id.end(), O.trec_id.begin(), O.trec_id.end());
     if (TP.contiguous) {
       TP.vert_off.push_back((*contig_off)[t + 1]);
     } else {
@@ -493,6 +650,9 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
     TP.max_ecol = std::max(TP.max_ecol, O.n_ecol);
     TP.max_tcol = std::max(TP.max_tcol, O.n_tcol);
     TP.max_tile_verts = std::max(TP.max_tile_verts, O.n_verts);
+    TP.max_chunks = std::max(TP.max_chunks, (uint32_t)O.chunks.size());
+    TP.n_edges += O.n_edges;
+    TP.n_tets += O.n_tets;
     O = TileOut();
   }
   if (TP.contiguous) TP.vert_off[0] = (*contig_off)[0];
@@ -632,24 +792,27 @@ void Plan::export_schedule(std::vector<int32_t> &order, std::vector<int64_t> &ba
     if ((int64_t)order.size() > batch_off.back()) batch_off.push_back((int64_t)order.size());
   };
   for (const TilePass &TP : passes) {
-    uint32_t nt = TP.n_tiles();
-    for (uint32_t c = 0; c < TP.max_ecol; c++) {
-      for (uint32_t t = 0; t < nt; t++)
-        if (c < TP.n_ecol[t]) {
-          U2 r = TP.ctab[TP.ctab_off[t] + c];
-          for (uint32_t k = 0; k < r.y; k++) order.push_back(TP.erec_id[r.x + k]);
-        }
-      close();
-    }
-    for (uint32_t c = 0; c < TP.max_tcol; c++) {
-      for (uint32_t t = 0; t < nt; t++) {
-        uint32_t ntc = TP.ctab_off[t + 1] - TP.ctab_off[t] - TP.n_ecol[t];
-        if (c < ntc) {
-          U2 r = TP.ctab[TP.ctab_off[t] + TP.n_ecol[t] + c];
-          for (uint32_t k = 0; k < r.y; k++) order.push_back((int32_t)(0x80000000u | (uint32_t)TP.trec_id[r.x + k]));
-        }
+    const uint32_t nt = TP.n_tiles();
+    // start of every colour of every tile inside TP.ents
+    std::vector<uint64_t> cstart(TP.col_cnt.size() + 1, 0);
+    for (uint32_t t = 0; t < nt; t++) {
+      uint64_t at = TP.ent_off[t];
+      for (uint32_t j = TP.col_off[t]; j < TP.col_off[t + 1]; j++) {
+        cstart[j] = at;
+        at += TP.col_cnt[j];
       }
-      close();
+    }
+    for (int kind = 0; kind < 2; kind++) {
+      const uint32_t maxc = kind ? TP.max_tcol : TP.max_ecol;
+      for (uint32_t c = 0; c < maxc; c++) {
+        for (uint32_t t = 0; t < nt; t++) {
+          const uint32_t nk = kind ? TP.col_off[t + 1] - TP.col_off[t] - TP.n_ecol[t] : TP.n_ecol[t];
+          if (c >= nk) continue;
+          const uint32_t j = TP.col_off[t] + (kind ? TP.n_ecol[t] : 0) + c;
+          for (uint32_t k = 0; k < TP.col_cnt[j]; k++) order.push_back(TP.ents[cstart[j] + k]);
+        }
+        close();
+      }
     }
   }
   for (const GlobalBatch &b : gbatches) {
@@ -690,13 +853,50 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   if (!err.empty()) return err;
 
   // ---- tiling ---------------------------------------------------------------
-  uint32_t cap = opt.tile_cap > 0 ? (uint32_t)opt.tile_cap : 6784u;
+  uint32_t cap = opt.tile_cap > 0 ? (uint32_t)opt.tile_cap : 3392u;
   cap = std::min(cap, 65536u);
   P.tile_cap = cap;
+  uint32_t slot_bytes = opt.slot_bytes > 0 ? (uint32_t)opt.slot_bytes : 8160u;
+  slot_bytes = std::max(192u, slot_bytes / 48 * 48);
+  uint32_t n_slots = opt.n_slots > 0 ? (uint32_t)std::min(opt.n_slots, 16) : 2u;
+  n_slots = std::max(n_slots, 2u);
+  P.slot_bytes = slot_bytes;
+  P.n_slots = n_slots;
   int max_passes = opt.max_tile_passes < 0 ? 6 : std::min(opt.max_tile_passes, 8);
 
+  // largest connected component decides the layout: many small bodies are packed whole
+  // into tiles (one pass, nothing cut); a big mesh gets the balanced shifted tilings
+  int n_tilings = opt.tilings;
+  std::vector<Tiling> tilings;
+  if (max_passes == 0) n_tilings = 1;
+  if (n_tilings <= 0) {
+    Uf uf(P.V);
+    for (uint32_t t = 0; t < P.T; t++) {
+      const int32_t *q = &P.tets[4 * (size_t)t];
+      uf.unite(q[0], q[1]); uf.unite(q[0], q[2]); uf.unite(q[0], q[3]);
+    }
+    std::vector<uint32_t> cs(P.V, 0);
+    uint32_t biggest = 0;
+    for (uint32_t v = 0; v < P.V; v++) biggest = std::max(biggest, ++cs[uf.find(v)]);
+    n_tilings = biggest > cap ? 4 : 1;
+  }
+  n_tilings = std::min(n_tilings, 8);
+  if (n_tilings >= 2 && !grid_tilings(P, cap, n_tilings, tilings)) n_tilings = 1;
+  P.n_tilings = (uint32_t)n_tilings;
+
   std::vector<uint32_t> tile_off;
-  if (max_passes > 0) {
+  if (n_tilings >= 2) {
+    // device numbering: tiles of tiling 0 are contiguous, ascending caller id inside a tile
+    const Tiling &T0 = tilings[0];
+    std::vector<uint32_t> cnt((size_t)T0.n_tiles + 1, 0);
+    for (uint32_t v = 0; v < P.V; v++) cnt[(size_t)T0.part[v] + 1]++;
+    for (uint32_t t = 0; t < T0.n_tiles; t++) cnt[t + 1] += cnt[t];
+    tile_off.assign(cnt.begin(), cnt.end());
+    P.perm.resize(P.V);
+    for (uint32_t v = 0; v < P.V; v++) P.perm[cnt[T0.part[v]]++] = v;
+    P.inv.resize(P.V);
+    for (uint32_t d = 0; d < P.V; d++) P.inv[P.perm[d]] = d;
+  } else if (max_passes > 0) {
     tile_off = tile_vertices(P, cap, opt.n_sm);
   } else {
     P.perm.resize(P.V);
@@ -712,28 +912,97 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   for (uint32_t d = 0; d < P.V; d++)
     for (int k = 0; k < 3; k++) dev_pos[3 * (size_t)d + k] = P.pos[3 * (size_t)P.perm[d] + k];
 
-  std::vector<int32_t> work((size_t)P.E + P.T), next;
-  for (uint32_t e = 0; e < P.E; e++) work[e] = (int32_t)e;
-  for (uint32_t t = 0; t < P.T; t++) work[(size_t)P.E + t] = (int32_t)(0x80000000u | t);
+  std::vector<int32_t> work, next;
+  std::vector<int32_t> part(P.V);
+  uint32_t n_tiles = 0;
+  bool have_parts = false;
 
-  if (max_passes > 0) {
-    std::vector<int32_t> part(P.V);
-    uint32_t n_tiles = (uint32_t)tile_off.size() - 1;
-    for (uint32_t t = 0; t < n_tiles; t++)
-      for (uint32_t d = tile_off[t]; d < tile_off[t + 1]; d++) part[d] = (int32_t)t;
-    for (int k = 0; k < max_passes && !work.empty(); k++) {
+  if (n_tilings >= 2) {
+    // parts in device numbering
+    std::vector<std::vector<int32_t>> dpart(n_tilings, std::vector<int32_t>(P.V));
+    for (int s = 0; s < n_tilings; s++)
+      parallel_for(P.V, threads, 1 << 18, [&](size_t d, int) { dpart[s][d] = tilings[s].part[P.perm[d]]; });
+    // deal every constraint to the least-loaded tiling it is interior to
+    std::vector<std::vector<int32_t>> assigned(n_tilings);
+    std::vector<uint64_t> load(n_tilings, 0);
+    std::vector<uint8_t> mask((size_t)P.E + P.T);
+    parallel_for(mask.size(), threads, 1 << 16, [&](size_t i, int) {
+      const int32_t ent = i < P.E ? (int32_t)i : (int32_t)(0x80000000u | (uint32_t)(i - P.E));
+      int32_t vs[4];
+      const int n = ent_verts(D, ent, vs);
+      uint8_t m = 0;
+      for (int s = 0; s < n_tilings; s++) {
+        const int32_t p = dpart[s][vs[0]];
+        bool in = true;
+        for (int k = 1; k < n; k++) in &= dpart[s][vs[k]] == p;
+        if (in) m |= (uint8_t)(1u << s);
+      }
+      mask[i] = m;
+    });
+    // Colours needed in a tile ~ the largest number of same-kind constraints meeting at one of
+    // its vertices, so deal each constraint to the eligible tiling where its vertices carry
+    // the fewest so far (ties: the globally least-loaded tiling).
+    std::vector<std::vector<uint8_t>> deg(2 * (size_t)n_tilings, std::vector<uint8_t>(P.V, 0));
+    for (size_t i = 0; i < mask.size(); i++) {
+      const int32_t ent = i < P.E ? (int32_t)i : (int32_t)(0x80000000u | (uint32_t)(i - P.E));
+      const int kind = ent < 0;
+      const uint64_t wgt = kind ? 5 : 2; // tets weigh more than edges in the kernels
+      int32_t vs[4];
+      const int n = ent_verts(D, ent, vs);
+      int best = -1;
+      uint32_t best_deg = 0;
+      for (int s = 0; s < n_tilings; s++) {
+        if (!(mask[i] >> s & 1)) continue;
+        const std::vector<uint8_t> &dg = deg[2 * (size_t)s + kind];
+        uint32_t md = 0;
+        for (int k = 0; k < n; k++) md = std::max<uint32_t>(md, dg[vs[k]]);
+        if (best < 0 || md < best_deg || (md == best_deg && load[s] < load[best])) {
+          best = s;
+          best_deg = md;
+        }
+      }
+      if (best < 0) { work.push_back(ent); continue; }
+      assigned[best].push_back(ent);
+      load[best] += wgt;
+      std::vector<uint8_t> &dg = deg[2 * (size_t)best + kind];
+      for (int k = 0; k < n; k++)
+        if (dg[vs[k]] < 255) dg[vs[k]]++;
+    }
+    deg.clear();
+    mask.clear();
+    mask.shrink_to_fit();
+    for (int s = 0; s < n_tilings; s++) {
       TilePass TP;
-      err = build_pass(P, D, part, n_tiles, k == 0 ? &tile_off : nullptr, work, next, TP, threads);
+      err = build_pass(P, D, dpart[s], tilings[s].n_tiles, s == 0 ? &tile_off : nullptr, assigned[s], next, TP, threads,
+                       slot_bytes, n_slots);
       if (!err.empty()) return err;
-      size_t consumed = work.size() - next.size();
-      work.swap(next);
-      if (consumed > 0 || k == 0) P.passes.push_back(std::move(TP));
-      if (work.empty() || k + 1 == max_passes) break;
-      if (consumed == 0 && k > 0) break; // no progress: hand the rest to the global colours
-      // size the next level so it offers about two tiles per SM, within [min_cap, cap]
+      work.insert(work.end(), next.begin(), next.end()); // empty by construction
+      P.passes.push_back(std::move(TP));
+      assigned[s] = std::vector<int32_t>();
+    }
+    part = dpart[0];
+    n_tiles = tilings[0].n_tiles;
+    have_parts = true;
+    std::sort(work.begin(), work.end(), [](int32_t a, int32_t b) { return (uint32_t)a < (uint32_t)b; });
+  } else {
+    work.resize((size_t)P.E + P.T);
+    for (uint32_t e = 0; e < P.E; e++) work[e] = (int32_t)e;
+    for (uint32_t t = 0; t < P.T; t++) work[(size_t)P.E + t] = (int32_t)(0x80000000u | t);
+    if (max_passes > 0) {
+      n_tiles = (uint32_t)tile_off.size() - 1;
+      for (uint32_t t = 0; t < n_tiles; t++)
+        for (uint32_t d = tile_off[t]; d < tile_off[t + 1]; d++) part[d] = (int32_t)t;
+      have_parts = true;
+    }
+  }
+
+  // hierarchical passes: constraints interior to a tile are taken, the cut ones go to a
+  // next level whose tiles straddle the previous level's boundaries (the only scheme when
+  // n_tilings == 1; the fallback for whatever the tilings left over otherwise)
+  if (have_parts && !work.empty()) {
+    auto level_cap = [&]() {
       uint32_t lcap = opt.later_cap > 0 ? (uint32_t)opt.later_cap : 0;
       if (!lcap) {
-        // upper bound on the vertices involved: 4 per cut constraint is too loose, so count
         std::vector<uint8_t> seen(P.V, 0);
         size_t nvr = 0;
         for (int32_t ent : work) {
@@ -744,8 +1013,22 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
         }
         lcap = (uint32_t)std::min<size_t>(cap, std::max<size_t>(2048, (nvr + 2 * opt.n_sm - 1) / (2 * opt.n_sm)));
       }
-      lcap = std::min(lcap, cap);
-      n_tiles = next_parts(P, D, work, part, lcap, dev_pos);
+      return std::min(lcap, cap);
+    };
+    bool first_level = n_tilings < 2; // the tilings already took everything interior to tiling 0
+    if (!first_level) n_tiles = next_parts(P, D, work, part, level_cap(), dev_pos);
+    const int levels = std::min(max_passes, 8 - (int)P.passes.size()); // sb_info reports at most 8 passes
+    for (int k = 0; k < levels && !work.empty(); k++) {
+      TilePass TP;
+      const bool contig = first_level && k == 0;
+      err = build_pass(P, D, part, n_tiles, contig ? &tile_off : nullptr, work, next, TP, threads, slot_bytes, n_slots);
+      if (!err.empty()) return err;
+      size_t consumed = work.size() - next.size();
+      work.swap(next);
+      if (consumed > 0 || contig) P.passes.push_back(std::move(TP));
+      if (work.empty() || k + 1 == levels) break;
+      if (consumed == 0 && !contig) break; // no progress: hand the rest to the global colours
+      n_tiles = next_parts(P, D, work, part, level_cap(), dev_pos);
     }
   }
   err = global_colouring(P, D, work);

@@ -24,23 +24,39 @@ struct PlanOptions {
   int max_tile_passes = -1; // -1 = auto
   int n_sm = 148;           // grid sizing target
   int threads = 0;          // host build threads (0 = hardware_concurrency)
+  int slot_bytes = 0;       // bytes per shared-memory staging slot (0 = 8160); multiple of 48
+  int n_slots = 0;          // staging slots per CTA (0 = 2)
+  int tilings = 0;          // 0 = auto; 1 = hierarchical passes only; N >= 2 = N balanced shifted tilings
 };
 
 // One shared-memory tile pass: every tile is a vertex-disjoint set of vertices
 // whose assigned constraints touch only those vertices.
+//
+// Device data: a tile's constraints are a byte stream cut into CHUNKS that the
+// kernel stages into shared memory with bulk copies.  A chunk holds records of
+// one kind and one colour:
+//   edge chunk, n records : n2 = roundup(n, 2) x { a | b << 16, bits(L0) }          (8 B each)
+//   tet chunk,  n records : n4 = roundup(n, 4) x { p0 | p1 << 16, p2 | p3 << 16 }   (8 B each)
+//                           followed by n4 x float (6 * rest volume)
+// (local 16-bit vertex ids; padding records are zero and never executed).
+// chunks[i] = { byte offset / 16 into `stream`, n | kind << 30 | barrier << 31 }:
+// `barrier` asks for a CTA barrier after the chunk (set on the last chunk of every
+// colour, and often enough that the staging ring can always be refilled).
 struct TilePass {
   bool contiguous = false;          // tile t == device vertex range [vert_off[t], vert_off[t+1])
   std::vector<uint32_t> vert_off;   // n_tiles + 1
   std::vector<uint32_t> tile_verts; // device vertex ids (empty when contiguous)
-  std::vector<uint32_t> ctab_off;   // n_tiles + 1 offsets into ctab
-  std::vector<uint32_t> n_ecol;     // edge colours of tile t (tet colours follow in ctab)
-  std::vector<U2> ctab;             // {first record, record count} per (tile, colour)
-  std::vector<U2> erec;             // {a | b << 16, bits(L0)}, local vertex ids
-  std::vector<U2> tidx;             // {p0 | p1 << 16, p2 | p3 << 16}
-  std::vector<float> trest;         // 6 * rest volume
-  std::vector<int32_t> erec_id;     // canonical edge id of erec[i]
-  std::vector<int32_t> trec_id;     // tet id of tidx[i]
-  uint32_t max_ecol = 0, max_tcol = 0, max_tile_verts = 0;
+  std::vector<uint32_t> chunk_off;  // n_tiles + 1 offsets into chunks
+  std::vector<U2> chunks;
+  std::vector<uint32_t> stream;     // 32-bit words; every chunk starts 16-byte aligned
+  // schedule bookkeeping (host only): per tile, constraints in processing order
+  std::vector<uint64_t> ent_off;    // n_tiles + 1 offsets into ents
+  std::vector<int32_t> ents;        // >= 0 edge id, < 0 tet id | 0x80000000
+  std::vector<uint32_t> col_off;    // n_tiles + 1 offsets into col_cnt
+  std::vector<uint32_t> col_cnt;    // constraints per colour, edge colours first
+  std::vector<uint32_t> n_ecol;     // edge colours of tile t
+  uint32_t max_ecol = 0, max_tcol = 0, max_tile_verts = 0, max_chunks = 0;
+  uint64_t n_edges = 0, n_tets = 0;
   uint32_t n_tiles() const { return vert_off.empty() ? 0u : (uint32_t)vert_off.size() - 1; }
 };
 
@@ -77,7 +93,7 @@ struct Plan {
   std::vector<int32_t> g_tid;
   std::vector<GlobalBatch> gbatches;
   // options actually used
-  uint32_t tile_cap = 0;
+  uint32_t tile_cap = 0, slot_bytes = 0, n_slots = 0, n_tilings = 1;
   double build_seconds = 0;
 
   // The equivalent sequential order of one iteration (see sb_get_schedule).

@@ -60,11 +60,11 @@ struct DevBuf {
 };
 
 struct PassBufs {
-  DevBuf<uint32_t> vert_off, tile_verts, ctab_off, n_ecol;
-  DevBuf<uint2> ctab, erec, tidx;
-  DevBuf<float> trest;
+  DevBuf<uint32_t> vert_off, tile_verts, chunk_off, stream;
+  DevBuf<uint2> chunks;
   PassDev dev{};
   uint32_t smem = 0;
+  uint32_t bt = 512; // threads per CTA for this pass
 };
 
 static const int kDiagBlocks = 592;
@@ -186,8 +186,8 @@ struct sb_solver {
       CK(cudaMemset(nrm.p, 0, (ns ? ns : 1) * sizeof(float4)));
     }
     // tile passes
-    uint32_t bt = m.block_threads > 0 ? (uint32_t)m.block_threads : 512u;
-    if (bt != 256 && bt != 512 && bt != 1024) throw std::string("block_threads must be 256, 512 or 1024");
+    uint32_t bt = m.block_threads > 0 ? (uint32_t)m.block_threads : 256u;
+    if (bt != 128 && bt != 256 && bt != 512 && bt != 1024) throw std::string("block_threads must be 128, 256, 512 or 1024");
     block_threads = bt;
     passes.resize(plan.passes.size());
     for (size_t k = 0; k < plan.passes.size(); k++) {
@@ -195,16 +195,25 @@ struct sb_solver {
       PassBufs &pb = passes[k];
       pb.vert_off.upload(tp.vert_off, &dev_bytes);
       if (!tp.contiguous) pb.tile_verts.upload(tp.tile_verts, &dev_bytes);
-      pb.ctab_off.upload(tp.ctab_off, &dev_bytes);
-      pb.n_ecol.upload(tp.n_ecol, &dev_bytes);
-      pb.ctab.upload(tp.ctab, &dev_bytes);
-      pb.erec.upload(tp.erec, &dev_bytes);
-      pb.tidx.upload(tp.tidx, &dev_bytes);
-      pb.trest.upload(tp.trest, &dev_bytes);
-      pb.dev = PassDev{pb.vert_off.p, tp.contiguous ? nullptr : pb.tile_verts.p, pb.ctab_off.p, pb.n_ecol.p,
-                       pb.ctab.p, pb.erec.p, pb.tidx.p, pb.trest.p, tp.n_tiles()};
-      pb.smem = tp.max_tile_verts * (uint32_t)sizeof(float4);
-      if (pb.smem > (uint32_t)prop.sharedMemPerBlockOptin) throw std::string("tile_cap exceeds the shared memory of this device");
+      pb.chunk_off.upload(tp.chunk_off, &dev_bytes);
+      pb.chunks.upload(tp.chunks, &dev_bytes);
+      pb.stream.upload(tp.stream, &dev_bytes);
+      const uint32_t pos_bytes = (tp.max_tile_verts * 16u + 127u) & ~127u;
+      const uint32_t ring = plan.n_slots * plan.slot_bytes;
+      const uint32_t fixed = pos_bytes + ring + (plan.n_slots + 1) * 8u;
+      const uint32_t limit = (uint32_t)prop.sharedMemPerBlockOptin;
+      if (fixed + 64 > limit) throw std::string("tile_cap and staging slots exceed the shared memory of this device");
+      uint32_t tab_entries = std::min<uint32_t>(tp.max_chunks, (limit - fixed) / 8u);
+      pb.dev = PassDev{pb.vert_off.p, tp.contiguous ? nullptr : pb.tile_verts.p, pb.chunk_off.p, pb.chunks.p,
+                       reinterpret_cast<const uint4 *>(pb.stream.p), tp.n_tiles(), pos_bytes, plan.slot_bytes,
+                       plan.n_slots, tab_entries};
+      pb.smem = fixed + tab_entries * 8u;
+      // CTA width: the given one, or by how many constraints a colour of one tile holds on average
+      pb.bt = bt;
+      if (m.block_threads <= 0 && tp.n_tiles()) {
+        const double per_colour = (double)(tp.n_edges + tp.n_tets) / ((double)tp.n_tiles() * std::max(1u, tp.max_ecol + tp.max_tcol));
+        pb.bt = per_colour < 160 ? 128u : per_colour < 448 ? 256u : 512u;
+      }
     }
     uint32_t max_smem = 0;
     for (auto &pb : passes) max_smem = std::max(max_smem, pb.smem);
@@ -223,8 +232,8 @@ struct sb_solver {
   }
   void set_smem_attr(uint32_t smem) {
     if (smem <= 48 * 1024) return;
-    set_attr_one<false, 256>(smem); set_attr_one<false, 512>(smem); set_attr_one<false, 1024>(smem);
-    set_attr_one<true, 256>(smem); set_attr_one<true, 512>(smem); set_attr_one<true, 1024>(smem);
+    set_attr_one<false, 128>(smem); set_attr_one<false, 256>(smem); set_attr_one<false, 512>(smem); set_attr_one<false, 1024>(smem);
+    set_attr_one<true, 128>(smem); set_attr_one<true, 256>(smem); set_attr_one<true, 512>(smem); set_attr_one<true, 1024>(smem);
   }
 
   // ---- parameters -----------------------------------------------------------------
@@ -270,7 +279,8 @@ struct sb_solver {
   template <bool FAST>
   void launch_tile(const PassBufs &pb, cudaStream_t s) {
     if (!pb.dev.n_tiles) return;
-    switch (block_threads) {
+    switch (pb.bt) {
+      case 128: k_tile_pass<FAST, 128><<<pb.dev.n_tiles, 128, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
       case 256: k_tile_pass<FAST, 256><<<pb.dev.n_tiles, 256, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
       case 1024: k_tile_pass<FAST, 1024><<<pb.dev.n_tiles, 1024, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
       default: k_tile_pass<FAST, 512><<<pb.dev.n_tiles, 512, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
@@ -578,7 +588,7 @@ static int create_impl(const sb_mesh_desc *mesh, const sb_params *params, sb_han
   *out = nullptr;
   g_create_error.clear();
   if (!mesh) { g_create_error = "mesh is NULL"; return SB_E_ARG; }
-  for (int k = 0; k < 6; k++)
+  for (int k = 0; k < 3; k++)
     if (mesh->reserved[k] != 0) { g_create_error = "reserved fields must be 0"; return SB_E_ARG; }
   sb_params dp;
   sb_default_params(&dp);
@@ -595,6 +605,9 @@ static int create_impl(const sb_mesh_desc *mesh, const sb_params *params, sb_han
     opt.max_tile_passes = mesh->max_tile_passes;
     opt.later_cap = mesh->later_tile_cap;
     opt.threads = mesh->host_threads;
+    opt.slot_bytes = mesh->slot_bytes;
+    opt.n_slots = mesh->n_slots;
+    opt.tilings = mesh->tilings;
     if (device) {
       int ndev = 0;
       CK(cudaGetDeviceCount(&ndev));
@@ -740,16 +753,22 @@ int sb_get_info(sb_handle h, sb_info *o) {
   o->n_verts = P.V; o->n_edges = P.E; o->n_tets = P.T; o->n_tris = P.F;
   o->n_surface_verts = (uint32_t)P.surf_ids.size();
   o->n_tile_passes = (uint32_t)P.passes.size();
+  o->n_tilings = P.n_tilings;
   uint32_t nb = 0;
   for (size_t k = 0; k < P.passes.size(); k++) {
     nb += P.passes[k].max_ecol + P.passes[k].max_tcol;
     if (k < 8) {
       o->tiles_in_pass[k] = P.passes[k].n_tiles();
       o->max_colours_in_pass[k] = P.passes[k].max_ecol + P.passes[k].max_tcol;
-      o->constraints_in_pass[k] = P.passes[k].erec.size() + P.passes[k].tidx.size();
+      o->constraints_in_pass[k] = P.passes[k].n_edges + P.passes[k].n_tets;
+      o->edges_in_pass[k] = P.passes[k].n_edges;
     }
-    o->smem_bytes = std::max<uint32_t>(o->smem_bytes, P.passes[k].max_tile_verts * 16u);
+    o->smem_bytes = std::max<uint32_t>(o->smem_bytes, h->on_device && k < h->passes.size()
+                                                          ? h->passes[k].smem
+                                                          : P.passes[k].max_tile_verts * 16u + P.n_slots * P.slot_bytes);
   }
+  o->slot_bytes = P.slot_bytes;
+  o->n_slots = P.n_slots;
   o->n_global_batches = (uint32_t)P.gbatches.size();
   o->n_batches = nb + (uint32_t)P.gbatches.size();
   o->constraints_global = P.g_edges.size() + P.g_tets.size();

@@ -125,6 +125,7 @@ def check_tiles(sb: SoftBody, edges, tets, order):
     ((9, 8, 7), dict(tile_cap=128, later_tile_cap=64)),
     ((12, 12, 12), dict(tile_cap=300, max_tile_passes=2)),
     ((6, 6, 6), dict(max_tile_passes=0)),
+    ((8, 8, 8), dict(slot_bytes=192, n_slots=2)),
 ])
 def test_schedule_is_a_valid_coloured_order(shape, kw):
     pos, tets, tris = meshgen.block(*shape, spacing=0.1)

@@ -1,0 +1,24 @@
+"""Short run for ncu: builds the 1 M block and steps a few projection sweeps (no graph)."""
+import argparse
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from softbodyunity_b200 import FLAG_FAST_MATH, FLAG_NO_GRAPH, SoftBody, meshgen
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=100)
+ap.add_argument("--substeps", type=int, default=1)
+ap.add_argument("--iterations", type=int, default=3)
+ap.add_argument("--frames", type=int, default=1)
+ap.add_argument("--block-threads", type=int, default=0)
+ap.add_argument("--fast-math", action="store_true")
+ap.add_argument("--tile-cap", type=int, default=0)
+ap.add_argument("--n-slots", type=int, default=0)
+ap.add_argument("--slot-bytes", type=int, default=0)
+a = ap.parse_args()
+pos, tets, tris = meshgen.block(a.n)
+sb = SoftBody(pos, tets, tris, substeps=a.substeps, iterations=a.iterations, block_threads=a.block_threads, tile_cap=a.tile_cap, n_slots=a.n_slots, slot_bytes=a.slot_bytes,
+              flags=FLAG_NO_GRAPH | (FLAG_FAST_MATH if a.fast_math else 0))
+sb.step(frames=a.frames)
+sb.synchronize()
+d = sb.diagnostics()
+print("ok", sb.info()["launches_per_frame"], d["min_y"], d["nonfinite"])
