@@ -39,7 +39,8 @@ def workload(args, rank=0):
     from softbodyunity_b200 import meshgen
     if args.workload == "block":
         n = args.n
-        pos, tets, tris = meshgen.block(n, n, n, spacing=0.01, origin=(0.0, 0.05, 0.0), jitter=0.1, seed=1234 + rank)
+        # lowest layer 2 mm above the ground: contact within the warm-up frames (the timed frames collide)
+        pos, tets, tris = meshgen.block(n, n, n, spacing=0.01, origin=(0.0, 0.002, 0.0), jitter=0.1, seed=1234 + rank)
         name = f"block{n}^3 ({n ** 3} verts) tet mesh, ground plane, S={args.substeps} I={args.iterations}"
     elif args.workload == "sphere":
         pos, tets, tris = meshgen.sphere(args.n, spacing=0.01, seed=1234 + rank)

@@ -108,6 +108,7 @@ typedef struct sb_info {
   uint32_t max_colours_in_pass[8];
   uint64_t constraints_in_pass[8];
   uint64_t edges_in_pass[8];     /* of which distance constraints */
+  uint64_t runs_in_pass[8];      /* contiguous vertex runs over all tiles (0: pass is one range per tile) */
   uint64_t constraints_global;
   uint32_t tile_cap;
   uint32_t block_threads;

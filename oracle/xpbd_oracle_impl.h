@@ -28,7 +28,7 @@
  *   distance(a,b):  d = x_a - x_b;  len2 = FMA(dz,dz, FMA(dy,dy, dx*dx))
  *                   skip unless w_a + w_b > 0 and len2 > 0
  *                   len = sqrt(len2);  C = len - L0
- *                   s = -C / ((w_a + w_b + a_d) * len)
+ *                   s = -C * RCP((w_a + w_b + a_d) * len)      RCP(x) = correctly rounded 1/x
  *                   x_a = FMA(s*w_a, d, x_a);  x_b = FMA(-(s*w_b), d, x_b)
  *   volume(p0..p3): e_k = x_pk - x_p0 (k=1..3)
  *                   G1 = e2 x e3, G2 = e3 x e1, G3 = e1 x e2, G0 = -((G1+G2)+G3)
@@ -37,7 +37,9 @@
  *                   n_k = FMA(G.z,G.z, FMA(G.y,G.y, G.x*G.x))
  *                   den = FMA(w3,n3, FMA(w2,n2, FMA(w1,n1, w0*n0))) + a_v36
  *                   skip unless den > 0
- *                   s = -(det - R6) / den;   x_pk = FMA(s*w_k, G_k, x_pk)
+ *                   s = -(det - R6) * RCP(den);   x_pk = FMA(s*w_k, G_k, x_pk)
+ *   (a reciprocal and a multiply instead of one division: the GPU's IEEE reciprocal never
+ *    leaves its fast path for these operand ranges, its IEEE division almost always does)
  *   finish(i), w_i > 0:   if x.y < ground_y: x.y = ground_y,
  *                             x.xz = FMA(keep, x.xz - x_prev.xz, x_prev.xz)
  *                         spheres: see SPHERE below
@@ -99,7 +101,7 @@ static inline void FN(distance_one)(REAL *xa, REAL *xb, REAL L0, REAL a_d) {
   if (!(wsum > 0) || !(len2 > 0)) return;
   REAL len = SQRT(len2);
   REAL C = len - L0;
-  REAL s = -C / ((wsum + a_d) * len);
+  REAL s = -C * ((REAL)1 / ((wsum + a_d) * len));
   REAL sa = s * wa, sb = -(s * wb);
   xa[0] = FMA(sa, dx, xa[0]); xa[1] = FMA(sa, dy, xa[1]); xa[2] = FMA(sa, dz, xa[2]);
   xb[0] = FMA(sb, dx, xb[0]); xb[1] = FMA(sb, dy, xb[1]); xb[2] = FMA(sb, dz, xb[2]);
@@ -132,7 +134,7 @@ static inline void FN(volume_one)(REAL *p0, REAL *p1, REAL *p2, REAL *p3, REAL R
   REAL n0 = DOT3(G0, G0), n1 = DOT3(G1, G1), n2 = DOT3(G2, G2), n3 = DOT3(G3, G3);
   REAL den = FMA(p3[3], n3, FMA(p2[3], n2, FMA(p1[3], n1, p0[3] * n0))) + a_v36;
   if (!(den > 0)) return;
-  REAL s = -(det - R6) / den;
+  REAL s = -(det - R6) * ((REAL)1 / den);
   REAL s0 = s * p0[3], s1 = s * p1[3], s2 = s * p2[3], s3 = s * p3[3];
   for (int k = 0; k < 3; k++) {
     p0[k] = FMA(s0, G0[k], p0[k]);
@@ -145,7 +147,7 @@ static inline void FN(volume_one)(REAL *p0, REAL *p1, REAL *p2, REAL *p3, REAL R
 /*
  * SPHERE collider (centre c, radius r), after the ground plane, in list order:
  *   d = x - c;  l2 = FMA(dz,dz, FMA(dy,dy, dx*dx));  if 0 < l2 < r*r:
- *       q = r / sqrt(l2);  x = FMA(q, d, c)
+ *       q = r * RCP(sqrt(l2));  x = FMA(q, d, c)
  */
 static inline void FN(finish_one)(REAL *x, const REAL *xp, REAL *v, const FN(step_consts) *c,
                                   int n_spheres, const float *spheres) {
@@ -160,7 +162,7 @@ static inline void FN(finish_one)(REAL *x, const REAL *xp, REAL *v, const FN(ste
     REAL dx = x[0] - cx, dy = x[1] - cy, dz = x[2] - cz;
     REAL l2 = FMA(dz, dz, FMA(dy, dy, dx * dx));
     if (l2 > 0 && l2 < r * r) {
-      REAL q = r / SQRT(l2);
+      REAL q = r * ((REAL)1 / SQRT(l2));
       x[0] = FMA(q, dx, cx); x[1] = FMA(q, dy, cy); x[2] = FMA(q, dz, cz);
     }
   }

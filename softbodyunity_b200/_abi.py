@@ -50,7 +50,7 @@ class SbInfo(C.Structure):
         ("n_surface_verts", C.c_uint32), ("n_tile_passes", C.c_uint32), ("n_tilings", C.c_uint32),
         ("n_global_batches", C.c_uint32), ("n_batches", C.c_uint32),
         ("tiles_in_pass", C.c_uint32 * 8), ("max_colours_in_pass", C.c_uint32 * 8),
-        ("constraints_in_pass", C.c_uint64 * 8), ("edges_in_pass", C.c_uint64 * 8),
+        ("constraints_in_pass", C.c_uint64 * 8), ("edges_in_pass", C.c_uint64 * 8), ("runs_in_pass", C.c_uint64 * 8),
         ("constraints_global", C.c_uint64),
         ("tile_cap", C.c_uint32), ("block_threads", C.c_uint32), ("smem_bytes", C.c_uint32),
         ("slot_bytes", C.c_uint32), ("n_slots", C.c_uint32),

@@ -304,7 +304,10 @@ struct Tiling {
   uint32_t n_tiles = 0;
 };
 
-bool grid_tilings(const Plan &P, uint32_t cap, int n_tilings, std::vector<Tiling> &out) {
+// `atom_key` (per caller vertex) orders vertices inside a box of tiling 0 by the 1/N_T-box
+// sub-box ("atom") they fall in, z-major, so that every box of every shifted tiling is a
+// union of a few contiguous runs of the device numbering.
+bool grid_tilings(const Plan &P, uint32_t cap, int n_tilings, std::vector<Tiling> &out, std::vector<uint32_t> &atom_key) {
   const uint32_t V = P.V;
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (uint32_t v = 0; v < V; v++)
@@ -334,6 +337,19 @@ bool grid_tilings(const Plan &P, uint32_t cap, int n_tilings, std::vector<Tiling
     if ((double)(n[0] + 1) * (n[1] + 1) * (n[2] + 1) > 64e6) return false;
     out.assign(n_tilings, Tiling());
     bool ok = true;
+    // fine-grid ("atom") coordinates: boxes of every tiling are unions of atoms
+    std::vector<int32_t> atom(3 * (size_t)V);
+    atom_key.resize(V);
+    for (uint32_t v = 0; v < V; v++) {
+      uint32_t key = 0;
+      for (int k = 2; k >= 0; k--) {
+        const double f = ext[k] > 0 ? ((double)P.pos[3 * (size_t)v + k] - lo[k]) / wa[k] * n_tilings : 0.0;
+        const int a = std::min(n[k] * n_tilings - 1, std::max(0, (int)std::floor(f)));
+        atom[3 * (size_t)v + k] = a;
+        key = key * (uint32_t)n_tilings + (uint32_t)(a % n_tilings);
+      }
+      atom_key[v] = key;
+    }
     for (int s = 0; s < n_tilings && ok; s++) {
       const int m[3] = {n[0] + (s > 0), n[1] + (s > 0), n[2] + (s > 0)};
       count.assign((size_t)m[0] * m[1] * m[2], 0u);
@@ -341,10 +357,7 @@ bool grid_tilings(const Plan &P, uint32_t cap, int n_tilings, std::vector<Tiling
       T.part.resize(V);
       for (uint32_t v = 0; v < V; v++) {
         int c[3];
-        for (int k = 0; k < 3; k++) {
-          double f = ext[k] > 0 ? ((double)P.pos[3 * (size_t)v + k] - lo[k]) / wa[k] + (double)s / n_tilings : 0.0;
-          c[k] = std::min(m[k] - 1, std::max(0, (int)std::floor(f)));
-        }
+        for (int k = 0; k < 3; k++) c[k] = std::min(m[k] - 1, (atom[3 * (size_t)v + k] + s) / n_tilings);
         const uint32_t cell = (uint32_t)c[0] + (uint32_t)m[0] * ((uint32_t)c[1] + (uint32_t)m[1] * (uint32_t)c[2]);
         T.part[v] = (int32_t)cell;
         count[cell]++;
@@ -617,6 +630,7 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
   TP.contiguous = contig_off != nullptr;
   TP.vert_off.push_back(0);
   TP.chunk_off.push_back(0);
+  TP.run_off.push_back(0);
   TP.ent_off.push_back(0);
   TP.col_off.push_back(0);
   size_t nw = 0, nen = 0, nv = 0;
@@ -646,6 +660,11 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
     } else {
       TP.tile_verts.insert(TP.tile_verts.end(), O.verts.begin(), O.verts.end());
       TP.vert_off.push_back((uint32_t)TP.tile_verts.size());
+      // maximal runs of consecutive device ids: {first device id, first local id}, closed by {0, n}
+      for (uint32_t k = 0; k < O.n_verts; k++)
+        if (k == 0 || O.verts[k] != O.verts[k - 1] + 1) TP.runs.push_back({O.verts[k], k});
+      TP.runs.push_back({0u, O.n_verts});
+      TP.run_off.push_back((uint32_t)TP.runs.size());
     }
     TP.max_ecol = std::max(TP.max_ecol, O.n_ecol);
     TP.max_tcol = std::max(TP.max_tcol, O.n_tcol);
@@ -881,7 +900,8 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     n_tilings = biggest > cap ? 4 : 1;
   }
   n_tilings = std::min(n_tilings, 8);
-  if (n_tilings >= 2 && !grid_tilings(P, cap, n_tilings, tilings)) n_tilings = 1;
+  std::vector<uint32_t> atom_key;
+  if (n_tilings >= 2 && !grid_tilings(P, cap, n_tilings, tilings, atom_key)) n_tilings = 1;
   P.n_tilings = (uint32_t)n_tilings;
 
   std::vector<uint32_t> tile_off;
@@ -894,6 +914,11 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     tile_off.assign(cnt.begin(), cnt.end());
     P.perm.resize(P.V);
     for (uint32_t v = 0; v < P.V; v++) P.perm[cnt[T0.part[v]]++] = v;
+    parallel_for(T0.n_tiles, threads, 1, [&](size_t t, int) {
+      std::sort(P.perm.begin() + tile_off[t], P.perm.begin() + tile_off[t + 1], [&](uint32_t a, uint32_t b) {
+        return atom_key[a] < atom_key[b] || (atom_key[a] == atom_key[b] && a < b);
+      });
+    });
     P.inv.resize(P.V);
     for (uint32_t d = 0; d < P.V; d++) P.inv[P.perm[d]] = d;
   } else if (max_passes > 0) {

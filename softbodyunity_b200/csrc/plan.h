@@ -46,6 +46,8 @@ struct TilePass {
   bool contiguous = false;          // tile t == device vertex range [vert_off[t], vert_off[t+1])
   std::vector<uint32_t> vert_off;   // n_tiles + 1
   std::vector<uint32_t> tile_verts; // device vertex ids (empty when contiguous)
+  std::vector<uint32_t> run_off;    // n_tiles + 1 offsets into runs (non-contiguous passes)
+  std::vector<U2> runs;             // per tile: {first device id, first local id} per run, then {0, n_verts}
   std::vector<uint32_t> chunk_off;  // n_tiles + 1 offsets into chunks
   std::vector<U2> chunks;
   std::vector<uint32_t> stream;     // 32-bit words; every chunk starts 16-byte aligned

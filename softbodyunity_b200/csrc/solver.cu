@@ -60,8 +60,8 @@ struct DevBuf {
 };
 
 struct PassBufs {
-  DevBuf<uint32_t> vert_off, tile_verts, chunk_off, stream;
-  DevBuf<uint2> chunks;
+  DevBuf<uint32_t> vert_off, tile_verts, chunk_off, stream, run_off;
+  DevBuf<uint2> chunks, runs;
   PassDev dev{};
   uint32_t smem = 0;
   uint32_t bt = 512; // threads per CTA for this pass
@@ -187,7 +187,8 @@ struct sb_solver {
     }
     // tile passes
     uint32_t bt = m.block_threads > 0 ? (uint32_t)m.block_threads : 256u;
-    if (bt != 128 && bt != 256 && bt != 512 && bt != 1024) throw std::string("block_threads must be 128, 256, 512 or 1024");
+    if (bt != 32 && bt != 64 && bt != 128 && bt != 256 && bt != 512 && bt != 1024)
+      throw std::string("block_threads must be 32, 64, 128, 256, 512 or 1024");
     block_threads = bt;
     passes.resize(plan.passes.size());
     for (size_t k = 0; k < plan.passes.size(); k++) {
@@ -204,7 +205,15 @@ struct sb_solver {
       const uint32_t limit = (uint32_t)prop.sharedMemPerBlockOptin;
       if (fixed + 64 > limit) throw std::string("tile_cap and staging slots exceed the shared memory of this device");
       uint32_t tab_entries = std::min<uint32_t>(tp.max_chunks, (limit - fixed) / 8u);
-      pb.dev = PassDev{pb.vert_off.p, tp.contiguous ? nullptr : pb.tile_verts.p, pb.chunk_off.p, pb.chunks.p,
+      // bulk copies per run pay off when runs are long; else threads gather vertex by vertex
+      const bool use_runs = !tp.contiguous && !tp.tile_verts.empty() &&
+                            (double)tp.tile_verts.size() / (double)(tp.runs.size() - tp.n_tiles()) >= 8.0;
+      if (use_runs) {
+        pb.run_off.upload(tp.run_off, &dev_bytes);
+        pb.runs.upload(tp.runs, &dev_bytes);
+      }
+      pb.dev = PassDev{pb.vert_off.p, tp.contiguous ? nullptr : pb.tile_verts.p, use_runs ? pb.run_off.p : nullptr,
+                       use_runs ? pb.runs.p : nullptr, pb.chunk_off.p, pb.chunks.p,
                        reinterpret_cast<const uint4 *>(pb.stream.p), tp.n_tiles(), pos_bytes, plan.slot_bytes,
                        plan.n_slots, tab_entries};
       pb.smem = fixed + tab_entries * 8u;
@@ -232,6 +241,7 @@ struct sb_solver {
   }
   void set_smem_attr(uint32_t smem) {
     if (smem <= 48 * 1024) return;
+    set_attr_one<false, 32>(smem); set_attr_one<false, 64>(smem); set_attr_one<true, 32>(smem); set_attr_one<true, 64>(smem);
     set_attr_one<false, 128>(smem); set_attr_one<false, 256>(smem); set_attr_one<false, 512>(smem); set_attr_one<false, 1024>(smem);
     set_attr_one<true, 128>(smem); set_attr_one<true, 256>(smem); set_attr_one<true, 512>(smem); set_attr_one<true, 1024>(smem);
   }
@@ -280,6 +290,8 @@ struct sb_solver {
   void launch_tile(const PassBufs &pb, cudaStream_t s) {
     if (!pb.dev.n_tiles) return;
     switch (pb.bt) {
+      case 32: k_tile_pass<FAST, 32><<<pb.dev.n_tiles, 32, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
+      case 64: k_tile_pass<FAST, 64><<<pb.dev.n_tiles, 64, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
       case 128: k_tile_pass<FAST, 128><<<pb.dev.n_tiles, 128, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
       case 256: k_tile_pass<FAST, 256><<<pb.dev.n_tiles, 256, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
       case 1024: k_tile_pass<FAST, 1024><<<pb.dev.n_tiles, 1024, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
@@ -762,6 +774,7 @@ int sb_get_info(sb_handle h, sb_info *o) {
       o->max_colours_in_pass[k] = P.passes[k].max_ecol + P.passes[k].max_tcol;
       o->constraints_in_pass[k] = P.passes[k].n_edges + P.passes[k].n_tets;
       o->edges_in_pass[k] = P.passes[k].n_edges;
+      o->runs_in_pass[k] = P.passes[k].contiguous ? 0 : P.passes[k].runs.size() - P.passes[k].n_tiles();
     }
     o->smem_bytes = std::max<uint32_t>(o->smem_bytes, h->on_device && k < h->passes.size()
                                                           ? h->passes[k].smem
