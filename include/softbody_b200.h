@@ -87,7 +87,7 @@ typedef struct sb_mesh_desc {
   int32_t device;           /* CUDA device ordinal */
   int32_t tile_cap;         /* max vertices per shared-memory tile; 0 = auto */
   int32_t max_tile_passes;  /* -1 = auto; 0 = global colour batches only */
-  int32_t block_threads;    /* threads per tile CTA (128, 256, 512 or 1024); 0 = auto per pass */
+  int32_t block_threads;    /* consumer threads per tile CTA (32..512, power of two; one producer warp is added); 0 = auto per pass */
   int32_t later_tile_cap;   /* max vertices per tile in passes after the first; 0 = auto */
   int32_t host_threads;     /* threads for the host-side build; 0 = auto */
   int32_t slot_bytes;       /* bytes per shared-memory staging slot of the constraint stream; 0 = auto */
@@ -189,6 +189,9 @@ int sb_time_frames(sb_handle h, int32_t n_frames, float dt, float *elapsed_ms);
  * The state is saved and restored around the run.
  */
 int sb_time_kernel(sb_handle h, int32_t which, int32_t reps, float *avg_ms);
+
+/* Debug aid: timestamps of one run of tile pass `pass` (see solver.cu); out holds 64 * 80 words. */
+int sb_debug_trace_pass(sb_handle h, uint32_t pass, unsigned long long *out, uint32_t n_words);
 
 const char *sb_last_error(sb_handle h); /* h may be NULL: last sb_create failure on this thread */
 

@@ -19,7 +19,7 @@ EXPORTS = [
     "sb_get_params", "sb_set_colliders", "sb_step", "sb_synchronize", "sb_read_positions",
     "sb_read_normals", "sb_surface_vertices", "sb_read_surface", "sb_get_state", "sb_set_state",
     "sb_diagnostics", "sb_get_info", "sb_get_topology", "sb_get_schedule", "sb_get_tiles",
-    "sb_time_frames", "sb_time_kernel", "sb_last_error",
+    "sb_time_frames", "sb_time_kernel", "sb_debug_trace_pass", "sb_last_error",
 ]
 
 
@@ -111,6 +111,7 @@ def load():
         "sb_get_tiles": (C.c_int, [vp, u32, vp, P(u32)]),
         "sb_time_frames": (C.c_int, [vp, i32, f32, P(f32)]),
         "sb_time_kernel": (C.c_int, [vp, i32, i32, P(f32)]),
+        "sb_debug_trace_pass": (C.c_int, [vp, u32, vp, u32]),
         "sb_last_error": (C.c_char_p, [vp]),
     }
     for name, (res, args) in sig.items():

@@ -872,12 +872,12 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   if (!err.empty()) return err;
 
   // ---- tiling ---------------------------------------------------------------
-  uint32_t cap = opt.tile_cap > 0 ? (uint32_t)opt.tile_cap : 3392u;
+  uint32_t cap = opt.tile_cap > 0 ? (uint32_t)opt.tile_cap : 1024u;
   cap = std::min(cap, 65536u);
   P.tile_cap = cap;
-  uint32_t slot_bytes = opt.slot_bytes > 0 ? (uint32_t)opt.slot_bytes : 8160u;
+  uint32_t slot_bytes = opt.slot_bytes > 0 ? (uint32_t)opt.slot_bytes : 2016u;
   slot_bytes = std::max(192u, slot_bytes / 48 * 48);
-  uint32_t n_slots = opt.n_slots > 0 ? (uint32_t)std::min(opt.n_slots, 16) : 2u;
+  uint32_t n_slots = opt.n_slots > 0 ? (uint32_t)std::min(opt.n_slots, 16) : 4u;
   n_slots = std::max(n_slots, 2u);
   P.slot_bytes = slot_bytes;
   P.n_slots = n_slots;

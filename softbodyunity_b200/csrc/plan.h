@@ -24,8 +24,8 @@ struct PlanOptions {
   int max_tile_passes = -1; // -1 = auto
   int n_sm = 148;           // grid sizing target
   int threads = 0;          // host build threads (0 = hardware_concurrency)
-  int slot_bytes = 0;       // bytes per shared-memory staging slot (0 = 8160); multiple of 48
-  int n_slots = 0;          // staging slots per CTA (0 = 2)
+  int slot_bytes = 0;       // bytes per shared-memory staging slot (0 = 2016); multiple of 48
+  int n_slots = 0;          // staging slots per CTA (0 = 4)
   int tilings = 0;          // 0 = auto; 1 = hierarchical passes only; N >= 2 = N balanced shifted tilings
 };
 

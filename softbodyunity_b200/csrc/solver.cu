@@ -186,9 +186,9 @@ struct sb_solver {
       CK(cudaMemset(nrm.p, 0, (ns ? ns : 1) * sizeof(float4)));
     }
     // tile passes
-    uint32_t bt = m.block_threads > 0 ? (uint32_t)m.block_threads : 256u;
-    if (bt != 32 && bt != 64 && bt != 128 && bt != 256 && bt != 512 && bt != 1024)
-      throw std::string("block_threads must be 32, 64, 128, 256, 512 or 1024");
+    uint32_t bt = m.block_threads > 0 ? (uint32_t)m.block_threads : 64u;
+    if (bt != 32 && bt != 64 && bt != 128 && bt != 256 && bt != 512)
+      throw std::string("block_threads must be 32, 64, 128, 256 or 512");
     block_threads = bt;
     passes.resize(plan.passes.size());
     for (size_t k = 0; k < plan.passes.size(); k++) {
@@ -201,7 +201,7 @@ struct sb_solver {
       pb.stream.upload(tp.stream, &dev_bytes);
       const uint32_t pos_bytes = (tp.max_tile_verts * 16u + 127u) & ~127u;
       const uint32_t ring = plan.n_slots * plan.slot_bytes;
-      const uint32_t fixed = pos_bytes + ring + (plan.n_slots + 1) * 8u;
+      const uint32_t fixed = pos_bytes + ring + (2 * plan.n_slots + 1) * 8u;
       const uint32_t limit = (uint32_t)prop.sharedMemPerBlockOptin;
       if (fixed + 64 > limit) throw std::string("tile_cap and staging slots exceed the shared memory of this device");
       uint32_t tab_entries = std::min<uint32_t>(tp.max_chunks, (limit - fixed) / 8u);
@@ -215,13 +215,13 @@ struct sb_solver {
       pb.dev = PassDev{pb.vert_off.p, tp.contiguous ? nullptr : pb.tile_verts.p, use_runs ? pb.run_off.p : nullptr,
                        use_runs ? pb.runs.p : nullptr, pb.chunk_off.p, pb.chunks.p,
                        reinterpret_cast<const uint4 *>(pb.stream.p), tp.n_tiles(), pos_bytes, plan.slot_bytes,
-                       plan.n_slots, tab_entries};
+                       plan.n_slots, tab_entries, nullptr};
       pb.smem = fixed + tab_entries * 8u;
       // CTA width: the given one, or by how many constraints a colour of one tile holds on average
       pb.bt = bt;
       if (m.block_threads <= 0 && tp.n_tiles()) {
         const double per_colour = (double)(tp.n_edges + tp.n_tets) / ((double)tp.n_tiles() * std::max(1u, tp.max_ecol + tp.max_tcol));
-        pb.bt = per_colour < 160 ? 128u : per_colour < 448 ? 256u : 512u;
+        pb.bt = per_colour < 192 ? 64u : per_colour < 448 ? 128u : 256u;
       }
     }
     uint32_t max_smem = 0;
@@ -242,8 +242,8 @@ struct sb_solver {
   void set_smem_attr(uint32_t smem) {
     if (smem <= 48 * 1024) return;
     set_attr_one<false, 32>(smem); set_attr_one<false, 64>(smem); set_attr_one<true, 32>(smem); set_attr_one<true, 64>(smem);
-    set_attr_one<false, 128>(smem); set_attr_one<false, 256>(smem); set_attr_one<false, 512>(smem); set_attr_one<false, 1024>(smem);
-    set_attr_one<true, 128>(smem); set_attr_one<true, 256>(smem); set_attr_one<true, 512>(smem); set_attr_one<true, 1024>(smem);
+    set_attr_one<false, 128>(smem); set_attr_one<false, 256>(smem); set_attr_one<false, 512>(smem);
+    set_attr_one<true, 128>(smem); set_attr_one<true, 256>(smem); set_attr_one<true, 512>(smem);
   }
 
   // ---- parameters -----------------------------------------------------------------
@@ -290,12 +290,11 @@ struct sb_solver {
   void launch_tile(const PassBufs &pb, cudaStream_t s) {
     if (!pb.dev.n_tiles) return;
     switch (pb.bt) {
-      case 32: k_tile_pass<FAST, 32><<<pb.dev.n_tiles, 32, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
-      case 64: k_tile_pass<FAST, 64><<<pb.dev.n_tiles, 64, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
-      case 128: k_tile_pass<FAST, 128><<<pb.dev.n_tiles, 128, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
-      case 256: k_tile_pass<FAST, 256><<<pb.dev.n_tiles, 256, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
-      case 1024: k_tile_pass<FAST, 1024><<<pb.dev.n_tiles, 1024, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
-      default: k_tile_pass<FAST, 512><<<pb.dev.n_tiles, 512, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
+      case 32: k_tile_pass<FAST, 32><<<pb.dev.n_tiles, 32 + 32, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
+      case 64: k_tile_pass<FAST, 64><<<pb.dev.n_tiles, 64 + 32, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
+      case 128: k_tile_pass<FAST, 128><<<pb.dev.n_tiles, 128 + 32, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
+      case 256: k_tile_pass<FAST, 256><<<pb.dev.n_tiles, 256 + 32, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
+      default: k_tile_pass<FAST, 512><<<pb.dev.n_tiles, 512 + 32, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
     }
   }
   void launch_pass(size_t k, cudaStream_t s) {
@@ -856,6 +855,30 @@ int sb_time_kernel(sb_handle h, int32_t which, int32_t reps, float *avg_ms) {
   if (reps < 1 || !avg_ms) return SB_E_ARG;
   return guarded(h, [&]() -> int {
     *avg_ms = h->time_kernel(which, reps);
+    return SB_OK;
+  });
+}
+
+/* Debug aid (not part of the component surface): run tile pass `pass` once with per-CTA
+   timestamps and copy them out: out[cta * 80 + k], k = 0 start, 1 loop start, 2 loop end,
+   3 CTA end, 4 + i start of chunk i (globaltimer ns; first 64 CTAs). */
+int sb_debug_trace_pass(sb_handle h, uint32_t pass, unsigned long long *out, uint32_t n_words) {
+  NEED_DEVICE(h);
+  if (pass >= h->passes.size() || !out || n_words < 64u * 80u) { h->err = "bad trace arguments"; return SB_E_ARG; }
+  return guarded(h, [&]() -> int {
+    CK(cudaSetDevice(h->device));
+    if (h->cur_dt < 0) h->refresh_params(h->prm.dt);
+    DevBuf<unsigned long long> buf;
+    buf.alloc(64 * 80, nullptr);
+    CK(cudaMemsetAsync(buf.p, 0, 64 * 80 * 8, h->stream));
+    PassBufs &pb = h->passes[pass];
+    h->launch_pass(pass, h->stream); // warm
+    pb.dev.trace = buf.p;
+    h->launch_pass(pass, h->stream);
+    pb.dev.trace = nullptr;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, buf.p, 64 * 80 * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return SB_OK;
   });
 }

@@ -223,6 +223,12 @@ class SoftBody:
         self._ck(self._lib.sb_time_frames(self._h, n_frames, dt, C.byref(ms)))
         return ms.value
 
+    def trace_pass(self, p: int):
+        """Debug: (64, 80) uint64 globaltimer stamps of one run of tile pass p."""
+        out = np.zeros((64, 80), np.uint64)
+        self._ck(self._lib.sb_debug_trace_pass(self._h, p, _ptr(out), out.size))
+        return out
+
     def time_kernel(self, which: int, reps: int = 20) -> float:
         ms = C.c_float()
         self._ck(self._lib.sb_time_kernel(self._h, which, reps, C.byref(ms)))
