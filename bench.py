@@ -35,7 +35,7 @@ METRIC = "vertex-substeps/sec"
 B_PREDICT, B_FINISH = 64.0, 64.0  # bytes per vertex
 
 
-def workload(args, rank=0):
+def workload(args, rank=0, world=1):
     from softbodyunity_b200 import meshgen
     if args.workload == "block":
         n = args.n
@@ -46,8 +46,11 @@ def workload(args, rank=0):
         pos, tets, tris = meshgen.sphere(args.n, spacing=0.01, seed=1234 + rank)
         name = f"sphere n={args.n} ({len(pos)} verts) tet mesh, S={args.substeps} I={args.iterations}"
     elif args.workload == "bodies":
-        pos, tets, tris = meshgen.bodies(args.n, dims=(13, 13, 12), spacing=0.02, seed=1234 + rank)
-        name = f"{args.n} independent 2028-vertex bodies ({len(pos)} verts), S={args.substeps} I={args.iterations}"
+        # BASELINE.json configs[3]: the bodies are dealt to the ranks (contiguous balanced ranges)
+        from softbodyunity_b200.shard import shard_range
+        lo, hi = shard_range(args.n, rank, world)
+        pos, tets, tris = meshgen.bodies(hi - lo, dims=(13, 13, 12), spacing=0.02, base_height=0.004, seed=1234 + rank)
+        name = f"{args.n} independent 2028-vertex bodies sharded over {world} rank(s), S={args.substeps} I={args.iterations}"
     else:
         raise SystemExit(f"unknown workload {args.workload}")
     return pos, tets, tris, name
@@ -57,6 +60,16 @@ def bytes_per_substep(n_verts, n_edges, n_tets, iterations):
     """Algorithmic bytes per vertex-substep: predict 64 + I*(12 E/V + 20 T/V + 32) + finish 64."""
     b_iter = 12.0 * n_edges / n_verts + 20.0 * n_tets / n_verts + 32.0
     return B_PREDICT + iterations * b_iter + B_FINISH
+
+
+def measured_traffic():
+    """DRAM bytes per launch of the first tile pass from the committed ncu capture (profiles/), or None."""
+    try:
+        files = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
+        d = json.load(open(os.path.join(ROOT, "profiles", files[-1])))["launches"][0]
+        return d["dram_read_bytes"] + d["dram_write_bytes"], files[-1]
+    except Exception:
+        return None, None
 
 
 def peaks():
@@ -212,7 +225,7 @@ def main():
     if rank == 0:
         clocks.start()  # nvidia-smi takes a moment to come up; samples are windowed by timestamp
     from softbodyunity_b200 import FLAG_FAST_MATH, SoftBody
-    pos, tets, tris, name = workload(args, rank)
+    pos, tets, tris, name = workload(args, rank, world)
     flags = FLAG_FAST_MATH if args.fast_math else 0
     sb = SoftBody(pos, tets, tris, device=local, substeps=args.substeps, iterations=args.iterations, flags=flags,
                   tile_cap=args.tile_cap, later_tile_cap=args.later_tile_cap, block_threads=args.block_threads,
@@ -226,6 +239,13 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
 
     def max_over_ranks(x):
         if world == 1:
@@ -249,7 +269,8 @@ def main():
         sb.synchronize()
     clocks.mark_end()
     clk = clocks.stop() if rank == 0 else None
-    value = world * V * args.substeps * args.steps / (ms * 1e-3)
+    V_all = V if world == 1 else int(round(sum_over_ranks(V)))
+    value = V_all * args.substeps * args.steps / (ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ---------------------------------
     x4 = torch.empty((V, 4), dtype=torch.float32).pin_memory()
@@ -277,7 +298,7 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     h2d = 2 * V * 16
     d2h = V * 12 + 2 * ns * 12 + 2 * V * 16
-    e2e_val = world * V * args.substeps * args.steps / e2e_s
+    e2e_val = V_all * args.substeps * args.steps / e2e_s
 
     # ---- roofline of the dominant kernel (first tile pass), timed alone --------------------
     hbm, peak_src = peaks()
@@ -291,10 +312,12 @@ def main():
         k_ms = sb.time_kernel(16, reps=30)
         ach = launch_bytes / (k_ms * 1e-3) / 1e9
         launches0 = args.substeps * args.iterations
+        traffic, traffic_src = measured_traffic()
         roof = {"bound": "hbm", "kernel": "k_tile_pass (pass 0)", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                "frac": ach / hbm, "traffic": None, "peak_source": peak_src, "bytes_per_launch": launch_bytes,
+                "frac": ach / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_launch": launch_bytes,
                 "launch_ms": k_ms, "share_of_step": k_ms * launches0 / (ms / args.steps),
-                "step_achieved": value / world * B_sub / 1e9, "step_frac": value / world * B_sub / 1e9 / hbm,
+                "step_achieved": V * args.substeps * args.steps / (ms * 1e-3) * B_sub / 1e9,
+                "step_frac": V * args.substeps * args.steps / (ms * 1e-3) * B_sub / 1e9 / hbm,
                 "bytes_per_vertex_substep": B_sub}
         if args.kernel_breakdown:
             breakdown = {"predict_ms": sb.time_kernel(0, 30), "finish_ms": sb.time_kernel(1, 30),
@@ -317,9 +340,9 @@ def main():
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": "vertex-substeps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.workload == "bodies" else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name + (" per GPU, independent bodies, no communication" if world > 1 else ""),
+            "config": {"workload": name + (" per GPU, independent bodies, no communication" if world > 1 and args.workload != "bodies" else ""),
                        "n_verts": V, "n_edges": E, "n_tets": T, "math": "fast" if args.fast_math else "exact (bit-identical to CPU oracle)",
                        "tile_passes": info["n_tile_passes"], "tiles_in_pass": info["tiles_in_pass"][:info["n_tile_passes"]],
                        "tile_cap": info["tile_cap"], "block_threads": info["block_threads"],

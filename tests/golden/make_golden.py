@@ -1,0 +1,49 @@
+"""Generates tests/golden/*.npz: small pinned cases of the substep path.
+
+There are no golden vectors in the reference (its mount is /root/reference/README.md:1 only), so these
+are REGRESSION PINS produced by this repo's own CPU oracle (oracle/xpbd_oracle.c) under the Gauss-Seidel
+order the planner exports; they pin the oracle, the planner's schedule and -- on a GPU -- the kernels
+against silent change.  Run from the repo root:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import xpbd_oracle as orc  # noqa: E402
+from softbodyunity_b200 import SoftBody, meshgen  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = {
+    # config 1 substitute: soft cube dropped on the ground plane, 60 Hz, 10 x 10
+    "sample_cube_6": dict(gen=lambda: meshgen.sample_cube(6, centre_height=0.55, jitter=0.05, seed=1234),
+                          plan=dict(tile_cap=100), prm=dict(), frames=30),
+    # soft body with compliance, damping, friction and a tilted gravity vector
+    "soft_block": dict(gen=lambda: meshgen.block(7, 5, 6, spacing=0.05, origin=(0.0, 0.02, 0.0), seed=7),
+                       plan=dict(tile_cap=64, later_tile_cap=48),
+                       prm=dict(stiffness_distance=3.0e4, stiffness_volume=1.0e9, damping=0.5, friction=0.3,
+                                gravity=(0.4, -9.81, -0.2), substeps=6, iterations=5), frames=20),
+}
+
+
+def main():
+    for name, c in CASES.items():
+        pos, tets, tris = c["gen"]()
+        kw = dict(c["prm"])
+        sb = SoftBody(pos, tets, tris, host_only=True, **c["plan"],
+                      **{{"stiffness_distance": "stiffness", "stiffness_volume": "volume_stiffness"}.get(k, k): v for k, v in kw.items()})
+        order, off = sb.schedule()
+        m = orc.Model(pos, tets)
+        m.simulate(orc.params(**kw), n_frames=c["frames"], order=order, batch_off=off)
+        normals = m.normals(tris)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), pos=pos, tets=tets, tris=tris, order=order, batch_off=off,
+                            x4=m.x4, v4=m.v4, normals=normals, frames=c["frames"],
+                            plan=np.array(sorted(c["plan"].items()), dtype=object), prm=np.array(sorted(kw.items()), dtype=object))
+        print(name, pos.shape, tets.shape, "batches", len(off) - 1, "min y", float(m.x4[:, 1].min()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,17 @@
+#!/bin/bash
+# Round artefacts for profiles/: bench line, ncu launch list of the same command, one ncu --set full of the tile pass.
+# usage (on the GPU box): tools/profile_round.sh <round-tag>
+set -u
+tag=${1:-r01}
+out=gpurun_out
+python bench.py --steps 20 --warmup 3 --kernel-breakdown > $out/bench_${tag}.json 2> $out/bench_${tag}.err || { tail -5 $out/bench_${tag}.err; exit 1; }
+python bench.py --steps 20 --warmup 3 --kernel-breakdown --fast-math --no-cpu-baseline > $out/bench_${tag}_fast.json 2>> $out/bench_${tag}.err
+python bench.py --impl reference --steps 5 --warmup 3 > $out/bench_${tag}_reference.json 2>> $out/bench_${tag}.err
+# launch list of a short run of the same command (cold-cache, serialised: compare shares)
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/plain_${tag}.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -s 1400 -c 900 --csv --log-file $out/launches_${tag}.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/ncu_launch_${tag}.log 2>&1
+python tools/profile_step.py > $out/plain2_${tag}.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_tile_pass -s 8 -c 4 -o $out/prof_${tag} \
+    python tools/profile_step.py > $out/ncu_full_${tag}.log 2>&1
+tail -2 $out/ncu_full_${tag}.log
