@@ -80,6 +80,8 @@ typedef struct sb_mesh_desc {
   const int32_t *surf_tris; /* n_tris * 3 vertex ids, may be NULL when n_tris == 0 */
   const float *inv_mass;    /* n_verts, or NULL: lumped from density; 0 pins a vertex */
   void *stream;             /* cudaStream_t to run on, or NULL: the library creates one */
+  const int32_t *edges;     /* n_edges * 2 vertex ids, or NULL: the unique edges of the tets.  Given explicitly by
+                               a partitioner, whose ranks must each sweep an edge exactly once */
   uint32_t n_verts;
   uint32_t n_tets;
   uint32_t n_tris;
@@ -93,8 +95,11 @@ typedef struct sb_mesh_desc {
   int32_t slot_bytes;       /* bytes per shared-memory staging slot of the constraint stream; 0 = auto */
   int32_t n_slots;          /* staging slots per CTA (2..16); 0 = auto */
   int32_t tilings;          /* 0 = auto; 1 = hierarchical tile passes only; N >= 2 = N balanced shifted tilings */
-  int32_t reserved[3];      /* must be 0 */
-} sb_mesh_desc; /* 104 bytes */
+  int32_t n_ghost_verts;    /* partitioned meshes: the LAST n_ghost_verts vertices are ghost copies of vertices
+                               another rank owns (never integrated here; constraints among ghosts are dropped) */
+  uint32_t n_edges;         /* entries of `edges` (ignored when edges == NULL) */
+  int32_t reserved[1];      /* must be 0 */
+} sb_mesh_desc; /* 112 bytes */
 
 /* Sizes and build statistics, for logs, benches and the byte model. */
 typedef struct sb_info {
@@ -102,6 +107,9 @@ typedef struct sb_info {
   uint32_t n_surface_verts;
   uint32_t n_tile_passes;        /* shared-memory tile passes per iteration */
   uint32_t n_tilings;            /* balanced shifted tilings among them (1 = hierarchical only) */
+  uint32_t n_ghost_verts;
+  uint32_t first_cut_pass;       /* first pass of constraint group 1 (those touching ghosts); == n_tile_passes if none */
+  uint64_t constraints_cut;      /* constraints in group 1 */
   uint32_t n_global_batches;     /* leftover global colour batches per iteration */
   uint32_t n_batches;            /* independent sets per iteration in the exported schedule */
   uint32_t tiles_in_pass[8];
@@ -189,6 +197,23 @@ int sb_time_frames(sb_handle h, int32_t n_frames, float dt, float *elapsed_ms);
  * The state is saved and restored around the run.
  */
 int sb_time_kernel(sb_handle h, int32_t which, int32_t reps, float *avg_ms);
+
+/*
+ * Phased stepping, for one rank of a mesh partitioned over several GPUs.  The caller interleaves
+ * these with its halo exchange (INTEGRATION.md / DESIGN.md section 7); all work is enqueued on the
+ * handle's stream without synchronising.  sb_step is the same sequence with no exchange.
+ */
+#define SB_OP_PREDICT 0
+#define SB_OP_PROJECT 1 /* arg: constraint group (0 interior, 1 touching ghosts), -1 both */
+#define SB_OP_FINISH 2
+#define SB_OP_NORMALS 3
+int sb_set_stream(sb_handle h, void *stream);
+int sb_prepare(sb_handle h, float dt); /* pushes parameters for this dt; synchronises */
+int sb_enqueue(sb_handle h, int32_t op, int32_t arg);
+int sb_halo_set(sb_handle h, int32_t list_id, const int32_t *vertex_ids, uint32_t n);
+int sb_halo_pack(sb_handle h, int32_t list_id, void *dst_device);        /* n float4 positions -> dst */
+int sb_halo_unpack(sb_handle h, int32_t list_id, const void *src_device); /* src -> positions */
+int sb_lumped_inv_mass(const float *pos_xyz, uint32_t n_verts, const int32_t *tets, uint32_t n_tets, float density, float *out);
 
 /* Debug aid: timestamps of one run of tile pass `pass` (see solver.cu); out holds 64 * 80 words. */
 int sb_debug_trace_pass(sb_handle h, uint32_t pass, unsigned long long *out, uint32_t n_words);

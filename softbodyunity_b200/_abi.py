@@ -20,6 +20,7 @@ EXPORTS = [
     "sb_read_normals", "sb_surface_vertices", "sb_read_surface", "sb_get_state", "sb_set_state",
     "sb_diagnostics", "sb_get_info", "sb_get_topology", "sb_get_schedule", "sb_get_tiles",
     "sb_time_frames", "sb_time_kernel", "sb_debug_trace_pass", "sb_last_error",
+    "sb_set_stream", "sb_prepare", "sb_enqueue", "sb_halo_set", "sb_halo_pack", "sb_halo_unpack", "sb_lumped_inv_mass",
 ]
 
 
@@ -35,19 +36,19 @@ class SbParams(C.Structure):
 class SbMeshDesc(C.Structure):
     _fields_ = [
         ("pos_xyz", C.c_void_p), ("tets", C.c_void_p), ("surf_tris", C.c_void_p),
-        ("inv_mass", C.c_void_p), ("stream", C.c_void_p),
+        ("inv_mass", C.c_void_p), ("stream", C.c_void_p), ("edges", C.c_void_p),
         ("n_verts", C.c_uint32), ("n_tets", C.c_uint32), ("n_tris", C.c_uint32),
         ("density", C.c_float), ("device", C.c_int32), ("tile_cap", C.c_int32),
         ("max_tile_passes", C.c_int32), ("block_threads", C.c_int32),
         ("later_tile_cap", C.c_int32), ("host_threads", C.c_int32), ("slot_bytes", C.c_int32),
-        ("n_slots", C.c_int32), ("tilings", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("n_slots", C.c_int32), ("tilings", C.c_int32), ("n_ghost_verts", C.c_int32), ("n_edges", C.c_uint32), ("reserved", C.c_int32 * 1),
     ]
 
 
 class SbInfo(C.Structure):
     _fields_ = [
         ("n_verts", C.c_uint32), ("n_edges", C.c_uint32), ("n_tets", C.c_uint32), ("n_tris", C.c_uint32),
-        ("n_surface_verts", C.c_uint32), ("n_tile_passes", C.c_uint32), ("n_tilings", C.c_uint32),
+        ("n_surface_verts", C.c_uint32), ("n_tile_passes", C.c_uint32), ("n_tilings", C.c_uint32), ("n_ghost_verts", C.c_uint32), ("first_cut_pass", C.c_uint32), ("constraints_cut", C.c_uint64),
         ("n_global_batches", C.c_uint32), ("n_batches", C.c_uint32),
         ("tiles_in_pass", C.c_uint32 * 8), ("max_colours_in_pass", C.c_uint32 * 8),
         ("constraints_in_pass", C.c_uint64 * 8), ("edges_in_pass", C.c_uint64 * 8), ("runs_in_pass", C.c_uint64 * 8),
@@ -113,6 +114,13 @@ def load():
         "sb_time_kernel": (C.c_int, [vp, i32, i32, P(f32)]),
         "sb_debug_trace_pass": (C.c_int, [vp, u32, vp, u32]),
         "sb_last_error": (C.c_char_p, [vp]),
+        "sb_set_stream": (C.c_int, [vp, vp]),
+        "sb_prepare": (C.c_int, [vp, f32]),
+        "sb_enqueue": (C.c_int, [vp, i32, i32]),
+        "sb_halo_set": (C.c_int, [vp, i32, vp, u32]),
+        "sb_halo_pack": (C.c_int, [vp, i32, vp]),
+        "sb_halo_unpack": (C.c_int, [vp, i32, vp]),
+        "sb_lumped_inv_mass": (C.c_int, [vp, u32, vp, u32, f32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

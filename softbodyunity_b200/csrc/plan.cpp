@@ -773,14 +773,17 @@ std::string global_colouring(Plan &P, const DevTopo &D, const std::vector<int32_
   std::vector<uint32_t> eoff(ecount.size() + 1, 0), tof(tcount.size() + 1, 0);
   for (size_t c = 0; c < ecount.size(); c++) eoff[c + 1] = eoff[c] + ecount[c];
   for (size_t c = 0; c < tcount.size(); c++) tof[c + 1] = tof[c] + tcount[c];
+  const uint32_t e0 = (uint32_t)P.g_edges.size(), t0 = (uint32_t)P.g_tets.size(); // a second group appends
+  for (auto &o : eoff) o += e0;
+  for (auto &o : tof) o += t0;
   P.g_edges.resize(eoff.back());
   P.g_elen.resize(eoff.back());
   P.g_eid.resize(eoff.back());
   P.g_tets.resize(tof.back());
   P.g_trest.resize(tof.back());
   P.g_tid.resize(tof.back());
-  for (size_t c = 0; c < ecount.size(); c++) P.gbatches.push_back({false, eoff[c], ecount[c]});
-  for (size_t c = 0; c < tcount.size(); c++) P.gbatches.push_back({true, tof[c], tcount[c]});
+  for (size_t c = 0; c < ecount.size(); c++) P.gbatches.push_back({false, eoff[c], ecount[c], 0});
+  for (size_t c = 0; c < tcount.size(); c++) P.gbatches.push_back({true, tof[c], tcount[c], 0});
   std::vector<uint32_t> ecur(eoff.begin(), eoff.end() - 1), tcur(tof.begin(), tof.end() - 1);
   for (size_t i = 0; i < rest.size(); i++) {
     int32_t vs[4];
@@ -803,6 +806,16 @@ std::string global_colouring(Plan &P, const DevTopo &D, const std::vector<int32_
 
 } // namespace
 
+void lumped_inv_mass_into(const float *pos, uint32_t V, const int32_t *tets, uint32_t T, float density, float *out) {
+  Plan tmp;
+  tmp.V = V;
+  tmp.T = T;
+  tmp.pos.assign(pos, pos + 3 * (size_t)V);
+  tmp.tets.assign(tets, tets + 4 * (size_t)T);
+  lumped_inv_mass(tmp, density);
+  std::copy(tmp.inv_mass.begin(), tmp.inv_mass.end(), out);
+}
+
 void Plan::export_schedule(std::vector<int32_t> &order, std::vector<int64_t> &batch_off) const {
   order.clear();
   batch_off.clear();
@@ -810,7 +823,9 @@ void Plan::export_schedule(std::vector<int32_t> &order, std::vector<int64_t> &ba
   auto close = [&]() {
     if ((int64_t)order.size() > batch_off.back()) batch_off.push_back((int64_t)order.size());
   };
+  for (int group = 0; group < 2; group++) {
   for (const TilePass &TP : passes) {
+    if (TP.group != group) continue;
     const uint32_t nt = TP.n_tiles();
     // start of every colour of every tile inside TP.ents
     std::vector<uint64_t> cstart(TP.col_cnt.size() + 1, 0);
@@ -835,9 +850,11 @@ void Plan::export_schedule(std::vector<int32_t> &order, std::vector<int64_t> &ba
     }
   }
   for (const GlobalBatch &b : gbatches) {
+    if (b.group != group) continue;
     for (uint32_t k = 0; k < b.cnt; k++)
       order.push_back(b.tet ? (int32_t)(0x80000000u | (uint32_t)g_tid[b.off + k]) : g_eid[b.off + k]);
     close();
+  }
   }
 }
 
@@ -852,13 +869,37 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   P.V = in.n_verts;
   P.T = in.n_tets;
   P.F = in.n_tris;
+  if (in.n_ghost > in.n_verts) return "n_ghost_verts exceeds n_verts";
+  P.n_ghost = in.n_ghost;
   P.pos.assign(in.pos_xyz, in.pos_xyz + 3 * (size_t)P.V);
   for (float c : P.pos)
     if (!std::isfinite(c)) return "non-finite rest position";
   P.tets.assign(in.tets, in.tets + 4 * (size_t)P.T);
   if (P.F) P.tris.assign(in.surf_tris, in.surf_tris + 3 * (size_t)P.F);
-  std::string err = build_edges(P, threads);
-  if (!err.empty()) return err;
+  std::string err;
+  if (in.edges) {
+    // explicit edge set: canonical (a < b), sorted, unique; tets are still validated
+    for (size_t i = 0; i < 4 * (size_t)P.T; i++)
+      if (P.tets[i] < 0 || (uint32_t)P.tets[i] >= P.V) return "tet vertex index out of range";
+    std::vector<uint64_t> keys(in.n_edges);
+    for (uint32_t e = 0; e < in.n_edges; e++) {
+      int32_t a = in.edges[2 * (size_t)e], b = in.edges[2 * (size_t)e + 1];
+      if (a < 0 || b < 0 || (uint32_t)a >= P.V || (uint32_t)b >= P.V || a == b) return "edge vertex index out of range or repeated";
+      if (a > b) std::swap(a, b);
+      keys[e] = ((uint64_t)(uint32_t)a << 32) | (uint32_t)b;
+    }
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    P.E = (uint32_t)keys.size();
+    P.edges.resize(2 * (size_t)P.E);
+    for (uint32_t e = 0; e < P.E; e++) {
+      P.edges[2 * (size_t)e] = (int32_t)(keys[e] >> 32);
+      P.edges[2 * (size_t)e + 1] = (int32_t)(keys[e] & 0xffffffffu);
+    }
+  } else {
+    err = build_edges(P, threads);
+    if (!err.empty()) return err;
+  }
   if (in.inv_mass) {
     P.inv_mass.assign(in.inv_mass, in.inv_mass + P.V);
     for (float w : P.inv_mass)
@@ -937,6 +978,8 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   for (uint32_t d = 0; d < P.V; d++)
     for (int k = 0; k < 3; k++) dev_pos[3 * (size_t)d + k] = P.pos[3 * (size_t)P.perm[d] + k];
 
+  auto plan_group = [&](const std::vector<int32_t> &cons, int group) -> std::string {
+  const size_t first_pass = P.passes.size(), first_gb = P.gbatches.size();
   std::vector<int32_t> work, next;
   std::vector<int32_t> part(P.V);
   uint32_t n_tiles = 0;
@@ -950,9 +993,9 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     // deal every constraint to the least-loaded tiling it is interior to
     std::vector<std::vector<int32_t>> assigned(n_tilings);
     std::vector<uint64_t> load(n_tilings, 0);
-    std::vector<uint8_t> mask((size_t)P.E + P.T);
+    std::vector<uint8_t> mask(cons.size());
     parallel_for(mask.size(), threads, 1 << 16, [&](size_t i, int) {
-      const int32_t ent = i < P.E ? (int32_t)i : (int32_t)(0x80000000u | (uint32_t)(i - P.E));
+      const int32_t ent = cons[i];
       int32_t vs[4];
       const int n = ent_verts(D, ent, vs);
       uint8_t m = 0;
@@ -969,7 +1012,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     // the fewest so far (ties: the globally least-loaded tiling).
     std::vector<std::vector<uint8_t>> deg(2 * (size_t)n_tilings, std::vector<uint8_t>(P.V, 0));
     for (size_t i = 0; i < mask.size(); i++) {
-      const int32_t ent = i < P.E ? (int32_t)i : (int32_t)(0x80000000u | (uint32_t)(i - P.E));
+      const int32_t ent = cons[i];
       const int kind = ent < 0;
       const uint64_t wgt = kind ? 5 : 2; // tets weigh more than edges in the kernels
       int32_t vs[4];
@@ -1010,9 +1053,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     have_parts = true;
     std::sort(work.begin(), work.end(), [](int32_t a, int32_t b) { return (uint32_t)a < (uint32_t)b; });
   } else {
-    work.resize((size_t)P.E + P.T);
-    for (uint32_t e = 0; e < P.E; e++) work[e] = (int32_t)e;
-    for (uint32_t t = 0; t < P.T; t++) work[(size_t)P.E + t] = (int32_t)(0x80000000u | t);
+    work = cons;
     if (max_passes > 0) {
       n_tiles = (uint32_t)tile_off.size() - 1;
       for (uint32_t t = 0; t < n_tiles; t++)
@@ -1050,7 +1091,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
       if (!err.empty()) return err;
       size_t consumed = work.size() - next.size();
       work.swap(next);
-      if (consumed > 0 || contig) P.passes.push_back(std::move(TP));
+      if (consumed > 0 || (contig && group == 0)) P.passes.push_back(std::move(TP));
       if (work.empty() || k + 1 == levels) break;
       if (consumed == 0 && !contig) break; // no progress: hand the rest to the global colours
       n_tiles = next_parts(P, D, work, part, level_cap(), dev_pos);
@@ -1058,6 +1099,36 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   }
   err = global_colouring(P, D, work);
   if (!err.empty()) return err;
+  for (size_t k = first_pass; k < P.passes.size(); k++) P.passes[k].group = group;
+  for (size_t k = first_gb; k < P.gbatches.size(); k++) P.gbatches[k].group = group;
+  return "";
+  };
+
+  // constraint groups: 0 = no ghost vertex (interior), 1 = touches a ghost (owned cut constraint);
+  // constraints among ghosts only belong to another rank and are dropped
+  const uint32_t first_ghost = P.V - P.n_ghost;
+  std::vector<int32_t> cons0, cons1;
+  cons0.reserve((size_t)P.E + P.T);
+  for (size_t i = 0; i < (size_t)P.E + P.T; i++) {
+    const int32_t ent = i < P.E ? (int32_t)i : (int32_t)(0x80000000u | (uint32_t)(i - P.E));
+    int ng = 0, n;
+    if (ent >= 0) {
+      n = 2;
+      ng = ((uint32_t)P.edges[2 * (size_t)ent] >= first_ghost) + ((uint32_t)P.edges[2 * (size_t)ent + 1] >= first_ghost);
+    } else {
+      n = 4;
+      const int32_t *q = &P.tets[4 * (size_t)(ent & 0x7fffffff)];
+      for (int k = 0; k < 4; k++) ng += (uint32_t)q[k] >= first_ghost;
+    }
+    if (ng == 0) cons0.push_back(ent);
+    else if (ng < n) cons1.push_back(ent);
+  }
+  err = plan_group(cons0, 0);
+  if (!err.empty()) return err;
+  if (P.n_ghost) {
+    err = plan_group(cons1, 1);
+    if (!err.empty()) return err;
+  }
   P.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return "";
 }

@@ -58,6 +58,7 @@ struct TilePass {
   std::vector<uint32_t> col_cnt;    // constraints per colour, edge colours first
   std::vector<uint32_t> n_ecol;     // edge colours of tile t
   uint32_t max_ecol = 0, max_tcol = 0, max_tile_verts = 0, max_chunks = 0;
+  int group = 0;                    // 0 interior constraints, 1 constraints that touch a ghost vertex
   uint64_t n_edges = 0, n_tets = 0;
   uint32_t n_tiles() const { return vert_off.empty() ? 0u : (uint32_t)vert_off.size() - 1; }
 };
@@ -65,11 +66,13 @@ struct TilePass {
 struct GlobalBatch {
   bool tet;
   uint32_t off, cnt; // into g_edges/g_tets
+  int group;
 };
 
 struct Plan {
   // sizes
   uint32_t V = 0, E = 0, T = 0, F = 0;
+  uint32_t n_ghost = 0; // the last n_ghost caller vertices are ghost copies owned by another rank
   // canonical topology, caller's numbering
   std::vector<float> pos;       // 3V rest pose
   std::vector<int32_t> tets;    // 4T
@@ -109,7 +112,12 @@ struct MeshInput {
   const float *inv_mass;
   uint32_t n_verts, n_tets, n_tris;
   float density;
+  uint32_t n_ghost = 0;
+  const int32_t *edges = nullptr; // optional explicit constraint edges (2 * n_edges ids)
+  uint32_t n_edges = 0;
 };
+
+void lumped_inv_mass_into(const float *pos, uint32_t V, const int32_t *tets, uint32_t T, float density, float *out);
 
 // Returns an empty string on success, else a message (argument errors).
 std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &out);

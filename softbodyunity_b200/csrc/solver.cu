@@ -89,7 +89,8 @@ struct sb_solver {
 
   DevBuf<float4> x, v, xp, nrm, stage_a, stage_b;
   DevBuf<float> stage_f;
-  DevBuf<uint32_t> inv, surf_slot, surf_tri_off, surf_tri_ids;
+  DevBuf<uint32_t> inv, surf_slot, surf_tri_off, surf_tri_ids, ghost_slot;
+  std::map<int, DevBuf<uint32_t>> halo; // registered halo index lists (device slots)
   DevBuf<int32_t> tris_dev;
   DevBuf<DevParams> dprm;
   DevParams *hprm = nullptr; // pinned
@@ -170,6 +171,13 @@ struct sb_solver {
       CK(cudaMemcpy(x.p, hx.data(), V * sizeof(float4), cudaMemcpyHostToDevice));
       CK(cudaMemcpy(xp.p, hx.data(), V * sizeof(float4), cudaMemcpyHostToDevice));
       CK(cudaMemcpy(v.p, hv.data(), V * sizeof(float4), cudaMemcpyHostToDevice));
+    }
+    if (plan.n_ghost) {
+      std::vector<uint32_t> gs(plan.n_ghost);
+      for (uint32_t k = 0; k < plan.n_ghost; k++) gs[k] = plan.inv[V - plan.n_ghost + k];
+      ghost_slot.upload(gs, &dev_bytes);
+      k_mark_ghosts<<<grid_for(plan.n_ghost, 256), 256>>>(plan.n_ghost, ghost_slot.p, v.p);
+      CK(cudaGetLastError());
     }
     // surface
     {
@@ -301,9 +309,9 @@ struct sb_solver {
     if (fast()) launch_tile<true>(passes[k], s);
     else launch_tile<false>(passes[k], s);
   }
-  void launch_global(cudaStream_t s) {
+  void launch_global(cudaStream_t s, int group = -1) {
     for (const GlobalBatch &b : plan.gbatches) {
-      if (!b.cnt) continue;
+      if (!b.cnt || (group >= 0 && b.group != group)) continue;
       int g = grid_for(b.cnt, 256);
       if (b.tet) {
         if (fast()) k_global_tets<true><<<g, 256, 0, s>>>(g_tets.p + b.off, g_trest.p + b.off, b.cnt, x.p, dprm.p);
@@ -313,6 +321,11 @@ struct sb_solver {
         else k_global_edges<false><<<g, 256, 0, s>>>(g_edges.p + b.off, g_elen.p + b.off, b.cnt, x.p, dprm.p);
       }
     }
+  }
+  void launch_group(int group, cudaStream_t s) {
+    for (size_t k = 0; k < passes.size(); k++)
+      if (plan.passes[k].group == group) launch_pass(k, s);
+    launch_global(s, group);
   }
   void launch_predict(cudaStream_t s) { k_predict<<<grid_for(plan.V, 256), 256, 0, s>>>(plan.V, x.p, v.p, xp.p, dprm.p); }
   void launch_finish(cudaStream_t s) { k_finish<<<grid_for(plan.V, 256), 256, 0, s>>>(plan.V, x.p, v.p, xp.p, dprm.p); }
@@ -335,8 +348,7 @@ struct sb_solver {
     for (int ss = 0; ss < prm.substeps; ss++) {
       launch_predict(s);
       for (int it = 0; it < prm.iterations; it++) {
-        for (size_t k = 0; k < passes.size(); k++) launch_pass(k, s);
-        launch_global(s);
+        for (int g = 0; g < 2; g++) launch_group(g, s);
       }
       launch_finish(s);
     }
@@ -435,6 +447,7 @@ struct sb_solver {
     if (v4) {
       CK(cudaMemcpyAsync(stage_b.p, v4, V * sizeof(float4), cudaMemcpyHostToDevice, stream));
       k_scatter4<<<grid_for(V, 256), 256, 0, stream>>>(V, inv.p, stage_b.p, v.p);
+      if (plan.n_ghost) k_mark_ghosts<<<grid_for(plan.n_ghost, 256), 256, 0, stream>>>(plan.n_ghost, ghost_slot.p, v.p);
     }
     CK(cudaGetLastError());
     // the host buffers belong to the caller again when this returns
@@ -599,7 +612,7 @@ static int create_impl(const sb_mesh_desc *mesh, const sb_params *params, sb_han
   *out = nullptr;
   g_create_error.clear();
   if (!mesh) { g_create_error = "mesh is NULL"; return SB_E_ARG; }
-  for (int k = 0; k < 3; k++)
+  for (int k = 0; k < 1; k++)
     if (mesh->reserved[k] != 0) { g_create_error = "reserved fields must be 0"; return SB_E_ARG; }
   sb_params dp;
   sb_default_params(&dp);
@@ -610,7 +623,8 @@ static int create_impl(const sb_mesh_desc *mesh, const sb_params *params, sb_han
   int rc = guarded(nullptr, [&]() -> int {
     s = new sb_solver();
     s->prm = dp;
-    MeshInput in{mesh->pos_xyz, mesh->tets, mesh->surf_tris, mesh->inv_mass, mesh->n_verts, mesh->n_tets, mesh->n_tris, mesh->density};
+    MeshInput in{mesh->pos_xyz, mesh->tets, mesh->surf_tris, mesh->inv_mass, mesh->n_verts, mesh->n_tets, mesh->n_tris, mesh->density,
+                 (uint32_t)std::max(0, mesh->n_ghost_verts), mesh->edges, mesh->edges ? mesh->n_edges : 0u};
     PlanOptions opt;
     opt.tile_cap = mesh->tile_cap;
     opt.max_tile_passes = mesh->max_tile_passes;
@@ -764,6 +778,14 @@ int sb_get_info(sb_handle h, sb_info *o) {
   o->n_verts = P.V; o->n_edges = P.E; o->n_tets = P.T; o->n_tris = P.F;
   o->n_surface_verts = (uint32_t)P.surf_ids.size();
   o->n_tile_passes = (uint32_t)P.passes.size();
+  o->n_ghost_verts = P.n_ghost;
+  o->first_cut_pass = (uint32_t)P.passes.size();
+  for (size_t k = P.passes.size(); k-- > 0;)
+    if (P.passes[k].group == 1) o->first_cut_pass = (uint32_t)k;
+  for (size_t k = 0; k < P.passes.size(); k++)
+    if (P.passes[k].group == 1) o->constraints_cut += P.passes[k].n_edges + P.passes[k].n_tets;
+  for (const GlobalBatch &b : P.gbatches)
+    if (b.group == 1) o->constraints_cut += b.cnt;
   o->n_tilings = P.n_tilings;
   uint32_t nb = 0;
   for (size_t k = 0; k < P.passes.size(); k++) {
@@ -855,6 +877,99 @@ int sb_time_kernel(sb_handle h, int32_t which, int32_t reps, float *avg_ms) {
   if (reps < 1 || !avg_ms) return SB_E_ARG;
   return guarded(h, [&]() -> int {
     *avg_ms = h->time_kernel(which, reps);
+    return SB_OK;
+  });
+}
+
+/* ---- phased stepping for partitioned meshes (one rank of a multi-GPU body) -----------------
+   The caller interleaves these with its halo exchange; everything is enqueued on the handle's
+   stream and nothing synchronises, so the sequence can be captured in a CUDA graph. */
+int sb_set_stream(sb_handle h, void *stream) {
+  NEED_DEVICE(h);
+  if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); h->own_stream = false; }
+  h->stream = (cudaStream_t)stream;
+  return SB_OK;
+}
+
+int sb_prepare(sb_handle h, float dt) {
+  NEED_DEVICE(h);
+  return guarded(h, [&]() -> int {
+    CK(cudaSetDevice(h->device));
+    if (!(dt > 0)) dt = h->prm.dt;
+    h->refresh_params(dt);
+    CK(cudaStreamSynchronize(h->stream));
+    return SB_OK;
+  });
+}
+
+int sb_enqueue(sb_handle h, int32_t op, int32_t arg) {
+  NEED_DEVICE(h);
+  return guarded(h, [&]() -> int {
+    if (h->cur_dt < 0 || h->prm_dirty) throw std::string("call sb_prepare after creating the handle or changing parameters");
+    switch (op) {
+      case SB_OP_PREDICT: h->launch_predict(h->stream); break;
+      case SB_OP_PROJECT:
+        if (arg < 0) { h->launch_group(0, h->stream); h->launch_group(1, h->stream); }
+        else if (arg <= 1) h->launch_group(arg, h->stream);
+        else throw std::string("no such constraint group");
+        break;
+      case SB_OP_FINISH: h->launch_finish(h->stream); break;
+      case SB_OP_NORMALS: h->launch_normals(h->stream); break;
+      default: throw std::string("unknown op");
+    }
+    CK(cudaGetLastError());
+    return SB_OK;
+  });
+}
+
+int sb_halo_set(sb_handle h, int32_t list_id, const int32_t *vertex_ids, uint32_t n) {
+  NEED_DEVICE(h);
+  if (n && !vertex_ids) return SB_E_ARG;
+  return guarded(h, [&]() -> int {
+    CK(cudaSetDevice(h->device));
+    std::vector<uint32_t> slots(n);
+    for (uint32_t k = 0; k < n; k++) {
+      if (vertex_ids[k] < 0 || (uint32_t)vertex_ids[k] >= h->plan.V) throw std::string("halo vertex id out of range");
+      slots[k] = h->plan.inv[vertex_ids[k]];
+    }
+    h->halo[list_id].upload(slots, &h->dev_bytes);
+    return SB_OK;
+  });
+}
+
+/* positions (float4) of the list's vertices -> n * 16 bytes of device memory at dst, in list order */
+int sb_halo_pack(sb_handle h, int32_t list_id, void *dst_device) {
+  NEED_DEVICE(h);
+  return guarded(h, [&]() -> int {
+    auto it = h->halo.find(list_id);
+    if (it == h->halo.end() || !dst_device) throw std::string("unknown halo list or NULL buffer");
+    const uint32_t n = (uint32_t)it->second.n;
+    if (n) k_gather4<<<h->grid_for(n, 256), 256, 0, h->stream>>>(n, it->second.p, h->x.p, (float4 *)dst_device);
+    CK(cudaGetLastError());
+    return SB_OK;
+  });
+}
+
+int sb_halo_unpack(sb_handle h, int32_t list_id, const void *src_device) {
+  NEED_DEVICE(h);
+  return guarded(h, [&]() -> int {
+    auto it = h->halo.find(list_id);
+    if (it == h->halo.end() || !src_device) throw std::string("unknown halo list or NULL buffer");
+    const uint32_t n = (uint32_t)it->second.n;
+    if (n) k_scatter4<<<h->grid_for(n, 256), 256, 0, h->stream>>>(n, it->second.p, (const float4 *)src_device, h->x.p);
+    CK(cudaGetLastError());
+    return SB_OK;
+  });
+}
+
+/* lumped inverse masses of a whole mesh, exactly as sb_create derives them (host only): a
+   partitioner needs the global values because a rank does not see every tet of its vertices */
+int sb_lumped_inv_mass(const float *pos_xyz, uint32_t n_verts, const int32_t *tets, uint32_t n_tets, float density, float *out) {
+  if (!pos_xyz || !out || (n_tets && !tets) || !(density > 0)) return SB_E_ARG;
+  for (size_t i = 0; i < 4 * (size_t)n_tets; i++)
+    if (tets[i] < 0 || (uint32_t)tets[i] >= n_verts) return SB_E_ARG;
+  return guarded(nullptr, [&]() -> int {
+    sb::lumped_inv_mass_into(pos_xyz, n_verts, tets, n_tets, density, out);
     return SB_OK;
   });
 }

@@ -39,6 +39,17 @@ def default_params(**over) -> SbParams:
     return p
 
 
+def lumped_inv_mass(pos, tets, density=1000.0):
+    """Inverse lumped masses of a whole mesh, exactly as sb_create derives them (host only)."""
+    pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+    tets = np.ascontiguousarray(tets, np.int32).reshape(-1, 4)
+    out = np.empty(len(pos), np.float32)
+    rc = _abi.load().sb_lumped_inv_mass(_ptr(pos), len(pos), _ptr(tets), len(tets), density, _ptr(out))
+    if rc != 0:
+        raise SbError(rc, "sb_lumped_inv_mass: bad arguments")
+    return out
+
+
 class SoftBody:
     """One soft body (or a batch of independent bodies in one mesh) on one GPU.
 
@@ -46,11 +57,11 @@ class SoftBody:
     inf = rigid), `volume_stiffness`, `damping`, `substeps`, `iterations`.
     """
 
-    def __init__(self, pos, tets, surf_tris=None, inv_mass=None, *, density=1000.0, device=0,
+    def __init__(self, pos, tets, surf_tris=None, inv_mass=None, *, edges=None, density=1000.0, device=0,
                  stiffness=math.inf, volume_stiffness=math.inf, damping=0.0, friction=0.0,
                  substeps=10, iterations=10, dt=1.0 / 60.0, gravity=(0.0, -9.81, 0.0), ground_y=0.0,
                  flags=0, tile_cap=0, max_tile_passes=-1, block_threads=0, later_tile_cap=0,
-                 host_threads=0, slot_bytes=0, n_slots=0, tilings=0, stream=None, host_only=False):
+                 host_threads=0, slot_bytes=0, n_slots=0, tilings=0, n_ghost_verts=0, stream=None, host_only=False):
         self._lib = _abi.load()
         self._h = C.c_void_p()
         pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
@@ -64,11 +75,14 @@ class SoftBody:
         d = SbMeshDesc()
         d.pos_xyz, d.tets, d.surf_tris, d.inv_mass = _ptr(pos), _ptr(tets), _ptr(tris), _ptr(w)
         d.stream = C.c_void_p(stream) if stream else None
+        e = None if edges is None else np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 2)
+        d.edges, d.n_edges = _ptr(e), 0 if e is None else len(e)
         d.n_verts, d.n_tets, d.n_tris = self.n_verts, self.n_tets, self.n_tris
         d.density, d.device = density, device
         d.tile_cap, d.max_tile_passes, d.block_threads = tile_cap, max_tile_passes, block_threads
         d.later_tile_cap, d.host_threads = later_tile_cap, host_threads
         d.slot_bytes, d.n_slots, d.tilings = slot_bytes, n_slots, tilings
+        d.n_ghost_verts = n_ghost_verts
         self._params = default_params(
             dt=dt, substeps=substeps, iterations=iterations, stiffness_distance=stiffness,
             stiffness_volume=volume_stiffness, damping=damping, friction=friction, gravity=gravity,
@@ -141,6 +155,28 @@ class SoftBody:
 
     def synchronize(self):
         self._ck(self._lib.sb_synchronize(self._h))
+
+    # -- phased stepping (one rank of a partitioned mesh; see partition.py) ---------------
+    OP_PREDICT, OP_PROJECT, OP_FINISH, OP_NORMALS = 0, 1, 2, 3
+
+    def set_stream(self, stream_ptr: int):
+        self._ck(self._lib.sb_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def prepare(self, dt: float = 0.0):
+        self._ck(self._lib.sb_prepare(self._h, dt))
+
+    def enqueue(self, op: int, arg: int = -1):
+        self._ck(self._lib.sb_enqueue(self._h, op, arg))
+
+    def halo_set(self, list_id: int, vertex_ids):
+        ids = np.ascontiguousarray(vertex_ids, np.int32)
+        self._ck(self._lib.sb_halo_set(self._h, list_id, _ptr(ids) if len(ids) else None, len(ids)))
+
+    def halo_pack(self, list_id: int, dst_device_ptr: int):
+        self._ck(self._lib.sb_halo_pack(self._h, list_id, C.c_void_p(dst_device_ptr)))
+
+    def halo_unpack(self, list_id: int, src_device_ptr: int):
+        self._ck(self._lib.sb_halo_unpack(self._h, list_id, C.c_void_p(src_device_ptr)))
 
     # -- write-back -------------------------------------------------------------------
     def positions(self, out=None):

@@ -26,13 +26,14 @@ public struct SbParams            // sb_params, 48 bytes
 }
 
 [StructLayout(LayoutKind.Sequential)]
-public struct SbMeshDesc          // sb_mesh_desc, 104 bytes
+public struct SbMeshDesc          // sb_mesh_desc, 112 bytes
 {
-    public IntPtr posXyz, tets, surfTris, invMass, stream;
+    public IntPtr posXyz, tets, surfTris, invMass, stream, edges;
     public uint nVerts, nTets, nTris;
     public float density;
-    public int device, tileCap, maxTilePasses, blockThreads, laterTileCap, hostThreads, slotBytes, nSlots, tilings;
-    public int reserved0, reserved1, reserved2;
+    public int device, tileCap, maxTilePasses, blockThreads, laterTileCap, hostThreads, slotBytes, nSlots, tilings, nGhostVerts;
+    public uint nEdges;
+    public int reserved0;
 }
 
 internal static class SbNative
@@ -103,7 +104,7 @@ public class SoftbodyB200 : MonoBehaviour
         {
             var d = new SbMeshDesc {
                 posXyz = p.AddrOfPinnedObject(), tets = t.AddrOfPinnedObject(), surfTris = s.AddrOfPinnedObject(),
-                invMass = IntPtr.Zero, stream = IntPtr.Zero,
+                invMass = IntPtr.Zero, stream = IntPtr.Zero, edges = IntPtr.Zero,
                 nVerts = (uint)restPositions.Length, nTets = (uint)(tets.Length / 4), nTris = (uint)(surfaceTriangles.Length / 3),
                 density = density, device = device, maxTilePasses = -1 };
             Check(SbNative.sb_create(ref d, ref prm, out handle), IntPtr.Zero);

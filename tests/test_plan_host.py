@@ -32,7 +32,7 @@ def test_struct_layouts_match_the_header():
     lib = _abi.load()
     v, a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
     assert lib.sb_abi_check(C.byref(v), C.byref(a), C.byref(b), C.byref(c)) == 0
-    assert (v.value, a.value, b.value) == (1, 48, 104)
+    assert (v.value, a.value, b.value) == (1, 48, 112)
     assert c.value == C.sizeof(_abi.SbInfo)
     assert C.sizeof(orc.OrcParams) == 48  # the oracle takes the same parameter block
     p = _abi.SbParams()
