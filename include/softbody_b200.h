@@ -207,12 +207,21 @@ int sb_time_kernel(sb_handle h, int32_t which, int32_t reps, float *avg_ms);
 #define SB_OP_PROJECT 1 /* arg: constraint group (0 interior, 1 touching ghosts), -1 both */
 #define SB_OP_FINISH 2
 #define SB_OP_NORMALS 3
+#define SB_OP_EXCHANGE 4 /* arg: 0 = exchange A (ghosts refreshed), 1 = exchange B (ghost values returned) */
+#define SB_OP_HALO_SEND 5 /* arg: list id; the two halves of an exchange, for several ranks driven from one stream */
+#define SB_OP_HALO_RECV 6
 int sb_set_stream(sb_handle h, void *stream);
 int sb_prepare(sb_handle h, float dt); /* pushes parameters for this dt; synchronises */
 int sb_enqueue(sb_handle h, int32_t op, int32_t arg);
 int sb_halo_set(sb_handle h, int32_t list_id, const int32_t *vertex_ids, uint32_t n);
 int sb_halo_pack(sb_handle h, int32_t list_id, void *dst_device);        /* n float4 positions -> dst */
 int sb_halo_unpack(sb_handle h, int32_t list_id, const void *src_device); /* src -> positions */
+/* halo exchange over peer memory (NVLink P2P stores + flag words), see solver.cu */
+int sb_halo_alloc(sb_handle h, int32_t list_id, void **base_out, uint64_t *bytes_out);
+int sb_halo_connect(sb_handle h, int32_t list_id, void *peer_base);
+int sb_halo_error(sb_handle h, int32_t *out);
+int sb_ipc_export(void *device_ptr, unsigned char *handle64);
+int sb_ipc_open(int32_t device, const unsigned char *handle64, void **ptr_out);
 int sb_lumped_inv_mass(const float *pos_xyz, uint32_t n_verts, const int32_t *tets, uint32_t n_tets, float density, float *out);
 
 /* Debug aid: timestamps of one run of tile pass `pass` (see solver.cu); out holds 64 * 80 words. */

@@ -21,6 +21,7 @@ EXPORTS = [
     "sb_diagnostics", "sb_get_info", "sb_get_topology", "sb_get_schedule", "sb_get_tiles",
     "sb_time_frames", "sb_time_kernel", "sb_debug_trace_pass", "sb_last_error",
     "sb_set_stream", "sb_prepare", "sb_enqueue", "sb_halo_set", "sb_halo_pack", "sb_halo_unpack", "sb_lumped_inv_mass",
+    "sb_halo_alloc", "sb_halo_connect", "sb_halo_error", "sb_ipc_export", "sb_ipc_open",
 ]
 
 
@@ -121,6 +122,11 @@ def load():
         "sb_halo_pack": (C.c_int, [vp, i32, vp]),
         "sb_halo_unpack": (C.c_int, [vp, i32, vp]),
         "sb_lumped_inv_mass": (C.c_int, [vp, u32, vp, u32, f32, vp]),
+        "sb_halo_alloc": (C.c_int, [vp, i32, P(vp), P(C.c_uint64)]),
+        "sb_halo_connect": (C.c_int, [vp, i32, vp]),
+        "sb_halo_error": (C.c_int, [vp, P(i32)]),
+        "sb_ipc_export": (C.c_int, [vp, vp]),
+        "sb_ipc_open": (C.c_int, [i32, vp, P(vp)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

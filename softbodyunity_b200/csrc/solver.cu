@@ -91,6 +91,14 @@ struct sb_solver {
   DevBuf<float> stage_f;
   DevBuf<uint32_t> inv, surf_slot, surf_tri_off, surf_tri_ids, ghost_slot;
   std::map<int, DevBuf<uint32_t>> halo; // registered halo index lists (device slots)
+  // peer-memory exchange state per list: my receive buffer (+ flag word after it), where to send
+  struct HaloLink {
+    DevBuf<unsigned char> recv; // n * 16 bytes + 16 (flag)
+    DevBuf<uint32_t> ctl_send, ctl_recv;
+    float4 *peer_buf = nullptr;
+    uint32_t *peer_flag = nullptr;
+  };
+  std::map<int, HaloLink> links;
   DevBuf<int32_t> tris_dev;
   DevBuf<DevParams> dprm;
   DevParams *hprm = nullptr; // pinned
@@ -327,6 +335,29 @@ struct sb_solver {
       if (plan.passes[k].group == group) launch_pass(k, s);
     launch_global(s, group);
   }
+  bool halo_active() const { return !links.empty(); }
+  void halo_send(int list, cudaStream_t s) {
+    auto li = links.find(list);
+    auto hl = halo.find(list);
+    if (li == links.end() || hl == halo.end() || !li->second.peer_buf || !hl->second.n) return;
+    const uint32_t n = (uint32_t)hl->second.n;
+    k_halo_send<<<std::min(grid_for(n, 256), 32), 256, 0, s>>>(n, hl->second.p, x.p, li->second.peer_buf, li->second.peer_flag,
+                                                              li->second.ctl_send.p);
+  }
+  void halo_recv(int list, cudaStream_t s) {
+    auto li = links.find(list);
+    auto hl = halo.find(list);
+    if (li == links.end() || hl == halo.end() || !li->second.recv.p || !hl->second.n) return;
+    const uint32_t n = (uint32_t)hl->second.n;
+    k_halo_recv<<<std::min(grid_for(n, 256), 32), 256, 0, s>>>(n, hl->second.p, x.p, (const float4 *)li->second.recv.p,
+                                                              (const uint32_t *)(li->second.recv.p + (size_t)n * 16), li->second.ctl_recv.p);
+  }
+  // exchange A: lower-boundary vertices (list 1) go down to the rank that holds them as ghosts (list 0)
+  // exchange B: the ghost values (list 0) go back up and overwrite the owner's copies (list 1)
+  void exchange(int phase, cudaStream_t s) {
+    if (phase == 0) { halo_send(1, s); halo_recv(0, s); }
+    else { halo_send(0, s); halo_recv(1, s); }
+  }
   void launch_predict(cudaStream_t s) { k_predict<<<grid_for(plan.V, 256), 256, 0, s>>>(plan.V, x.p, v.p, xp.p, dprm.p); }
   void launch_finish(cudaStream_t s) { k_finish<<<grid_for(plan.V, 256), 256, 0, s>>>(plan.V, x.p, v.p, xp.p, dprm.p); }
   void launch_normals(cudaStream_t s) {
@@ -348,7 +379,14 @@ struct sb_solver {
     for (int ss = 0; ss < prm.substeps; ss++) {
       launch_predict(s);
       for (int it = 0; it < prm.iterations; it++) {
-        for (int g = 0; g < 2; g++) launch_group(g, s);
+        if (halo_active()) {
+          launch_group(0, s);
+          exchange(0, s);
+          launch_group(1, s);
+          exchange(1, s);
+        } else {
+          for (int g = 0; g < 2; g++) launch_group(g, s);
+        }
       }
       launch_finish(s);
     }
@@ -915,6 +953,9 @@ int sb_enqueue(sb_handle h, int32_t op, int32_t arg) {
         break;
       case SB_OP_FINISH: h->launch_finish(h->stream); break;
       case SB_OP_NORMALS: h->launch_normals(h->stream); break;
+      case SB_OP_EXCHANGE: h->exchange(arg, h->stream); break;
+      case SB_OP_HALO_SEND: h->halo_send(arg, h->stream); break;
+      case SB_OP_HALO_RECV: h->halo_recv(arg, h->stream); break;
       default: throw std::string("unknown op");
     }
     CK(cudaGetLastError());
@@ -960,6 +1001,87 @@ int sb_halo_unpack(sb_handle h, int32_t list_id, const void *src_device) {
     CK(cudaGetLastError());
     return SB_OK;
   });
+}
+
+/* ---- halo exchange over peer memory: set-up ------------------------------------------------
+   sb_halo_alloc: receive buffer for a registered list (n float4 + a flag word); *base_out is its
+   device address (export it with sb_ipc_export for another process).  sb_halo_connect: where this
+   rank SENDS the list's vertices (the neighbour's receive buffer for the matching list; a pointer
+   in this process' address space: the neighbour's own pointer when both ranks live in one process,
+   else the result of sb_ipc_open).  Once any link exists, sb_step runs the exchanges inside the
+   frame graph: list 0 = ghosts (received in exchange A, sent back in B), list 1 = own vertices that
+   are ghosts on the lower rank (sent in A, received in B). */
+int sb_halo_alloc(sb_handle h, int32_t list_id, void **base_out, uint64_t *bytes_out) {
+  NEED_DEVICE(h);
+  return guarded(h, [&]() -> int {
+    CK(cudaSetDevice(h->device));
+    auto it = h->halo.find(list_id);
+    if (it == h->halo.end()) throw std::string("register the list with sb_halo_set first");
+    sb_solver::HaloLink &L = h->links[list_id];
+    const size_t bytes = it->second.n * 16 + 16;
+    L.recv.alloc(bytes, &h->dev_bytes);
+    CK(cudaMemset(L.recv.p, 0, bytes));
+    if (!L.ctl_recv.p) { L.ctl_recv.alloc(4, &h->dev_bytes); CK(cudaMemset(L.ctl_recv.p, 0, 16)); }
+    if (base_out) *base_out = L.recv.p;
+    if (bytes_out) *bytes_out = bytes;
+    for (auto &g : h->graphs) cudaGraphExecDestroy(g.second);
+    h->graphs.clear();
+    return SB_OK;
+  });
+}
+
+int sb_halo_connect(sb_handle h, int32_t list_id, void *peer_base) {
+  NEED_DEVICE(h);
+  return guarded(h, [&]() -> int {
+    CK(cudaSetDevice(h->device));
+    auto it = h->halo.find(list_id);
+    if (it == h->halo.end() || !peer_base) throw std::string("unknown halo list or NULL peer buffer");
+    sb_solver::HaloLink &L = h->links[list_id];
+    L.peer_buf = (float4 *)peer_base;
+    L.peer_flag = (uint32_t *)((unsigned char *)peer_base + it->second.n * 16);
+    if (!L.ctl_send.p) { L.ctl_send.alloc(4, &h->dev_bytes); CK(cudaMemset(L.ctl_send.p, 0, 16)); }
+    for (auto &g : h->graphs) cudaGraphExecDestroy(g.second);
+    h->graphs.clear();
+    return SB_OK;
+  });
+}
+
+/* 1 if a receive ever timed out waiting for its neighbour (the step's results are then invalid) */
+int sb_halo_error(sb_handle h, int32_t *out) {
+  NEED_DEVICE(h);
+  if (!out) return SB_E_ARG;
+  return guarded(h, [&]() -> int {
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    *out = 0;
+    for (auto &kv : h->links)
+      if (kv.second.ctl_recv.p) {
+        uint32_t c[4];
+        CK(cudaMemcpy(c, kv.second.ctl_recv.p, 16, cudaMemcpyDeviceToHost));
+        if (c[2]) *out = 1;
+      }
+    return SB_OK;
+  });
+}
+
+int sb_ipc_export(void *device_ptr, unsigned char *handle64) {
+  if (!device_ptr || !handle64) return SB_E_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  cudaIpcMemHandle_t hd;
+  if (cudaIpcGetMemHandle(&hd, device_ptr) != cudaSuccess) { cudaGetLastError(); return SB_E_CUDA; }
+  std::memcpy(handle64, &hd, 64);
+  return SB_OK;
+}
+
+int sb_ipc_open(int32_t device, const unsigned char *handle64, void **ptr_out) {
+  if (!handle64 || !ptr_out) return SB_E_ARG;
+  cudaIpcMemHandle_t hd;
+  std::memcpy(&hd, handle64, 64);
+  if (cudaSetDevice(device) != cudaSuccess || cudaIpcOpenMemHandle(ptr_out, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(cudaGetLastError());
+    return SB_E_CUDA;
+  }
+  return SB_OK;
 }
 
 /* lumped inverse masses of a whole mesh, exactly as sb_create derives them (host only): a

@@ -19,7 +19,7 @@ from typing import Dict, List
 
 import numpy as np
 
-from .solver import SoftBody, lumped_inv_mass
+from .solver import SoftBody, ipc_export, ipc_open, lumped_inv_mass
 
 # halo list ids registered with sb_halo_set
 H_GHOST, H_LOWER = 0, 1  # my ghost vertices (owned by rank+1) | my own vertices that are ghosts on rank-1
@@ -53,7 +53,8 @@ class RankMesh:
         return np.concatenate([self.own, self.ghost])
 
 
-def slab_partition(pos, tets, tris, n_ranks, density=1000.0, inv_mass=None) -> List[RankMesh]:
+def slab_partition(pos, tets, tris, n_ranks, density=1000.0, inv_mass=None, only_rank=None) -> List[RankMesh]:
+    """All ranks' meshes, or with only_rank=r a one-element list holding rank r's (what a process needs)."""
     pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
     tets = np.ascontiguousarray(tets, np.int32).reshape(-1, 4)
     tris = np.zeros((0, 3), np.int32) if tris is None else np.ascontiguousarray(tris, np.int32).reshape(-1, 3)
@@ -70,7 +71,7 @@ def slab_partition(pos, tets, tris, n_ranks, density=1000.0, inv_mass=None) -> L
     if (t_top - t_owner).max(initial=0) > 1:
         raise ValueError("a tet spans more than two slabs: too many ranks for this mesh")
     out = []
-    for r in range(n_ranks):
+    for r in (range(n_ranks) if only_rank is None else [only_rank]):
         own = np.flatnonzero(rank_of == r).astype(np.int64)
         sel = np.flatnonzero(t_owner == r)
         tv = tets[sel]
@@ -121,6 +122,48 @@ class LocalComm:
                     b._recv_buf(phase).copy_(bodies[src]._send_buf(phase))
         for b in bodies:
             b._unpack(phase)
+
+
+class LocalPeerComm:
+    """Virtual ranks in one process, exchanging through the SAME send/receive kernels as the
+    multi-GPU path (direct stores into the neighbour's receive buffer + sequence flags).  All sends
+    of an exchange are enqueued before any receive, so on the single shared stream no receive ever
+    has to wait."""
+
+    def __init__(self, bodies):
+        self.n = len(bodies)
+        for lo, hi in zip(bodies, bodies[1:]):
+            base_ghost = lo.sb.halo_alloc(H_GHOST)   # lo receives its ghosts here (exchange A)
+            base_lower = hi.sb.halo_alloc(H_LOWER)   # hi receives its lower-boundary vertices here (exchange B)
+            hi.sb.halo_connect(H_LOWER, base_ghost)  # A: hi sends list LOWER into lo's GHOST buffer
+            lo.sb.halo_connect(H_GHOST, base_lower)  # B: lo sends list GHOST into hi's LOWER buffer
+
+    def exchange(self, phase, bodies):
+        send, recv = (H_LOWER, H_GHOST) if phase == "A" else (H_GHOST, H_LOWER)
+        for b in bodies:
+            b.sb.enqueue(SoftBody.OP_HALO_SEND, send)
+        for b in bodies:
+            b.sb.enqueue(SoftBody.OP_HALO_RECV, recv)
+
+
+def connect_peers(body, device):
+    """Multi-process set-up of the peer-memory exchange: every rank allocates its receive buffers,
+    the CUDA IPC handles travel through torch.distributed (plumbing only), and each rank opens its
+    neighbours' buffers.  Afterwards body.sb.step() runs the exchanges inside the frame graph."""
+    import torch.distributed as dist
+    rank, n = body.rank, body.n_ranks
+    mine = {}
+    if body.mesh.n_ghost:
+        mine["ghost"] = ipc_export(body.sb.halo_alloc(H_GHOST))
+    if len(body.mesh.lower):
+        mine["lower"] = ipc_export(body.sb.halo_alloc(H_LOWER))
+    everyone = [None] * n
+    dist.all_gather_object(everyone, mine)
+    if rank > 0 and len(body.mesh.lower):       # exchange A: my LOWER list lands in (rank-1)'s GHOST buffer
+        body.sb.halo_connect(H_LOWER, ipc_open(device, everyone[rank - 1]["ghost"]))
+    if rank + 1 < n and body.mesh.n_ghost:      # exchange B: my GHOST list lands in (rank+1)'s LOWER buffer
+        body.sb.halo_connect(H_GHOST, ipc_open(device, everyone[rank + 1]["lower"]))
+    dist.barrier()
 
 
 class TorchComm:
@@ -189,12 +232,13 @@ class PartitionedBody:
             self.sb.halo_unpack(lst, buf.data_ptr())
 
 
-def step_partitioned(bodies: List[PartitionedBody], comm, dt: float = 0.0, frames: int = 1):
+def step_partitioned(bodies: List[PartitionedBody], comm, dt: float = 0.0, frames: int = 1, prepared: bool = False):
     """Advance every given rank by `frames` frames (all ranks of a LocalComm, or the single local
     rank of a TorchComm)."""
     p = bodies[0].sb.params
-    for b in bodies:
-        b.sb.prepare(dt)
+    if not prepared:
+        for b in bodies:
+            b.sb.prepare(dt)
     S = SoftBody
     for _ in range(frames):
         for _ in range(p.substeps):
@@ -211,6 +255,43 @@ def step_partitioned(bodies: List[PartitionedBody], comm, dt: float = 0.0, frame
                 b.sb.enqueue(S.OP_FINISH)
         for b in bodies:
             b.sb.enqueue(S.OP_NORMALS)
+
+
+class FrameRunner:
+    """Steps the local rank(s) frame by frame; with use_graph the whole frame -- kernels, halo
+    pack/unpack and the NCCL send/recv -- is captured once into a CUDA graph and replayed."""
+
+    def __init__(self, bodies: List[PartitionedBody], comm, dt: float = 0.0, use_graph: bool = True):
+        import torch
+        self.bodies, self.comm, self.dt, self.torch = bodies, comm, dt, torch
+        self.stream = bodies[0].stream
+        self.graph = None
+        self.graph_error = None
+        for b in bodies:
+            b.sb.prepare(dt)
+        if use_graph:
+            try:
+                self._one_frame_eager()  # warm-up: NCCL connections, lazy allocations
+                self.stream.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    self._one_frame_eager()
+                self.graph = g
+                self.warm_frames = 1
+            except Exception as e:  # capture not supported for this transport: stay eager
+                self.graph, self.graph_error = None, repr(e)[:200]
+                self.warm_frames = 1
+
+    def _one_frame_eager(self):
+        step_partitioned(self.bodies, self.comm, self.dt, frames=1, prepared=True)
+
+    def step(self, frames: int = 1):
+        for _ in range(frames):
+            if self.graph is not None:
+                with self.torch.cuda.stream(self.stream):
+                    self.graph.replay()
+            else:
+                self._one_frame_eager()
 
 
 def combined_order(meshes: List[RankMesh], bodies_or_plans, global_edges):

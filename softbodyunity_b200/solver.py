@@ -50,6 +50,23 @@ def lumped_inv_mass(pos, tets, density=1000.0):
     return out
 
 
+def ipc_export(device_ptr: int) -> bytes:
+    buf = (C.c_ubyte * 64)()
+    rc = _abi.load().sb_ipc_export(C.c_void_p(device_ptr), buf)
+    if rc != 0:
+        raise SbError(rc, "cudaIpcGetMemHandle failed")
+    return bytes(buf)
+
+
+def ipc_open(device: int, handle: bytes) -> int:
+    buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+    out = C.c_void_p()
+    rc = _abi.load().sb_ipc_open(device, buf, C.byref(out))
+    if rc != 0:
+        raise SbError(rc, _abi.load().sb_last_error(None).decode())
+    return out.value
+
+
 class SoftBody:
     """One soft body (or a batch of independent bodies in one mesh) on one GPU.
 
@@ -177,6 +194,23 @@ class SoftBody:
 
     def halo_unpack(self, list_id: int, src_device_ptr: int):
         self._ck(self._lib.sb_halo_unpack(self._h, list_id, C.c_void_p(src_device_ptr)))
+
+    # -- halo exchange over peer memory ------------------------------------------------
+    OP_EXCHANGE, OP_HALO_SEND, OP_HALO_RECV = 4, 5, 6
+
+    def halo_alloc(self, list_id: int) -> int:
+        """Allocates this rank's receive buffer for a registered list; returns its device address."""
+        base, nbytes = C.c_void_p(), C.c_uint64()
+        self._ck(self._lib.sb_halo_alloc(self._h, list_id, C.byref(base), C.byref(nbytes)))
+        return base.value
+
+    def halo_connect(self, list_id: int, peer_base: int):
+        self._ck(self._lib.sb_halo_connect(self._h, list_id, C.c_void_p(peer_base)))
+
+    def halo_error(self) -> bool:
+        out = C.c_int32()
+        self._ck(self._lib.sb_halo_error(self._h, C.byref(out)))
+        return bool(out.value)
 
     # -- write-back -------------------------------------------------------------------
     def positions(self, out=None):

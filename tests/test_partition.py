@@ -8,7 +8,7 @@ import pytest
 from helpers import bits_equal, oracle_params
 from oracle import xpbd_oracle as orc
 from softbodyunity_b200 import SoftBody, lumped_inv_mass, meshgen
-from softbodyunity_b200.partition import (LocalComm, PartitionedBody, combined_order, gather_global, slab_partition,
+from softbodyunity_b200.partition import (LocalComm, LocalPeerComm, PartitionedBody, combined_order, gather_global, slab_partition,
                                           step_partitioned)
 
 
@@ -65,13 +65,15 @@ def test_too_many_ranks_is_rejected():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n_ranks", [2, 3])
-def test_virtual_ranks_match_the_oracle_bitwise(n_ranks):
+@pytest.mark.parametrize("n_ranks,peer", [(2, False), (3, False), (2, True), (4, True)])
+def test_virtual_ranks_match_the_oracle_bitwise(n_ranks, peer):
+    # peer=False: pack / device copy / unpack (the NCCL transport's shape); peer=True: the peer-memory
+    # send / receive kernels of the multi-GPU path (stores into the neighbour's buffer + sequence flags)
     pos, tets, tris, meshes = make(n_ranks)
     import torch
     stream = torch.cuda.Stream()
     bodies = [PartitionedBody(m, stream=stream, tile_cap=256, substeps=5, iterations=6) for m in meshes]
-    comm = LocalComm(n_ranks)
+    comm = LocalPeerComm(bodies) if peer else LocalComm(n_ranks)
     step_partitioned(bodies, comm, frames=8)
     stream.synchronize()
     states = [b.sb.get_state() for b in bodies]
@@ -86,6 +88,7 @@ def test_virtual_ranks_match_the_oracle_bitwise(n_ranks):
     # ghosts hold their owner's final value only after exchange A of the next sweep; owners are authoritative
     for m, s in zip(meshes, states):
         assert s[1][m.n_own:, 3].min(initial=1.0) == 1.0  # ghost flag kept in v.w
+    assert not any(b.sb.halo_error() for b in bodies) if peer else True
 
 
 @pytest.mark.gpu
