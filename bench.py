@@ -51,6 +51,12 @@ def workload(args, rank=0, world=1):
         lo, hi = shard_range(args.n, rank, world)
         pos, tets, tris = meshgen.bodies(hi - lo, dims=(13, 13, 12), spacing=0.02, base_height=0.004, seed=1234 + rank)
         name = f"{args.n} independent 2028-vertex bodies sharded over {world} rank(s), S={args.substeps} I={args.iterations}"
+    elif args.workload == "partitioned":
+        # BASELINE.json configs[4]: ONE block of n^3 vertices (default 200^3 = 8 M) cut into `world` slabs
+        n = args.n
+        pos, tets, tris = meshgen.block(n, n, n, spacing=0.01, origin=(0.0, 0.002, 0.0), jitter=0.1, seed=1234)
+        name = (f"single block{n}^3 ({n ** 3} verts) partitioned over {world} rank(s), halo exchange over NVLink peer "
+                f"memory twice per sweep, S={args.substeps} I={args.iterations}")
     else:
         raise SystemExit(f"unknown workload {args.workload}")
     return pos, tets, tris, name
@@ -190,8 +196,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="block", choices=["block", "sphere", "bodies"])
-    ap.add_argument("--n", type=int, default=100)
+    ap.add_argument("--workload", default="block", choices=["block", "sphere", "bodies", "partitioned"])
+    ap.add_argument("--n", "--size", dest="n", type=int, default=100)
     ap.add_argument("--substeps", type=int, default=10)
     ap.add_argument("--iterations", type=int, default=10)
     ap.add_argument("--fast-math", action="store_true")
@@ -227,11 +233,21 @@ def main():
     from softbodyunity_b200 import FLAG_FAST_MATH, SoftBody
     pos, tets, tris, name = workload(args, rank, world)
     flags = FLAG_FAST_MATH if args.fast_math else 0
-    sb = SoftBody(pos, tets, tris, device=local, substeps=args.substeps, iterations=args.iterations, flags=flags,
-                  tile_cap=args.tile_cap, later_tile_cap=args.later_tile_cap, block_threads=args.block_threads,
-                  slot_bytes=args.slot_bytes, n_slots=args.n_slots)
+    kw = dict(substeps=args.substeps, iterations=args.iterations, flags=flags, tile_cap=args.tile_cap,
+              later_tile_cap=args.later_tile_cap, block_threads=args.block_threads, slot_bytes=args.slot_bytes, n_slots=args.n_slots)
+    part_mesh = None
+    if args.workload == "partitioned" and world > 1:
+        from softbodyunity_b200.partition import PartitionedBody, connect_peers, slab_partition
+        (part_mesh,) = slab_partition(pos, tets, tris, world, only_rank=rank)
+        V_global, T_global = len(pos), len(tets)
+        del pos, tets, tris
+        body = PartitionedBody(part_mesh, device=local, **kw)
+        connect_peers(body, local)     # CUDA IPC handles travel over torch.distributed once; the data path is P2P stores
+        sb = body.sb
+    else:
+        sb = SoftBody(pos, tets, tris, device=local, **kw)
     info = sb.info()
-    V, E, T = info["n_verts"], info["n_edges"], info["n_tets"]
+    V, E, T = info["n_verts"] - info["n_ghost_verts"], info["n_edges"], info["n_tets"]
     ns = info["n_surface_verts"]
 
     def barrier():
@@ -271,6 +287,24 @@ def main():
     clk = clocks.stop() if rank == 0 else None
     V_all = V if world == 1 else int(round(sum_over_ranks(V)))
     value = V_all * args.substeps * args.steps / (ms * 1e-3)
+
+    if part_mesh is not None:
+        # strong scaling of ONE mesh: report the device-timed figure only (the host-buffer protocol of the
+        # single-body e2e leg would have to re-send ghosts as well; not measured for this workload)
+        if sb.halo_error():
+            raise SystemExit("bench.py: a halo receive timed out")
+        if rank == 0:
+            print(json.dumps({
+                "metric": METRIC, "value": V_global * args.substeps * args.steps / (ms * 1e-3), "unit": "vertex-substeps/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": name, "n_verts": V_global, "n_tets": T_global, "own_verts_rank0": V,
+                           "ghost_verts_rank0": info["n_ghost_verts"], "constraints_cut_rank0": info["constraints_cut"],
+                           "math": "fast" if args.fast_math else "exact (bit-identical to CPU oracle)",
+                           "tile_passes": info["n_tile_passes"], "build_seconds": info["build_seconds"]},
+                "e2e": None, "gpu_launches": info["launches_per_frame"] * args.steps, "clocks": clk}), flush=True)
+        dist.destroy_process_group()
+        return
 
     # ---- end to end through the C ABI with host buffers ---------------------------------
     x4 = torch.empty((V, 4), dtype=torch.float32).pin_memory()

@@ -370,6 +370,11 @@ struct sb_solver {
     uint32_t per_iter = 0;
     for (auto &pb : passes) per_iter += pb.dev.n_tiles ? 1 : 0;
     for (auto &b : plan.gbatches) per_iter += b.cnt ? 1 : 0;
+    for (auto &kv : links) {
+      auto hl = halo.find(kv.first);
+      if (hl == halo.end() || !hl->second.n) continue;
+      per_iter += (kv.second.peer_buf ? 1 : 0) + (kv.second.recv.p ? 1 : 0); // one send and one receive kernel per sweep
+    }
     uint32_t n = (uint32_t)prm.substeps * (2 + (uint32_t)prm.iterations * per_iter);
     if (!plan.surf_ids.empty() && !(prm.flags & SB_FLAG_NO_NORMALS)) n++;
     return n;
