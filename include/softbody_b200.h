@@ -53,6 +53,8 @@ typedef enum sb_status {
                                 (default is IEEE sqrt/div, bit-identical to the CPU oracle) */
 #define SB_FLAG_NO_GRAPH 4   /* launch kernels one by one instead of one CUDA graph per frame */
 #define SB_FLAG_NO_NORMALS 8 /* skip the per-frame normal recompute */
+#define SB_FLAG_PDL 16       /* launch the tile passes with programmatic dependent launch (prologue overlaps the
+                                previous pass's tail; measured neutral at 1 M vertices, so off by default) */
 
 /*
  * Solver parameters (the inspector fields).  Names per BASELINE.json:5; units,

@@ -302,15 +302,29 @@ struct sb_solver {
     return (int)std::max<size_t>(1, std::min(g, cap));
   }
 
+  template <bool FAST, int BT>
+  void launch_tile_bt(const PassBufs &pb, cudaStream_t s) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(pb.dev.n_tiles);
+    cfg.blockDim = dim3(BT + 32);
+    cfg.dynamicSmemBytes = pb.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (prm.flags & SB_FLAG_PDL) ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, k_tile_pass<FAST, BT>, pb.dev, x.p, (const DevParams *)dprm.p));
+  }
   template <bool FAST>
   void launch_tile(const PassBufs &pb, cudaStream_t s) {
     if (!pb.dev.n_tiles) return;
     switch (pb.bt) {
-      case 32: k_tile_pass<FAST, 32><<<pb.dev.n_tiles, 32 + 32, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
-      case 64: k_tile_pass<FAST, 64><<<pb.dev.n_tiles, 64 + 32, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
-      case 128: k_tile_pass<FAST, 128><<<pb.dev.n_tiles, 128 + 32, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
-      case 256: k_tile_pass<FAST, 256><<<pb.dev.n_tiles, 256 + 32, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
-      default: k_tile_pass<FAST, 512><<<pb.dev.n_tiles, 512 + 32, pb.smem, s>>>(pb.dev, x.p, dprm.p); break;
+      case 32: launch_tile_bt<FAST, 32>(pb, s); break;
+      case 64: launch_tile_bt<FAST, 64>(pb, s); break;
+      case 128: launch_tile_bt<FAST, 128>(pb, s); break;
+      case 256: launch_tile_bt<FAST, 256>(pb, s); break;
+      default: launch_tile_bt<FAST, 512>(pb, s); break;
     }
   }
   void launch_pass(size_t k, cudaStream_t s) {
@@ -1106,20 +1120,20 @@ int sb_lumped_inv_mass(const float *pos_xyz, uint32_t n_verts, const int32_t *te
    3 CTA end, 4 + i start of chunk i (globaltimer ns; first 64 CTAs). */
 int sb_debug_trace_pass(sb_handle h, uint32_t pass, unsigned long long *out, uint32_t n_words) {
   NEED_DEVICE(h);
-  if (pass >= h->passes.size() || !out || n_words < 64u * 80u) { h->err = "bad trace arguments"; return SB_E_ARG; }
+  if (pass >= h->passes.size() || !out || n_words < 64u * 80u + 256u) { h->err = "bad trace arguments"; return SB_E_ARG; }
   return guarded(h, [&]() -> int {
     CK(cudaSetDevice(h->device));
     if (h->cur_dt < 0) h->refresh_params(h->prm.dt);
     DevBuf<unsigned long long> buf;
-    buf.alloc(64 * 80, nullptr);
-    CK(cudaMemsetAsync(buf.p, 0, 64 * 80 * 8, h->stream));
+    buf.alloc(64 * 80 + 256, nullptr);
+    CK(cudaMemsetAsync(buf.p, 0, (64 * 80 + 256) * 8, h->stream));
     PassBufs &pb = h->passes[pass];
     h->launch_pass(pass, h->stream); // warm
     pb.dev.trace = buf.p;
     h->launch_pass(pass, h->stream);
     pb.dev.trace = nullptr;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out, buf.p, 64 * 80 * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out, buf.p, (64 * 80 + 256) * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return SB_OK;
   });

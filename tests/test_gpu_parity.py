@@ -41,6 +41,7 @@ CASES = {
     "bt512": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=700, block_threads=512)),
     "bt32": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=300, block_threads=32, slot_bytes=480, n_slots=3)),
     "bt256": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=700, block_threads=256)),
+    "pdl": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=300, flags=16)),
     "tiny_slots": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=1500, slot_bytes=192, n_slots=2)),
     "many_slots": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=1500, slot_bytes=480, n_slots=7, block_threads=256)),
 }
