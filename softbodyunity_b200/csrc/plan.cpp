@@ -1011,30 +1011,51 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     // its vertices, so deal each constraint to the eligible tiling where its vertices carry
     // the fewest so far (ties: the globally least-loaded tiling).
     std::vector<std::vector<uint8_t>> deg(2 * (size_t)n_tilings, std::vector<uint8_t>(P.V, 0));
-    for (size_t i = 0; i < mask.size(); i++) {
+    // most constrained first: constraints with one eligible tiling have no choice, so they are placed
+    // before the flexible ones, which then fill in around them
+    std::vector<uint32_t> deal_order(mask.size());
+    {
+      uint32_t cnt[9] = {0};
+      for (size_t i = 0; i < mask.size(); i++) cnt[__builtin_popcount(mask[i])]++;
+      uint32_t start[9], acc = 0;
+      for (int b = 0; b < 9; b++) { start[b] = acc; acc += cnt[b]; }
+      for (size_t i = 0; i < mask.size(); i++) deal_order[start[__builtin_popcount(mask[i])]++] = (uint32_t)i;
+    }
+    std::vector<int8_t> chosen(mask.size(), -1);
+    for (size_t oi = 0; oi < mask.size(); oi++) {
+      const size_t i = deal_order[oi];
       const int32_t ent = cons[i];
       const int kind = ent < 0;
       const uint64_t wgt = kind ? 5 : 2; // tets weigh more than edges in the kernels
       int32_t vs[4];
       const int n = ent_verts(D, ent, vs);
       int best = -1;
-      uint32_t best_deg = 0;
+      uint32_t best_deg = 0, best_sum = 0;
       for (int s = 0; s < n_tilings; s++) {
         if (!(mask[i] >> s & 1)) continue;
         const std::vector<uint8_t> &dg = deg[2 * (size_t)s + kind];
-        uint32_t md = 0;
-        for (int k = 0; k < n; k++) md = std::max<uint32_t>(md, dg[vs[k]]);
-        if (best < 0 || md < best_deg || (md == best_deg && load[s] < load[best])) {
+        uint32_t md = 0, sd = 0;
+        for (int k = 0; k < n; k++) {
+          md = std::max<uint32_t>(md, dg[vs[k]]);
+          sd += dg[vs[k]];
+        }
+        if (best < 0 || md < best_deg || (md == best_deg && (sd < best_sum || (sd == best_sum && load[s] < load[best])))) {
           best = s;
           best_deg = md;
+          best_sum = sd;
         }
       }
-      if (best < 0) { work.push_back(ent); continue; }
-      assigned[best].push_back(ent);
+      if (best < 0) continue;
+      chosen[i] = (int8_t)best;
       load[best] += wgt;
       std::vector<uint8_t> &dg = deg[2 * (size_t)best + kind];
       for (int k = 0; k < n; k++)
         if (dg[vs[k]] < 255) dg[vs[k]]++;
+    }
+    // keep ascending constraint id inside every tiling (the tile builder relies on a stable order)
+    for (size_t i = 0; i < mask.size(); i++) {
+      if (chosen[i] < 0) work.push_back(cons[i]);
+      else assigned[chosen[i]].push_back(cons[i]);
     }
     deg.clear();
     mask.clear();

@@ -254,6 +254,7 @@ struct sb_solver {
   template <bool FAST, int BT>
   static void set_attr_one(uint32_t smem) {
     CK(cudaFuncSetAttribute(k_tile_pass<FAST, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_tile_pass<FAST, BT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   void set_smem_attr(uint32_t smem) {
     if (smem <= 48 * 1024) return;
@@ -314,7 +315,8 @@ struct sb_solver {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (prm.flags & SB_FLAG_PDL) ? 1 : 0;
-    CK(cudaLaunchKernelEx(&cfg, k_tile_pass<FAST, BT>, pb.dev, x.p, (const DevParams *)dprm.p));
+    if (pb.dev.trace) CK(cudaLaunchKernelEx(&cfg, k_tile_pass<FAST, BT, true>, pb.dev, x.p, (const DevParams *)dprm.p));
+    else CK(cudaLaunchKernelEx(&cfg, k_tile_pass<FAST, BT>, pb.dev, x.p, (const DevParams *)dprm.p));
   }
   template <bool FAST>
   void launch_tile(const PassBufs &pb, cudaStream_t s) {
@@ -1120,20 +1122,20 @@ int sb_lumped_inv_mass(const float *pos_xyz, uint32_t n_verts, const int32_t *te
    3 CTA end, 4 + i start of chunk i (globaltimer ns; first 64 CTAs). */
 int sb_debug_trace_pass(sb_handle h, uint32_t pass, unsigned long long *out, uint32_t n_words) {
   NEED_DEVICE(h);
-  if (pass >= h->passes.size() || !out || n_words < 64u * 80u + 256u) { h->err = "bad trace arguments"; return SB_E_ARG; }
+  if (pass >= h->passes.size() || !out || n_words < 64u * 80u + 256u + 3u * 4096u) { h->err = "bad trace arguments"; return SB_E_ARG; }
   return guarded(h, [&]() -> int {
     CK(cudaSetDevice(h->device));
     if (h->cur_dt < 0) h->refresh_params(h->prm.dt);
     DevBuf<unsigned long long> buf;
-    buf.alloc(64 * 80 + 256, nullptr);
-    CK(cudaMemsetAsync(buf.p, 0, (64 * 80 + 256) * 8, h->stream));
+    buf.alloc(64 * 80 + 256 + 3 * 4096, nullptr);
+    CK(cudaMemsetAsync(buf.p, 0, (64 * 80 + 256 + 3 * 4096) * 8, h->stream));
     PassBufs &pb = h->passes[pass];
     h->launch_pass(pass, h->stream); // warm
     pb.dev.trace = buf.p;
     h->launch_pass(pass, h->stream);
     pb.dev.trace = nullptr;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out, buf.p, (64 * 80 + 256) * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out, buf.p, (64 * 80 + 256 + 3 * 4096) * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return SB_OK;
   });

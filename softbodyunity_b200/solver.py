@@ -295,9 +295,10 @@ class SoftBody:
 
     def trace_pass(self, p: int):
         """Debug: (64, 80) uint64 globaltimer stamps of one run of tile pass p."""
-        out = np.zeros(64 * 80 + 256, np.uint64)
+        out = np.zeros(64 * 80 + 256 + 3 * 4096, np.uint64)
         self._ck(self._lib.sb_debug_trace_pass(self._h, p, _ptr(out), out.size))
         self.last_fine_trace = out[64 * 80:].reshape(-1)[:240].reshape(40, 6)
+        self.last_cta_trace = out[64 * 80 + 256:].reshape(4096, 3)  # start ns, end ns, SM id per CTA
         return out[:64 * 80].reshape(64, 80)
 
     def time_kernel(self, which: int, reps: int = 20) -> float:

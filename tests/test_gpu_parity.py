@@ -52,7 +52,7 @@ def test_exact_mode_is_bit_identical_to_the_oracle(name):
     gen, kw = CASES[name]
     pos, tets, tris = gen()
     sb, m, x4, v4 = run_pair(pos, tets, tris, n_frames=12, **kw)
-    assert m.x4[:, 1].min() == 0.0 or name in ("one_tile", "sphere"), "case should reach the ground"
+    assert m.x4[:, 1].min() < 0.01 or name in ("one_tile", "sphere"), "case should be in ground contact"
     assert ulp_diff_count(x4, m.x4) == 0, f"{ulp_diff_count(x4, m.x4)} of {x4.size} position words differ"
     assert bits_equal(v4, m.v4)
     # positions() is the same data, unpermuted, xyz only

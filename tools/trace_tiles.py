@@ -30,3 +30,13 @@ for i in range(min(30, len(f) - 1)):
     if r[0] == 0: break
     nxt = f[i + 1][0] if f[i + 1][0] else r[4]
     print(i, [int(r[1] - r[0]), int(r[2] - r[1]), int(r[3] - r[2]), int(r[4] - r[3])], "next", int(nxt - r[4]))
+
+ct = sb.last_cta_trace.astype(np.int64)
+ct = ct[ct[:, 0] > 0]
+t0 = ct[:, 0].min()
+st, en, sm = ct[:, 0] - t0, ct[:, 1] - t0, ct[:, 2]
+print(f"all {len(ct)} CTAs: start min/median/p90/max {st.min()}/{int(np.median(st))}/{int(np.percentile(st,90))}/{st.max()} ns; end min/median/p90/max {en.min()}/{int(np.median(en))}/{int(np.percentile(en,90))}/{en.max()} ns; lifetime median/max {int(np.median(en-st))}/{(en-st).max()} ns")
+per_sm = np.bincount(sm, minlength=148)
+print("CTAs per SM min/max:", per_sm[per_sm > 0].min(), per_sm.max(), " SMs used:", (per_sm > 0).sum())
+late = np.argsort(-en)[:8]
+print("latest-ending CTAs (id, sm, start, end, ctas on that sm):", [(int(i), int(sm[i]), int(st[i]), int(en[i]), int(per_sm[sm[i]])) for i in late])
