@@ -205,8 +205,7 @@ def main():
     ap.add_argument("--tile-cap", type=int, default=0)
     ap.add_argument("--later-tile-cap", type=int, default=0)
     ap.add_argument("--block-threads", type=int, default=0)
-    ap.add_argument("--slot-bytes", type=int, default=0)
-    ap.add_argument("--n-slots", type=int, default=0)
+    ap.add_argument("--round-width", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-breakdown", action="store_true")
     args = ap.parse_args()
@@ -235,7 +234,7 @@ def main():
     pos, tets, tris, name = workload(args, rank, world)
     flags = (FLAG_FAST_MATH if args.fast_math else 0) | (16 if args.pdl else 0)
     kw = dict(substeps=args.substeps, iterations=args.iterations, flags=flags, tile_cap=args.tile_cap,
-              later_tile_cap=args.later_tile_cap, block_threads=args.block_threads, slot_bytes=args.slot_bytes, n_slots=args.n_slots)
+              later_tile_cap=args.later_tile_cap, block_threads=args.block_threads, round_width=args.round_width)
     part_mesh = None
     if args.workload == "partitioned" and world > 1:
         from softbodyunity_b200.partition import PartitionedBody, connect_peers, slab_partition
@@ -348,7 +347,7 @@ def main():
         ach = launch_bytes / (k_ms * 1e-3) / 1e9
         launches0 = args.substeps * args.iterations
         traffic, traffic_src = measured_traffic()
-        roof = {"bound": "hbm", "kernel": "k_tile_pass (pass 0)", "achieved": ach, "peak": hbm, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": "k_tile_rounds (pass 0)", "achieved": ach, "peak": hbm, "unit": "GB/s",
                 "frac": ach / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_launch": launch_bytes,
                 "launch_ms": k_ms, "share_of_step": k_ms * launches0 / (ms / args.steps),
                 "step_achieved": V * args.substeps * args.steps / (ms * 1e-3) * B_sub / 1e9,
@@ -380,9 +379,11 @@ def main():
             "config": {"workload": name + (" per GPU, independent bodies, no communication" if world > 1 and args.workload != "bodies" else ""),
                        "n_verts": V, "n_edges": E, "n_tets": T, "math": "fast" if args.fast_math else "exact (bit-identical to CPU oracle)",
                        "tile_passes": info["n_tile_passes"], "tiles_in_pass": info["tiles_in_pass"][:info["n_tile_passes"]],
-                       "tile_cap": info["tile_cap"], "block_threads": info["block_threads"],
+                       "tile_cap": info["tile_cap"], "block_threads": info["block_threads"], "round_width": info["round_width"],
+                       "rounds_per_tile": [round(r / max(1, t), 1) for r, t in zip(info["rounds_in_pass"][:info["n_tile_passes"]],
+                                                                                  info["tiles_in_pass"][:info["n_tile_passes"]])],
                        "l2": "no flush: per-step working set (constraint streams + state) %.0f MB exceeds the 126 MB L2" %
-                             ((8.0 * E + 12.0 * T + 48.0 * V) / 1e6),
+                             ((8.0 * E + 16.0 * T + 48.0 * V) / 1e6),
                        "build_seconds": info["build_seconds"]},
             "e2e": {"value": e2e_val, "unit": "vertex-substeps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps},

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SB_ABI_VERSION 1u
+#define SB_ABI_VERSION 2u
 
 typedef struct sb_solver *sb_handle;
 
@@ -91,11 +91,12 @@ typedef struct sb_mesh_desc {
   int32_t device;           /* CUDA device ordinal */
   int32_t tile_cap;         /* max vertices per shared-memory tile; 0 = auto */
   int32_t max_tile_passes;  /* -1 = auto; 0 = global colour batches only */
-  int32_t block_threads;    /* consumer threads per tile CTA (32..512, power of two; one producer warp is added); 0 = auto per pass */
+  int32_t block_threads;    /* threads per tile CTA (32, 64, 128 or 256); 0 = auto per pass */
   int32_t later_tile_cap;   /* max vertices per tile in passes after the first; 0 = auto */
   int32_t host_threads;     /* threads for the host-side build; 0 = auto */
-  int32_t slot_bytes;       /* bytes per shared-memory staging slot of the constraint stream; 0 = auto */
-  int32_t n_slots;          /* staging slots per CTA (2..16); 0 = auto */
+  int32_t round_width;      /* 16-byte constraint-record words per thread per round (1 or 2): a round = one colour of
+                               2 * width * block_threads edges or width * block_threads tets; 0 = auto (1) */
+  int32_t reserved0;        /* must be 0 */
   int32_t tilings;          /* 0 = auto; 1 = hierarchical tile passes only; N >= 2 = N balanced shifted tilings */
   int32_t n_ghost_verts;    /* partitioned meshes: the LAST n_ghost_verts vertices are ghost copies of vertices
                                another rank owns (never integrated here; constraints among ghosts are dropped) */
@@ -123,7 +124,9 @@ typedef struct sb_info {
   uint32_t tile_cap;
   uint32_t block_threads;
   uint32_t smem_bytes;           /* dynamic shared memory per tile CTA */
-  uint32_t slot_bytes, n_slots;
+  uint32_t round_width;          /* 16-byte record words per thread per round */
+  uint32_t reserved0;
+  uint64_t rounds_in_pass[8];    /* rounds (barrier-separated colours) summed over the tiles of the pass */
   uint32_t launches_per_frame;   /* kernel launches inside one sb_step at current params */
   uint64_t device_bytes;         /* device memory held by the handle */
   double build_seconds;          /* host time spent in sb_create */

@@ -26,9 +26,10 @@
  *   predict(i), w_i > 0:  v = FMA(h, g, v);  x_prev = x;  x = FMA(h, v, x)
  *            w_i == 0:    x_prev = x
  *   distance(a,b):  d = x_a - x_b;  len2 = FMA(dz,dz, FMA(dy,dy, dx*dx))
- *                   skip unless w_a + w_b > 0 and len2 > 0
- *                   len = sqrt(len2);  C = len - L0
- *                   s = -C * RCP((w_a + w_b + a_d) * len)      RCP(x) = correctly rounded 1/x
+ *                   skip unless w_a + w_b > 0 and 2^-101 <= len2 <= FLT_MAX
+ *                   len = sqrt(len2);  C = len - L0;  den = (w_a + w_b + a_d) * len
+ *                   skip unless 2^-126 <= den < 2^126
+ *                   s = -C * RCP(den)                          RCP(x) = correctly rounded 1/x
  *                   x_a = FMA(s*w_a, d, x_a);  x_b = FMA(-(s*w_b), d, x_b)
  *   volume(p0..p3): e_k = x_pk - x_p0 (k=1..3)
  *                   G1 = e2 x e3, G2 = e3 x e1, G3 = e1 x e2, G0 = -((G1+G2)+G3)
@@ -36,10 +37,13 @@
  *                   det = FMA(e1.z,G1.z, FMA(e1.y,G1.y, e1.x*G1.x))
  *                   n_k = FMA(G.z,G.z, FMA(G.y,G.y, G.x*G.x))
  *                   den = FMA(w3,n3, FMA(w2,n2, FMA(w1,n1, w0*n0))) + a_v36
- *                   skip unless den > 0
+ *                   skip unless 2^-126 <= den < 2^126
  *                   s = -(det - R6) * RCP(den);   x_pk = FMA(s*w_k, G_k, x_pk)
- *   (a reciprocal and a multiply instead of one division: the GPU's IEEE reciprocal never
- *    leaves its fast path for these operand ranges, its IEEE division almost always does)
+ *   (a reciprocal and a multiply instead of one division: the GPU's IEEE division almost always
+ *    leaves its fast path for these operands.  The operand windows are those in which the GPU's
+ *    branch-free sqrt / reciprocal sequences -- MUFU seed + FMA correction -- are correctly
+ *    rounded; outside them (lengths below 1e-15 or non-finite state) a projection is skipped
+ *    instead of taking a slow path, here and in the kernels alike.)
  *   finish(i), w_i > 0:   if x.y < ground_y: x.y = ground_y,
  *                             x.xz = FMA(keep, x.xz - x_prev.xz, x_prev.xz)
  *                         spheres: see SPHERE below
@@ -48,6 +52,14 @@
 
 #ifndef REAL
 #error "include from xpbd_oracle.c"
+#endif
+
+/* operand windows of the arithmetic contract (same numbers for float and double) */
+#ifndef ORC_SQRT_MIN
+#define ORC_SQRT_MIN ((REAL)0x1p-101)
+#define ORC_SQRT_MAX ((REAL)3.40282346638528859812e+38) /* FLT_MAX */
+#define ORC_RCP_MIN ((REAL)0x1p-126)
+#define ORC_RCP_MAX ((REAL)0x1p126)
 #endif
 
 #define CAT_(a, b) a##b
@@ -98,10 +110,12 @@ static inline void FN(distance_one)(REAL *xa, REAL *xb, REAL L0, REAL a_d) {
   REAL wsum = wa + wb;
   REAL dx = xa[0] - xb[0], dy = xa[1] - xb[1], dz = xa[2] - xb[2];
   REAL len2 = FMA(dz, dz, FMA(dy, dy, dx * dx));
-  if (!(wsum > 0) || !(len2 > 0)) return;
+  if (!(wsum > 0) || !(len2 >= ORC_SQRT_MIN && len2 <= ORC_SQRT_MAX)) return;
   REAL len = SQRT(len2);
   REAL C = len - L0;
-  REAL s = -C * ((REAL)1 / ((wsum + a_d) * len));
+  REAL den = (wsum + a_d) * len;
+  if (!(den >= ORC_RCP_MIN && den < ORC_RCP_MAX)) return;
+  REAL s = -C * ((REAL)1 / den);
   REAL sa = s * wa, sb = -(s * wb);
   xa[0] = FMA(sa, dx, xa[0]); xa[1] = FMA(sa, dy, xa[1]); xa[2] = FMA(sa, dz, xa[2]);
   xb[0] = FMA(sb, dx, xb[0]); xb[1] = FMA(sb, dy, xb[1]); xb[2] = FMA(sb, dz, xb[2]);
@@ -133,7 +147,7 @@ static inline void FN(volume_one)(REAL *p0, REAL *p1, REAL *p2, REAL *p3, REAL R
   REAL det = DOT3(e1, G1);
   REAL n0 = DOT3(G0, G0), n1 = DOT3(G1, G1), n2 = DOT3(G2, G2), n3 = DOT3(G3, G3);
   REAL den = FMA(p3[3], n3, FMA(p2[3], n2, FMA(p1[3], n1, p0[3] * n0))) + a_v36;
-  if (!(den > 0)) return;
+  if (!(den >= ORC_RCP_MIN && den < ORC_RCP_MAX)) return;
   REAL s = -(det - R6) * ((REAL)1 / den);
   REAL s0 = s * p0[3], s1 = s * p1[3], s2 = s * p2[3], s3 = s * p3[3];
   for (int k = 0; k < 3; k++) {

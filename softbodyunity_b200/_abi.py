@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 SB_OK, SB_E_ARG, SB_E_CUDA, SB_E_NCCL, SB_E_NAN, SB_E_STATE, SB_E_NOMEM = 0, -1, -2, -3, -4, -5, -6
 FLAG_NO_GROUND, FLAG_FAST_MATH, FLAG_NO_GRAPH, FLAG_NO_NORMALS, FLAG_PDL = 1, 2, 4, 8, 16
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = [
     "sb_abi_check", "sb_default_params", "sb_create", "sb_plan", "sb_destroy", "sb_set_params",
@@ -41,8 +41,8 @@ class SbMeshDesc(C.Structure):
         ("n_verts", C.c_uint32), ("n_tets", C.c_uint32), ("n_tris", C.c_uint32),
         ("density", C.c_float), ("device", C.c_int32), ("tile_cap", C.c_int32),
         ("max_tile_passes", C.c_int32), ("block_threads", C.c_int32),
-        ("later_tile_cap", C.c_int32), ("host_threads", C.c_int32), ("slot_bytes", C.c_int32),
-        ("n_slots", C.c_int32), ("tilings", C.c_int32), ("n_ghost_verts", C.c_int32), ("n_edges", C.c_uint32), ("reserved", C.c_int32 * 1),
+        ("later_tile_cap", C.c_int32), ("host_threads", C.c_int32), ("round_width", C.c_int32),
+        ("reserved0", C.c_int32), ("tilings", C.c_int32), ("n_ghost_verts", C.c_int32), ("n_edges", C.c_uint32), ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -55,7 +55,7 @@ class SbInfo(C.Structure):
         ("constraints_in_pass", C.c_uint64 * 8), ("edges_in_pass", C.c_uint64 * 8), ("runs_in_pass", C.c_uint64 * 8),
         ("constraints_global", C.c_uint64),
         ("tile_cap", C.c_uint32), ("block_threads", C.c_uint32), ("smem_bytes", C.c_uint32),
-        ("slot_bytes", C.c_uint32), ("n_slots", C.c_uint32),
+        ("round_width", C.c_uint32), ("reserved0", C.c_uint32), ("rounds_in_pass", C.c_uint64 * 8),
         ("launches_per_frame", C.c_uint32), ("device_bytes", C.c_uint64), ("build_seconds", C.c_double),
     ]
 

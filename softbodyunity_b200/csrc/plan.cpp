@@ -396,8 +396,7 @@ inline void set_bit(Mask128 &m, int c) {
 struct TileOut {
   std::vector<uint32_t> verts; // device ids (non-contiguous passes)
   uint32_t n_ecol = 0, n_tcol = 0, n_verts = 0;
-  std::vector<U2> chunks;        // byte offsets relative to this tile's stream
-  std::vector<uint32_t> stream;  // words
+  std::vector<uint32_t> stream;  // words: edge rounds, then tet rounds
   std::vector<int32_t> ents;     // processing order
   std::vector<uint32_t> col_cnt; // per colour, edge colours first
   uint64_t n_edges = 0, n_tets = 0;
@@ -424,7 +423,7 @@ inline int ent_verts(const DevTopo &D, int32_t ent, int32_t *vs) {
 // `in` whose vertices all lie in one tile are consumed; the rest go to `out`.
 std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_t> &part, uint32_t n_tiles,
                        const std::vector<uint32_t> *contig_off, const std::vector<int32_t> &in,
-                       std::vector<int32_t> &out, TilePass &TP, int threads, uint32_t slot_bytes, uint32_t n_slots) {
+                       std::vector<int32_t> &out, TilePass &TP, int threads, uint32_t bt_opt, uint32_t width) {
   // 1. classify and bucket by tile (stable)
   std::vector<uint64_t> toff((size_t)n_tiles + 1, 0);
   std::vector<int32_t> owner(in.size());
@@ -451,7 +450,18 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
   owner.clear();
   owner.shrink_to_fit();
 
-  // 2. per tile: local numbering, greedy colouring, records
+  // CTA width of this pass: as given, else by how many constraints a tile holds (a round should be
+  // full, and a tile should not need many more rounds than its valence asks for)
+  uint32_t bt = bt_opt;
+  if (!bt) {
+    uint32_t busy = 0;
+    for (uint32_t t = 0; t < n_tiles; t++) busy += toff[t + 1] > toff[t];
+    const double per_tile = busy ? (double)toff[n_tiles] / busy : 0.0;
+    bt = per_tile < 6000 * width ? 64u : per_tile < 24000 * width ? 128u : 256u;
+  }
+  const uint32_t cap_e = 2 * width * bt, cap_t = width * bt;
+
+  // 2. per tile: local numbering, capacity-limited greedy colouring, rounds
   std::vector<TileOut> outs(n_tiles);
   int nt = std::max(1, threads);
   std::vector<std::vector<uint32_t>> loc_scratch(nt);
@@ -485,31 +495,69 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
       return;
     }
     auto local = [&](int32_t v) -> uint32_t { return contig_off ? (uint32_t)v - base : loc[v]; };
-    std::vector<Mask128> me(nv), mt(nv);
-    std::vector<uint8_t> col(ne);
+    // colour = round.  Per kind: a bit set per vertex of the colours it already carries, plus the set
+    // of full colours; a constraint takes the first colour that is free at all its vertices and not full.
+    size_t n_kind[2] = {0, 0};
+    for (size_t i = 0; i < ne; i++) n_kind[ents[i] < 0]++;
+    const size_t words[2] = {(n_kind[0] / cap_e + 256) / 64 + 1, (n_kind[1] / cap_t + 256) / 64 + 1};
+    std::vector<uint64_t> mask[2], full[2], soft[2];
+    for (int k = 0; k < 2; k++) {
+      if (n_kind[k]) mask[k].assign((size_t)nv * words[k], 0);
+      full[k].assign(words[k], 0);
+      soft[k].assign(words[k], 0);
+    }
+    std::vector<uint32_t> col(ne);
     std::vector<uint32_t> ecount, tcount;
-    for (size_t i = 0; i < ne; i++) {
+    // Constraints are coloured in a scattered order (a fixed hash of the constraint id): colouring them in
+    // id order, which is spatial order, fills the early colours from one corner of the tile and leaves
+    // the last corner a long tail of nearly empty colours.
+    std::vector<uint32_t> cord(ne);
+    std::iota(cord.begin(), cord.end(), 0u);
+    {
+      auto hash = [](uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; };
+      std::vector<uint64_t> key(ne);
+      for (size_t i = 0; i < ne; i++) key[i] = ((uint64_t)hash((uint32_t)ents[i]) << 32) | (uint32_t)i;
+      std::sort(key.begin(), key.end());
+      for (size_t i = 0; i < ne; i++) cord[i] = (uint32_t)key[i];
+    }
+    for (size_t oi = 0; oi < ne; oi++) {
+      const size_t i = cord[oi];
       int32_t vs[4];
-      int n = ent_verts(D, ents[i], vs);
-      bool tet = ents[i] < 0;
-      std::vector<Mask128> &M = tet ? mt : me;
-      Mask128 u;
-      for (int k = 0; k < n; k++) {
-        const Mask128 &m = M[local(vs[k])];
-        u.lo |= m.lo;
-        u.hi |= m.hi;
+      const int n = ent_verts(D, ents[i], vs);
+      const int kind = ents[i] < 0;
+      const size_t W = words[kind];
+      uint64_t *M = mask[kind].data();
+      // first colour free at every vertex that is below the soft capacity; failing that, one below the
+      // hard capacity (the slack the soft limit left is what absorbs the stragglers); failing that, a new one
+      auto first_free_colour = [&](const std::vector<uint64_t> &closed) {
+        for (size_t wd = 0; wd < W; wd++) {
+          uint64_t u = closed[wd];
+          for (int k = 0; k < n; k++) u |= M[(size_t)local(vs[k]) * W + wd];
+          if (~u) return (int)(wd * 64) + __builtin_ctzll(~u);
+        }
+        return -1;
+      };
+      std::vector<uint32_t> &cnt = kind ? tcount : ecount;
+      const uint32_t hard = kind ? cap_t : cap_e, slack = std::max(1u, hard / 32);
+      const size_t k_target = (n_kind[kind] + (hard - slack) - 1) / (hard - slack);
+      int c = first_free_colour(soft[kind]);
+      if ((c < 0 || (size_t)c >= cnt.size()) && cnt.size() >= k_target) {
+        const int c2 = first_free_colour(full[kind]);
+        if (c2 >= 0 && (size_t)c2 < cnt.size()) c = c2;
       }
-      int c = first_free(u);
       if (c < 0) {
-        O.err = "vertex valence needs more than 128 colours";
+        O.err = "vertex valence needs more than 256 colours beyond the capacity bound";
         return;
       }
-      for (int k = 0; k < n; k++) set_bit(M[local(vs[k])], c);
-      col[i] = (uint8_t)c;
-      std::vector<uint32_t> &cnt = tet ? tcount : ecount;
+      for (int k = 0; k < n; k++) M[(size_t)local(vs[k]) * W + (size_t)c / 64] |= 1ull << (c & 63);
+      col[i] = (uint32_t)c;
       if ((size_t)c >= cnt.size()) cnt.resize(c + 1, 0);
-      cnt[c]++;
+      ++cnt[c];
+      if (cnt[c] >= hard - slack) soft[kind][(size_t)c / 64] |= 1ull << (c & 63);
+      if (cnt[c] == hard) full[kind][(size_t)c / 64] |= 1ull << (c & 63);
     }
+    mask[0] = std::vector<uint64_t>();
+    mask[1] = std::vector<uint64_t>();
     O.n_ecol = (uint32_t)ecount.size();
     O.n_tcol = (uint32_t)tcount.size();
     // bucket by colour (stable): edge colours first, then tet colours
@@ -580,47 +628,31 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
         std::copy(tmp.begin(), tmp.end(), O.ents.begin() + lo);
       }
     }
-    // cut every colour into chunks that fit one staging slot
-    const uint32_t max_e = slot_bytes / 8, max_t = (slot_bytes / 12) & ~3u;
-    uint32_t since_barrier = 0;
+    // Rounds.  Record k of a colour goes to thread k % bt, sub-slot k / bt, so that every thread has
+    // one record before any has two, and the octets above are the lanes of one LDS wavefront.
+    const uint32_t round_words = 4 * width * bt;
+    O.stream.assign((size_t)ncol * round_words, 0u);
     for (uint32_t c = 0; c < ncol; c++) {
       const bool tet = c >= O.n_ecol;
-      const uint32_t cap_n = tet ? max_t : max_e;
-      for (uint32_t lo = coff[c]; lo < coff[c + 1]; lo += cap_n) {
-        const uint32_t n = std::min(cap_n, coff[c + 1] - lo);
-        const bool last = lo + n == coff[c + 1];
-        since_barrier++;
-        const bool bar = last || since_barrier + 1 >= n_slots;
-        if (bar) since_barrier = 0;
-        const uint32_t word0 = (uint32_t)O.stream.size();
-        O.chunks.push_back({word0 / 4, n | (tet ? 1u << 30 : 0u) | (bar ? 1u << 31 : 0u)});
+      uint32_t *rw = O.stream.data() + (size_t)c * round_words;
+      for (uint32_t k = 0; k < O.col_cnt[c]; k++) {
+        int32_t vs[4];
+        const int32_t e = O.ents[coff[c] + k];
+        ent_verts(D, e, vs);
+        const uint32_t thr = k % bt, sub = k / bt;
         if (!tet) {
-          const uint32_t n2 = (n + 1) & ~1u;
-          O.stream.resize(word0 + 2 * (size_t)n2, 0u);
-          for (uint32_t k = 0; k < n; k++) {
-            int32_t vs[4];
-            const int32_t e = O.ents[lo + k];
-            ent_verts(D, e, vs);
-            O.stream[word0 + 2 * k] = local(vs[0]) | (local(vs[1]) << 16);
-            O.stream[word0 + 2 * k + 1] = f2u(P.rest_len[e]);
-          }
-          O.n_edges += n;
+          uint32_t *r = rw + (size_t)thr * 4 * width + 2 * sub;
+          r[0] = local(vs[0]) | (local(vs[1]) << 16);
+          r[1] = f2u(P.rest_len[e]);
         } else {
-          const uint32_t n4 = (n + 3) & ~3u;
-          O.stream.resize(word0 + 3 * (size_t)n4, 0u);
-          for (uint32_t k = 0; k < n; k++) {
-            int32_t vs[4];
-            const int32_t e = O.ents[lo + k];
-            ent_verts(D, e, vs);
-            O.stream[word0 + 2 * k] = local(vs[0]) | (local(vs[1]) << 16);
-            O.stream[word0 + 2 * k + 1] = local(vs[2]) | (local(vs[3]) << 16);
-            O.stream[word0 + 2 * n4 + k] = f2u(P.rest_vol6[e & 0x7fffffff]);
-          }
-          O.n_tets += n;
+          uint32_t *r = rw + (size_t)thr * 4 * width + 4 * sub;
+          r[0] = local(vs[0]) | (local(vs[1]) << 16);
+          r[1] = local(vs[2]) | (local(vs[3]) << 16);
+          r[2] = f2u(P.rest_vol6[e & 0x7fffffff]);
         }
       }
+      (tet ? O.n_tets : O.n_edges) += O.col_cnt[c];
     }
-    if (!O.chunks.empty()) O.chunks.back().y |= 1u << 31;
     if (!contig_off)
       for (uint32_t v : O.verts) loc[v] = 0xffffffffu;
   });
@@ -629,7 +661,8 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
   TP = TilePass();
   TP.contiguous = contig_off != nullptr;
   TP.vert_off.push_back(0);
-  TP.chunk_off.push_back(0);
+  TP.bt = bt;
+  TP.width = width;
   TP.run_off.push_back(0);
   TP.ent_off.push_back(0);
   TP.col_off.push_back(0);
@@ -646,9 +679,7 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
   TP.tile_verts.reserve(nv);
   for (uint32_t t = 0; t < n_tiles; t++) {
     TileOut &O = outs[t];
-    const uint32_t base16 = (uint32_t)(TP.stream.size() / 4);
-    for (const U2 &c : O.chunks) TP.chunks.push_back({c.x + base16, c.y});
-    TP.chunk_off.push_back((uint32_t)TP.chunks.size());
+    TP.rounds.push_back({(uint32_t)(TP.stream.size() / 4), O.n_ecol, O.n_tcol, 0u});
     TP.stream.insert(TP.stream.end(), O.stream.begin(), O.stream.end());
     TP.ents.insert(TP.ents.end(), O.ents.begin(), O.ents.end());
     TP.ent_off.push_back(TP.ents.size());
@@ -669,9 +700,9 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
     TP.max_ecol = std::max(TP.max_ecol, O.n_ecol);
     TP.max_tcol = std::max(TP.max_tcol, O.n_tcol);
     TP.max_tile_verts = std::max(TP.max_tile_verts, O.n_verts);
-    TP.max_chunks = std::max(TP.max_chunks, (uint32_t)O.chunks.size());
     TP.n_edges += O.n_edges;
     TP.n_tets += O.n_tets;
+    TP.rounds_total += O.n_ecol + O.n_tcol;
     O = TileOut();
   }
   if (TP.contiguous) TP.vert_off[0] = (*contig_off)[0];
@@ -916,12 +947,11 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   uint32_t cap = opt.tile_cap > 0 ? (uint32_t)opt.tile_cap : 1024u;
   cap = std::min(cap, 65536u);
   P.tile_cap = cap;
-  uint32_t slot_bytes = opt.slot_bytes > 0 ? (uint32_t)opt.slot_bytes : 2016u;
-  slot_bytes = std::max(192u, slot_bytes / 48 * 48);
-  uint32_t n_slots = opt.n_slots > 0 ? (uint32_t)std::min(opt.n_slots, 16) : 4u;
-  n_slots = std::max(n_slots, 2u);
-  P.slot_bytes = slot_bytes;
-  P.n_slots = n_slots;
+  const uint32_t bt_opt = opt.block_threads > 0 ? (uint32_t)opt.block_threads : 0u;
+  if (bt_opt && bt_opt != 32 && bt_opt != 64 && bt_opt != 128 && bt_opt != 256) return "block_threads must be 32, 64, 128 or 256";
+  if (opt.round_width < 0 || opt.round_width > 2) return "round_width must be 1 or 2";
+  const uint32_t width = opt.round_width > 0 ? (uint32_t)opt.round_width : 1u;
+  P.round_width = width;
   int max_passes = opt.max_tile_passes < 0 ? 6 : std::min(opt.max_tile_passes, 8);
 
   // largest connected component decides the layout: many small bodies are packed whole
@@ -1063,11 +1093,30 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     for (int s = 0; s < n_tilings; s++) {
       TilePass TP;
       err = build_pass(P, D, dpart[s], tilings[s].n_tiles, s == 0 ? &tile_off : nullptr, assigned[s], next, TP, threads,
-                       slot_bytes, n_slots);
+                       bt_opt, width);
       if (!err.empty()) return err;
       work.insert(work.end(), next.begin(), next.end()); // empty by construction
       P.passes.push_back(std::move(TP));
       assigned[s] = std::vector<int32_t>();
+    }
+    // dependencies between consecutive tilings (cyclic): tile t of tiling s must wait for every tile of
+    // tiling s-1 that shares a vertex with it, by full box membership so that chains through vertices a
+    // pass does not touch still order passes two apart
+    if (group == 0) {
+      const size_t base_pass = P.passes.size() - (size_t)n_tilings;
+      for (int s = 0; s < n_tilings; s++) {
+        const int q = (s + n_tilings - 1) % n_tilings;
+        std::vector<uint64_t> pairs(P.V);
+        parallel_for(P.V, threads, 1 << 18, [&](size_t d, int) { pairs[d] = ((uint64_t)(uint32_t)dpart[s][d] << 32) | (uint32_t)dpart[q][d]; });
+        std::sort(pairs.begin(), pairs.end());
+        pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+        TilePass &TP = P.passes[base_pass + s];
+        TP.dep_off.assign((size_t)tilings[s].n_tiles + 1, 0);
+        for (uint64_t pr : pairs) TP.dep_off[(size_t)(pr >> 32) + 1]++;
+        for (uint32_t t = 0; t < tilings[s].n_tiles; t++) TP.dep_off[t + 1] += TP.dep_off[t];
+        TP.dep_list.resize(pairs.size());
+        for (size_t k = 0; k < pairs.size(); k++) TP.dep_list[k] = (uint32_t)pairs[k]; // sorted by (t, q): in place
+      }
     }
     part = dpart[0];
     n_tiles = tilings[0].n_tiles;
@@ -1108,7 +1157,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     for (int k = 0; k < levels && !work.empty(); k++) {
       TilePass TP;
       const bool contig = first_level && k == 0;
-      err = build_pass(P, D, part, n_tiles, contig ? &tile_off : nullptr, work, next, TP, threads, slot_bytes, n_slots);
+      err = build_pass(P, D, part, n_tiles, contig ? &tile_off : nullptr, work, next, TP, threads, bt_opt, width);
       if (!err.empty()) return err;
       size_t consumed = work.size() - next.size();
       work.swap(next);
@@ -1146,6 +1195,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   }
   err = plan_group(cons0, 0);
   if (!err.empty()) return err;
+  P.dag_ok = n_tilings >= 2 && !P.n_ghost && P.passes.size() == (size_t)n_tilings && P.gbatches.empty();
   if (P.n_ghost) {
     err = plan_group(cons1, 1);
     if (!err.empty()) return err;

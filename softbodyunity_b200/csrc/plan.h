@@ -15,6 +15,7 @@
 namespace sb {
 
 struct U2 { uint32_t x, y; };
+struct U4 { uint32_t x, y, z, w; };
 struct I2 { int32_t x, y; };
 struct I4 { int32_t x, y, z, w; };
 
@@ -24,42 +25,47 @@ struct PlanOptions {
   int max_tile_passes = -1; // -1 = auto
   int n_sm = 148;           // grid sizing target
   int threads = 0;          // host build threads (0 = hardware_concurrency)
-  int slot_bytes = 0;       // bytes per shared-memory staging slot (0 = 2016); multiple of 48
-  int n_slots = 0;          // staging slots per CTA (0 = 4)
+  int block_threads = 0;    // threads per tile CTA: 32, 64, 128 or 256 (0 = auto per pass, by constraints per tile)
+  int round_width = 0;      // 16-byte record words per thread per round: 1 or 2 (0 = 1)
   int tilings = 0;          // 0 = auto; 1 = hierarchical passes only; N >= 2 = N balanced shifted tilings
 };
 
 // One shared-memory tile pass: every tile is a vertex-disjoint set of vertices
 // whose assigned constraints touch only those vertices.
 //
-// Device data: a tile's constraints are a byte stream cut into CHUNKS that the
-// kernel stages into shared memory with bulk copies.  A chunk holds records of
-// one kind and one colour:
-//   edge chunk, n records : n2 = roundup(n, 2) x { a | b << 16, bits(L0) }          (8 B each)
-//   tet chunk,  n records : n4 = roundup(n, 4) x { p0 | p1 << 16, p2 | p3 << 16 }   (8 B each)
-//                           followed by n4 x float (6 * rest volume)
-// (local 16-bit vertex ids; padding records are zero and never executed).
-// chunks[i] = { byte offset / 16 into `stream`, n | kind << 30 | barrier << 31 }:
-// `barrier` asks for a CTA barrier after the chunk (set on the last chunk of every
-// colour, and often enough that the staging ring can always be refilled).
+// Device data: a tile's constraints are a stream of ROUNDS.  A round is one colour of
+// one kind, capped at what the CTA projects in one go: every thread owns `width`
+// 16-byte words of every round,
+//   edge round: word = 2 x { a | b << 16, bits(L0) }              -> 2 * width * bt edges per colour
+//   tet round : word = { p0 | p1 << 16, p2 | p3 << 16, bits(6 V0), 0 } -> width * bt tets per colour
+// (local 16-bit vertex ids; an all-zero record is padding: a == b / p0 == p1 is never projected).
+// Thread `tid` reads its words of round r at stream[off + (r * bt + tid) * width ...], a fully
+// coalesced access that it prefetches several rounds ahead; the CTA synchronises after every
+// round.  The colouring is capacity-limited (first free colour that is not full), so a tile
+// needs max(valence, ceil(n / capacity)) rounds and every round but the last is full.
+// rounds[t] = { offset / 16 of tile t's first round in `stream`, edge rounds, tet rounds, 0 }.
 struct TilePass {
   bool contiguous = false;          // tile t == device vertex range [vert_off[t], vert_off[t+1])
   std::vector<uint32_t> vert_off;   // n_tiles + 1
   std::vector<uint32_t> tile_verts; // device vertex ids (empty when contiguous)
   std::vector<uint32_t> run_off;    // n_tiles + 1 offsets into runs (non-contiguous passes)
   std::vector<U2> runs;             // per tile: {first device id, first local id} per run, then {0, n_verts}
-  std::vector<uint32_t> chunk_off;  // n_tiles + 1 offsets into chunks
-  std::vector<U2> chunks;
-  std::vector<uint32_t> stream;     // 32-bit words; every chunk starts 16-byte aligned
+  std::vector<U4> rounds;           // n_tiles
+  std::vector<uint32_t> stream;     // 32-bit words; every round starts 16-byte aligned
+  uint32_t bt = 64, width = 1;      // CTA threads and 16-byte words per thread per round of this pass
   // schedule bookkeeping (host only): per tile, constraints in processing order
   std::vector<uint64_t> ent_off;    // n_tiles + 1 offsets into ents
   std::vector<int32_t> ents;        // >= 0 edge id, < 0 tet id | 0x80000000
   std::vector<uint32_t> col_off;    // n_tiles + 1 offsets into col_cnt
   std::vector<uint32_t> col_cnt;    // constraints per colour, edge colours first
   std::vector<uint32_t> n_ecol;     // edge colours of tile t
-  uint32_t max_ecol = 0, max_tcol = 0, max_tile_verts = 0, max_chunks = 0;
+  uint32_t max_ecol = 0, max_tcol = 0, max_tile_verts = 0;
   int group = 0;                    // 0 interior constraints, 1 constraints that touch a ghost vertex
-  uint64_t n_edges = 0, n_tets = 0;
+  // tile dependencies for the persistent (DAG) kernel: tiles of the PREVIOUS tiling pass (cyclically) that
+  // share a vertex with tile t, by full box membership (empty unless the plan is DAG-capable)
+  std::vector<uint32_t> dep_off;    // n_tiles + 1
+  std::vector<uint32_t> dep_list;
+  uint64_t n_edges = 0, n_tets = 0, rounds_total = 0;
   uint32_t n_tiles() const { return vert_off.empty() ? 0u : (uint32_t)vert_off.size() - 1; }
 };
 
@@ -98,7 +104,8 @@ struct Plan {
   std::vector<int32_t> g_tid;
   std::vector<GlobalBatch> gbatches;
   // options actually used
-  uint32_t tile_cap = 0, slot_bytes = 0, n_slots = 0, n_tilings = 1;
+  uint32_t tile_cap = 0, round_width = 1, n_tilings = 1;
+  bool dag_ok = false; // the passes are exactly the balanced tilings (one group, no leftovers): DAG kernel usable
   double build_seconds = 0;
 
   // The equivalent sequential order of one iteration (see sb_get_schedule).

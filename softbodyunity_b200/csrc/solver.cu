@@ -60,11 +60,12 @@ struct DevBuf {
 };
 
 struct PassBufs {
-  DevBuf<uint32_t> vert_off, tile_verts, chunk_off, stream, run_off;
-  DevBuf<uint2> chunks, runs;
+  DevBuf<uint32_t> vert_off, tile_verts, stream, run_off;
+  DevBuf<uint2> runs;
+  DevBuf<uint4> rounds;
   PassDev dev{};
   uint32_t smem = 0;
-  uint32_t bt = 512; // threads per CTA for this pass
+  uint32_t bt = 64, width = 1; // threads per CTA and record words per thread per round of this pass
 };
 
 static const int kDiagBlocks = 592;
@@ -83,7 +84,7 @@ struct sb_solver {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaStream_t cap_stream = nullptr;
-  uint32_t block_threads = 512;
+  uint32_t block_threads = 64;
   uint64_t dev_bytes = 0;
   std::string err;
 
@@ -202,25 +203,21 @@ struct sb_solver {
       CK(cudaMemset(nrm.p, 0, (ns ? ns : 1) * sizeof(float4)));
     }
     // tile passes
-    uint32_t bt = m.block_threads > 0 ? (uint32_t)m.block_threads : 64u;
-    if (bt != 32 && bt != 64 && bt != 128 && bt != 256 && bt != 512)
-      throw std::string("block_threads must be 32, 64, 128, 256 or 512");
-    block_threads = bt;
     passes.resize(plan.passes.size());
     for (size_t k = 0; k < plan.passes.size(); k++) {
       const TilePass &tp = plan.passes[k];
       PassBufs &pb = passes[k];
       pb.vert_off.upload(tp.vert_off, &dev_bytes);
       if (!tp.contiguous) pb.tile_verts.upload(tp.tile_verts, &dev_bytes);
-      pb.chunk_off.upload(tp.chunk_off, &dev_bytes);
-      pb.chunks.upload(tp.chunks, &dev_bytes);
+      {
+        std::vector<uint4> r4(tp.rounds.size());
+        for (size_t i = 0; i < r4.size(); i++) r4[i] = make_uint4(tp.rounds[i].x, tp.rounds[i].y, tp.rounds[i].z, tp.rounds[i].w);
+        pb.rounds.upload(r4, &dev_bytes);
+      }
       pb.stream.upload(tp.stream, &dev_bytes);
       const uint32_t pos_bytes = (tp.max_tile_verts * 16u + 127u) & ~127u;
-      const uint32_t ring = plan.n_slots * plan.slot_bytes;
-      const uint32_t fixed = pos_bytes + ring + (2 * plan.n_slots + 1) * 8u;
-      const uint32_t limit = (uint32_t)prop.sharedMemPerBlockOptin;
-      if (fixed + 64 > limit) throw std::string("tile_cap and staging slots exceed the shared memory of this device");
-      uint32_t tab_entries = std::min<uint32_t>(tp.max_chunks, (limit - fixed) / 8u);
+      pb.smem = pos_bytes + 16u; // positions + the mbarrier their bulk copies complete on
+      if (pb.smem > (uint32_t)prop.sharedMemPerBlockOptin) throw std::string("tile_cap exceeds the shared memory of this device");
       // bulk copies per run pay off when runs are long; else threads gather vertex by vertex
       const bool use_runs = !tp.contiguous && !tp.tile_verts.empty() &&
                             (double)tp.tile_verts.size() / (double)(tp.runs.size() - tp.n_tiles()) >= 8.0;
@@ -229,16 +226,11 @@ struct sb_solver {
         pb.runs.upload(tp.runs, &dev_bytes);
       }
       pb.dev = PassDev{pb.vert_off.p, tp.contiguous ? nullptr : pb.tile_verts.p, use_runs ? pb.run_off.p : nullptr,
-                       use_runs ? pb.runs.p : nullptr, pb.chunk_off.p, pb.chunks.p,
-                       reinterpret_cast<const uint4 *>(pb.stream.p), tp.n_tiles(), pos_bytes, plan.slot_bytes,
-                       plan.n_slots, tab_entries, nullptr};
-      pb.smem = fixed + tab_entries * 8u;
-      // CTA width: the given one, or by how many constraints a colour of one tile holds on average
-      pb.bt = bt;
-      if (m.block_threads <= 0 && tp.n_tiles()) {
-        const double per_colour = (double)(tp.n_edges + tp.n_tets) / ((double)tp.n_tiles() * std::max(1u, tp.max_ecol + tp.max_tcol));
-        pb.bt = per_colour < 192 ? 64u : per_colour < 448 ? 128u : 256u;
-      }
+                       use_runs ? pb.runs.p : nullptr, pb.rounds.p, reinterpret_cast<const uint4 *>(pb.stream.p),
+                       tp.n_tiles(), pos_bytes, nullptr};
+      pb.bt = tp.bt;
+      pb.width = tp.width;
+      if (k == 0) block_threads = tp.bt;
     }
     uint32_t max_smem = 0;
     for (auto &pb : passes) max_smem = std::max(max_smem, pb.smem);
@@ -251,18 +243,21 @@ struct sb_solver {
     CK(cudaDeviceSynchronize());
   }
 
-  template <bool FAST, int BT>
+  template <bool FAST, int BT, int W16>
   static void set_attr_one(uint32_t smem) {
-    CK(cudaFuncSetAttribute(k_tile_pass<FAST, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k_tile_pass<FAST, BT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_tile_rounds<FAST, BT, W16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if constexpr (!FAST) CK(cudaFuncSetAttribute(k_tile_rounds<FAST, BT, W16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  template <bool FAST>
+  static void set_attr_math(uint32_t smem) {
+    set_attr_one<FAST, 32, 1>(smem); set_attr_one<FAST, 64, 1>(smem); set_attr_one<FAST, 128, 1>(smem); set_attr_one<FAST, 256, 1>(smem);
+    set_attr_one<FAST, 32, 2>(smem); set_attr_one<FAST, 64, 2>(smem); set_attr_one<FAST, 128, 2>(smem); set_attr_one<FAST, 256, 2>(smem);
   }
   void set_smem_attr(uint32_t smem) {
     if (smem <= 48 * 1024) return;
-    set_attr_one<false, 32>(smem); set_attr_one<false, 64>(smem); set_attr_one<true, 32>(smem); set_attr_one<true, 64>(smem);
-    set_attr_one<false, 128>(smem); set_attr_one<false, 256>(smem); set_attr_one<false, 512>(smem);
-    set_attr_one<true, 128>(smem); set_attr_one<true, 256>(smem); set_attr_one<true, 512>(smem);
+    set_attr_math<false>(smem);
+    set_attr_math<true>(smem);
   }
-
   // ---- parameters -----------------------------------------------------------------
   void refresh_params(float dt) {
     if (!prm_dirty && dt == cur_dt) return;
@@ -303,11 +298,11 @@ struct sb_solver {
     return (int)std::max<size_t>(1, std::min(g, cap));
   }
 
-  template <bool FAST, int BT>
-  void launch_tile_bt(const PassBufs &pb, cudaStream_t s) {
+  template <bool FAST, int BT, int W16>
+  void launch_tile_cfg(const PassBufs &pb, cudaStream_t s) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(pb.dev.n_tiles);
-    cfg.blockDim = dim3(BT + 32);
+    cfg.blockDim = dim3(BT);
     cfg.dynamicSmemBytes = pb.smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -315,19 +310,28 @@ struct sb_solver {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (prm.flags & SB_FLAG_PDL) ? 1 : 0;
-    if (pb.dev.trace) CK(cudaLaunchKernelEx(&cfg, k_tile_pass<FAST, BT, true>, pb.dev, x.p, (const DevParams *)dprm.p));
-    else CK(cudaLaunchKernelEx(&cfg, k_tile_pass<FAST, BT>, pb.dev, x.p, (const DevParams *)dprm.p));
+    if constexpr (!FAST) {
+      if (pb.dev.trace) {
+        CK(cudaLaunchKernelEx(&cfg, k_tile_rounds<FAST, BT, W16, true>, pb.dev, x.p, (const DevParams *)dprm.p));
+        return;
+      }
+    }
+    CK(cudaLaunchKernelEx(&cfg, k_tile_rounds<FAST, BT, W16>, pb.dev, x.p, (const DevParams *)dprm.p));
+  }
+  template <bool FAST, int W16>
+  void launch_tile_w(const PassBufs &pb, cudaStream_t s) {
+    switch (pb.bt) {
+      case 32: launch_tile_cfg<FAST, 32, W16>(pb, s); break;
+      case 64: launch_tile_cfg<FAST, 64, W16>(pb, s); break;
+      case 128: launch_tile_cfg<FAST, 128, W16>(pb, s); break;
+      default: launch_tile_cfg<FAST, 256, W16>(pb, s); break;
+    }
   }
   template <bool FAST>
   void launch_tile(const PassBufs &pb, cudaStream_t s) {
     if (!pb.dev.n_tiles) return;
-    switch (pb.bt) {
-      case 32: launch_tile_bt<FAST, 32>(pb, s); break;
-      case 64: launch_tile_bt<FAST, 64>(pb, s); break;
-      case 128: launch_tile_bt<FAST, 128>(pb, s); break;
-      case 256: launch_tile_bt<FAST, 256>(pb, s); break;
-      default: launch_tile_bt<FAST, 512>(pb, s); break;
-    }
+    if (pb.width == 2) launch_tile_w<FAST, 2>(pb, s);
+    else launch_tile_w<FAST, 1>(pb, s);
   }
   void launch_pass(size_t k, cudaStream_t s) {
     if (fast()) launch_tile<true>(passes[k], s);
@@ -671,8 +675,7 @@ static int create_impl(const sb_mesh_desc *mesh, const sb_params *params, sb_han
   *out = nullptr;
   g_create_error.clear();
   if (!mesh) { g_create_error = "mesh is NULL"; return SB_E_ARG; }
-  for (int k = 0; k < 1; k++)
-    if (mesh->reserved[k] != 0) { g_create_error = "reserved fields must be 0"; return SB_E_ARG; }
+  if (mesh->reserved[0] != 0 || mesh->reserved0 != 0) { g_create_error = "reserved fields must be 0"; return SB_E_ARG; }
   sb_params dp;
   sb_default_params(&dp);
   if (params) dp = *params;
@@ -689,8 +692,8 @@ static int create_impl(const sb_mesh_desc *mesh, const sb_params *params, sb_han
     opt.max_tile_passes = mesh->max_tile_passes;
     opt.later_cap = mesh->later_tile_cap;
     opt.threads = mesh->host_threads;
-    opt.slot_bytes = mesh->slot_bytes;
-    opt.n_slots = mesh->n_slots;
+    opt.block_threads = mesh->block_threads;
+    opt.round_width = mesh->round_width;
     opt.tilings = mesh->tilings;
     if (device) {
       int ndev = 0;
@@ -858,15 +861,15 @@ int sb_get_info(sb_handle h, sb_info *o) {
     }
     o->smem_bytes = std::max<uint32_t>(o->smem_bytes, h->on_device && k < h->passes.size()
                                                           ? h->passes[k].smem
-                                                          : P.passes[k].max_tile_verts * 16u + P.n_slots * P.slot_bytes);
+                                                          : P.passes[k].max_tile_verts * 16u + 16u);
+    if (k < 8) o->rounds_in_pass[k] = P.passes[k].rounds_total;
   }
-  o->slot_bytes = P.slot_bytes;
-  o->n_slots = P.n_slots;
+  o->round_width = P.round_width;
   o->n_global_batches = (uint32_t)P.gbatches.size();
   o->n_batches = nb + (uint32_t)P.gbatches.size();
   o->constraints_global = P.g_edges.size() + P.g_tets.size();
   o->tile_cap = P.tile_cap;
-  o->block_threads = h->block_threads;
+  o->block_threads = P.passes.empty() ? 0u : P.passes[0].bt;
   o->launches_per_frame = h->on_device ? h->launches_per_frame() : 0;
   o->device_bytes = h->dev_bytes;
   o->build_seconds = P.build_seconds;

@@ -78,7 +78,7 @@ class SoftBody:
                  stiffness=math.inf, volume_stiffness=math.inf, damping=0.0, friction=0.0,
                  substeps=10, iterations=10, dt=1.0 / 60.0, gravity=(0.0, -9.81, 0.0), ground_y=0.0,
                  flags=0, tile_cap=0, max_tile_passes=-1, block_threads=0, later_tile_cap=0,
-                 host_threads=0, slot_bytes=0, n_slots=0, tilings=0, n_ghost_verts=0, stream=None, host_only=False):
+                 host_threads=0, round_width=0, tilings=0, n_ghost_verts=0, stream=None, host_only=False):
         self._lib = _abi.load()
         self._h = C.c_void_p()
         pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
@@ -98,7 +98,7 @@ class SoftBody:
         d.density, d.device = density, device
         d.tile_cap, d.max_tile_passes, d.block_threads = tile_cap, max_tile_passes, block_threads
         d.later_tile_cap, d.host_threads = later_tile_cap, host_threads
-        d.slot_bytes, d.n_slots, d.tilings = slot_bytes, n_slots, tilings
+        d.round_width, d.tilings = round_width, tilings
         d.n_ghost_verts = n_ghost_verts
         self._params = default_params(
             dt=dt, substeps=substeps, iterations=iterations, stiffness_distance=stiffness,

@@ -38,12 +38,12 @@ CASES = {
     "one_pass_then_global": (lambda: meshgen.block(12, 10, 9, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=200, max_tile_passes=1)),
     "sphere": (lambda: meshgen.sphere(16, spacing=0.05), dict(tile_cap=512)),
     "soft": (lambda: meshgen.block(10, 8, 8, spacing=0.05, origin=(0, 0.02, 0)), dict(stiffness=2.0e4, volume_stiffness=1.0e9, damping=0.5, friction=0.4, tile_cap=300)),
-    "bt512": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=700, block_threads=512)),
-    "bt32": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=300, block_threads=32, slot_bytes=480, n_slots=3)),
+    "bt128": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=700, block_threads=128)),
+    "bt32": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=300, block_threads=32)),
     "bt256": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=700, block_threads=256)),
     "pdl": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=300, flags=16)),
-    "tiny_slots": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=1500, slot_bytes=192, n_slots=2)),
-    "many_slots": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=1500, slot_bytes=480, n_slots=7, block_threads=256)),
+    "wide_rounds": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=1500, round_width=2)),
+    "wide_bt32": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=300, round_width=2, block_threads=32)),
 }
 
 

@@ -32,7 +32,7 @@ def test_struct_layouts_match_the_header():
     lib = _abi.load()
     v, a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
     assert lib.sb_abi_check(C.byref(v), C.byref(a), C.byref(b), C.byref(c)) == 0
-    assert (v.value, a.value, b.value) == (1, 48, 112)
+    assert (v.value, a.value, b.value) == (2, 48, 112)
     assert c.value == C.sizeof(_abi.SbInfo)
     assert C.sizeof(orc.OrcParams) == 48  # the oracle takes the same parameter block
     p = _abi.SbParams()
@@ -125,7 +125,7 @@ def check_tiles(sb: SoftBody, edges, tets, order):
     ((9, 8, 7), dict(tile_cap=128, later_tile_cap=64)),
     ((12, 12, 12), dict(tile_cap=300, max_tile_passes=2)),
     ((6, 6, 6), dict(max_tile_passes=0)),
-    ((8, 8, 8), dict(slot_bytes=192, n_slots=2)),
+    ((8, 8, 8), dict(round_width=2, block_threads=32)),
 ])
 def test_schedule_is_a_valid_coloured_order(shape, kw):
     pos, tets, tris = meshgen.block(*shape, spacing=0.1)

@@ -12,11 +12,10 @@ ap.add_argument("--frames", type=int, default=2)
 ap.add_argument("--block-threads", type=int, default=0)
 ap.add_argument("--fast-math", action="store_true")
 ap.add_argument("--tile-cap", type=int, default=0)
-ap.add_argument("--n-slots", type=int, default=0)
-ap.add_argument("--slot-bytes", type=int, default=0)
+ap.add_argument("--round-width", type=int, default=0)
 a = ap.parse_args()
 pos, tets, tris = meshgen.block(a.n, spacing=0.01, origin=(0.0, 0.002, 0.0))
-sb = SoftBody(pos, tets, tris, substeps=a.substeps, iterations=a.iterations, block_threads=a.block_threads, tile_cap=a.tile_cap, n_slots=a.n_slots, slot_bytes=a.slot_bytes,
+sb = SoftBody(pos, tets, tris, substeps=a.substeps, iterations=a.iterations, block_threads=a.block_threads, tile_cap=a.tile_cap, round_width=a.round_width,
               flags=FLAG_NO_GRAPH | (FLAG_FAST_MATH if a.fast_math else 0))
 sb.step(frames=a.frames)
 sb.synchronize()

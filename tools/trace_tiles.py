@@ -4,13 +4,13 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from softbodyunity_b200 import SoftBody, meshgen, FLAG_FAST_MATH
 ap = argparse.ArgumentParser()
-for k in ("tile-cap", "block-threads", "n-slots", "slot-bytes"):
+for k in ("tile-cap", "block-threads", "round-width"):
     ap.add_argument("--" + k, type=int, default=0)
 ap.add_argument("--fast-math", action="store_true")
 ap.add_argument("--pass-index", type=int, default=1)
 a = ap.parse_args()
 pos, tets, tris = meshgen.block(100, spacing=0.01, origin=(0.0, 0.002, 0.0))
-sb = SoftBody(pos, tets, tris, tile_cap=a.tile_cap, block_threads=a.block_threads, n_slots=a.n_slots, slot_bytes=a.slot_bytes,
+sb = SoftBody(pos, tets, tris, tile_cap=a.tile_cap, block_threads=a.block_threads, round_width=a.round_width,
               flags=FLAG_FAST_MATH if a.fast_math else 0)
 sb.step(frames=3); sb.synchronize()
 tr = sb.trace_pass(a.pass_index).astype(np.int64)
