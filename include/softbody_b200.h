@@ -56,6 +56,9 @@ typedef enum sb_status {
 #define SB_FLAG_PDL 16       /* launch the tile passes with programmatic dependent launch (prologue overlaps the
                                 previous pass's tail; measured neutral at 1 M vertices, so off by default) */
 
+#define SB_FLAG_DAG 32       /* run all tile passes of a substep as ONE persistent kernel over the tile dependency graph
+                                (single-GPU meshes planned as balanced shifted tilings; ignored otherwise) */
+
 /*
  * Solver parameters (the inspector fields).  Names per BASELINE.json:5; units,
  * defaults and the stiffness->compliance mapping are [SPEC]:
@@ -198,7 +201,8 @@ int sb_get_tiles(sb_handle h, uint32_t pass, int32_t *tile_of, uint32_t *n_tiles
 int sb_time_frames(sb_handle h, int32_t n_frames, float dt, float *elapsed_ms);
 /*
  * Time `reps` back-to-back launches of one kernel of the path in isolation
- * (which: 0 predict, 1 finish, 2 normals, 16+p tile pass p, 32 all global batches).
+ * (which: 0 predict, 1 finish, 2 normals, 16+p tile pass p, 32 all global batches,
+ * 48 the persistent tile-DAG kernel = every pass of every iteration of one substep).
  * The state is saved and restored around the run.
  */
 int sb_time_kernel(sb_handle h, int32_t which, int32_t reps, float *avg_ms);
@@ -231,6 +235,10 @@ int sb_lumped_inv_mass(const float *pos_xyz, uint32_t n_verts, const int32_t *te
 
 /* Debug aid: timestamps of one run of tile pass `pass` (see solver.cu); out holds 64 * 80 words. */
 int sb_debug_trace_pass(sb_handle h, uint32_t pass, unsigned long long *out, uint32_t n_words);
+
+/* Debug aid, host only: decodes the device constraint streams as the kernel reads them and compares them with
+   the exported schedule; *n_bad = records that differ (0 on a sound plan). */
+int sb_debug_verify_streams(sb_handle h, uint64_t *n_bad);
 
 const char *sb_last_error(sb_handle h); /* h may be NULL: last sb_create failure on this thread */
 

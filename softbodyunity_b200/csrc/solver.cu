@@ -104,6 +104,11 @@ struct sb_solver {
   DevBuf<DevParams> dprm;
   DevParams *hprm = nullptr; // pinned
   std::vector<PassBufs> passes;
+  // persistent tile-DAG kernel (plan.dag_ok): dependency lists, completion counters + ticket + error word
+  DevBuf<uint32_t> dag_dep_off[SB_DAG_MAX_PASSES], dag_dep_list[SB_DAG_MAX_PASSES], dag_ctr;
+  DagDev dag{};
+  bool dag_ready = false;
+  uint32_t dag_smem = 0, dag_grid = 0, dag_bt = 64, dag_width = 1;
   DevBuf<int2> g_edges;
   DevBuf<float> g_elen;
   DevBuf<int4> g_tets;
@@ -235,6 +240,7 @@ struct sb_solver {
     uint32_t max_smem = 0;
     for (auto &pb : passes) max_smem = std::max(max_smem, pb.smem);
     set_smem_attr(max_smem);
+    setup_dag(max_smem);
     g_edges.upload(plan.g_edges, &dev_bytes);
     g_elen.upload(plan.g_elen, &dev_bytes);
     g_tets.upload(plan.g_tets, &dev_bytes);
@@ -333,6 +339,80 @@ struct sb_solver {
     if (pb.width == 2) launch_tile_w<FAST, 2>(pb, s);
     else launch_tile_w<FAST, 1>(pb, s);
   }
+  // ---- persistent tile-DAG kernel -----------------------------------------------------
+  template <bool FAST, int BT, int W16>
+  void dag_config(bool launch, cudaStream_t s) {
+    auto kern = k_tile_dag<FAST, BT, W16>;
+    if (!launch) {
+      if (dag_smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dag_smem));
+      int per_sm = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, dag_smem));
+      dag_grid = std::max(dag_grid, (uint32_t)std::max(1, per_sm) * (uint32_t)n_sm);
+      return;
+    }
+    DagDev g = dag;
+    g.iterations = (uint32_t)prm.iterations;
+    const uint64_t total = (uint64_t)g.tile_base[g.n_pass] * g.iterations;
+    if (!total) return;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(dag_grid, total);
+    kern<<<grid, BT, dag_smem, s>>>(g, x.p, (const DevParams *)dprm.p);
+  }
+  template <bool FAST>
+  void dag_dispatch(bool launch, cudaStream_t s) {
+#define SB_DAG_CASE(BT_, W_) if (dag_bt == BT_ && dag_width == W_) return dag_config<FAST, BT_, W_>(launch, s)
+    SB_DAG_CASE(32, 1); SB_DAG_CASE(64, 1); SB_DAG_CASE(128, 1); SB_DAG_CASE(256, 1);
+    SB_DAG_CASE(32, 2); SB_DAG_CASE(64, 2); SB_DAG_CASE(128, 2); SB_DAG_CASE(256, 2);
+#undef SB_DAG_CASE
+  }
+  void setup_dag(uint32_t max_smem) {
+    dag_ready = false;
+    const size_t np = plan.passes.size();
+    if (!plan.dag_ok || np < 2 || np > SB_DAG_MAX_PASSES) return;
+    for (size_t k = 0; k < np; k++)
+      if (plan.passes[k].bt != plan.passes[0].bt || plan.passes[k].width != plan.passes[0].width ||
+          plan.passes[k].dep_off.size() != (size_t)plan.passes[k].n_tiles() + 1)
+        return;
+    dag = DagDev{};
+    uint32_t pos_bytes = 0;
+    for (size_t k = 0; k < np; k++) pos_bytes = std::max(pos_bytes, passes[k].dev.pos_bytes);
+    for (size_t k = 0; k < np; k++) {
+      dag_dep_off[k].upload(plan.passes[k].dep_off, &dev_bytes);
+      dag_dep_list[k].upload(plan.passes[k].dep_list, &dev_bytes);
+      dag.pass[k] = passes[k].dev;
+      dag.pass[k].pos_bytes = pos_bytes; // one barrier address for the whole run
+      dag.dep_off[k] = dag_dep_off[k].p;
+      dag.dep_list[k] = dag_dep_list[k].p;
+      dag.tile_base[k + 1] = dag.tile_base[k] + plan.passes[k].n_tiles();
+    }
+    dag.n_pass = (uint32_t)np;
+    dag_ctr.alloc((size_t)dag.tile_base[np] + 2, &dev_bytes);
+    CK(cudaMemset(dag_ctr.p, 0, ((size_t)dag.tile_base[np] + 2) * sizeof(uint32_t)));
+    dag.done = dag_ctr.p;
+    dag.ticket = dag_ctr.p + dag.tile_base[np];
+    dag.error = dag_ctr.p + dag.tile_base[np] + 1;
+    dag_bt = plan.passes[0].bt;
+    dag_width = plan.passes[0].width;
+    dag_smem = std::max(max_smem, pos_bytes + 16u);
+    dag_grid = 0;
+    dag_dispatch<false>(false, nullptr);
+    dag_dispatch<true>(false, nullptr);
+    dag_ready = dag_grid > 0;
+  }
+  bool use_dag() const { return dag_ready && (prm.flags & SB_FLAG_DAG) && !halo_active() && prm.iterations > 0; }
+  // all passes of all iterations of one substep: counters and ticket (not the error word) are cleared first
+  void launch_dag(cudaStream_t s) {
+    CK(cudaMemsetAsync(dag_ctr.p, 0, ((size_t)dag.tile_base[dag.n_pass] + 1) * sizeof(uint32_t), s));
+    if (fast()) dag_dispatch<true>(true, s);
+    else dag_dispatch<false>(true, s);
+  }
+  int dag_error() {
+    if (!dag_ready) return 0;
+    uint32_t e = 0;
+    CK(cudaMemcpyAsync(&e, dag.error, sizeof e, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return (int)e;
+  }
+
   void launch_pass(size_t k, cudaStream_t s) {
     if (fast()) launch_tile<true>(passes[k], s);
     else launch_tile<false>(passes[k], s);
@@ -395,7 +475,7 @@ struct sb_solver {
       if (hl == halo.end() || !hl->second.n) continue;
       per_iter += (kv.second.peer_buf ? 1 : 0) + (kv.second.recv.p ? 1 : 0); // one send and one receive kernel per sweep
     }
-    uint32_t n = (uint32_t)prm.substeps * (2 + (uint32_t)prm.iterations * per_iter);
+    uint32_t n = (uint32_t)prm.substeps * (2 + (use_dag() ? 1u : (uint32_t)prm.iterations * per_iter));
     if (!plan.surf_ids.empty() && !(prm.flags & SB_FLAG_NO_NORMALS)) n++;
     return n;
   }
@@ -403,6 +483,11 @@ struct sb_solver {
   void enqueue_frame(cudaStream_t s) {
     for (int ss = 0; ss < prm.substeps; ss++) {
       launch_predict(s);
+      if (use_dag()) {
+        launch_dag(s);
+        launch_finish(s);
+        continue;
+      }
       for (int it = 0; it < prm.iterations; it++) {
         if (halo_active()) {
           launch_group(0, s);
@@ -578,6 +663,7 @@ struct sb_solver {
       else if (which == 2) launch_normals(stream);
       else if (which >= 16 && which < 16 + (int)passes.size()) launch_pass((size_t)(which - 16), stream);
       else if (which == 32) launch_global(stream);
+      else if (which == 48 && dag_ready) launch_dag(stream);
       else throw std::string("unknown kernel selector");
     };
     run(); // warm-up
@@ -769,6 +855,7 @@ int sb_synchronize(sb_handle h) {
   return guarded(h, [&]() -> int {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->dag_error()) { h->err = "tile DAG: a dependency wait timed out"; return SB_E_STATE; }
     return SB_OK;
   });
 }
@@ -916,6 +1003,62 @@ int sb_get_tiles(sb_handle h, uint32_t pass, int32_t *tile_of, uint32_t *n_tiles
         tile_of[P.perm[d]] = (int32_t)t;
       }
   }
+  return SB_OK;
+}
+
+/* Debug aid (host only): decode the device constraint streams the way the kernel reads them -- tile by
+   tile, round by round, thread by thread -- and compare every record with the schedule bookkeeping that
+   sb_get_schedule exports (same constraint, same vertex roles, same rest value).  Returns the number of
+   mismatching or misplaced records in *n_bad. */
+int sb_debug_verify_streams(sb_handle h, uint64_t *n_bad) {
+  NEED_HANDLE(h);
+  if (!n_bad) return SB_E_ARG;
+  const Plan &P = h->plan;
+  uint64_t bad = 0;
+  for (const TilePass &tp : P.passes) {
+    const uint32_t bt = tp.bt, W = tp.width;
+    for (uint32_t t = 0; t < tp.n_tiles(); t++) {
+      const U4 meta = tp.rounds[t];
+      const uint32_t ncol = tp.col_off[t + 1] - tp.col_off[t];
+      if (meta.y != tp.n_ecol[t] || meta.y + meta.z != ncol) { bad++; continue; }
+      const uint32_t v0 = tp.vert_off[t];
+      auto dev_id = [&](uint32_t local) { return tp.contiguous ? v0 + local : tp.tile_verts[v0 + local]; };
+      uint64_t at = tp.ent_off[t];
+      for (uint32_t c = 0; c < ncol; c++) {
+        const bool tet = c >= meta.y;
+        const uint32_t cnt = tp.col_cnt[tp.col_off[t] + c];
+        const uint32_t *rw = tp.stream.data() + ((size_t)meta.x * 4 + (size_t)c * 4 * W * bt);
+        uint32_t seen = 0;
+        for (uint32_t thr = 0; thr < bt; thr++)
+          for (uint32_t sub = 0; sub < (tet ? W : 2 * W); sub++) {
+            const uint32_t *r = rw + (size_t)thr * 4 * W + (tet ? 4 : 2) * sub;
+            const uint32_t k = sub * bt + thr;
+            const bool pad = (r[0] & 0xffffu) == (r[0] >> 16);
+            if (k >= cnt) { bad += !pad; continue; }
+            if (pad) { bad++; continue; }
+            seen++;
+            const int32_t ent = tp.ents[at + k];
+            if ((ent < 0) != tet) { bad++; continue; }
+            if (!tet) {
+              const int32_t a = P.edges[2 * (size_t)ent], b = P.edges[2 * (size_t)ent + 1];
+              float L0; std::memcpy(&L0, &r[1], 4);
+              bad += P.perm[dev_id(r[0] & 0xffffu)] != (uint32_t)a || P.perm[dev_id(r[0] >> 16)] != (uint32_t)b ||
+                     std::memcmp(&L0, &P.rest_len[ent], 4) != 0;
+            } else {
+              const int32_t *q = &P.tets[4 * (size_t)(ent & 0x7fffffff)];
+              const uint32_t l[4] = {r[0] & 0xffffu, r[0] >> 16, r[1] & 0xffffu, r[1] >> 16};
+              bool ok = std::memcmp(&r[2], &P.rest_vol6[ent & 0x7fffffff], 4) == 0;
+              for (int j = 0; j < 4; j++) ok = ok && P.perm[dev_id(l[j])] == (uint32_t)q[j];
+              bad += !ok;
+            }
+          }
+        bad += seen != cnt;
+        at += cnt;
+      }
+      bad += at != tp.ent_off[t + 1];
+    }
+  }
+  *n_bad = bad;
   return SB_OK;
 }
 

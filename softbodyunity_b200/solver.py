@@ -293,11 +293,16 @@ class SoftBody:
         self._ck(self._lib.sb_time_frames(self._h, n_frames, dt, C.byref(ms)))
         return ms.value
 
+    def verify_streams(self) -> int:
+        """Debug (host only): records of the device constraint streams that disagree with the exported schedule."""
+        n = C.c_uint64()
+        self._ck(self._lib.sb_debug_verify_streams(self._h, C.byref(n)))
+        return n.value
+
     def trace_pass(self, p: int):
         """Debug: (64, 80) uint64 globaltimer stamps of one run of tile pass p."""
         out = np.zeros(64 * 80 + 256 + 3 * 4096, np.uint64)
         self._ck(self._lib.sb_debug_trace_pass(self._h, p, _ptr(out), out.size))
-        self.last_fine_trace = out[64 * 80:].reshape(-1)[:240].reshape(40, 6)
         self.last_cta_trace = out[64 * 80 + 256:].reshape(4096, 3)  # start ns, end ns, SM id per CTA
         return out[:64 * 80].reshape(64, 80)
 

@@ -12,6 +12,6 @@ python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/plain_${tag}.log 2
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1400 -c 900 --csv --log-file $out/launches_${tag}.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/ncu_launch_${tag}.log 2>&1
 python tools/profile_step.py > $out/plain2_${tag}.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_tile_pass -s 8 -c 4 -o $out/prof_${tag} \
+ncu --set full --clock-control none --import-source on -k regex:k_tile_rounds -s 8 -c 4 -o $out/prof_${tag} \
     python tools/profile_step.py > $out/ncu_full_${tag}.log 2>&1
 tail -2 $out/ncu_full_${tag}.log

@@ -17,19 +17,11 @@ tr = sb.trace_pass(a.pass_index).astype(np.int64)
 t0 = tr[:, 0].min()
 for cta in (0, 1, 7, 31, 63):
     r = tr[cta]
-    chunks = r[4:][r[4:] > 0]
-    d = np.diff(np.concatenate([chunks, [r[2]]]))
-    print(f"cta {cta}: start +{r[0]-t0} ns, prologue {r[1]-r[0]} ns, loop {r[2]-r[1]} ns ({len(chunks)} chunks, per chunk min/med/max {d.min()}/{int(np.median(d))}/{d.max()} ns), epilogue {r[3]-r[2]} ns, total {r[3]-r[0]} ns")
-print("chunk durations cta 7:", np.diff(np.concatenate([tr[7][4:][tr[7][4:] > 0], [tr[7][2]]])).tolist())
+    rounds = r[4:][r[4:] > 0]
+    d = np.diff(np.concatenate([rounds, [r[2]]]))
+    print(f"cta {cta}: start +{r[0]-t0} ns, prologue {r[1]-r[0]} ns, loop {r[2]-r[1]} ns ({len(rounds)} rounds, per round min/med/max {d.min()}/{int(np.median(d))}/{d.max()} ns), epilogue {r[3]-r[2]} ns, total {r[3]-r[0]} ns")
+print("round durations cta 7:", np.diff(np.concatenate([tr[7][4:][tr[7][4:] > 0], [tr[7][2]]])).tolist())
 print("pass time (kernel alone, ms):", sb.time_kernel(16 + a.pass_index, 20))
-
-f = sb.last_fine_trace.astype(np.int64)
-print("fine trace of CTA 7 (SM cycles): per chunk [tab+wait_full, records, release, ->barrier_start, barrier], then gap to next chunk")
-for i in range(min(30, len(f) - 1)):
-    r = f[i]
-    if r[0] == 0: break
-    nxt = f[i + 1][0] if f[i + 1][0] else r[4]
-    print(i, [int(r[1] - r[0]), int(r[2] - r[1]), int(r[3] - r[2]), int(r[4] - r[3])], "next", int(nxt - r[4]))
 
 ct = sb.last_cta_trace.astype(np.int64)
 ct = ct[ct[:, 0] > 0]
