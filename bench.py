@@ -142,10 +142,10 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons)}
 
 
-def cpu_oracle_rate(pos, tets, order, off, substeps, iterations, threads, reps):
+def cpu_oracle_rate(pos, tets, order, off, substeps, iterations, threads, reps, roles=None):
     """vertex-substeps/s of the CPU oracle on `reps` steps of `substeps` substeps each."""
     from oracle import xpbd_oracle as orc
-    m = orc.Model(pos, tets)
+    m = orc.Model(pos, tets, roles=roles)
     p = orc.params(dt=(1.0 / 60.0) * substeps / 10.0, substeps=substeps, iterations=iterations)
     m.simulate(p, n_frames=1, order=order, batch_off=off, threads=threads)  # touch memory
     t0 = time.perf_counter()
@@ -166,7 +166,7 @@ def run_reference(args, rank, world):
     info = plan.info()
     threads = os.cpu_count() or 1
     from oracle import xpbd_oracle as orc
-    m = orc.Model(pos, tets)
+    m = orc.Model(pos, tets, roles=plan.tet_roles())
     sub = 1  # one step of this arm = ONE substep (iterations sweeps) of the workload: bounded sample
     p = orc.params(dt=(1.0 / 60.0) / args.substeps, substeps=sub, iterations=args.iterations)
     for _ in range(args.warmup):
@@ -367,7 +367,8 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         order, off = sb.schedule()
         threads = os.cpu_count() or 1
-        rate, secs = cpu_oracle_rate(pos, tets, order, off, 1, args.iterations, threads, reps=max(1, min(10, args.substeps)))
+        rate, secs = cpu_oracle_rate(pos, tets, order, off, 1, args.iterations, threads, reps=max(1, min(10, args.substeps)),
+                                     roles=sb.tet_roles())
         cpu = {"value": rate, "unit": "vertex-substeps/s", "cores": threads, "kind": "port",
                "sample": f"{max(1, min(10, args.substeps))} substeps x {args.iterations} iterations of the same mesh and colour order "
                          f"({secs:.1f} s); CPU oracle (C, OpenMP over colour batches), not the reference C# solver (not in the mount)"}

@@ -99,7 +99,9 @@ typedef struct sb_mesh_desc {
   int32_t host_threads;     /* threads for the host-side build; 0 = auto */
   int32_t round_width;      /* 16-byte constraint-record words per thread per round (1 or 2): a round = one colour of
                                2 * width * block_threads edges or width * block_threads tets; 0 = auto (1) */
-  int32_t reserved0;        /* must be 0 */
+  int32_t attach_edges;     /* 0 = auto, 1 = on, 2 = off: project each edge right after a tet that contains it, from the
+                               registers holding the tet's vertices (the tet's vertex ROLES are then an even permutation
+                               of the caller's order, see sb_get_tet_roles).  Auto: on unless n_ghost_verts / edges are set */
   int32_t tilings;          /* 0 = auto; 1 = hierarchical tile passes only; N >= 2 = N balanced shifted tilings */
   int32_t n_ghost_verts;    /* partitioned meshes: the LAST n_ghost_verts vertices are ghost copies of vertices
                                another rank owns (never integrated here; constraints among ghosts are dropped) */
@@ -129,6 +131,7 @@ typedef struct sb_info {
   uint32_t smem_bytes;           /* dynamic shared memory per tile CTA */
   uint32_t round_width;          /* 16-byte record words per thread per round */
   uint32_t reserved0;
+  uint64_t edges_attached;       /* distance constraints that ride with a tet instead of an edge round */
   uint64_t rounds_in_pass[8];    /* rounds (barrier-separated colours) summed over the tiles of the pass */
   uint32_t launches_per_frame;   /* kernel launches inside one sb_step at current params */
   uint64_t device_bytes;         /* device memory held by the handle */
@@ -178,6 +181,14 @@ int sb_set_state(sb_handle h, const float *x4, const float *v4, uint32_t n_verts
 int sb_diagnostics(sb_handle h, double *out16);
 
 int sb_get_info(sb_handle h, sb_info *out);
+
+/*
+ * The vertex roles the tet-volume projection uses: tets_4T[4t..4t+3] is an even permutation of the caller's tet t
+ * (same orientation, same volume; the floating-point rounding of the projection follows the roles, so a CPU
+ * replay must use them), and the edges projected right after tet t from its roles (0,1) and (2,3), or -1.
+ * Identity / -1 when attach_edges is off.  Any pointer may be NULL.
+ */
+int sb_get_tet_roles(sb_handle h, int32_t *tets_4T, int32_t *edge01_T, int32_t *edge23_T);
 
 /* Derived topology in the caller's numbering (any pointer may be NULL). */
 int sb_get_topology(sb_handle h, int32_t *edges_2E, float *rest_len_E, float *rest_vol6_T, float *inv_mass_V);
@@ -237,8 +248,9 @@ int sb_lumped_inv_mass(const float *pos_xyz, uint32_t n_verts, const int32_t *te
 int sb_debug_trace_pass(sb_handle h, uint32_t pass, unsigned long long *out, uint32_t n_words);
 
 /* Debug aid, host only: decodes the device constraint streams as the kernel reads them and compares them with
-   the exported schedule; *n_bad = records that differ (0 on a sound plan). */
-int sb_debug_verify_streams(sb_handle h, uint64_t *n_bad);
+   the exported schedule; *n_bad = records that differ (0 on a sound plan).  Optionally also the modelled
+   shared-memory load wavefronts of one sweep (bank conflicts included) and their conflict-free count. */
+int sb_debug_verify_streams(sb_handle h, uint64_t *n_bad, uint64_t *wavefronts, uint64_t *wavefronts_ideal);
 
 const char *sb_last_error(sb_handle h); /* h may be NULL: last sb_create failure on this thread */
 

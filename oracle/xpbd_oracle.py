@@ -79,12 +79,17 @@ def lumped_inv_mass(pos, tets, density=1000.0):
 class Model:
     """Mesh + derived rest data in the oracle's own derivation (independent of the product)."""
 
-    def __init__(self, pos, tets, inv_mass=None, density=1000.0, dtype=np.float32):
+    def __init__(self, pos, tets, inv_mass=None, density=1000.0, dtype=np.float32, roles=None):
+        """roles: the tets again, each row a permutation of the same row of `tets` -- the vertex order the
+        volume projection is evaluated in (the product picks it, sb_get_tet_roles).  Edges and lumped masses
+        are derived from `tets`; rest volumes and the projection follow `roles`."""
         self.dtype = np.dtype(dtype)
         self.sfx = "_f32" if self.dtype == np.float32 else "_f64"
         self.pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
         self.tets = np.ascontiguousarray(tets, np.int32).reshape(-1, 4)
         self.V, self.T = len(self.pos), len(self.tets)
+        self.roles = self.tets if roles is None else np.ascontiguousarray(roles, np.int32).reshape(-1, 4)
+        assert self.roles.shape == self.tets.shape and (np.sort(self.roles, 1) == np.sort(self.tets, 1)).all()
         self.edges = build_edges(self.V, self.tets)
         self.E = len(self.edges)
         self.inv_mass = (lumped_inv_mass(self.pos, self.tets, density) if inv_mass is None
@@ -96,7 +101,7 @@ class Model:
         self.rest_len = np.empty(self.E, self.dtype)
         self.rest_vol6 = np.empty(self.T, self.dtype)
         getattr(lib(), "orc_rest_values" + self.sfx)(_p(self.x4), C.c_int32(self.E), _p(self.edges), _p(self.rest_len),
-                                                     C.c_int32(self.T), _p(self.tets), _p(self.rest_vol6))
+                                                     C.c_int32(self.T), _p(self.roles), _p(self.rest_vol6))
 
     def natural_order(self):
         """All edges in canonical order, then all tets: plain sequential Gauss-Seidel."""
@@ -110,7 +115,7 @@ class Model:
         sph = None if spheres is None else np.ascontiguousarray(spheres, np.float32).reshape(-1, 4)
         rc = getattr(lib(), "orc_simulate" + self.sfx)(
             C.c_int32(self.V), _p(self.x4), _p(self.v4), C.c_int32(self.E), _p(self.edges), _p(self.rest_len),
-            C.c_int32(self.T), _p(self.tets), _p(self.rest_vol6), C.byref(prm), C.c_int64(len(order)), _p(order),
+            C.c_int32(self.T), _p(self.roles), _p(self.rest_vol6), C.byref(prm), C.c_int64(len(order)), _p(order),
             C.c_int32(nb), _p(boff), C.c_int32(0 if sph is None else len(sph)), _p(sph), C.c_int32(n_frames),
             C.c_int32(threads))
         if rc != 0:

@@ -18,7 +18,7 @@ EXPORTS = [
     "sb_abi_check", "sb_default_params", "sb_create", "sb_plan", "sb_destroy", "sb_set_params",
     "sb_get_params", "sb_set_colliders", "sb_step", "sb_synchronize", "sb_read_positions",
     "sb_read_normals", "sb_surface_vertices", "sb_read_surface", "sb_get_state", "sb_set_state",
-    "sb_diagnostics", "sb_get_info", "sb_get_topology", "sb_get_schedule", "sb_get_tiles",
+    "sb_diagnostics", "sb_get_info", "sb_get_topology", "sb_get_tet_roles", "sb_get_schedule", "sb_get_tiles",
     "sb_time_frames", "sb_time_kernel", "sb_debug_trace_pass", "sb_debug_verify_streams", "sb_last_error",
     "sb_set_stream", "sb_prepare", "sb_enqueue", "sb_halo_set", "sb_halo_pack", "sb_halo_unpack", "sb_lumped_inv_mass",
     "sb_halo_alloc", "sb_halo_connect", "sb_halo_error", "sb_ipc_export", "sb_ipc_open",
@@ -42,7 +42,7 @@ class SbMeshDesc(C.Structure):
         ("density", C.c_float), ("device", C.c_int32), ("tile_cap", C.c_int32),
         ("max_tile_passes", C.c_int32), ("block_threads", C.c_int32),
         ("later_tile_cap", C.c_int32), ("host_threads", C.c_int32), ("round_width", C.c_int32),
-        ("reserved0", C.c_int32), ("tilings", C.c_int32), ("n_ghost_verts", C.c_int32), ("n_edges", C.c_uint32), ("reserved", C.c_int32 * 1),
+        ("attach_edges", C.c_int32), ("tilings", C.c_int32), ("n_ghost_verts", C.c_int32), ("n_edges", C.c_uint32), ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -55,7 +55,7 @@ class SbInfo(C.Structure):
         ("constraints_in_pass", C.c_uint64 * 8), ("edges_in_pass", C.c_uint64 * 8), ("runs_in_pass", C.c_uint64 * 8),
         ("constraints_global", C.c_uint64),
         ("tile_cap", C.c_uint32), ("block_threads", C.c_uint32), ("smem_bytes", C.c_uint32),
-        ("round_width", C.c_uint32), ("reserved0", C.c_uint32), ("rounds_in_pass", C.c_uint64 * 8),
+        ("round_width", C.c_uint32), ("reserved0", C.c_uint32), ("edges_attached", C.c_uint64), ("rounds_in_pass", C.c_uint64 * 8),
         ("launches_per_frame", C.c_uint32), ("device_bytes", C.c_uint64), ("build_seconds", C.c_double),
     ]
 
@@ -114,7 +114,8 @@ def load():
         "sb_time_frames": (C.c_int, [vp, i32, f32, P(f32)]),
         "sb_time_kernel": (C.c_int, [vp, i32, i32, P(f32)]),
         "sb_debug_trace_pass": (C.c_int, [vp, u32, vp, u32]),
-        "sb_debug_verify_streams": (C.c_int, [vp, vp]),
+        "sb_get_tet_roles": (C.c_int, [vp, vp, vp, vp]),
+        "sb_debug_verify_streams": (C.c_int, [vp, vp, vp, vp]),
         "sb_last_error": (C.c_char_p, [vp]),
         "sb_set_stream": (C.c_int, [vp, vp]),
         "sb_prepare": (C.c_int, [vp, f32]),

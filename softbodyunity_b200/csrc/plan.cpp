@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstring>
 #include <functional>
+#include <limits>
 #include <numeric>
 #include <thread>
 
@@ -138,7 +139,7 @@ void rest_values(Plan &P, int threads) {
     P.rest_len[e] = std::sqrt(std::fmaf(dz, dz, std::fmaf(dy, dy, dx * dx)));
   });
   parallel_for(P.T, threads, 65536, [&](size_t t, int) {
-    const int32_t *q = &P.tets[4 * t];
+    const int32_t *q = &P.tet_roles[4 * t];
     const float *p0 = &P.pos[3 * (size_t)q[0]], *p1 = &P.pos[3 * (size_t)q[1]];
     const float *p2 = &P.pos[3 * (size_t)q[2]], *p3 = &P.pos[3 * (size_t)q[3]];
     float e1[3], e2[3], e3[3], G1[3];
@@ -150,6 +151,104 @@ void rest_values(Plan &P, int threads) {
     cross_c(G1, e2, e3);
     P.rest_vol6[t] = std::fmaf(e1[2], G1[2], std::fmaf(e1[1], G1[1], e1[0] * G1[0]));
   });
+}
+
+// Edge ownership ("compounds").  Every edge of a tet joins two of its four vertices, so a thread that holds
+// a tet's vertices in registers can project that edge as well, at no shared-memory cost.  Each edge is
+// attached to at most one tet, each tet takes at most two edges and they must be opposite ones (vertex-
+// disjoint): they become the edges between roles (0,1) and (2,3) after an even permutation of the tet's
+// vertices (swapping the two ends of an edge is bit-neutral for the edge and flips the permutation's
+// parity, so an even one always exists and the tet keeps its orientation).  Greedy, scarcest edges first.
+void attach_edges(Plan &P, bool enable) {
+  static const int pr[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+  const uint32_t T = P.T, E = P.E;
+  P.tet_roles = P.tets;
+  P.tet_e01.assign(T, -1);
+  P.tet_e23.assign(T, -1);
+  P.edge_owner.assign(E, -1);
+  P.edges_attached = 0;
+  if (!enable || !T || !E) return;
+  // first edge of every vertex a in the sorted list (a < b)
+  std::vector<uint32_t> first((size_t)P.V + 1, 0);
+  for (uint32_t e = 0; e < E; e++) first[(size_t)P.edges[2 * (size_t)e] + 1]++;
+  for (uint32_t v = 0; v < P.V; v++) first[v + 1] += first[v];
+  auto edge_id = [&](int32_t a, int32_t b) -> int32_t {
+    if (a > b) std::swap(a, b);
+    uint32_t lo = first[a], hi = first[(size_t)a + 1];
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) / 2;
+      if (P.edges[2 * (size_t)mid + 1] < b) lo = mid + 1;
+      else hi = mid;
+    }
+    return lo < first[(size_t)a + 1] && P.edges[2 * (size_t)lo + 1] == b ? (int32_t)lo : -1;
+  };
+  // incidence: edge -> (tet, which of its six vertex pairs)
+  std::vector<int32_t> te(6 * (size_t)T);
+  std::vector<uint32_t> ioff((size_t)E + 1, 0);
+  for (uint32_t t = 0; t < T; t++)
+    for (int k = 0; k < 6; k++) {
+      const int32_t e = edge_id(P.tets[4 * (size_t)t + pr[k][0]], P.tets[4 * (size_t)t + pr[k][1]]);
+      te[6 * (size_t)t + k] = e;
+      if (e >= 0) ioff[(size_t)e + 1]++;
+    }
+  uint32_t max_inc = 0;
+  for (uint32_t e = 0; e < E; e++) {
+    max_inc = std::max(max_inc, ioff[e + 1]);
+    ioff[e + 1] += ioff[e];
+  }
+  std::vector<uint32_t> inc(ioff[E]); // tet * 8 + pair
+  {
+    std::vector<uint32_t> cur(ioff.begin(), ioff.end() - 1);
+    for (uint32_t t = 0; t < T; t++)
+      for (int k = 0; k < 6; k++)
+        if (te[6 * (size_t)t + k] >= 0) inc[cur[te[6 * (size_t)t + k]]++] = t * 8u + (uint32_t)k;
+  }
+  // edges by ascending number of incident tets (counting sort, stable in edge id)
+  std::vector<uint32_t> by_inc(E);
+  {
+    std::vector<uint32_t> cnt((size_t)max_inc + 2, 0);
+    for (uint32_t e = 0; e < E; e++) cnt[(size_t)(ioff[e + 1] - ioff[e]) + 1]++;
+    for (uint32_t k = 0; k <= max_inc; k++) cnt[k + 1] += cnt[k];
+    for (uint32_t e = 0; e < E; e++) by_inc[cnt[ioff[e + 1] - ioff[e]]++] = e;
+  }
+  std::vector<int8_t> pair01(T, -1), pair23(T, -1);
+  for (uint32_t oi = 0; oi < E; oi++) {
+    const uint32_t e = by_inc[oi];
+    int64_t pick = -1;
+    for (uint32_t k = ioff[e]; k < ioff[e + 1] && pick < 0; k++)
+      if (pair01[inc[k] >> 3] < 0) pick = inc[k];
+    if (pick >= 0) {
+      pair01[pick >> 3] = (int8_t)(pick & 7);
+      P.tet_e01[pick >> 3] = (int32_t)e;
+      P.edge_owner[e] = (int32_t)(pick >> 3);
+      continue;
+    }
+    for (uint32_t k = ioff[e]; k < ioff[e + 1] && pick < 0; k++) {
+      const uint32_t t = inc[k] >> 3, pk = inc[k] & 7;
+      if (pair23[t] < 0 && pair01[t] == (int8_t)(5 - pk)) pick = inc[k]; // pair 5 - k is the opposite edge
+    }
+    if (pick >= 0) {
+      pair23[pick >> 3] = (int8_t)(pick & 7);
+      P.tet_e23[pick >> 3] = (int32_t)e;
+      P.edge_owner[e] = (int32_t)(pick >> 3);
+    }
+  }
+  // roles: (a, b, c, d) with (a, b) the first attached edge and (c, d) the other two vertices in their
+  // original relative order; if that permutation is odd, swap a and b
+  for (uint32_t t = 0; t < T; t++) {
+    if (pair01[t] < 0) continue;
+    const int i0 = pr[pair01[t]][0], i1 = pr[pair01[t]][1];
+    int perm[4] = {i0, i1, -1, -1};
+    int at = 2;
+    for (int j = 0; j < 4; j++)
+      if (j != i0 && j != i1) perm[at++] = j;
+    int inversions = 0;
+    for (int x = 0; x < 4; x++)
+      for (int y = x + 1; y < 4; y++) inversions += perm[x] > perm[y];
+    if (inversions & 1) std::swap(perm[0], perm[1]);
+    for (int j = 0; j < 4; j++) P.tet_roles[4 * (size_t)t + j] = P.tets[4 * (size_t)t + perm[j]];
+    P.edges_attached += 1 + (pair23[t] >= 0);
+  }
 }
 
 std::string build_surface(Plan &P) {
@@ -397,6 +496,8 @@ struct TileOut {
   std::vector<uint32_t> verts; // device ids (non-contiguous passes)
   uint32_t n_ecol = 0, n_tcol = 0, n_verts = 0;
   std::vector<uint32_t> stream;  // words: edge rounds, then tet rounds
+  std::vector<float> aux;        // per tet round
+  std::vector<uint8_t> has01, has23; // per tet colour
   std::vector<int32_t> ents;     // processing order
   std::vector<uint32_t> col_cnt; // per colour, edge colours first
   uint64_t n_edges = 0, n_tets = 0;
@@ -529,6 +630,8 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
       uint64_t *M = mask[kind].data();
       // first colour free at every vertex that is below the soft capacity; failing that, one below the
       // hard capacity (the slack the soft limit left is what absorbs the stragglers); failing that, a new one
+      const uint32_t hard = kind ? cap_t : cap_e, slack = std::max(1u, hard / 32);
+      std::vector<uint32_t> &cnt = kind ? tcount : ecount;
       auto first_free_colour = [&](const std::vector<uint64_t> &closed) {
         for (size_t wd = 0; wd < W; wd++) {
           uint64_t u = closed[wd];
@@ -537,8 +640,6 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
         }
         return -1;
       };
-      std::vector<uint32_t> &cnt = kind ? tcount : ecount;
-      const uint32_t hard = kind ? cap_t : cap_e, slack = std::max(1u, hard / 32);
       const size_t k_target = (n_kind[kind] + (hard - slack) - 1) / (hard - slack);
       int c = first_free_colour(soft[kind]);
       if ((c < 0 || (size_t)c >= cnt.size()) && cnt.size() >= k_target) {
@@ -574,33 +675,45 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
     }
     // Within a colour any order is equivalent; pick one where each run of 8 records (the
     // quarter-warp an LDS.128 serves per wavefront) touches 8 different 16-byte bank groups
-    // (local id mod 8) in every vertex slot.
+    // (local id mod 8) in every vertex slot.  Compounds with a second attached edge come first,
+    // so that the warps behind them skip that code.
     {
       std::vector<int32_t> tmp;
+      std::vector<uint8_t> cls;
       std::vector<uint32_t> bucket[8];
       for (uint32_t c = 0; c < ncol; c++) {
         const uint32_t lo = coff[c], n = coff[c + 1] - coff[c];
+        const bool tet = c >= O.n_ecol;
+        const int nvs = tet ? 4 : 2;
+        auto second_edge = [&](int32_t e) { return tet && P.tet_e23[e & 0x7fffffff] >= 0; };
+        if (tet) std::stable_partition(O.ents.begin() + lo, O.ents.begin() + lo + n, second_edge);
         if (n < 16) continue;
-        const int nvs = c >= O.n_ecol ? 4 : 2;
-        for (auto &b : bucket) b.clear();
         std::vector<uint8_t> res((size_t)n * 4);
         for (uint32_t k = 0; k < n; k++) {
           int32_t vs[4];
           ent_verts(D, O.ents[lo + k], vs);
           for (int j = 0; j < nvs; j++) res[(size_t)k * 4 + j] = (uint8_t)(local(vs[j]) & 7u);
-          bucket[res[(size_t)k * 4]].push_back(k);
         }
-        for (auto &b : bucket) std::reverse(b.begin(), b.end()); // pop_back takes ascending ids first
+        uint32_t n_first = 0;
+        while (n_first < n && second_edge(O.ents[lo + n_first])) n_first++;
         tmp.clear();
         tmp.reserve(n);
-        uint32_t left = n;
-        while (left) {
-          uint8_t used[4] = {0, 0, 0, 0};
-          for (int pos = 0; pos < 8 && left; pos++) {
+        cls.clear();
+        uint8_t used[4] = {0, 0, 0, 0};
+        // greedy octets, class by class; the octet that straddles the class boundary keeps its residues
+        for (int pass = 0; pass < 2; pass++) {
+          const uint32_t k0 = pass ? n_first : 0, k1 = pass ? n : n_first;
+          for (auto &bk : bucket) bk.clear();
+          for (uint32_t k = k0; k < k1; k++) bucket[res[(size_t)k * 4]].push_back(k);
+          for (auto &bk : bucket) std::reverse(bk.begin(), bk.end()); // pop_back takes ascending ids first
+          uint32_t left = k1 - k0;
+          while (left) {
+            const uint32_t pos = (uint32_t)tmp.size() & 7u;
+            if (pos == 0) used[0] = used[1] = used[2] = used[3] = 0;
             // prefer the bucket whose slot-0 residue is still free in this octet
             int b = -1;
             for (int r = 0; r < 8; r++) {
-              const int cand = (pos + r) & 7;
+              const int cand = (int)((pos + r) & 7);
               if (!bucket[cand].empty() && !(used[0] >> cand & 1)) { b = cand; break; }
             }
             if (b < 0) {
@@ -622,7 +735,60 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
             B.erase(B.begin() + (ptrdiff_t)pick);
             for (int j = 0; j < nvs; j++) used[j] |= (uint8_t)(1u << res[(size_t)k * 4 + j]);
             tmp.push_back(O.ents[lo + k]);
+            cls.push_back((uint8_t)pass);
             left--;
+          }
+        }
+        // local search: swap records of the same class between octets while that lowers the wavefront
+        // count (per octet and vertex slot: the largest number of records in one bank group)
+        {
+          const uint32_t n_oct = (n + 7) / 8;
+          std::vector<uint8_t> rr((size_t)n * 4);
+          for (uint32_t k = 0; k < n; k++) {
+            int32_t vs[4];
+            ent_verts(D, tmp[k], vs);
+            for (int j = 0; j < nvs; j++) rr[(size_t)k * 4 + j] = (uint8_t)(local(vs[j]) & 7u);
+          }
+          auto oct_cost = [&](uint32_t o, uint32_t swap_pos, uint32_t swap_with) {
+            // cost of octet o with the record at swap_pos replaced by the one at swap_with (swap_pos == ~0u: as is)
+            uint32_t cost = 0;
+            const uint32_t k0 = o * 8, k1 = std::min(n, k0 + 8);
+            for (int j = 0; j < nvs; j++) {
+              uint8_t cntb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+              uint8_t m = 0;
+              for (uint32_t k = k0; k < k1; k++) {
+                const uint32_t src = k == swap_pos ? swap_with : k;
+                m = std::max(m, ++cntb[rr[(size_t)src * 4 + j]]);
+              }
+              cost += m;
+            }
+            return cost;
+          };
+          std::vector<uint32_t> oc(n_oct);
+          for (uint32_t o = 0; o < n_oct; o++) oc[o] = oct_cost(o, ~0u, 0);
+          uint32_t rng = 0x9e3779b9u ^ (uint32_t)(t * 2654435761u) ^ (c * 40503u);
+          for (int sweep = 0; sweep < 6; sweep++) {
+            bool improved = false;
+            for (uint32_t a = 0; a < n; a++) {
+              const uint32_t oa = a / 8;
+              if (oc[oa] <= (uint32_t)nvs) continue; // already conflict-free
+              for (int tries = 0; tries < 24; tries++) {
+                rng = rng * 1664525u + 1013904223u;
+                const uint32_t b = (uint32_t)(((uint64_t)(rng >> 8) * n) >> 24);
+                const uint32_t ob = b / 8;
+                if (ob == oa || b >= n || cls[a] != cls[b]) continue;
+                const uint32_t na = oct_cost(oa, a, b), nb = oct_cost(ob, b, a);
+                if (na + nb < oc[oa] + oc[ob]) {
+                  std::swap(tmp[a], tmp[b]);
+                  for (int j = 0; j < 4; j++) std::swap(rr[(size_t)a * 4 + j], rr[(size_t)b * 4 + j]);
+                  oc[oa] = na;
+                  oc[ob] = nb;
+                  improved = true;
+                  break;
+                }
+              }
+            }
+            if (!improved) break;
           }
         }
         std::copy(tmp.begin(), tmp.end(), O.ents.begin() + lo);
@@ -632,6 +798,9 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
     // one record before any has two, and the octets above are the lanes of one LDS wavefront.
     const uint32_t round_words = 4 * width * bt;
     O.stream.assign((size_t)ncol * round_words, 0u);
+    O.aux.assign((size_t)O.n_tcol * width * bt, std::numeric_limits<float>::quiet_NaN());
+    O.has01.assign(O.n_tcol, 0);
+    O.has23.assign(O.n_tcol, 0);
     for (uint32_t c = 0; c < ncol; c++) {
       const bool tet = c >= O.n_ecol;
       uint32_t *rw = O.stream.data() + (size_t)c * round_words;
@@ -646,9 +815,16 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
           r[1] = f2u(P.rest_len[e]);
         } else {
           uint32_t *r = rw + (size_t)thr * 4 * width + 4 * sub;
+          const int32_t id = e & 0x7fffffff, e01 = P.tet_e01[id], e23 = P.tet_e23[id];
           r[0] = local(vs[0]) | (local(vs[1]) << 16);
           r[1] = local(vs[2]) | (local(vs[3]) << 16);
-          r[2] = f2u(P.rest_vol6[e & 0x7fffffff]);
+          r[2] = f2u(P.rest_vol6[id]);
+          r[3] = e01 >= 0 ? f2u(P.rest_len[e01]) : 0x7fc00000u;
+          O.aux[(size_t)(c - O.n_ecol) * width * bt + (size_t)thr * width + sub] =
+              e23 >= 0 ? P.rest_len[e23] : std::numeric_limits<float>::quiet_NaN();
+          O.n_edges += (e01 >= 0) + (e23 >= 0);
+          if (e01 >= 0) O.has01[c - O.n_ecol] = 1;
+          if (e23 >= 0) O.has23[c - O.n_ecol] = 1;
         }
       }
       (tet ? O.n_tets : O.n_edges) += O.col_cnt[c];
@@ -679,7 +855,16 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
   TP.tile_verts.reserve(nv);
   for (uint32_t t = 0; t < n_tiles; t++) {
     TileOut &O = outs[t];
-    TP.rounds.push_back({(uint32_t)(TP.stream.size() / 4), O.n_ecol, O.n_tcol, 0u});
+    TP.rounds.push_back({(uint32_t)(TP.stream.size() / 4), O.n_ecol, O.n_tcol, (uint32_t)TP.aux.size()});
+    TP.aux.insert(TP.aux.end(), O.aux.begin(), O.aux.end());
+    if (TP.col_has01.size() < O.n_tcol) {
+      TP.col_has01.resize(O.n_tcol, 0);
+      TP.col_has23.resize(O.n_tcol, 0);
+    }
+    for (uint32_t c = 0; c < O.n_tcol; c++) {
+      TP.col_has01[c] |= O.has01[c];
+      TP.col_has23[c] |= O.has23[c];
+    }
     TP.stream.insert(TP.stream.end(), O.stream.begin(), O.stream.end());
     TP.ents.insert(TP.ents.end(), O.ents.begin(), O.ents.end());
     TP.ent_off.push_back(TP.ents.size());
@@ -778,8 +963,21 @@ uint32_t next_parts(const Plan &P, const DevTopo &D, const std::vector<int32_t> 
   return n_tiles;
 }
 
-std::string global_colouring(Plan &P, const DevTopo &D, const std::vector<int32_t> &rest) {
-  if (rest.empty()) return "";
+std::string global_colouring(Plan &P, const DevTopo &D, const std::vector<int32_t> &rest_in) {
+  if (rest_in.empty()) return "";
+  // a tet that ends up here brings its attached edges along as plain edges
+  std::vector<int32_t> rest;
+  rest.reserve(rest_in.size());
+  for (int32_t ent : rest_in)
+    if (ent >= 0) rest.push_back(ent);
+  for (int32_t ent : rest_in)
+    if (ent < 0) {
+      const int32_t id = ent & 0x7fffffff;
+      if (P.tet_e01[id] >= 0) rest.push_back(P.tet_e01[id]);
+      if (P.tet_e23[id] >= 0) rest.push_back(P.tet_e23[id]);
+    }
+  for (int32_t ent : rest_in)
+    if (ent < 0) rest.push_back(ent);
   std::vector<Mask128> me(P.V), mt(P.V);
   std::vector<uint8_t> col(rest.size());
   std::vector<uint32_t> ecount, tcount;
@@ -877,6 +1075,23 @@ void Plan::export_schedule(std::vector<int32_t> &order, std::vector<int64_t> &ba
           for (uint32_t k = 0; k < TP.col_cnt[j]; k++) order.push_back(TP.ents[cstart[j] + k]);
         }
         close();
+        if (!kind) continue;
+        // the edges attached to this colour's tets: a thread projects tet, edge (0,1), edge (2,3) in a row;
+        // records of one colour are vertex-disjoint, so "all tets, all (0,1) edges, all (2,3) edges" is the
+        // same computation written as independent batches
+        for (int which = 0; which < 2; which++) {
+          const std::vector<int32_t> &att = which ? tet_e23 : tet_e01;
+          for (uint32_t t = 0; t < nt; t++) {
+            const uint32_t nk = TP.col_off[t + 1] - TP.col_off[t] - TP.n_ecol[t];
+            if (c >= nk) continue;
+            const uint32_t j = TP.col_off[t] + TP.n_ecol[t] + c;
+            for (uint32_t k = 0; k < TP.col_cnt[j]; k++) {
+              const int32_t e = att[TP.ents[cstart[j] + k] & 0x7fffffff];
+              if (e >= 0) order.push_back(e);
+            }
+          }
+          close();
+        }
       }
     }
   }
@@ -939,6 +1154,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     if (!(in.density > 0)) return "density must be > 0 when inv_mass is NULL";
     lumped_inv_mass(P, in.density);
   }
+  attach_edges(P, opt.compounds > 0 || (opt.compounds < 0 && !in.edges && !in.n_ghost));
   rest_values(P, threads);
   err = build_surface(P);
   if (!err.empty()) return err;
@@ -1003,7 +1219,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   D.edges.resize(2 * (size_t)P.E);
   D.tets.resize(4 * (size_t)P.T);
   parallel_for(2 * (size_t)P.E, threads, 1 << 18, [&](size_t i, int) { D.edges[i] = (int32_t)P.inv[P.edges[i]]; });
-  parallel_for(4 * (size_t)P.T, threads, 1 << 18, [&](size_t i, int) { D.tets[i] = (int32_t)P.inv[P.tets[i]]; });
+  parallel_for(4 * (size_t)P.T, threads, 1 << 18, [&](size_t i, int) { D.tets[i] = (int32_t)P.inv[P.tet_roles[i]]; });
   std::vector<float> dev_pos(3 * (size_t)P.V);
   for (uint32_t d = 0; d < P.V; d++)
     for (int k = 0; k < 3; k++) dev_pos[3 * (size_t)d + k] = P.pos[3 * (size_t)P.perm[d] + k];
@@ -1056,7 +1272,8 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
       const size_t i = deal_order[oi];
       const int32_t ent = cons[i];
       const int kind = ent < 0;
-      const uint64_t wgt = kind ? 5 : 2; // tets weigh more than edges in the kernels
+      // tets weigh more than edges in the kernels, and carry their attached edges
+      const uint64_t wgt = kind ? 5 + 2 * ((P.tet_e01[ent & 0x7fffffff] >= 0) + (P.tet_e23[ent & 0x7fffffff] >= 0)) : 2;
       int32_t vs[4];
       const int n = ent_verts(D, ent, vs);
       int best = -1;
@@ -1181,6 +1398,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   cons0.reserve((size_t)P.E + P.T);
   for (size_t i = 0; i < (size_t)P.E + P.T; i++) {
     const int32_t ent = i < P.E ? (int32_t)i : (int32_t)(0x80000000u | (uint32_t)(i - P.E));
+    if (i < P.E && P.edge_owner[i] >= 0) continue; // rides with its tet
     int ng = 0, n;
     if (ent >= 0) {
       n = 2;

@@ -27,6 +27,7 @@ struct PlanOptions {
   int threads = 0;          // host build threads (0 = hardware_concurrency)
   int block_threads = 0;    // threads per tile CTA: 32, 64, 128 or 256 (0 = auto per pass, by constraints per tile)
   int round_width = 0;      // 16-byte record words per thread per round: 1 or 2 (0 = 1)
+  int compounds = -1;       // attach edges to tets (-1 = auto: on unless the mesh is one rank of a partition, 0 off, 1 on)
   int tilings = 0;          // 0 = auto; 1 = hierarchical passes only; N >= 2 = N balanced shifted tilings
 };
 
@@ -37,13 +38,18 @@ struct PlanOptions {
 // one kind, capped at what the CTA projects in one go: every thread owns `width`
 // 16-byte words of every round,
 //   edge round: word = 2 x { a | b << 16, bits(L0) }              -> 2 * width * bt edges per colour
-//   tet round : word = { p0 | p1 << 16, p2 | p3 << 16, bits(6 V0), 0 } -> width * bt tets per colour
+//   tet round : word = { p0 | p1 << 16, p2 | p3 << 16, bits(6 V0), bits(L01) } -> width * bt tets per colour
+//               plus one float per word in `aux`: L23.  A tet record is a COMPOUND: the tet, then the edge
+//               between its roles (0,1) with rest length L01, then the edge between roles (2,3) with rest
+//               length L23 (NaN = no such edge attached).  An attached edge is projected from the registers
+//               that already hold the tet's vertices, so it costs no shared-memory traffic and no round.
 // (local 16-bit vertex ids; an all-zero record is padding: a == b / p0 == p1 is never projected).
 // Thread `tid` reads its words of round r at stream[off + (r * bt + tid) * width ...], a fully
 // coalesced access that it prefetches several rounds ahead; the CTA synchronises after every
 // round.  The colouring is capacity-limited (first free colour that is not full), so a tile
 // needs max(valence, ceil(n / capacity)) rounds and every round but the last is full.
-// rounds[t] = { offset / 16 of tile t's first round in `stream`, edge rounds, tet rounds, 0 }.
+// rounds[t] = { offset / 16 of tile t's first round in `stream`, edge rounds, tet rounds, offset of its first
+//               tet round in `aux` (floats) }.
 struct TilePass {
   bool contiguous = false;          // tile t == device vertex range [vert_off[t], vert_off[t+1])
   std::vector<uint32_t> vert_off;   // n_tiles + 1
@@ -52,6 +58,8 @@ struct TilePass {
   std::vector<U2> runs;             // per tile: {first device id, first local id} per run, then {0, n_verts}
   std::vector<U4> rounds;           // n_tiles
   std::vector<uint32_t> stream;     // 32-bit words; every round starts 16-byte aligned
+  std::vector<float> aux;           // per tet round: width * bt floats (L23 of the compound, NaN if none)
+  std::vector<uint8_t> col_has01, col_has23; // per tet colour index: some tile attaches a (0,1) / (2,3) edge there
   uint32_t bt = 64, width = 1;      // CTA threads and 16-byte words per thread per round of this pass
   // schedule bookkeeping (host only): per tile, constraints in processing order
   std::vector<uint64_t> ent_off;    // n_tiles + 1 offsets into ents
@@ -84,6 +92,10 @@ struct Plan {
   std::vector<int32_t> tets;    // 4T
   std::vector<int32_t> edges;   // 2E, a < b, sorted
   std::vector<int32_t> tris;    // 3F
+  std::vector<int32_t> tet_roles; // 4T: tets[t] in the role order the projection uses (an even permutation)
+  std::vector<int32_t> tet_e01, tet_e23; // T: edge attached to roles (0,1) / (2,3) of the tet, or -1
+  std::vector<int32_t> edge_owner;       // E: tet the edge is attached to, or -1 (projected in an edge round)
+  uint64_t edges_attached = 0;
   std::vector<float> rest_len;  // E
   std::vector<float> rest_vol6; // T
   std::vector<float> inv_mass;  // V

@@ -63,6 +63,7 @@ struct PassBufs {
   DevBuf<uint32_t> vert_off, tile_verts, stream, run_off;
   DevBuf<uint2> runs;
   DevBuf<uint4> rounds;
+  DevBuf<float> aux;
   PassDev dev{};
   uint32_t smem = 0;
   uint32_t bt = 64, width = 1; // threads per CTA and record words per thread per round of this pass
@@ -220,6 +221,7 @@ struct sb_solver {
         pb.rounds.upload(r4, &dev_bytes);
       }
       pb.stream.upload(tp.stream, &dev_bytes);
+      pb.aux.upload(tp.aux, &dev_bytes);
       const uint32_t pos_bytes = (tp.max_tile_verts * 16u + 127u) & ~127u;
       pb.smem = pos_bytes + 16u; // positions + the mbarrier their bulk copies complete on
       if (pb.smem > (uint32_t)prop.sharedMemPerBlockOptin) throw std::string("tile_cap exceeds the shared memory of this device");
@@ -232,7 +234,7 @@ struct sb_solver {
       }
       pb.dev = PassDev{pb.vert_off.p, tp.contiguous ? nullptr : pb.tile_verts.p, use_runs ? pb.run_off.p : nullptr,
                        use_runs ? pb.runs.p : nullptr, pb.rounds.p, reinterpret_cast<const uint4 *>(pb.stream.p),
-                       tp.n_tiles(), pos_bytes, nullptr};
+                       pb.aux.p, tp.n_tiles(), pos_bytes, nullptr};
       pb.bt = tp.bt;
       pb.width = tp.width;
       if (k == 0) block_threads = tp.bt;
@@ -761,7 +763,8 @@ static int create_impl(const sb_mesh_desc *mesh, const sb_params *params, sb_han
   *out = nullptr;
   g_create_error.clear();
   if (!mesh) { g_create_error = "mesh is NULL"; return SB_E_ARG; }
-  if (mesh->reserved[0] != 0 || mesh->reserved0 != 0) { g_create_error = "reserved fields must be 0"; return SB_E_ARG; }
+  if (mesh->reserved[0] != 0) { g_create_error = "reserved fields must be 0"; return SB_E_ARG; }
+  if (mesh->attach_edges < 0 || mesh->attach_edges > 2) { g_create_error = "attach_edges must be 0, 1 or 2"; return SB_E_ARG; }
   sb_params dp;
   sb_default_params(&dp);
   if (params) dp = *params;
@@ -780,6 +783,7 @@ static int create_impl(const sb_mesh_desc *mesh, const sb_params *params, sb_han
     opt.threads = mesh->host_threads;
     opt.block_threads = mesh->block_threads;
     opt.round_width = mesh->round_width;
+    opt.compounds = mesh->attach_edges == 0 ? -1 : mesh->attach_edges == 1 ? 1 : 0;
     opt.tilings = mesh->tilings;
     if (device) {
       int ndev = 0;
@@ -939,6 +943,8 @@ int sb_get_info(sb_handle h, sb_info *o) {
   uint32_t nb = 0;
   for (size_t k = 0; k < P.passes.size(); k++) {
     nb += P.passes[k].max_ecol + P.passes[k].max_tcol;
+    for (uint8_t f : P.passes[k].col_has01) nb += f;
+    for (uint8_t f : P.passes[k].col_has23) nb += f;
     if (k < 8) {
       o->tiles_in_pass[k] = P.passes[k].n_tiles();
       o->max_colours_in_pass[k] = P.passes[k].max_ecol + P.passes[k].max_tcol;
@@ -952,6 +958,7 @@ int sb_get_info(sb_handle h, sb_info *o) {
     if (k < 8) o->rounds_in_pass[k] = P.passes[k].rounds_total;
   }
   o->round_width = P.round_width;
+  o->edges_attached = P.edges_attached;
   o->n_global_batches = (uint32_t)P.gbatches.size();
   o->n_batches = nb + (uint32_t)P.gbatches.size();
   o->constraints_global = P.g_edges.size() + P.g_tets.size();
@@ -960,6 +967,15 @@ int sb_get_info(sb_handle h, sb_info *o) {
   o->launches_per_frame = h->on_device ? h->launches_per_frame() : 0;
   o->device_bytes = h->dev_bytes;
   o->build_seconds = P.build_seconds;
+  return SB_OK;
+}
+
+int sb_get_tet_roles(sb_handle h, int32_t *tets_4T, int32_t *edge01_T, int32_t *edge23_T) {
+  NEED_HANDLE(h);
+  const Plan &P = h->plan;
+  if (tets_4T) std::memcpy(tets_4T, P.tet_roles.data(), P.tet_roles.size() * sizeof(int32_t));
+  if (edge01_T) std::memcpy(edge01_T, P.tet_e01.data(), P.tet_e01.size() * sizeof(int32_t));
+  if (edge23_T) std::memcpy(edge23_T, P.tet_e23.data(), P.tet_e23.size() * sizeof(int32_t));
   return SB_OK;
 }
 
@@ -1010,11 +1026,11 @@ int sb_get_tiles(sb_handle h, uint32_t pass, int32_t *tile_of, uint32_t *n_tiles
    tile, round by round, thread by thread -- and compare every record with the schedule bookkeeping that
    sb_get_schedule exports (same constraint, same vertex roles, same rest value).  Returns the number of
    mismatching or misplaced records in *n_bad. */
-int sb_debug_verify_streams(sb_handle h, uint64_t *n_bad) {
+int sb_debug_verify_streams(sb_handle h, uint64_t *n_bad, uint64_t *wavefronts, uint64_t *wavefronts_ideal) {
   NEED_HANDLE(h);
   if (!n_bad) return SB_E_ARG;
   const Plan &P = h->plan;
-  uint64_t bad = 0;
+  uint64_t bad = 0, wf = 0, wf_ideal = 0;
   for (const TilePass &tp : P.passes) {
     const uint32_t bt = tp.bt, W = tp.width;
     for (uint32_t t = 0; t < tp.n_tiles(); t++) {
@@ -1028,6 +1044,25 @@ int sb_debug_verify_streams(sb_handle h, uint64_t *n_bad) {
         const bool tet = c >= meta.y;
         const uint32_t cnt = tp.col_cnt[tp.col_off[t] + c];
         const uint32_t *rw = tp.stream.data() + ((size_t)meta.x * 4 + (size_t)c * 4 * W * bt);
+        // shared-memory model: one LDS.128 per vertex slot and sub-record; a quarter-warp (8 lanes) costs as
+        // many wavefronts as its most crowded 16-byte bank group holds distinct addresses
+        for (uint32_t sub = 0; sub < (tet ? W : 2 * W); sub++)
+          for (uint32_t slot = 0; slot < (tet ? 4u : 2u); slot++)
+            for (uint32_t o = 0; o < bt; o += 8) {
+              uint32_t ids[8], nid = 0, mult[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+              for (uint32_t l = 0; l < 8; l++) {
+                const uint32_t *r = rw + (size_t)(o + l) * 4 * W + (tet ? 4 : 2) * sub;
+                const uint32_t wd = r[tet ? slot / 2 : 0];
+                const uint32_t id = tet ? (slot & 1 ? wd >> 16 : wd & 0xffffu) : (slot ? wd >> 16 : wd & 0xffffu);
+                bool dup = false;
+                for (uint32_t q = 0; q < nid; q++) dup |= ids[q] == id;
+                if (!dup) { ids[nid++] = id; mult[id & 7]++; }
+              }
+              uint32_t m = 0;
+              for (uint32_t q = 0; q < 8; q++) m = std::max(m, mult[q]);
+              wf += m;
+              wf_ideal += 1;
+            }
         uint32_t seen = 0;
         for (uint32_t thr = 0; thr < bt; thr++)
           for (uint32_t sub = 0; sub < (tet ? W : 2 * W); sub++) {
@@ -1045,10 +1080,22 @@ int sb_debug_verify_streams(sb_handle h, uint64_t *n_bad) {
               bad += P.perm[dev_id(r[0] & 0xffffu)] != (uint32_t)a || P.perm[dev_id(r[0] >> 16)] != (uint32_t)b ||
                      std::memcmp(&L0, &P.rest_len[ent], 4) != 0;
             } else {
-              const int32_t *q = &P.tets[4 * (size_t)(ent & 0x7fffffff)];
+              const int32_t id = ent & 0x7fffffff;
+              const int32_t *q = &P.tet_roles[4 * (size_t)id];
               const uint32_t l[4] = {r[0] & 0xffffu, r[0] >> 16, r[1] & 0xffffu, r[1] >> 16};
-              bool ok = std::memcmp(&r[2], &P.rest_vol6[ent & 0x7fffffff], 4) == 0;
+              bool ok = std::memcmp(&r[2], &P.rest_vol6[id], 4) == 0;
               for (int j = 0; j < 4; j++) ok = ok && P.perm[dev_id(l[j])] == (uint32_t)q[j];
+              // attached edges: rest lengths in the record / aux stream, and they do join roles (0,1) / (2,3)
+              const float a23 = tp.aux[(size_t)meta.w + (size_t)(c - meta.y) * W * bt + (size_t)thr * W + sub];
+              const int32_t e01 = P.tet_e01[id], e23 = P.tet_e23[id];
+              auto joins = [&](int32_t e, int32_t u, int32_t v) {
+                return (P.edges[2 * (size_t)e] == std::min(u, v)) && (P.edges[2 * (size_t)e + 1] == std::max(u, v)) &&
+                       P.edge_owner[e] == id;
+              };
+              if (e01 >= 0) ok = ok && std::memcmp(&r[3], &P.rest_len[e01], 4) == 0 && joins(e01, q[0], q[1]);
+              else ok = ok && r[3] == 0x7fc00000u;
+              if (e23 >= 0) ok = ok && std::memcmp(&a23, &P.rest_len[e23], 4) == 0 && joins(e23, q[2], q[3]);
+              else ok = ok && a23 != a23;
               bad += !ok;
             }
           }
@@ -1059,6 +1106,8 @@ int sb_debug_verify_streams(sb_handle h, uint64_t *n_bad) {
     }
   }
   *n_bad = bad;
+  if (wavefronts) *wavefronts = wf;
+  if (wavefronts_ideal) *wavefronts_ideal = wf_ideal;
   return SB_OK;
 }
 

@@ -78,7 +78,7 @@ class SoftBody:
                  stiffness=math.inf, volume_stiffness=math.inf, damping=0.0, friction=0.0,
                  substeps=10, iterations=10, dt=1.0 / 60.0, gravity=(0.0, -9.81, 0.0), ground_y=0.0,
                  flags=0, tile_cap=0, max_tile_passes=-1, block_threads=0, later_tile_cap=0,
-                 host_threads=0, round_width=0, tilings=0, n_ghost_verts=0, stream=None, host_only=False):
+                 host_threads=0, round_width=0, attach_edges=0, tilings=0, n_ghost_verts=0, stream=None, host_only=False):
         self._lib = _abi.load()
         self._h = C.c_void_p()
         pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
@@ -98,7 +98,7 @@ class SoftBody:
         d.density, d.device = density, device
         d.tile_cap, d.max_tile_passes, d.block_threads = tile_cap, max_tile_passes, block_threads
         d.later_tile_cap, d.host_threads = later_tile_cap, host_threads
-        d.round_width, d.tilings = round_width, tilings
+        d.round_width, d.attach_edges, d.tilings = round_width, attach_edges, tilings
         d.n_ghost_verts = n_ghost_verts
         self._params = default_params(
             dt=dt, substeps=substeps, iterations=iterations, stiffness_distance=stiffness,
@@ -272,6 +272,19 @@ class SoftBody:
         self._ck(self._lib.sb_get_topology(self._h, _ptr(edges), _ptr(rest_len), _ptr(rest_vol6), _ptr(inv_mass)))
         return edges, rest_len, rest_vol6, inv_mass
 
+    def tet_roles(self):
+        """Tets in the vertex-role order the volume projection uses (an even permutation of the caller's order);
+        a CPU replay of the schedule must use these roles to be bit-identical (see sb_get_tet_roles)."""
+        roles = np.empty((self.n_tets, 4), np.int32)
+        self._ck(self._lib.sb_get_tet_roles(self._h, _ptr(roles), None, None))
+        return roles
+
+    def attached_edges(self):
+        e01 = np.empty(self.n_tets, np.int32)
+        e23 = np.empty(self.n_tets, np.int32)
+        self._ck(self._lib.sb_get_tet_roles(self._h, None, _ptr(e01), _ptr(e23)))
+        return e01, e23
+
     def schedule(self):
         """(order, batch_off): the Gauss-Seidel order of one iteration (see sb_get_schedule)."""
         n, nb = C.c_int64(), C.c_int32()
@@ -295,8 +308,9 @@ class SoftBody:
 
     def verify_streams(self) -> int:
         """Debug (host only): records of the device constraint streams that disagree with the exported schedule."""
-        n = C.c_uint64()
-        self._ck(self._lib.sb_debug_verify_streams(self._h, C.byref(n)))
+        n, wf, wfi = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.sb_debug_verify_streams(self._h, C.byref(n), C.byref(wf), C.byref(wfi)))
+        self.smem_model = (wf.value, wfi.value)  # load wavefronts per sweep: with bank conflicts, conflict-free
         return n.value
 
     def trace_pass(self, p: int):

@@ -36,10 +36,10 @@ def main():
         sb = SoftBody(pos, tets, tris, host_only=True, **c["plan"],
                       **{{"stiffness_distance": "stiffness", "stiffness_volume": "volume_stiffness"}.get(k, k): v for k, v in kw.items()})
         order, off = sb.schedule()
-        m = orc.Model(pos, tets)
+        m = orc.Model(pos, tets, roles=sb.tet_roles())
         m.simulate(orc.params(**kw), n_frames=c["frames"], order=order, batch_off=off)
         normals = m.normals(tris)
-        np.savez_compressed(os.path.join(HERE, name + ".npz"), pos=pos, tets=tets, tris=tris, order=order, batch_off=off,
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), pos=pos, tets=tets, tris=tris, order=order, batch_off=off, roles=sb.tet_roles(),
                             x4=m.x4, v4=m.v4, normals=normals, frames=c["frames"],
                             plan=np.array(sorted(c["plan"].items()), dtype=object), prm=np.array(sorted(kw.items()), dtype=object))
         print(name, pos.shape, tets.shape, "batches", len(off) - 1, "min y", float(m.x4[:, 1].min()))

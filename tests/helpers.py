@@ -17,7 +17,7 @@ def oracle_params(sb: SoftBody, dt=None):
 
 def oracle_for(sb: SoftBody, pos, tets, inv_mass=None, density=1000.0, dtype=np.float32):
     """Oracle model driven by the product's exported Gauss-Seidel order."""
-    m = orc.Model(pos, tets, inv_mass=inv_mass, density=density, dtype=dtype)
+    m = orc.Model(pos, tets, inv_mass=inv_mass, density=density, dtype=dtype, roles=sb.tet_roles())
     order, off = sb.schedule()
     return m, order, off
 

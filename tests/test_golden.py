@@ -33,7 +33,8 @@ def test_oracle_and_planner_reproduce_the_fixture(path):
     sb = SoftBody(z["pos"], z["tets"], z["tris"], host_only=True, **plan, **{ALIAS.get(k, k): v for k, v in prm.items()})
     order, off = sb.schedule()
     assert np.array_equal(order, z["order"]) and np.array_equal(off, z["batch_off"]), "the planner's schedule changed"
-    m = orc.Model(z["pos"], z["tets"])
+    m = orc.Model(z["pos"], z["tets"], roles=z["roles"])
+    assert np.array_equal(sb.tet_roles(), z["roles"]), "the planner's tet roles changed"
     m.simulate(orc.params(**prm), n_frames=int(z["frames"]), order=z["order"], batch_off=z["batch_off"])
     assert bits_equal(m.x4, z["x4"]) and bits_equal(m.v4, z["v4"])
     assert bits_equal(m.normals(z["tris"]), z["normals"])

@@ -24,7 +24,7 @@ def run_pair(pos, tets, tris, n_frames, spheres=None, inv_mass=None, **kw):
     if spheres is not None:
         sb.set_colliders(spheres)
     order, off = sb.schedule()
-    m = orc.Model(pos, tets, inv_mass=inv_mass, density=kw.get("density", 1000.0))
+    m = orc.Model(pos, tets, inv_mass=inv_mass, density=kw.get("density", 1000.0), roles=sb.tet_roles())
     sb.step(frames=n_frames)
     x4, v4 = sb.get_state()
     m.simulate(oracle_params(sb), n_frames=n_frames, order=order, batch_off=off, spheres=spheres, threads=8)
@@ -114,7 +114,7 @@ def test_graph_and_direct_launch_agree_and_params_update():
     assert bits_equal(xa, xb) and bits_equal(va, vb)
     # oracle through the same parameter changes
     order, off = a.schedule()
-    m = orc.Model(pos, tets)
+    m = orc.Model(pos, tets, roles=a.tet_roles())
     m.simulate(orc.params(substeps=10, iterations=10), n_frames=3, order=order, batch_off=off)
     m.simulate(orc.params(substeps=4, iterations=7, damping=1.0), n_frames=3, order=order, batch_off=off)
     m.simulate(orc.params(dt=0.005, substeps=4, iterations=7, damping=1.0), n_frames=2, order=order, batch_off=off)
@@ -152,7 +152,7 @@ def test_energy_and_volume_drift_track_the_oracle():
     pos, tets, tris = meshgen.sample_cube(7, centre_height=0.8, jitter=0.05)
     sb = SoftBody(pos, tets, tris, stiffness=1e5, substeps=5, iterations=4)
     order, off = sb.schedule()
-    m = orc.Model(pos, tets)
+    m = orc.Model(pos, tets, roles=sb.tet_roles())
     p = oracle_params(sb)
     for _ in range(10):
         sb.step(frames=10)
@@ -183,7 +183,7 @@ def test_large_mesh_properties():
     sb.step(frames=2)
     x4, v4 = sb.get_state()
     order, off = sb.schedule()
-    m = orc.Model(pos, tets)
+    m = orc.Model(pos, tets, roles=sb.tet_roles())
     m.simulate(oracle_params(sb), n_frames=2, order=order, batch_off=off, threads=16)
     assert ulp_diff_count(x4, m.x4) == 0
     sb.step(frames=8)

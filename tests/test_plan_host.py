@@ -144,7 +144,8 @@ def test_topology_matches_the_oracles_own_derivation_bitwise():
     for pos, tets, tris in (meshgen.block(7, 6, 5, spacing=0.03), meshgen.sphere(12, spacing=0.05)):
         sb = SoftBody(pos, tets, tris, host_only=True, density=850.0)
         edges, rest_len, rest_vol6, inv_mass = sb.topology()
-        m = orc.Model(pos, tets, density=850.0)
+        m = orc.Model(pos, tets, density=850.0, roles=sb.tet_roles())
+        assert sb.info()["edges_attached"] > 0.8 * len(edges)  # most edges ride with a tet
         assert np.array_equal(edges, m.edges)
         assert np.array_equal(rest_len.view(np.uint32), m.rest_len.view(np.uint32))
         assert np.array_equal(rest_vol6.view(np.uint32), m.rest_vol6.view(np.uint32))
@@ -212,7 +213,7 @@ def test_oracle_runs_the_planners_order(tmp_path):
     pos, tets, tris = meshgen.sample_cube(6, centre_height=0.6)
     sb = SoftBody(pos, tets, tris, host_only=True, tile_cap=100, stiffness=INF)
     order, off = sb.schedule()
-    m = orc.Model(pos, tets)
+    m = orc.Model(pos, tets, roles=sb.tet_roles())
     m.simulate(orc.params(), n_frames=30, order=order, batch_off=off)
     assert np.isfinite(m.x4).all() and m.x4[:, 1].min() >= 0.0
     d = m.diagnostics()

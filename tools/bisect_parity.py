@@ -21,7 +21,7 @@ for name, (gen, kw) in cases.items():
         k.update(kw); k.update(extra)
         sb = SoftBody(pos, tets, tris, **k)
         order, off = sb.schedule()
-        m = orc.Model(pos, tets)
+        m = orc.Model(pos, tets, roles=sb.tet_roles())
         sb.step(frames=1)
         x4, v4 = sb.get_state()
         m.simulate(oracle_params(sb), n_frames=1, order=order, batch_off=off, threads=1)
