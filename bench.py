@@ -201,7 +201,7 @@ def main():
     ap.add_argument("--substeps", type=int, default=10)
     ap.add_argument("--iterations", type=int, default=10)
     ap.add_argument("--fast-math", action="store_true")
-    ap.add_argument("--pdl", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--dag", action="store_true", help="persistent tile-DAG kernel (one launch per substep)")
     ap.add_argument("--tile-cap", type=int, default=0)
     ap.add_argument("--later-tile-cap", type=int, default=0)
@@ -233,7 +233,7 @@ def main():
         clocks.start()  # nvidia-smi takes a moment to come up; samples are windowed by timestamp
     from softbodyunity_b200 import FLAG_FAST_MATH, SoftBody
     pos, tets, tris, name = workload(args, rank, world)
-    flags = (FLAG_FAST_MATH if args.fast_math else 0) | (16 if args.pdl else 0) | (32 if args.dag else 0)
+    flags = (FLAG_FAST_MATH if args.fast_math else 0) | (16 if args.no_pdl else 0) | (32 if args.dag else 0)
     kw = dict(substeps=args.substeps, iterations=args.iterations, flags=flags, tile_cap=args.tile_cap,
               later_tile_cap=args.later_tile_cap, block_threads=args.block_threads, round_width=args.round_width)
     part_mesh = None

@@ -53,9 +53,9 @@ typedef enum sb_status {
                                 (default is IEEE sqrt/div, bit-identical to the CPU oracle) */
 #define SB_FLAG_NO_GRAPH 4   /* launch kernels one by one instead of one CUDA graph per frame */
 #define SB_FLAG_NO_NORMALS 8 /* skip the per-frame normal recompute */
-#define SB_FLAG_PDL 16       /* launch the tile passes with programmatic dependent launch (prologue overlaps the
-                                previous pass's tail; measured neutral at 1 M vertices, so off by default) */
-
+#define SB_FLAG_NO_PDL 16    /* launch the tile passes WITHOUT programmatic dependent launch.  By default each pass releases
+                                its dependents once its rounds are done, so the next pass's prologue (tile tables, first
+                                constraint records) runs under this pass's tail: 8.8 -> 8.5 ms per frame at 1 M vertices */
 #define SB_FLAG_DAG 32       /* run all tile passes of a substep as ONE persistent kernel over the tile dependency graph
                                 (single-GPU meshes planned as balanced shifted tilings; ignored otherwise) */
 

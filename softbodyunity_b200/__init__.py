@@ -5,7 +5,7 @@ kernels + host planner + C ABI), the ctypes binding, the component mirror and th
 synthetic mesh generators used by tests and benches.
 """
 from . import meshgen  # noqa: F401
-from ._abi import (FLAG_FAST_MATH, FLAG_NO_GRAPH, FLAG_NO_GROUND, FLAG_NO_NORMALS, FLAG_PDL,  # noqa: F401
+from ._abi import (FLAG_FAST_MATH, FLAG_NO_GRAPH, FLAG_NO_GROUND, FLAG_NO_NORMALS, FLAG_NO_PDL,  # noqa: F401
                    SbError, SbInfo, SbMeshDesc, SbParams, lib_path, load)
 from .solver import SoftBody, default_params, lumped_inv_mass  # noqa: F401
 

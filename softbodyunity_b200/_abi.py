@@ -11,7 +11,7 @@ from . import build as _build
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 SB_OK, SB_E_ARG, SB_E_CUDA, SB_E_NCCL, SB_E_NAN, SB_E_STATE, SB_E_NOMEM = 0, -1, -2, -3, -4, -5, -6
-FLAG_NO_GROUND, FLAG_FAST_MATH, FLAG_NO_GRAPH, FLAG_NO_NORMALS, FLAG_PDL = 1, 2, 4, 8, 16
+FLAG_NO_GROUND, FLAG_FAST_MATH, FLAG_NO_GRAPH, FLAG_NO_NORMALS, FLAG_NO_PDL, FLAG_DAG = 1, 2, 4, 8, 16, 32
 ABI_VERSION = 2
 
 EXPORTS = [

@@ -6,6 +6,8 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <limits>
@@ -558,7 +560,7 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
     uint32_t busy = 0;
     for (uint32_t t = 0; t < n_tiles; t++) busy += toff[t + 1] > toff[t];
     const double per_tile = busy ? (double)toff[n_tiles] / busy : 0.0;
-    bt = per_tile < 6000 * width ? 64u : per_tile < 24000 * width ? 128u : 256u;
+    bt = per_tile < 1400 * width ? 64u : per_tile < 5600 * width ? 128u : 256u;
   }
   const uint32_t cap_e = 2 * width * bt, cap_t = width * bt;
 
@@ -794,8 +796,8 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
         std::copy(tmp.begin(), tmp.end(), O.ents.begin() + lo);
       }
     }
-    // Rounds.  Record k of a colour goes to thread k % bt, sub-slot k / bt, so that every thread has
-    // one record before any has two, and the octets above are the lanes of one LDS wavefront.
+    // Rounds.  Record k of a colour goes to the slot round_slot() names: packed towards the first warps,
+    // the octets above on the eight lanes of one LDS wavefront.
     const uint32_t round_words = 4 * width * bt;
     O.stream.assign((size_t)ncol * round_words, 0u);
     O.aux.assign((size_t)O.n_tcol * width * bt, std::numeric_limits<float>::quiet_NaN());
@@ -808,7 +810,8 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
         int32_t vs[4];
         const int32_t e = O.ents[coff[c] + k];
         ent_verts(D, e, vs);
-        const uint32_t thr = k % bt, sub = k / bt;
+        uint32_t thr, sub;
+        round_slot(k, tet ? width : 2 * width, thr, sub);
         if (!tet) {
           uint32_t *r = rw + (size_t)thr * 4 * width + 2 * sub;
           r[0] = local(vs[0]) | (local(vs[1]) << 16);
@@ -1106,6 +1109,10 @@ void Plan::export_schedule(std::vector<int32_t> &order, std::vector<int64_t> &ba
 
 std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   auto t0 = std::chrono::steady_clock::now();
+  const bool timing = getenv("SB_PLAN_TIMING") != nullptr;
+  auto lap = [&](const char *what) {
+    if (timing) fprintf(stderr, "[plan] %-28s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  };
   if (!in.pos_xyz || in.n_verts == 0) return "no vertices";
   if (in.n_tets && !in.tets) return "tets is NULL";
   if (in.n_tris && !in.surf_tris) return "surf_tris is NULL";
@@ -1154,13 +1161,18 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     if (!(in.density > 0)) return "density must be > 0 when inv_mass is NULL";
     lumped_inv_mass(P, in.density);
   }
+  lap("edges, masses");
   attach_edges(P, opt.compounds > 0 || (opt.compounds < 0 && !in.edges && !in.n_ghost));
+  lap("attach edges");
   rest_values(P, threads);
   err = build_surface(P);
+  lap("rest values, surface");
   if (!err.empty()) return err;
 
   // ---- tiling ---------------------------------------------------------------
-  uint32_t cap = opt.tile_cap > 0 ? (uint32_t)opt.tile_cap : 1024u;
+  // default tile: 1024 vertices; a mesh big enough to fill every SM with several of them gets boxes of up to
+  // 1728 (four warps per tile at the same rounds per tile: more warps in flight per SM)
+  uint32_t cap = opt.tile_cap > 0 ? (uint32_t)opt.tile_cap : (P.V >= 300000u ? 1728u : 1024u);
   cap = std::min(cap, 65536u);
   P.tile_cap = cap;
   const uint32_t bt_opt = opt.block_threads > 0 ? (uint32_t)opt.block_threads : 0u;
@@ -1215,6 +1227,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     std::iota(P.perm.begin(), P.perm.end(), 0u);
     P.inv = P.perm;
   }
+  lap("tilings, numbering");
   DevTopo D;
   D.edges.resize(2 * (size_t)P.E);
   D.tets.resize(4 * (size_t)P.T);
@@ -1413,6 +1426,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   }
   err = plan_group(cons0, 0);
   if (!err.empty()) return err;
+  lap("passes (deal, colour, order)");
   P.dag_ok = n_tilings >= 2 && !P.n_ghost && P.passes.size() == (size_t)n_tilings && P.gbatches.empty();
   if (P.n_ghost) {
     err = plan_group(cons1, 1);

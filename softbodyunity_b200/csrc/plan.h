@@ -19,6 +19,14 @@ struct U4 { uint32_t x, y, z, w; };
 struct I2 { int32_t x, y; };
 struct I4 { int32_t x, y, z, w; };
 
+// Where record k of a colour sits in its round: records fill the CTA's warps from the front (so that the
+// warps behind the last record hold nothing but padding and skip the round), eight consecutive records
+// on eight consecutive lanes (the octets the bank-aware ordering arranges), sub-records interleaved by octet.
+inline void round_slot(uint32_t k, uint32_t subs, uint32_t &thr, uint32_t &sub) {
+  thr = 8u * (k / (8u * subs)) + (k & 7u);
+  sub = (k >> 3) % subs;
+}
+
 struct PlanOptions {
   int tile_cap = 0;         // max vertices per tile (0 = auto)
   int later_cap = 0;        // max vertices per tile in passes >= 1 (0 = auto)
@@ -46,7 +54,8 @@ struct PlanOptions {
 // (local 16-bit vertex ids; an all-zero record is padding: a == b / p0 == p1 is never projected).
 // Thread `tid` reads its words of round r at stream[off + (r * bt + tid) * width ...], a fully
 // coalesced access that it prefetches several rounds ahead; the CTA synchronises after every
-// round.  The colouring is capacity-limited (first free colour that is not full), so a tile
+// round.  Records are packed towards the first warps (round_slot): a warp that holds only padding
+// skips the round's work.  The colouring is capacity-limited (first free colour that is not full), so a tile
 // needs max(valence, ceil(n / capacity)) rounds and every round but the last is full.
 // rounds[t] = { offset / 16 of tile t's first round in `stream`, edge rounds, tet rounds, offset of its first
 //               tet round in `aux` (floats) }.

@@ -317,7 +317,7 @@ struct sb_solver {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (prm.flags & SB_FLAG_PDL) ? 1 : 0;
+    cfg.numAttrs = (prm.flags & SB_FLAG_NO_PDL) ? 0 : 1;
     if constexpr (!FAST) {
       if (pb.dev.trace) {
         CK(cudaLaunchKernelEx(&cfg, k_tile_rounds<FAST, BT, W16, true>, pb.dev, x.p, (const DevParams *)dprm.p));
@@ -1067,7 +1067,8 @@ int sb_debug_verify_streams(sb_handle h, uint64_t *n_bad, uint64_t *wavefronts, 
         for (uint32_t thr = 0; thr < bt; thr++)
           for (uint32_t sub = 0; sub < (tet ? W : 2 * W); sub++) {
             const uint32_t *r = rw + (size_t)thr * 4 * W + (tet ? 4 : 2) * sub;
-            const uint32_t k = sub * bt + thr;
+            const uint32_t subs = tet ? W : 2 * W;
+            const uint32_t k = 8u * subs * (thr / 8u) + 8u * sub + (thr & 7u); // inverse of round_slot
             const bool pad = (r[0] & 0xffffu) == (r[0] >> 16);
             if (k >= cnt) { bad += !pad; continue; }
             if (pad) { bad++; continue; }

@@ -41,7 +41,7 @@ CASES = {
     "bt128": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=700, block_threads=128)),
     "bt32": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=300, block_threads=32)),
     "bt256": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=700, block_threads=256)),
-    "pdl": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=300, flags=16)),
+    "no_pdl": (lambda: meshgen.block(12, 12, 10, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=300, flags=16)),
     "dag": (lambda: meshgen.block(14, 12, 11, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=256, flags=32)),
     "dag_bt32": (lambda: meshgen.block(14, 12, 11, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=128, flags=32, block_threads=32)),
     "dag_wide": (lambda: meshgen.block(16, 16, 16, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=512, flags=32, round_width=2, block_threads=128)),
