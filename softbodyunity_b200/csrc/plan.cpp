@@ -526,7 +526,7 @@ inline int ent_verts(const DevTopo &D, int32_t ent, int32_t *vs) {
 // `in` whose vertices all lie in one tile are consumed; the rest go to `out`.
 std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_t> &part, uint32_t n_tiles,
                        const std::vector<uint32_t> *contig_off, const std::vector<int32_t> &in,
-                       std::vector<int32_t> &out, TilePass &TP, int threads, uint32_t bt_opt, uint32_t width) {
+                       std::vector<int32_t> &out, TilePass &TP, int threads, uint32_t bt_opt, uint32_t width, int n_sm) {
   // 1. classify and bucket by tile (stable)
   std::vector<uint64_t> toff((size_t)n_tiles + 1, 0);
   std::vector<int32_t> owner(in.size());
@@ -556,11 +556,10 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
   // CTA width of this pass: as given, else by how many constraints a tile holds (a round should be
   // full, and a tile should not need many more rounds than its valence asks for)
   uint32_t bt = bt_opt;
-  if (!bt) {
-    uint32_t busy = 0;
-    for (uint32_t t = 0; t < n_tiles; t++) busy += toff[t + 1] > toff[t];
-    const double per_tile = busy ? (double)toff[n_tiles] / busy : 0.0;
-    bt = per_tile < 1400 * width ? 64u : per_tile < 5600 * width ? 128u : 256u;
+  if (!bt) { // by the fullest tile: partial tiles at the rim of a tiling must not talk the pass into narrow CTAs
+    uint64_t per_tile = 0;
+    for (uint32_t t = 0; t < n_tiles; t++) per_tile = std::max<uint64_t>(per_tile, toff[t + 1] - toff[t]);
+    bt = per_tile < 1600 * width ? 64u : per_tile < 6400 * width ? 128u : 256u;
   }
   const uint32_t cap_e = 2 * width * bt, cap_t = width * bt;
 
@@ -894,6 +893,20 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
     O = TileOut();
   }
   if (TP.contiguous) TP.vert_off[0] = (*contig_off)[0];
+  // Launch order.  All CTAs of a pass are resident at once and the hardware deals them to the SMs
+  // breadth-first, so CTA j lands on SM j mod n_sm: sort the tiles by work (rounds, then constraints),
+  // heaviest first, and reverse every other layer of n_sm so that the per-SM sums even out.
+  {
+    TP.launch_order.resize(n_tiles);
+    std::iota(TP.launch_order.begin(), TP.launch_order.end(), 0u);
+    auto work = [&](uint32_t t) {
+      return ((uint64_t)(TP.rounds[t].y + TP.rounds[t].z) << 32) | (uint32_t)(TP.ent_off[t + 1] - TP.ent_off[t]);
+    };
+    std::stable_sort(TP.launch_order.begin(), TP.launch_order.end(), [&](uint32_t a, uint32_t b) { return work(a) > work(b); });
+    const uint32_t layer = (uint32_t)std::max(1, n_sm);
+    for (uint32_t lo = layer; lo < n_tiles; lo += 2 * layer)
+      std::reverse(TP.launch_order.begin() + lo, TP.launch_order.begin() + std::min(n_tiles, lo + layer));
+  }
   return "";
 }
 
@@ -1312,6 +1325,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
       for (int k = 0; k < n; k++)
         if (dg[vs[k]] < 255) dg[vs[k]]++;
     }
+    lap("  deal to tilings");
     // keep ascending constraint id inside every tiling (the tile builder relies on a stable order)
     for (size_t i = 0; i < mask.size(); i++) {
       if (chosen[i] < 0) work.push_back(cons[i]);
@@ -1322,12 +1336,14 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     mask.shrink_to_fit();
     for (int s = 0; s < n_tilings; s++) {
       TilePass TP;
+      // every tiling runs with the CTA width chosen for the unshifted one (whole boxes only)
       err = build_pass(P, D, dpart[s], tilings[s].n_tiles, s == 0 ? &tile_off : nullptr, assigned[s], next, TP, threads,
-                       bt_opt, width);
+                       s == 0 ? bt_opt : P.passes[P.passes.size() - (size_t)s].bt, width, opt.n_sm);
       if (!err.empty()) return err;
       work.insert(work.end(), next.begin(), next.end()); // empty by construction
       P.passes.push_back(std::move(TP));
       assigned[s] = std::vector<int32_t>();
+      lap("  tile pass built");
     }
     // dependencies between consecutive tilings (cyclic): tile t of tiling s must wait for every tile of
     // tiling s-1 that shares a vertex with it, by full box membership so that chains through vertices a
@@ -1348,6 +1364,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
         for (size_t k = 0; k < pairs.size(); k++) TP.dep_list[k] = (uint32_t)pairs[k]; // sorted by (t, q): in place
       }
     }
+    lap("  tile dependencies");
     part = dpart[0];
     n_tiles = tilings[0].n_tiles;
     have_parts = true;
@@ -1387,7 +1404,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     for (int k = 0; k < levels && !work.empty(); k++) {
       TilePass TP;
       const bool contig = first_level && k == 0;
-      err = build_pass(P, D, part, n_tiles, contig ? &tile_off : nullptr, work, next, TP, threads, bt_opt, width);
+      err = build_pass(P, D, part, n_tiles, contig ? &tile_off : nullptr, work, next, TP, threads, bt_opt, width, opt.n_sm);
       if (!err.empty()) return err;
       size_t consumed = work.size() - next.size();
       work.swap(next);

@@ -66,6 +66,8 @@ struct TilePass {
   std::vector<uint32_t> run_off;    // n_tiles + 1 offsets into runs (non-contiguous passes)
   std::vector<U2> runs;             // per tile: {first device id, first local id} per run, then {0, n_verts}
   std::vector<U4> rounds;           // n_tiles
+  std::vector<uint32_t> launch_order; // CTA j of the pass runs tile launch_order[j]: heaviest tiles first, dealt to
+                                      // the SMs in a snake so that every SM's single wave of CTAs weighs the same
   std::vector<uint32_t> stream;     // 32-bit words; every round starts 16-byte aligned
   std::vector<float> aux;           // per tet round: width * bt floats (L23 of the compound, NaN if none)
   std::vector<uint8_t> col_has01, col_has23; // per tet colour index: some tile attaches a (0,1) / (2,3) edge there

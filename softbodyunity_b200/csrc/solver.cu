@@ -60,7 +60,7 @@ struct DevBuf {
 };
 
 struct PassBufs {
-  DevBuf<uint32_t> vert_off, tile_verts, stream, run_off;
+  DevBuf<uint32_t> vert_off, tile_verts, stream, run_off, order;
   DevBuf<uint2> runs;
   DevBuf<uint4> rounds;
   DevBuf<float> aux;
@@ -232,7 +232,8 @@ struct sb_solver {
         pb.run_off.upload(tp.run_off, &dev_bytes);
         pb.runs.upload(tp.runs, &dev_bytes);
       }
-      pb.dev = PassDev{pb.vert_off.p, tp.contiguous ? nullptr : pb.tile_verts.p, use_runs ? pb.run_off.p : nullptr,
+      pb.order.upload(tp.launch_order, &dev_bytes);
+      pb.dev = PassDev{pb.order.p, pb.vert_off.p, tp.contiguous ? nullptr : pb.tile_verts.p, use_runs ? pb.run_off.p : nullptr,
                        use_runs ? pb.runs.p : nullptr, pb.rounds.p, reinterpret_cast<const uint4 *>(pb.stream.p),
                        pb.aux.p, tp.n_tiles(), pos_bytes, nullptr};
       pb.bt = tp.bt;
@@ -381,6 +382,7 @@ struct sb_solver {
       dag_dep_off[k].upload(plan.passes[k].dep_off, &dev_bytes);
       dag_dep_list[k].upload(plan.passes[k].dep_list, &dev_bytes);
       dag.pass[k] = passes[k].dev;
+      dag.pass[k].order = nullptr; // tasks are numbered by tile: the dependency lists speak of tiles
       dag.pass[k].pos_bytes = pos_bytes; // one barrier address for the whole run
       dag.dep_off[k] = dag_dep_off[k].p;
       dag.dep_list[k] = dag_dep_list[k].p;
