@@ -382,7 +382,10 @@ struct sb_solver {
       dag_dep_off[k].upload(plan.passes[k].dep_off, &dev_bytes);
       dag_dep_list[k].upload(plan.passes[k].dep_list, &dev_bytes);
       dag.pass[k] = passes[k].dev;
-      dag.pass[k].order = nullptr; // tasks are numbered by tile: the dependency lists speak of tiles
+      // tickets walk a pass in tile order (spatial), not in the balanced launch order: a tile's dependencies
+      // then finish at about the same point of the previous pass as the tile itself starts in this one
+      // (measured: heaviest-first tickets turn the end of every pass into a global barrier, 9.3 -> 10.8 ms)
+      dag.pass[k].order = nullptr;
       dag.pass[k].pos_bytes = pos_bytes; // one barrier address for the whole run
       dag.dep_off[k] = dag_dep_off[k].p;
       dag.dep_list[k] = dag_dep_list[k].p;

@@ -1,6 +1,6 @@
 #!/bin/bash
-# Round artefacts for profiles/: bench line, ncu launch list of the same command, one ncu --set full of the tile pass.
-# usage (on the GPU box): tools/profile_round.sh <round-tag>
+# Round artefacts for profiles/: bench lines, ncu launch list of the same command, one ncu --set full of the tile pass.
+# usage (on the GPU box): tools/profile_round.sh <round-tag>        (then copy gpurun_out/* summaries into profiles/)
 set -u
 tag=${1:-r01}
 out=gpurun_out
@@ -11,7 +11,18 @@ python bench.py --impl reference --steps 5 --warmup 3 > $out/bench_${tag}_refere
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/plain_${tag}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1400 -c 900 --csv --log-file $out/launches_${tag}.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/ncu_launch_${tag}.log 2>&1
+python tools/launch_summary.py $out/launches_${tag}.csv $out/${tag}_launches.md > /dev/null
 python tools/profile_step.py > $out/plain2_${tag}.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_tile_rounds -s 8 -c 4 -o $out/prof_${tag} \
     python tools/profile_step.py > $out/ncu_full_${tag}.log 2>&1
 tail -2 $out/ncu_full_${tag}.log
+python tools/ncu_summary.py $out/prof_${tag}.ncu-rep $out/${tag}_ncu_tile_rounds.md > /dev/null
+python tools/traffic_json.py $out/prof_${tag}.ncu-rep $out/${tag}_traffic.json "${tag}"
+for f in bench_${tag}.json bench_${tag}_fast.json bench_${tag}_reference.json; do python - $out/$f <<'PY'
+import json, sys
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print(sys.argv[1], "value %.4g" % d["value"], d.get("unit"), "ms/step %.3f" % d["ms_per_step"], "e2e %.4g" % (d.get("e2e") or {}).get("value", 0),
+      "roofline", {k: (round(v, 4) if isinstance(v, float) else v) for k, v in (d.get("roofline") or {}).items() if k in ("frac", "achieved", "step_frac", "launch_ms", "share_of_step")},
+      "cpu", (d.get("cpu_baseline") or {}).get("value"))
+PY
+done
