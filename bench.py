@@ -344,7 +344,9 @@ def main():
         # dominant kernel = the tile pass (k_tile_rounds; n_pass launches per sweep).  Average launch duration
         # measured live: the device-timed step minus the per-vertex kernels, divided by the pass launches in it.
         n_pass = info["n_tile_passes"]
-        launch_bytes = (12.0 * E + 20.0 * T) / n_pass + 32.0 * V
+        # algorithmic bytes of one sweep (12 E + 20 T + 32 V), shared out over its n_pass launches;
+        # the positions a pass re-reads from L2 are this design's overhead, not algorithmic traffic
+        launch_bytes = (12.0 * E + 20.0 * T + 32.0 * V) / n_pass
         t_pred, t_fin, t_nrm = sb.time_kernel(0, 30), sb.time_kernel(1, 30), sb.time_kernel(2, 30)
         n_launch = args.substeps * args.iterations * n_pass
         step_ms = ms / args.steps

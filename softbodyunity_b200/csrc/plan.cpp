@@ -1209,6 +1209,12 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     std::vector<uint32_t> cs(P.V, 0);
     uint32_t biggest = 0;
     for (uint32_t v = 0; v < P.V; v++) biggest = std::max(biggest, ++cs[uf.find(v)]);
+    // bodies that fit one tile are kept whole (one pass, nothing cut): raise the tile size to the largest
+    // body when that still leaves shared memory for several tiles per SM
+    if (biggest > cap && biggest <= 3072 && opt.tile_cap <= 0) {
+      cap = biggest;
+      P.tile_cap = cap;
+    }
     n_tilings = biggest > cap ? 4 : 1;
   }
   n_tilings = std::min(n_tilings, 8);
