@@ -101,7 +101,7 @@ typedef struct sb_mesh_desc {
                                2 * width * block_threads edges or width * block_threads tets; 0 = auto (1) */
   int32_t attach_edges;     /* 0 = auto, 1 = on, 2 = off: project each edge right after a tet that contains it, from the
                                registers holding the tet's vertices (the tet's vertex ROLES are then an even permutation
-                               of the caller's order, see sb_get_tet_roles).  Auto: on unless n_ghost_verts / edges are set */
+                               of the caller's order, see sb_get_tet_roles).  Auto: on */
   int32_t tilings;          /* 0 = auto; 1 = hierarchical tile passes only; N >= 2 = N balanced shifted tilings */
   int32_t n_ghost_verts;    /* partitioned meshes: the LAST n_ghost_verts vertices are ghost copies of vertices
                                another rank owns (never integrated here; constraints among ghosts are dropped) */

@@ -214,11 +214,31 @@ void attach_edges(Plan &P, bool enable) {
     for (uint32_t e = 0; e < E; e++) by_inc[cnt[ioff[e + 1] - ioff[e]]++] = e;
   }
   std::vector<int8_t> pair01(T, -1), pair23(T, -1);
+  // partitioned meshes: an edge rides only with a tet of its own constraint group (both touch a ghost vertex
+  // or neither does), and edges / tets among ghosts only belong to another rank
+  const uint32_t first_ghost = P.V - P.n_ghost;
+  auto n_ghosts = [&](const int32_t *v, int n) {
+    int g = 0;
+    for (int k = 0; k < n; k++) g += (uint32_t)v[k] >= first_ghost;
+    return g;
+  };
+  std::vector<uint8_t> tet_cut(P.n_ghost ? T : 0);
+  for (uint32_t t = 0; t < (uint32_t)tet_cut.size(); t++) {
+    const int g = n_ghosts(&P.tets[4 * (size_t)t], 4);
+    tet_cut[t] = g == 0 ? 0 : g == 4 ? 2 : 1;
+  }
   for (uint32_t oi = 0; oi < E; oi++) {
     const uint32_t e = by_inc[oi];
+    uint8_t e_cut = 0;
+    if (P.n_ghost) {
+      const int g = n_ghosts(&P.edges[2 * (size_t)e], 2);
+      if (g == 2) continue;
+      e_cut = (uint8_t)g;
+    }
+    auto same_group = [&](uint32_t t) { return !P.n_ghost || tet_cut[t] == e_cut; };
     int64_t pick = -1;
     for (uint32_t k = ioff[e]; k < ioff[e + 1] && pick < 0; k++)
-      if (pair01[inc[k] >> 3] < 0) pick = inc[k];
+      if (pair01[inc[k] >> 3] < 0 && same_group(inc[k] >> 3)) pick = inc[k];
     if (pick >= 0) {
       pair01[pick >> 3] = (int8_t)(pick & 7);
       P.tet_e01[pick >> 3] = (int32_t)e;
@@ -227,7 +247,7 @@ void attach_edges(Plan &P, bool enable) {
     }
     for (uint32_t k = ioff[e]; k < ioff[e + 1] && pick < 0; k++) {
       const uint32_t t = inc[k] >> 3, pk = inc[k] & 7;
-      if (pair23[t] < 0 && pair01[t] == (int8_t)(5 - pk)) pick = inc[k]; // pair 5 - k is the opposite edge
+      if (pair23[t] < 0 && pair01[t] == (int8_t)(5 - pk) && same_group(t)) pick = inc[k]; // pair 5 - k is the opposite edge
     }
     if (pick >= 0) {
       pair23[pick >> 3] = (int8_t)(pick & 7);
@@ -1175,7 +1195,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     lumped_inv_mass(P, in.density);
   }
   lap("edges, masses");
-  attach_edges(P, opt.compounds > 0 || (opt.compounds < 0 && !in.edges && !in.n_ghost));
+  attach_edges(P, opt.compounds != 0);
   lap("attach edges");
   rest_values(P, threads);
   err = build_surface(P);
@@ -1310,7 +1330,10 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
       const int n = ent_verts(D, ent, vs);
       int best = -1;
       uint32_t best_deg = 0, best_sum = 0;
-      for (int s = 0; s < n_tilings; s++) {
+      // cut constraints (group 1) are few and their tiles nearly empty: there the cost is the number of
+      // passes, not the rounds per tile, so they all go to the first tiling that can take them
+      if (group == 1 && mask[i]) best = __builtin_ctz(mask[i]);
+      for (int s = 0; s < n_tilings && group != 1; s++) {
         if (!(mask[i] >> s & 1)) continue;
         const std::vector<uint8_t> &dg = deg[2 * (size_t)s + kind];
         uint32_t md = 0, sd = 0;

@@ -67,6 +67,7 @@ struct PassBufs {
   PassDev dev{};
   uint32_t smem = 0;
   uint32_t bt = 64, width = 1; // threads per CTA and record words per thread per round of this pass
+  bool empty = false;          // no constraint in the pass: never launched
 };
 
 static const int kDiagBlocks = 592;
@@ -238,6 +239,7 @@ struct sb_solver {
                        pb.aux.p, tp.n_tiles(), pos_bytes, nullptr};
       pb.bt = tp.bt;
       pb.width = tp.width;
+      pb.empty = tp.n_edges + tp.n_tets == 0;
       if (k == 0) block_threads = tp.bt;
     }
     uint32_t max_smem = 0;
@@ -338,7 +340,7 @@ struct sb_solver {
   }
   template <bool FAST>
   void launch_tile(const PassBufs &pb, cudaStream_t s) {
-    if (!pb.dev.n_tiles) return;
+    if (!pb.dev.n_tiles || pb.empty) return;
     if (pb.width == 2) launch_tile_w<FAST, 2>(pb, s);
     else launch_tile_w<FAST, 1>(pb, s);
   }
@@ -475,7 +477,7 @@ struct sb_solver {
 
   uint32_t launches_per_frame() const {
     uint32_t per_iter = 0;
-    for (auto &pb : passes) per_iter += pb.dev.n_tiles ? 1 : 0;
+    for (auto &pb : passes) per_iter += pb.dev.n_tiles && !pb.empty ? 1 : 0;
     for (auto &b : plan.gbatches) per_iter += b.cnt ? 1 : 0;
     for (auto &kv : links) {
       auto hl = halo.find(kv.first);

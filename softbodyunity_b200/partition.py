@@ -332,6 +332,15 @@ def combined_order(meshes: List[RankMesh], bodies_or_plans, global_edges):
     return order, np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
 
 
+def combined_roles(meshes: List[RankMesh], bodies_or_plans, global_tets):
+    """The vertex roles of every GLOBAL tet as the rank that owns it projects it (sb_get_tet_roles, mapped to
+    global vertex ids): what a CPU replay of combined_order() needs to be bit-identical."""
+    roles = np.ascontiguousarray(global_tets, np.int32).reshape(-1, 4).copy()
+    for m, sb in zip(meshes, bodies_or_plans):
+        roles[m.tet_gid] = m.gids[sb.tet_roles()]
+    return roles
+
+
 def gather_global(meshes: List[RankMesh], states):
     """Assemble a global (V, 4) array from per-rank (own + ghost) arrays: owners win."""
     V = int(max(m.gids.max() for m in meshes)) + 1

@@ -8,7 +8,7 @@ import pytest
 from helpers import bits_equal, oracle_params
 from oracle import xpbd_oracle as orc
 from softbodyunity_b200 import SoftBody, lumped_inv_mass, meshgen
-from softbodyunity_b200.partition import (LocalComm, LocalPeerComm, PartitionedBody, combined_order, gather_global, slab_partition,
+from softbodyunity_b200.partition import (LocalComm, LocalPeerComm, PartitionedBody, combined_order, combined_roles, gather_global, slab_partition,
                                           step_partitioned)
 
 
@@ -35,7 +35,7 @@ def test_partition_and_combined_order_are_valid(n_ranks):
         if m.rank + 1 < n_ranks:  # my ghosts are exactly the next rank's lower-boundary vertices
             assert np.array_equal(m.ghost, meshes[m.rank + 1].lower)
     plans = [SoftBody(m.pos, m.tets, m.tris, inv_mass=m.inv_mass, edges=m.edges, n_ghost_verts=m.n_ghost, host_only=True, tile_cap=256) for m in meshes]
-    ref = orc.Model(pos, tets)
+    ref = orc.Model(pos, tets, roles=combined_roles(meshes, plans, tets))
     order, off = combined_order(meshes, plans, ref.edges)
     ids, kind = order & 0x7fffffff, order < 0
     assert np.array_equal(np.sort(ids[~kind]), np.arange(ref.E)) and np.array_equal(np.sort(ids[kind]), np.arange(ref.T))
@@ -79,7 +79,7 @@ def test_virtual_ranks_match_the_oracle_bitwise(n_ranks, peer):
     states = [b.sb.get_state() for b in bodies]
     x4 = gather_global(meshes, [s[0] for s in states])
     v4 = gather_global(meshes, [s[1] for s in states])
-    ref = orc.Model(pos, tets)
+    ref = orc.Model(pos, tets, roles=combined_roles(meshes, [b.sb for b in bodies], tets))
     order, off = combined_order(meshes, [b.sb for b in bodies], ref.edges)
     ref.simulate(oracle_params(bodies[0].sb), n_frames=8, order=order, batch_off=off, threads=8)
     assert ref.x4[:, 1].min() == 0.0
@@ -95,7 +95,7 @@ def test_virtual_ranks_match_the_oracle_bitwise(n_ranks, peer):
 def test_partitioned_equals_single_handle_phased_run():
     # one rank, no ghosts: the phased API is the same sequence as sb_step
     pos, tets, tris = meshgen.block(9, 9, 8, spacing=0.05, origin=(0, 0.02, 0))
-    a = SoftBody(pos, tets, tris, tile_cap=300, attach_edges=2)  # a partition passes explicit edges: nothing attached
+    a = SoftBody(pos, tets, tris, tile_cap=300)
     a.step(frames=4)
     (m,) = slab_partition(pos, tets, tris, 1)
     b = PartitionedBody(m, tile_cap=300)

@@ -218,3 +218,46 @@ def test_oracle_runs_the_planners_order(tmp_path):
     assert np.isfinite(m.x4).all() and m.x4[:, 1].min() >= 0.0
     d = m.diagnostics()
     assert abs(d[2] - 1.0) < 0.02  # volume of the unit cube survives the drop
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(tile_cap=128), dict(tile_cap=300, block_threads=32, round_width=2),
+                                dict(attach_edges=2), dict(max_tile_passes=0)])
+def test_device_streams_decode_to_the_exported_schedule(kw):
+    # the constraint streams the kernel reads (rounds, records, aux lengths) against the schedule bookkeeping
+    pos, tets, tris = meshgen.block(11, 10, 9, spacing=0.1, jitter=0.1, seed=3)
+    sb = SoftBody(pos, tets, tris, host_only=True, **kw)
+    assert sb.verify_streams() == 0
+    wf, wf_ideal = sb.smem_model
+    assert wf >= wf_ideal
+
+
+def test_attached_edges_and_tet_roles():
+    pos, tets, tris = meshgen.block(9, 8, 7, spacing=0.1, jitter=0.1, seed=5)
+    sb = SoftBody(pos, tets, tris, host_only=True, tile_cap=200)
+    roles = sb.tet_roles()
+    e01, e23 = sb.attached_edges()
+    edges = sb.topology()[0]
+    # a permutation of every tet, and an even one: the signed volume keeps its sign
+    assert np.array_equal(np.sort(roles, 1), np.sort(tets, 1))
+    def det(q):
+        p = pos[q].astype(np.float64)
+        return np.einsum("ij,ij->i", p[:, 1] - p[:, 0], np.cross(p[:, 2] - p[:, 0], p[:, 3] - p[:, 0]))
+    assert (np.sign(det(roles)) == np.sign(det(tets))).all()
+    # attached edges join roles (0,1) and (2,3); no edge is attached twice
+    has01, has23 = e01 >= 0, e23 >= 0
+    assert np.array_equal(np.sort(roles[has01][:, :2], 1), edges[e01[has01]])
+    assert np.array_equal(np.sort(roles[has23][:, 2:], 1), edges[e23[has23]])
+    att = np.concatenate([e01[has01], e23[has23]])
+    assert len(np.unique(att)) == len(att) == sb.info()["edges_attached"]
+    assert (~has01 & has23).sum() == 0  # the (2,3) slot is only used after the (0,1) slot
+    # switched off: identity roles, nothing attached
+    off = SoftBody(pos, tets, tris, host_only=True, tile_cap=200, attach_edges=2)
+    assert np.array_equal(off.tet_roles(), tets) and off.info()["edges_attached"] == 0
+
+
+def test_small_bodies_are_kept_whole_by_default():
+    pos, tets, tris = meshgen.bodies(6, dims=(13, 13, 12), spacing=0.02)  # 2028 vertices each: over the 1024 default
+    sb = SoftBody(pos, tets, tris, host_only=True)
+    i = sb.info()
+    assert i["n_tile_passes"] == 1 and i["tiles_in_pass"][0] == 6 and i["constraints_global"] == 0
+    assert i["tile_cap"] == 2028 and i["block_threads"] == 256

@@ -19,7 +19,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 from softbodyunity_b200 import SoftBody, meshgen
-from softbodyunity_b200.partition import FrameRunner, PartitionedBody, TorchComm, combined_order, connect_peers, gather_global, slab_partition
+from softbodyunity_b200.partition import FrameRunner, PartitionedBody, TorchComm, combined_order, combined_roles, connect_peers, gather_global, slab_partition
 
 pos, tets, tris = meshgen.block(*a.dims, spacing=0.02, origin=(0.0, 0.004, 0.0), seed=5)
 meshes = slab_partition(pos, tets, tris, world)
@@ -58,7 +58,7 @@ if rank == 0:
         for m, (xo, vo) in zip(meshes, xs):
             X[m.own] = xo; U[m.own] = vo
         plans = [SoftBody(m.pos, m.tets, m.tris if len(m.tris) else None, inv_mass=m.inv_mass, edges=m.edges, n_ghost_verts=m.n_ghost, host_only=True) for m in meshes]
-        ref = orc.Model(pos, tets)
+        ref = orc.Model(pos, tets, roles=combined_roles(meshes, plans, tets))
         order, off = combined_order(meshes, plans, ref.edges)
         p = body.sb.params
         ref.simulate(orc.params(dt=p.dt, substeps=p.substeps, iterations=p.iterations), n_frames=a.frames + pre, order=order, batch_off=off, threads=os.cpu_count())
