@@ -230,6 +230,7 @@ int sb_time_kernel(sb_handle h, int32_t which, int32_t reps, float *avg_ms);
 #define SB_OP_EXCHANGE 4 /* arg: 0 = exchange A (ghosts refreshed), 1 = exchange B (ghost values returned) */
 #define SB_OP_HALO_SEND 5 /* arg: list id; the two halves of an exchange, for several ranks driven from one stream */
 #define SB_OP_HALO_RECV 6
+#define SB_OP_PASS 7 /* arg: tile pass index (one launch; for drivers that interleave several handles on one stream) */
 int sb_set_stream(sb_handle h, void *stream);
 int sb_prepare(sb_handle h, float dt); /* pushes parameters for this dt; synchronises */
 int sb_enqueue(sb_handle h, int32_t op, int32_t arg);
@@ -243,6 +244,23 @@ int sb_halo_error(sb_handle h, int32_t *out);
 int sb_ipc_export(void *device_ptr, unsigned char *handle64);
 int sb_ipc_open(int32_t device, const unsigned char *handle64, void **ptr_out);
 int sb_lumped_inv_mass(const float *pos_xyz, uint32_t n_verts, const int32_t *tets, uint32_t n_tets, float density, float *out);
+
+/*
+ * ONE mesh over several GPUs with no ghosts and no exchange kernels: one address space over NVLink peer memory
+ * (DESIGN.md section 7).  Every rank creates the SAME handle (whole mesh, same options) on its own GPU, then:
+ *   sb_dist_setup    picks this rank's slab of the device numbering and its share of the tiles of every pass, and
+ *                    returns the device addresses of its position array and control block (export them with
+ *                    sb_ipc_export, or pass them directly between handles of one process);
+ *   sb_dist_connect  (once per peer) gives the peer's two addresses; when all peers are connected the handle is live.
+ * sb_step then runs this rank's tiles; a tile reads and writes each of its vertex runs in the memory of the rank that
+ * owns the run, and kernels of neighbouring ranks order themselves through an epoch word.  All ranks must issue the
+ * same sequence of steps.  Positions / state read back from a rank are valid for the vertices sb_dist_owned marks.
+ * Surface normals are not computed in this mode.
+ */
+int sb_dist_setup(sb_handle h, int32_t rank, int32_t n_ranks, void **x_base_out, void **ctl_base_out);
+int sb_dist_connect(sb_handle h, int32_t peer, void *peer_x, void *peer_ctl);
+int sb_dist_owned(sb_handle h, uint8_t *owned_V, uint32_t *tiles_per_pass8); /* either pointer may be NULL */
+int sb_dist_error(sb_handle h, int32_t *out); /* 1 if a wait for a peer ever timed out (results invalid) */
 
 /* Debug aid: timestamps of one run of tile pass `pass` (see solver.cu); out holds 64 * 80 words. */
 int sb_debug_trace_pass(sb_handle h, uint32_t pass, unsigned long long *out, uint32_t n_words);

@@ -17,6 +17,7 @@
 
 #include "../../include/softbody_b200.h"
 #include "kernels.cuh"
+#include <algorithm>
 #include "plan.h"
 
 namespace sb {
@@ -66,6 +67,7 @@ struct PassBufs {
   DevBuf<float> aux;
   PassDev dev{};
   uint32_t smem = 0;
+  uint32_t grid = 0;           // CTAs launched (tiles of the pass; this rank's share of them when distributed)
   uint32_t bt = 64, width = 1; // threads per CTA and record words per thread per round of this pass
   bool empty = false;          // no constraint in the pass: never launched
 };
@@ -111,6 +113,12 @@ struct sb_solver {
   DagDev dag{};
   bool dag_ready = false;
   uint32_t dag_smem = 0, dag_grid = 0, dag_bt = 64, dag_width = 1;
+  // one mesh over several GPUs through peer memory (sb_dist_setup / sb_dist_connect)
+  DistDev dist{};
+  DevBuf<DistDev> dist_dev;
+  DevBuf<uint32_t> dist_ctl;
+  bool dist_on = false;
+  uint32_t dist_connected = 0; // bit p: peer p connected
   DevBuf<int2> g_edges;
   DevBuf<float> g_elen;
   DevBuf<int4> g_tets;
@@ -237,6 +245,7 @@ struct sb_solver {
       pb.dev = PassDev{pb.order.p, pb.vert_off.p, tp.contiguous ? nullptr : pb.tile_verts.p, use_runs ? pb.run_off.p : nullptr,
                        use_runs ? pb.runs.p : nullptr, pb.rounds.p, reinterpret_cast<const uint4 *>(pb.stream.p),
                        pb.aux.p, tp.n_tiles(), pos_bytes, nullptr};
+      pb.grid = tp.n_tiles();
       pb.bt = tp.bt;
       pb.width = tp.width;
       pb.empty = tp.n_edges + tp.n_tets == 0;
@@ -312,7 +321,7 @@ struct sb_solver {
   template <bool FAST, int BT, int W16>
   void launch_tile_cfg(const PassBufs &pb, cudaStream_t s) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(pb.dev.n_tiles);
+    cfg.gridDim = dim3(pb.grid);
     cfg.blockDim = dim3(BT);
     cfg.dynamicSmemBytes = pb.smem;
     cfg.stream = s;
@@ -340,7 +349,7 @@ struct sb_solver {
   }
   template <bool FAST>
   void launch_tile(const PassBufs &pb, cudaStream_t s) {
-    if (!pb.dev.n_tiles || pb.empty) return;
+    if (!pb.grid || pb.empty) return;
     if (pb.width == 2) launch_tile_w<FAST, 2>(pb, s);
     else launch_tile_w<FAST, 1>(pb, s);
   }
@@ -407,7 +416,7 @@ struct sb_solver {
     dag_dispatch<true>(false, nullptr);
     dag_ready = dag_grid > 0;
   }
-  bool use_dag() const { return dag_ready && (prm.flags & SB_FLAG_DAG) && !halo_active() && prm.iterations > 0; }
+  bool use_dag() const { return dag_ready && (prm.flags & SB_FLAG_DAG) && !halo_active() && !dist_on && prm.iterations > 0; }
   // all passes of all iterations of one substep: counters and ticket (not the error word) are cleared first
   void launch_dag(cudaStream_t s) {
     CK(cudaMemsetAsync(dag_ctr.p, 0, ((size_t)dag.tile_base[dag.n_pass] + 1) * sizeof(uint32_t), s));
@@ -420,6 +429,82 @@ struct sb_solver {
     CK(cudaMemcpyAsync(&e, dag.error, sizeof e, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     return (int)e;
+  }
+
+  // ---- one mesh over several GPUs ------------------------------------------------------
+  void dist_setup(int rank, int n_ranks) {
+    if (n_ranks < 2 || n_ranks > SB_MAX_RANKS || rank < 0 || rank >= n_ranks) throw std::string("rank / n_ranks out of range (2..8 ranks)");
+    if (!plan.dag_ok) throw std::string("a distributed mesh must be planned as balanced shifted tilings (one big component, no ghosts, nothing left over)");
+    if (halo_active()) throw std::string("halo lists and the peer-memory distribution are alternatives");
+    const TilePass &t0 = plan.passes[0];
+    if (!t0.contiguous || t0.n_tiles() < (uint32_t)n_ranks) throw std::string("fewer tiles than ranks");
+    dist = DistDev{};
+    dist.n_ranks = (uint32_t)n_ranks;
+    dist.rank = (uint32_t)rank;
+    // slabs: consecutive tiles of the unshifted tiling (consecutive device ids), equal vertex counts
+    uint32_t prev_tile = 0;
+    for (int r = 1; r < n_ranks; r++) {
+      const uint64_t target = (uint64_t)plan.V * r / n_ranks;
+      uint32_t tile = (uint32_t)(std::lower_bound(t0.vert_off.begin(), t0.vert_off.end() - 1, (uint32_t)target) - t0.vert_off.begin());
+      tile = std::max(tile, prev_tile + 1);
+      tile = std::min(tile, t0.n_tiles() - (uint32_t)(n_ranks - r));
+      dist.slab_lo[r] = t0.vert_off[tile];
+      prev_tile = tile;
+    }
+    dist.slab_lo[0] = 0;
+    dist.slab_lo[n_ranks] = plan.V;
+    for (int r = n_ranks + 1; r <= SB_MAX_RANKS; r++) dist.slab_lo[r] = plan.V;
+    auto owner_of = [&](uint32_t dev) {
+      uint32_t r = 0;
+      while (r + 1 < dist.n_ranks && dev >= dist.slab_lo[r + 1]) r++;
+      return r;
+    };
+    // this rank's tiles of every pass: those with most of their vertices in its slab (ties: the lower rank),
+    // heaviest first, dealt to the SMs in a snake like the single-GPU launch order
+    for (size_t k = 0; k < plan.passes.size(); k++) {
+      const TilePass &tp = plan.passes[k];
+      std::vector<uint32_t> mine;
+      for (uint32_t t = 0; t < tp.n_tiles(); t++) {
+        const uint32_t a = tp.vert_off[t], b = tp.vert_off[t + 1];
+        if (a == b || tp.rounds[t].y + tp.rounds[t].z == 0) continue;
+        uint32_t cnt[SB_MAX_RANKS] = {0};
+        if (tp.contiguous) cnt[owner_of(a)] = b - a;
+        else
+          for (uint32_t i = a; i < b; i++) cnt[owner_of(tp.tile_verts[i])]++;
+        uint32_t best = 0;
+        for (uint32_t r = 1; r < dist.n_ranks; r++)
+          if (cnt[r] > cnt[best]) best = r;
+        if (best == dist.rank) mine.push_back(t);
+      }
+      auto work = [&](uint32_t t) { return ((uint64_t)(tp.rounds[t].y + tp.rounds[t].z) << 32) | (uint32_t)(tp.ent_off[t + 1] - tp.ent_off[t]); };
+      std::stable_sort(mine.begin(), mine.end(), [&](uint32_t a, uint32_t b) { return work(a) > work(b); });
+      const size_t layer = (size_t)std::max(1, n_sm);
+      for (size_t lo = layer; lo < mine.size(); lo += 2 * layer) std::reverse(mine.begin() + lo, mine.begin() + std::min(mine.size(), lo + layer));
+      passes[k].order.upload(mine, &dev_bytes);
+      passes[k].dev.order = passes[k].order.p;
+      passes[k].grid = (uint32_t)mine.size();
+    }
+    dist_ctl.alloc(4 + SB_MAX_RANKS, &dev_bytes);
+    CK(cudaMemset(dist_ctl.p, 0, (4 + SB_MAX_RANKS) * sizeof(uint32_t)));
+    dist.ctl = dist_ctl.p;
+    dist.x_of[rank] = x.p;
+    dist_connected = 1u << rank;
+    dist_on = false; // until every peer is connected
+  }
+  void dist_connect(int peer, void *peer_x, void *peer_ctl) {
+    if (!dist.ctl) throw std::string("call sb_dist_setup first");
+    if (peer < 0 || peer >= (int)dist.n_ranks || peer == (int)dist.rank || !peer_x || !peer_ctl) throw std::string("bad peer");
+    dist.x_of[peer] = (float4 *)peer_x;
+    dist.peer_flag[peer] = (uint32_t *)peer_ctl + 4 + dist.rank;
+    dist_connected |= 1u << peer;
+    if (dist_connected == (1u << dist.n_ranks) - 1u) {
+      dist_dev.alloc(1, &dev_bytes);
+      CK(cudaMemcpy(dist_dev.p, &dist, sizeof dist, cudaMemcpyHostToDevice));
+      for (auto &pb : passes) pb.dev.dist = dist_dev.p;
+      dist_on = true;
+      for (auto &g : graphs) cudaGraphExecDestroy(g.second);
+      graphs.clear();
+    }
   }
 
   void launch_pass(size_t k, cudaStream_t s) {
@@ -467,11 +552,18 @@ struct sb_solver {
     if (phase == 0) { halo_send(1, s); halo_recv(0, s); }
     else { halo_send(0, s); halo_recv(1, s); }
   }
-  void launch_predict(cudaStream_t s) { k_predict<<<grid_for(plan.V, 256), 256, 0, s>>>(plan.V, x.p, v.p, xp.p, dprm.p); }
-  void launch_finish(cudaStream_t s) { k_finish<<<grid_for(plan.V, 256), 256, 0, s>>>(plan.V, x.p, v.p, xp.p, dprm.p); }
+  // distributed: only this rank's slab of the device numbering is integrated here
+  void launch_predict(cudaStream_t s) {
+    const uint32_t lo = dist_on ? dist.slab_lo[dist.rank] : 0u, hi = dist_on ? dist.slab_lo[dist.rank + 1] : plan.V;
+    k_predict<<<grid_for(hi - lo, 256), 256, 0, s>>>(lo, hi, x.p, v.p, xp.p, dprm.p, dist_on ? dist_dev.p : nullptr);
+  }
+  void launch_finish(cudaStream_t s) {
+    const uint32_t lo = dist_on ? dist.slab_lo[dist.rank] : 0u, hi = dist_on ? dist.slab_lo[dist.rank + 1] : plan.V;
+    k_finish<<<grid_for(hi - lo, 256), 256, 0, s>>>(lo, hi, x.p, v.p, xp.p, dprm.p, dist_on ? dist_dev.p : nullptr);
+  }
   void launch_normals(cudaStream_t s) {
     const uint32_t ns = (uint32_t)plan.surf_ids.size();
-    if (!ns || (prm.flags & SB_FLAG_NO_NORMALS)) return;
+    if (!ns || (prm.flags & SB_FLAG_NO_NORMALS) || dist_on) return; // (distributed: normals are the caller's, from the gathered positions)
     k_normals<<<grid_for(ns, 256), 256, 0, s>>>(ns, surf_tri_off.p, surf_tri_ids.p, tris_dev.p, x.p, nrm.p);
   }
 
@@ -485,7 +577,7 @@ struct sb_solver {
       per_iter += (kv.second.peer_buf ? 1 : 0) + (kv.second.recv.p ? 1 : 0); // one send and one receive kernel per sweep
     }
     uint32_t n = (uint32_t)prm.substeps * (2 + (use_dag() ? 1u : (uint32_t)prm.iterations * per_iter));
-    if (!plan.surf_ids.empty() && !(prm.flags & SB_FLAG_NO_NORMALS)) n++;
+    if (!plan.surf_ids.empty() && !(prm.flags & SB_FLAG_NO_NORMALS) && !dist_on) n++;
     return n;
   }
 
@@ -517,6 +609,7 @@ struct sb_solver {
     CK(cudaSetDevice(device));
     if (!(dt > 0)) dt = prm.dt;
     if (!(dt > 0) || !std::isfinite(dt)) throw std::string("dt must be finite and > 0");
+    if (dist.ctl && !dist_on) throw std::string("distributed handle: not every peer is connected yet");
     refresh_params(dt);
     if (prm.flags & SB_FLAG_NO_GRAPH) {
       enqueue_frame(stream);
@@ -1180,6 +1273,10 @@ int sb_enqueue(sb_handle h, int32_t op, int32_t arg) {
       case SB_OP_EXCHANGE: h->exchange(arg, h->stream); break;
       case SB_OP_HALO_SEND: h->halo_send(arg, h->stream); break;
       case SB_OP_HALO_RECV: h->halo_recv(arg, h->stream); break;
+      case SB_OP_PASS:
+        if (arg < 0 || (size_t)arg >= h->passes.size()) throw std::string("no such tile pass");
+        h->launch_pass((size_t)arg, h->stream);
+        break;
       default: throw std::string("unknown op");
     }
     CK(cudaGetLastError());
@@ -1266,6 +1363,53 @@ int sb_halo_connect(sb_handle h, int32_t list_id, void *peer_base) {
     if (!L.ctl_send.p) { L.ctl_send.alloc(4, &h->dev_bytes); CK(cudaMemset(L.ctl_send.p, 0, 16)); }
     for (auto &g : h->graphs) cudaGraphExecDestroy(g.second);
     h->graphs.clear();
+    return SB_OK;
+  });
+}
+
+int sb_dist_setup(sb_handle h, int32_t rank, int32_t n_ranks, void **x_base_out, void **ctl_base_out) {
+  NEED_DEVICE(h);
+  return guarded(h, [&]() -> int {
+    CK(cudaSetDevice(h->device));
+    h->dist_setup(rank, n_ranks);
+    if (x_base_out) *x_base_out = h->x.p;
+    if (ctl_base_out) *ctl_base_out = h->dist_ctl.p;
+    return SB_OK;
+  });
+}
+
+int sb_dist_connect(sb_handle h, int32_t peer, void *peer_x, void *peer_ctl) {
+  NEED_DEVICE(h);
+  return guarded(h, [&]() -> int {
+    CK(cudaSetDevice(h->device));
+    h->dist_connect(peer, peer_x, peer_ctl);
+    return SB_OK;
+  });
+}
+
+int sb_dist_owned(sb_handle h, uint8_t *owned_V, uint32_t *tiles_per_pass8) {
+  NEED_DEVICE(h);
+  if (!h->dist.ctl) { h->err = "not a distributed handle"; return SB_E_STATE; }
+  if (owned_V) {
+    std::memset(owned_V, 0, h->plan.V);
+    for (uint32_t d = h->dist.slab_lo[h->dist.rank]; d < h->dist.slab_lo[h->dist.rank + 1]; d++) owned_V[h->plan.perm[d]] = 1;
+  }
+  if (tiles_per_pass8)
+    for (size_t k = 0; k < 8; k++) tiles_per_pass8[k] = k < h->passes.size() ? h->passes[k].grid : 0u;
+  return SB_OK;
+}
+
+int sb_dist_error(sb_handle h, int32_t *out) {
+  NEED_DEVICE(h);
+  if (!out) return SB_E_ARG;
+  return guarded(h, [&]() -> int {
+    CK(cudaSetDevice(h->device));
+    *out = 0;
+    if (!h->dist.ctl) return SB_OK;
+    uint32_t e = 0;
+    CK(cudaMemcpyAsync(&e, h->dist_ctl.p + 2, sizeof e, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *out = (int32_t)e;
     return SB_OK;
   });
 }

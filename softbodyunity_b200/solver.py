@@ -207,6 +207,28 @@ class SoftBody:
     def halo_connect(self, list_id: int, peer_base: int):
         self._ck(self._lib.sb_halo_connect(self._h, list_id, C.c_void_p(peer_base)))
 
+    # -- one mesh over several GPUs through peer memory (sb_dist_*) ----------------------------
+    def dist_setup(self, rank: int, n_ranks: int):
+        """-> (device address of this rank's position array, of its control block)."""
+        xb, cb = C.c_void_p(), C.c_void_p()
+        self._ck(self._lib.sb_dist_setup(self._h, rank, n_ranks, C.byref(xb), C.byref(cb)))
+        return xb.value, cb.value
+
+    def dist_connect(self, peer: int, peer_x: int, peer_ctl: int):
+        self._ck(self._lib.sb_dist_connect(self._h, peer, C.c_void_p(peer_x), C.c_void_p(peer_ctl)))
+
+    def dist_owned(self):
+        """-> (bool mask over the caller's vertices this rank owns, tiles this rank runs per pass)."""
+        m = np.zeros(self.n_verts, np.uint8)
+        t = np.zeros(8, np.uint32)
+        self._ck(self._lib.sb_dist_owned(self._h, _ptr(m), _ptr(t)))
+        return m.astype(bool), t[:self.info()["n_tile_passes"]].tolist()
+
+    def dist_error(self) -> bool:
+        out = C.c_int32()
+        self._ck(self._lib.sb_dist_error(self._h, C.byref(out)))
+        return bool(out.value)
+
     def halo_error(self) -> bool:
         out = C.c_int32()
         self._ck(self._lib.sb_halo_error(self._h, C.byref(out)))
