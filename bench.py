@@ -51,6 +51,12 @@ def workload(args, rank=0, world=1):
         lo, hi = shard_range(args.n, rank, world)
         pos, tets, tris = meshgen.bodies(hi - lo, dims=(13, 13, 12), spacing=0.02, base_height=0.004, seed=1234 + rank)
         name = f"{args.n} independent 2028-vertex bodies sharded over {world} rank(s), S={args.substeps} I={args.iterations}"
+    elif args.workload == "dist":
+        # BASELINE.json configs[4], peer-memory version: EVERY rank plans the whole block; a rank owns a slab of it
+        n = args.n
+        pos, tets, tris = meshgen.block(n, n, n, spacing=0.01, origin=(0.0, 0.002, 0.0), jitter=0.1, seed=1234)
+        name = (f"single block{n}^3 ({n ** 3} verts) over {world} rank(s): one address space over NVLink peer memory "
+                f"(no ghosts, no exchange kernels), S={args.substeps} I={args.iterations}")
     elif args.workload == "partitioned":
         # BASELINE.json configs[4]: ONE block of n^3 vertices (default 200^3 = 8 M) cut into `world` slabs
         n = args.n
@@ -196,7 +202,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="block", choices=["block", "sphere", "bodies", "partitioned"])
+    ap.add_argument("--workload", default="block", choices=["block", "sphere", "bodies", "partitioned", "dist"])
     ap.add_argument("--n", "--size", dest="n", type=int, default=100)
     ap.add_argument("--substeps", type=int, default=10)
     ap.add_argument("--iterations", type=int, default=10)
@@ -245,6 +251,12 @@ def main():
         body = PartitionedBody(part_mesh, device=local, **kw)
         connect_peers(body, local)     # CUDA IPC handles travel over torch.distributed once; the data path is P2P stores
         sb = body.sb
+    elif args.workload == "dist" and world > 1:
+        from softbodyunity_b200.dist import DistBody
+        V_global, T_global = len(pos), len(tets)
+        body = DistBody(pos, tets, tris, device=local, **kw)
+        sb = body.sb
+        part_mesh = body
     else:
         sb = SoftBody(pos, tets, tris, device=local, **kw)
     info = sb.info()
@@ -280,10 +292,15 @@ def main():
     barrier()
     ms = max_over_ranks(ms)
     # keep the GPU under the same load until the sampler has seen it (untimed)
-    t_soak = time.time()
-    while time.time() - t_soak < 0.6:
-        sb.step(frames=2)
+    if part_mesh is not None:
+        # ranks that share one mesh must issue the SAME number of frames: a count from the reduced time, not a clock
+        sb.step(frames=max(2, int(600.0 / max(ms / args.steps, 1e-3))))
         sb.synchronize()
+    else:
+        t_soak = time.time()
+        while time.time() - t_soak < 0.6:
+            sb.step(frames=2)
+            sb.synchronize()
     clocks.mark_end()
     clk = clocks.stop() if rank == 0 else None
     V_all = V if world == 1 else int(round(sum_over_ranks(V)))
@@ -292,14 +309,16 @@ def main():
     if part_mesh is not None:
         # strong scaling of ONE mesh: report the device-timed figure only (the host-buffer protocol of the
         # single-body e2e leg would have to re-send ghosts as well; not measured for this workload)
-        if sb.halo_error():
-            raise SystemExit("bench.py: a halo receive timed out")
+        if sb.halo_error() or sb.dist_error():
+            raise SystemExit("bench.py: a wait for a peer GPU timed out")
         if rank == 0:
             print(json.dumps({
                 "metric": METRIC, "value": V_global * args.substeps * args.steps / (ms * 1e-3), "unit": "vertex-substeps/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": name, "n_verts": V_global, "n_tets": T_global, "own_verts_rank0": V,
+                "config": {"workload": name, "n_verts": V_global, "n_tets": T_global,
+                           "own_verts_rank0": int(part_mesh.owned.sum()) if args.workload == "dist" else V,
+                           "tiles_rank0": part_mesh.tiles if args.workload == "dist" else None,
                            "ghost_verts_rank0": info["n_ghost_verts"], "constraints_cut_rank0": info["constraints_cut"],
                            "math": "fast" if args.fast_math else "exact (bit-identical to CPU oracle)",
                            "tile_passes": info["n_tile_passes"], "build_seconds": info["build_seconds"]},
