@@ -261,6 +261,9 @@ int sb_dist_setup(sb_handle h, int32_t rank, int32_t n_ranks, void **x_base_out,
 int sb_dist_connect(sb_handle h, int32_t peer, void *peer_x, void *peer_ctl);
 int sb_dist_owned(sb_handle h, uint8_t *owned_V, uint32_t *tiles_per_pass8); /* either pointer may be NULL */
 int sb_dist_error(sb_handle h, int32_t *out); /* 1 if a wait for a peer ever timed out (results invalid) */
+/* Host only (works on an sb_plan handle): the vertices rank would own and, for one pass, which tiles it would run
+   (tile_owner_pass[t] = 1 / 0; sb_get_tiles gives the tile count).  Either pointer may be NULL. */
+int sb_dist_layout(sb_handle h, int32_t rank, int32_t n_ranks, uint8_t *owned_V, int32_t *tile_owner_pass, uint32_t pass);
 
 /* Debug aid: timestamps of one run of tile pass `pass` (see solver.cu); out holds 64 * 80 words. */
 int sb_debug_trace_pass(sb_handle h, uint32_t pass, unsigned long long *out, uint32_t n_words);

@@ -22,7 +22,7 @@ EXPORTS = [
     "sb_time_frames", "sb_time_kernel", "sb_debug_trace_pass", "sb_debug_verify_streams", "sb_last_error",
     "sb_set_stream", "sb_prepare", "sb_enqueue", "sb_halo_set", "sb_halo_pack", "sb_halo_unpack", "sb_lumped_inv_mass",
     "sb_halo_alloc", "sb_halo_connect", "sb_halo_error", "sb_ipc_export", "sb_ipc_open",
-    "sb_dist_setup", "sb_dist_connect", "sb_dist_owned", "sb_dist_error",
+    "sb_dist_setup", "sb_dist_connect", "sb_dist_owned", "sb_dist_error", "sb_dist_layout",
 ]
 
 
@@ -134,6 +134,7 @@ def load():
         "sb_dist_connect": (C.c_int, [vp, i32, vp, vp]),
         "sb_dist_owned": (C.c_int, [vp, vp, vp]),
         "sb_dist_error": (C.c_int, [vp, P(i32)]),
+        "sb_dist_layout": (C.c_int, [vp, i32, i32, vp, vp, u32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

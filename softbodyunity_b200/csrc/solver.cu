@@ -432,15 +432,15 @@ struct sb_solver {
   }
 
   // ---- one mesh over several GPUs ------------------------------------------------------
-  void dist_setup(int rank, int n_ranks) {
+  // Host-only part: the slab of the device numbering a rank owns and the tiles of every pass it runs.
+  void dist_layout(int rank, int n_ranks, DistDev &D, std::vector<std::vector<uint32_t>> &tiles) const {
     if (n_ranks < 2 || n_ranks > SB_MAX_RANKS || rank < 0 || rank >= n_ranks) throw std::string("rank / n_ranks out of range (2..8 ranks)");
     if (!plan.dag_ok) throw std::string("a distributed mesh must be planned as balanced shifted tilings (one big component, no ghosts, nothing left over)");
-    if (halo_active()) throw std::string("halo lists and the peer-memory distribution are alternatives");
     const TilePass &t0 = plan.passes[0];
     if (!t0.contiguous || t0.n_tiles() < (uint32_t)n_ranks) throw std::string("fewer tiles than ranks");
-    dist = DistDev{};
-    dist.n_ranks = (uint32_t)n_ranks;
-    dist.rank = (uint32_t)rank;
+    D = DistDev{};
+    D.n_ranks = (uint32_t)n_ranks;
+    D.rank = (uint32_t)rank;
     // slabs: consecutive tiles of the unshifted tiling (consecutive device ids), equal vertex counts
     uint32_t prev_tile = 0;
     for (int r = 1; r < n_ranks; r++) {
@@ -448,22 +448,24 @@ struct sb_solver {
       uint32_t tile = (uint32_t)(std::lower_bound(t0.vert_off.begin(), t0.vert_off.end() - 1, (uint32_t)target) - t0.vert_off.begin());
       tile = std::max(tile, prev_tile + 1);
       tile = std::min(tile, t0.n_tiles() - (uint32_t)(n_ranks - r));
-      dist.slab_lo[r] = t0.vert_off[tile];
+      D.slab_lo[r] = t0.vert_off[tile];
       prev_tile = tile;
     }
-    dist.slab_lo[0] = 0;
-    dist.slab_lo[n_ranks] = plan.V;
-    for (int r = n_ranks + 1; r <= SB_MAX_RANKS; r++) dist.slab_lo[r] = plan.V;
+    D.slab_lo[0] = 0;
+    D.slab_lo[n_ranks] = plan.V;
+    for (int r = n_ranks + 1; r <= SB_MAX_RANKS; r++) D.slab_lo[r] = plan.V;
     auto owner_of = [&](uint32_t dev) {
       uint32_t r = 0;
-      while (r + 1 < dist.n_ranks && dev >= dist.slab_lo[r + 1]) r++;
+      while (r + 1 < D.n_ranks && dev >= D.slab_lo[r + 1]) r++;
       return r;
     };
     // this rank's tiles of every pass: those with most of their vertices in its slab (ties: the lower rank),
-    // heaviest first, dealt to the SMs in a snake like the single-GPU launch order
+    // heaviest first, dealt to the SMs in a snake like the single-GPU launch order.  (Dealing a spanning tile
+    // to the less loaded of its ranks instead was measured slower: more of its runs become remote.)
+    tiles.assign(plan.passes.size(), {});
     for (size_t k = 0; k < plan.passes.size(); k++) {
       const TilePass &tp = plan.passes[k];
-      std::vector<uint32_t> mine;
+      std::vector<uint32_t> &mine = tiles[k];
       for (uint32_t t = 0; t < tp.n_tiles(); t++) {
         const uint32_t a = tp.vert_off[t], b = tp.vert_off[t + 1];
         if (a == b || tp.rounds[t].y + tp.rounds[t].z == 0) continue;
@@ -472,17 +474,24 @@ struct sb_solver {
         else
           for (uint32_t i = a; i < b; i++) cnt[owner_of(tp.tile_verts[i])]++;
         uint32_t best = 0;
-        for (uint32_t r = 1; r < dist.n_ranks; r++)
+        for (uint32_t r = 1; r < D.n_ranks; r++)
           if (cnt[r] > cnt[best]) best = r;
-        if (best == dist.rank) mine.push_back(t);
+        if (best == D.rank) mine.push_back(t);
       }
       auto work = [&](uint32_t t) { return ((uint64_t)(tp.rounds[t].y + tp.rounds[t].z) << 32) | (uint32_t)(tp.ent_off[t + 1] - tp.ent_off[t]); };
       std::stable_sort(mine.begin(), mine.end(), [&](uint32_t a, uint32_t b) { return work(a) > work(b); });
       const size_t layer = (size_t)std::max(1, n_sm);
       for (size_t lo = layer; lo < mine.size(); lo += 2 * layer) std::reverse(mine.begin() + lo, mine.begin() + std::min(mine.size(), lo + layer));
-      passes[k].order.upload(mine, &dev_bytes);
+    }
+  }
+  void dist_setup(int rank, int n_ranks) {
+    if (halo_active()) throw std::string("halo lists and the peer-memory distribution are alternatives");
+    std::vector<std::vector<uint32_t>> tiles;
+    dist_layout(rank, n_ranks, dist, tiles);
+    for (size_t k = 0; k < plan.passes.size(); k++) {
+      passes[k].order.upload(tiles[k], &dev_bytes);
       passes[k].dev.order = passes[k].order.p;
-      passes[k].grid = (uint32_t)mine.size();
+      passes[k].grid = (uint32_t)tiles[k].size();
     }
     dist_ctl.alloc(4 + SB_MAX_RANKS, &dev_bytes);
     CK(cudaMemset(dist_ctl.p, 0, (4 + SB_MAX_RANKS) * sizeof(uint32_t)));
@@ -1397,6 +1406,26 @@ int sb_dist_owned(sb_handle h, uint8_t *owned_V, uint32_t *tiles_per_pass8) {
   if (tiles_per_pass8)
     for (size_t k = 0; k < 8; k++) tiles_per_pass8[k] = k < h->passes.size() ? h->passes[k].grid : 0u;
   return SB_OK;
+}
+
+/* Host only (works on an sb_plan handle): what sb_dist_setup(rank, n_ranks) would decide. */
+int sb_dist_layout(sb_handle h, int32_t rank, int32_t n_ranks, uint8_t *owned_V, int32_t *tile_owner_pass, uint32_t pass) {
+  NEED_HANDLE(h);
+  return guarded(h, [&]() -> int {
+    DistDev D;
+    std::vector<std::vector<uint32_t>> tiles;
+    h->dist_layout(rank, n_ranks, D, tiles);
+    if (owned_V) {
+      std::memset(owned_V, 0, h->plan.V);
+      for (uint32_t d = D.slab_lo[rank]; d < D.slab_lo[rank + 1]; d++) owned_V[h->plan.perm[d]] = 1;
+    }
+    if (tile_owner_pass) { // tile_owner_pass[t] = 1 if this rank runs tile t of pass `pass`, else 0
+      if (pass >= tiles.size()) throw std::string("no such pass");
+      for (uint32_t t = 0; t < h->plan.passes[pass].n_tiles(); t++) tile_owner_pass[t] = 0;
+      for (uint32_t t : tiles[pass]) tile_owner_pass[t] = 1;
+    }
+    return SB_OK;
+  });
 }
 
 int sb_dist_error(sb_handle h, int32_t *out) {

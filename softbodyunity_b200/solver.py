@@ -224,6 +224,13 @@ class SoftBody:
         self._ck(self._lib.sb_dist_owned(self._h, _ptr(m), _ptr(t)))
         return m.astype(bool), t[:self.info()["n_tile_passes"]].tolist()
 
+    def dist_layout(self, rank: int, n_ranks: int, pass_index: int = 0):
+        """Host only: (bool mask of the vertices `rank` would own, bool mask of the tiles of `pass_index` it would run)."""
+        own = np.zeros(self.n_verts, np.uint8)
+        tiles = np.zeros(self.info()["tiles_in_pass"][pass_index], np.int32)
+        self._ck(self._lib.sb_dist_layout(self._h, rank, n_ranks, _ptr(own), _ptr(tiles), pass_index))
+        return own.astype(bool), tiles.astype(bool)
+
     def dist_error(self) -> bool:
         out = C.c_int32()
         self._ck(self._lib.sb_dist_error(self._h, C.byref(out)))

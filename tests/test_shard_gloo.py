@@ -65,3 +65,44 @@ def test_two_gloo_ranks_shard_plan_and_reduce():
     per_body = one.info()["n_edges"] + one.info()["n_tets"]
     assert tc0 == tc1 == n_bodies * per_body
     assert slow0 == slow1 == 2.0 and ok0 == ok1 == 2.0
+
+
+def _dist_worker(rank, world, port, out):
+    """One mesh over `world` ranks through peer memory (sb_dist_*): the host-side layout every rank derives from
+    the SAME plan -- which vertices it owns, which tiles of every pass it runs -- reduced the way the ranks would."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pos, tets, tris = meshgen.block(14, 12, 26, spacing=0.05, origin=(0, 0.02, 0))
+        sb = SoftBody(pos, tets, tris, host_only=True, tile_cap=256)
+        info = sb.info()
+        own = None
+        covered = []
+        for p in range(info["n_tile_passes"]):
+            own, tiles = sb.dist_layout(rank, world, p)
+            t = torch.from_numpy(tiles.astype(np.int32))
+            dist.all_reduce(t)            # how many ranks run each tile of the pass
+            tile_of, n_tiles = sb.tiles(p)
+            busy = np.zeros(n_tiles, bool)
+            busy[np.unique(tile_of[tile_of >= 0])] = True
+            covered.append(bool(((t.numpy() == 1) | ~busy).all() and (t.numpy() <= 1).all() and tiles.any()))
+        o = torch.from_numpy(own.astype(np.int32))
+        dist.all_reduce(o)                # how many ranks own each vertex
+        out[rank] = (int(own.sum()), bool((o.numpy() == 1).all()), all(covered), reduce_sum(float(own.sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_ranks_agree_on_the_peer_memory_layout(world):
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_dist_worker, args=(world, port, out), nprocs=world, join=True)
+        res = [out[r] for r in range(world)]
+    n_verts = 14 * 12 * 26
+    sizes = [r[0] for r in res]
+    assert sum(sizes) == n_verts and all(r[3] == n_verts for r in res)
+    assert max(sizes) - min(sizes) <= 2 * 256          # slabs are whole tiles of the unshifted tiling
+    assert all(r[1] for r in res), "every vertex has exactly one owner"
+    assert all(r[2] for r in res), "every tile with constraints runs on exactly one rank, and every rank has work in every pass"
