@@ -291,3 +291,30 @@ def test_bad_arguments_are_rejected():
         m.simulate(orc.params(), order=np.array([99], np.int32))
     with pytest.raises(ValueError):
         orc.build_edges(3, TET)
+
+
+def test_operand_windows_skip_instead_of_dividing():
+    # arithmetic contract (oracle/xpbd_oracle_impl.h): a projection whose operand leaves the window in which the
+    # GPU's branch-free sqrt / reciprocal are correctly rounded is skipped, not evaluated on a slow path
+    tet = np.array([[0, 1, 2, 3]], np.int32)
+    w = np.ones(4, np.float32)
+    # (a) a (nearly) zero-length edge: len^2 = 1e-40 < 2^-101.  Edge (0,1) must not move its vertices; nothing may go NaN
+    pos = np.float32([[0, 0, 0], [1e-20, 0, 0], [0, 1, 0], [0, 0, 1]])
+    m = orc.Model(np.float32([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]]), tet, inv_mass=w)
+    e01 = int(np.nonzero((m.edges == [0, 1]).all(1))[0][0])
+    m.x4[:, :3] = pos
+    before = m.x4.copy()
+    m.simulate(orc.params(substeps=1, iterations=1, stiffness_volume=0, gravity=(0, 0, 0), flags=1), order=np.int32([e01]))
+    dt = np.float32(1.0 / 60.0)
+    assert np.isfinite(m.x4).all()
+    assert np.array_equal(m.x4[:, :3], before[:, :3])          # skipped: positions untouched (no velocity either)
+    # (b) the same edge at a length inside the window is projected
+    m.x4[1, 0] = 0.5
+    m.simulate(orc.params(substeps=1, iterations=1, stiffness_volume=0, gravity=(0, 0, 0), flags=1), order=np.int32([e01]))
+    assert abs(float(m.x4[1, 0] - m.x4[0, 0]) - 1.0) < 1e-6     # rigid edge restored to its rest length 1
+    # (c) a tet whose gradients all vanish (four coincident vertices) with zero compliance: den = 0 -> skipped
+    m2 = orc.Model(np.float32([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]]), tet, inv_mass=w)
+    m2.x4[:, :3] = 0.25
+    m2.simulate(orc.params(substeps=1, iterations=1, stiffness_distance=0, gravity=(0, 0, 0), flags=1),
+                order=np.array([0x80000000], np.uint32).view(np.int32))
+    assert np.isfinite(m2.x4).all() and (m2.x4[:, :3] == 0.25).all()
