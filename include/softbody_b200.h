@@ -159,6 +159,26 @@ int sb_get_params(sb_handle h, sb_params *out);
 int sb_set_colliders(sb_handle h, const float *spheres_xyzr, uint32_t n);
 
 /*
+ * Analytic colliders of mixed kinds (Unity's SphereCollider / CapsuleCollider / BoxCollider in world space), applied
+ * after the ground plane in list order; n <= SB_MAX_COLLIDERS, n == 0 clears; replaces what sb_set_colliders set
+ * (which is the same list with kind SPHERE and friction 0).  A vertex inside a collider is moved to its surface
+ * along the surface normal there (box: through the nearest face); `friction` in [0, 1] then removes that share of
+ * the vertex's tangential motion since the start of the substep.  The operation order is in
+ * oracle/xpbd_oracle_impl.h (COLLIDERS); the kernels follow it bit for bit.
+ */
+#define SB_MAX_COLLIDERS 16
+#define SB_COLLIDER_SPHERE 0  /* p = centre xyz, radius */
+#define SB_COLLIDER_CAPSULE 1 /* p = end point A xyz, radius, end point B xyz (segment AB swept by the radius) */
+#define SB_COLLIDER_BOX 2     /* p = centre xyz, half extents xyz, rotation quaternion (x, y, z, w) box -> world;
+                                 a zero quaternion means no rotation */
+typedef struct sb_collider {
+  int32_t kind;
+  float friction;
+  float p[10];
+} sb_collider; /* 48 bytes */
+int sb_set_colliders_ex(sb_handle h, const sb_collider *colliders, uint32_t n);
+
+/*
  * Advance one frame of `dt` seconds (dt <= 0: params.dt): substeps x (predict,
  * iterations x projection sweep, ground/collider response, velocity update), then
  * the surface normals.  Asynchronous: returns after the work is enqueued.

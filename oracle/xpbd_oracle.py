@@ -58,6 +58,22 @@ def _p(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
 
+# same layout as sb_collider (include/softbody_b200.h): kind 0 sphere / 1 capsule / 2 box
+COLLIDER = np.dtype([("kind", np.int32), ("friction", np.float32), ("p", np.float32, 10)])
+
+
+def colliders(items):
+    """[(kind, friction, params...)] -> array of COLLIDER; kind as int or "sphere" / "capsule" / "box"."""
+    names = {"sphere": 0, "capsule": 1, "box": 2}
+    out = np.zeros(len(items), COLLIDER)
+    for k, (kind, fr, *p) in enumerate(items):
+        p = np.asarray(p, np.float32).ravel()
+        out[k]["kind"] = names.get(kind, kind)
+        out[k]["friction"] = fr
+        out[k]["p"][:len(p)] = p
+    return out
+
+
 def build_edges(n_verts, tets):
     tets = np.ascontiguousarray(tets, np.int32)
     n = lib().orc_build_edges(C.c_int32(n_verts), C.c_int32(len(tets)), _p(tets), None)
@@ -108,11 +124,19 @@ class Model:
         return np.concatenate([np.arange(self.E, dtype=np.int32),
                                (np.arange(self.T, dtype=np.int64) | 0x80000000).astype(np.uint32).view(np.int32)])
 
-    def simulate(self, prm: OrcParams, n_frames=1, order=None, batch_off=None, spheres=None, threads=1):
+    def simulate(self, prm: OrcParams, n_frames=1, order=None, batch_off=None, spheres=None, threads=1, colliders=None):
         order = self.natural_order() if order is None else np.ascontiguousarray(order, np.int32)
         nb = 0 if batch_off is None else len(batch_off) - 1
         boff = None if batch_off is None else np.ascontiguousarray(batch_off, np.int64)
-        sph = None if spheres is None else np.ascontiguousarray(spheres, np.float32).reshape(-1, 4)
+        if colliders is not None:
+            assert spheres is None
+            sph = np.ascontiguousarray(colliders, COLLIDER)
+        elif spheres is not None:
+            s4 = np.ascontiguousarray(spheres, np.float32).reshape(-1, 4)
+            sph = np.zeros(len(s4), COLLIDER)
+            sph["p"][:, :4] = s4
+        else:
+            sph = None
         rc = getattr(lib(), "orc_simulate" + self.sfx)(
             C.c_int32(self.V), _p(self.x4), _p(self.v4), C.c_int32(self.E), _p(self.edges), _p(self.rest_len),
             C.c_int32(self.T), _p(self.roles), _p(self.rest_vol6), C.byref(prm), C.c_int64(len(order)), _p(order),

@@ -46,7 +46,7 @@
  *    instead of taking a slow path, here and in the kernels alike.)
  *   finish(i), w_i > 0:   if x.y < ground_y: x.y = ground_y,
  *                             x.xz = FMA(keep, x.xz - x_prev.xz, x_prev.xz)
- *                         spheres: see SPHERE below
+ *                         colliders: see COLLIDERS below
  *                         v = ((x - x_prev) * inv_h) * damp
  */
 
@@ -159,25 +159,116 @@ static inline void FN(volume_one)(REAL *p0, REAL *p1, REAL *p2, REAL *p3, REAL R
 }
 
 /*
- * SPHERE collider (centre c, radius r), after the ground plane, in list order:
- *   d = x - c;  l2 = FMA(dz,dz, FMA(dy,dy, dx*dx));  if 0 < l2 < r*r:
- *       q = r * RCP(sqrt(l2));  x = FMA(q, d, c)
+ * COLLIDERS, after the ground plane, in list order [SPEC] (the mount has no collider code; the kinds are Unity's
+ * SphereCollider / CapsuleCollider / BoxCollider).  xp = position at the start of the substep.
+ *
+ *   SPHERE(c, r):   d = x - c;  l2 = FMA(dz,dz, FMA(dy,dy, dx*dx));  hit iff 0 < l2 < r*r:
+ *                   rinv = RCP(sqrt(l2));  q = r * rinv;  x = FMA(q, d, c);  n = d * rinv
+ *   CAPSULE(A, B, r): ab = B - A, il2 = 1 / |ab|^2 (0 if A == B), both prepared in float;
+ *                   t = dot(x - A, ab) * il2 clamped to [0, 1] (t > 0 ? t : 0, then t < 1 ? t : 1);
+ *                   then SPHERE(FMA(t, ab, A), r)               dot(a,b) = FMA(a.z,b.z, FMA(a.y,b.y, a.x*b.x))
+ *   BOX(c, half, axes R_k): d = x - c;  l_k = dot(R_k, d);  p_k = half_k - |l_k|;  hit iff all p_k > 0:
+ *                   k = first axis of least p_k;  x = FMA(l_k >= 0 ? p_k : -p_k, R_k, x);  n = R_k
+ *   friction f > 0 on a hit:  m = x - xp;  mn = -dot(m, n);  x = FMA(-f, FMA(mn, n, m), x)
+ *
+ * Box axes: column k of the rotation matrix of the quaternion (x,y,z,w), evaluated in double as written in
+ * orc_prepare_collider and rounded to float once; a zero quaternion is the identity.
  */
+#ifndef ORC_COLLIDER_DEFINED
+#define ORC_COLLIDER_DEFINED
+typedef struct {
+  int32_t kind; /* 0 sphere, 1 capsule, 2 box: same layout as sb_collider */
+  float friction;
+  float p[10];
+} orc_collider;
+typedef struct {
+  int kind;
+  float friction;
+  float a[4], b[4], c[4], d[4];
+} orc_prepared;
+static void orc_prepare_collider(const orc_collider *in, orc_prepared *o) {
+  const float *p = in->p;
+  memset(o, 0, sizeof *o);
+  o->kind = in->kind;
+  o->friction = in->friction;
+  o->a[0] = p[0]; o->a[1] = p[1]; o->a[2] = p[2]; o->a[3] = p[3];
+  if (in->kind == 1) {
+    for (int k = 0; k < 3; k++) o->b[k] = p[4 + k] - p[k];
+    float l2 = fmaf(o->b[2], o->b[2], fmaf(o->b[1], o->b[1], o->b[0] * o->b[0]));
+    o->b[3] = l2 > 0 ? 1.0f / l2 : 0.0f;
+  } else if (in->kind == 2) {
+    double x = p[6], y = p[7], z = p[8], w = p[9];
+    double n2 = ((x * x + y * y) + z * z) + w * w;
+    double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    if (n2 > 0) {
+      double s = 2.0 / n2;
+      R[0][0] = 1.0 - s * (y * y + z * z); R[0][1] = s * (x * y - z * w); R[0][2] = s * (x * z + y * w);
+      R[1][0] = s * (x * y + z * w); R[1][1] = 1.0 - s * (x * x + z * z); R[1][2] = s * (y * z - x * w);
+      R[2][0] = s * (x * z - y * w); R[2][1] = s * (y * z + x * w); R[2][2] = 1.0 - s * (x * x + y * y);
+    }
+    float *ax[3] = {o->b, o->c, o->d};
+    for (int k = 0; k < 3; k++) {
+      for (int j = 0; j < 3; j++) ax[k][j] = (float)R[j][k];
+      ax[k][3] = p[3 + k];
+    }
+    o->a[3] = 0;
+  }
+}
+#endif
+
+static inline int FN(sphere_one)(REAL *x, REAL cx, REAL cy, REAL cz, REAL r, REAL *n) {
+  REAL dx = x[0] - cx, dy = x[1] - cy, dz = x[2] - cz;
+  REAL l2 = FMA(dz, dz, FMA(dy, dy, dx * dx));
+  if (!(l2 > 0 && l2 < r * r)) return 0;
+  REAL rinv = (REAL)1 / SQRT(l2);
+  REAL q = r * rinv;
+  x[0] = FMA(q, dx, cx); x[1] = FMA(q, dy, cy); x[2] = FMA(q, dz, cz);
+  n[0] = dx * rinv; n[1] = dy * rinv; n[2] = dz * rinv;
+  return 1;
+}
+
 static inline void FN(finish_one)(REAL *x, const REAL *xp, REAL *v, const FN(step_consts) *c,
-                                  int n_spheres, const float *spheres) {
+                                  int n_col, const orc_prepared *cols) {
   if (!(x[3] > 0)) return;
   if (c->use_ground && x[1] < c->ground_y) {
     x[1] = c->ground_y;
     x[0] = FMA(c->keep, x[0] - xp[0], xp[0]);
     x[2] = FMA(c->keep, x[2] - xp[2], xp[2]);
   }
-  for (int s = 0; s < n_spheres; s++) {
-    REAL cx = spheres[4 * s], cy = spheres[4 * s + 1], cz = spheres[4 * s + 2], r = spheres[4 * s + 3];
-    REAL dx = x[0] - cx, dy = x[1] - cy, dz = x[2] - cz;
-    REAL l2 = FMA(dz, dz, FMA(dy, dy, dx * dx));
-    if (l2 > 0 && l2 < r * r) {
-      REAL q = r * ((REAL)1 / SQRT(l2));
-      x[0] = FMA(q, dx, cx); x[1] = FMA(q, dy, cy); x[2] = FMA(q, dz, cz);
+  for (int s = 0; s < n_col; s++) {
+    const orc_prepared *o = cols + s;
+    REAL n[3] = {0, 0, 0};
+    int hit;
+    if (o->kind == 0) {
+      hit = FN(sphere_one)(x, o->a[0], o->a[1], o->a[2], o->a[3], n);
+    } else if (o->kind == 1) {
+      REAL abx = o->b[0], aby = o->b[1], abz = o->b[2];
+      REAL t = FMA(x[2] - (REAL)o->a[2], abz, FMA(x[1] - (REAL)o->a[1], aby, (x[0] - (REAL)o->a[0]) * abx)) * (REAL)o->b[3];
+      t = t > 0 ? t : 0;
+      t = t < 1 ? t : 1;
+      hit = FN(sphere_one)(x, FMA(t, abx, (REAL)o->a[0]), FMA(t, aby, (REAL)o->a[1]), FMA(t, abz, (REAL)o->a[2]), o->a[3], n);
+    } else {
+      const float *R[3] = {o->b, o->c, o->d};
+      REAL dx = x[0] - (REAL)o->a[0], dy = x[1] - (REAL)o->a[1], dz = x[2] - (REAL)o->a[2];
+      REAL l[3], pk[3];
+      for (int k = 0; k < 3; k++) {
+        l[k] = FMA((REAL)R[k][2], dz, FMA((REAL)R[k][1], dy, (REAL)R[k][0] * dx));
+        pk[k] = (REAL)R[k][3] - (l[k] < 0 ? -l[k] : l[k]);
+      }
+      hit = pk[0] > 0 && pk[1] > 0 && pk[2] > 0;
+      if (hit) {
+        int km = 0;
+        if (pk[1] < pk[km]) km = 1;
+        if (pk[2] < pk[km]) km = 2;
+        REAL dl = l[km] >= 0 ? pk[km] : -pk[km];
+        for (int k = 0; k < 3; k++) { n[k] = R[km][k]; x[k] = FMA(dl, n[k], x[k]); }
+      }
+    }
+    if (hit && o->friction > 0) {
+      REAL m[3] = {x[0] - xp[0], x[1] - xp[1], x[2] - xp[2]};
+      REAL mn = -FMA(m[2], n[2], FMA(m[1], n[1], m[0] * n[0]));
+      REAL f = -(REAL)o->friction;
+      for (int k = 0; k < 3; k++) x[k] = FMA(f, FMA(mn, n[k], m[k]), x[k]);
     }
   }
   v[0] = ((x[0] - xp[0]) * c->inv_h) * c->damp;
@@ -213,9 +304,14 @@ static inline void FN(apply_entry)(REAL *x4, int32_t ent, const int32_t *edges, 
 int FN(orc_simulate)(int32_t V, REAL *x4, REAL *v4, int32_t E, const int32_t *edges,
                      const REAL *rest_len, int32_t T, const int32_t *tets, const REAL *rest_vol6,
                      const orc_params *p, int64_t n_order, const int32_t *order, int32_t n_batches,
-                     const int64_t *batch_off, int32_t n_spheres, const float *spheres,
+                     const int64_t *batch_off, int32_t n_col, const orc_collider *colliders,
                      int32_t n_frames, int32_t threads) {
-  if (V < 0 || p->substeps <= 0 || p->iterations < 0 || !(p->dt > 0)) return -1;
+  if (V < 0 || p->substeps <= 0 || p->iterations < 0 || !(p->dt > 0) || n_col < 0 || n_col > 16) return -1;
+  orc_prepared cols[16];
+  for (int s = 0; s < n_col; s++) {
+    if (colliders[s].kind < 0 || colliders[s].kind > 2) return -1;
+    orc_prepare_collider(colliders + s, cols + s);
+  }
   for (int64_t k = 0; k < n_order; k++) {
     int32_t id = order[k] & 0x7fffffff;
     if (order[k] >= 0 ? id >= E : id >= T) return -2;
@@ -242,7 +338,7 @@ int FN(orc_simulate)(int32_t V, REAL *x4, REAL *v4, int32_t E, const int32_t *ed
       }
 #pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1)
       for (int32_t i = 0; i < V; i++)
-        FN(finish_one)(x4 + 4 * (size_t)i, xp + 3 * (size_t)i, v4 + 4 * (size_t)i, &c, n_spheres, spheres);
+        FN(finish_one)(x4 + 4 * (size_t)i, xp + 3 * (size_t)i, v4 + 4 * (size_t)i, &c, n_col, cols);
     }
   }
   free(xp);

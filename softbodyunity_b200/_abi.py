@@ -13,10 +13,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SB_OK, SB_E_ARG, SB_E_CUDA, SB_E_NCCL, SB_E_NAN, SB_E_STATE, SB_E_NOMEM = 0, -1, -2, -3, -4, -5, -6
 FLAG_NO_GROUND, FLAG_FAST_MATH, FLAG_NO_GRAPH, FLAG_NO_NORMALS, FLAG_NO_PDL, FLAG_DAG = 1, 2, 4, 8, 16, 32
 ABI_VERSION = 2
+COLLIDER_SPHERE, COLLIDER_CAPSULE, COLLIDER_BOX, MAX_COLLIDERS = 0, 1, 2, 16
 
 EXPORTS = [
     "sb_abi_check", "sb_default_params", "sb_create", "sb_plan", "sb_destroy", "sb_set_params",
-    "sb_get_params", "sb_set_colliders", "sb_step", "sb_synchronize", "sb_read_positions",
+    "sb_get_params", "sb_set_colliders", "sb_set_colliders_ex", "sb_step", "sb_synchronize", "sb_read_positions",
     "sb_read_normals", "sb_surface_vertices", "sb_read_surface", "sb_get_state", "sb_set_state",
     "sb_diagnostics", "sb_get_info", "sb_get_topology", "sb_get_tet_roles", "sb_get_schedule", "sb_get_tiles",
     "sb_time_frames", "sb_time_kernel", "sb_debug_trace_pass", "sb_debug_verify_streams", "sb_last_error",
@@ -99,6 +100,7 @@ def load():
         "sb_set_params": (C.c_int, [vp, P(SbParams)]),
         "sb_get_params": (C.c_int, [vp, P(SbParams)]),
         "sb_set_colliders": (C.c_int, [vp, vp, u32]),
+        "sb_set_colliders_ex": (C.c_int, [vp, vp, u32]),
         "sb_step": (C.c_int, [vp, f32]),
         "sb_synchronize": (C.c_int, [vp]),
         "sb_read_positions": (C.c_int, [vp, vp, u32]),

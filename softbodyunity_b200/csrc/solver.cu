@@ -74,6 +74,35 @@ struct PassBufs {
 
 static const int kDiagBlocks = 592;
 
+// Caller's collider -> what k_finish reads.  Same arithmetic as the oracle's orc_prepare_collider (host code is
+// built with -ffp-contract=off): capsule axis and 1/|axis|^2 in float, box axes from the quaternion in double
+// (normalised by 2/|q|^2, so any non-zero quaternion is a rotation), rounded to float once.
+static DevCollider prepare_collider(const sb_collider &c) {
+  DevCollider d{};
+  const float *p = c.p;
+  d.a = make_float4(p[0], p[1], p[2], p[3]);
+  if (c.kind == SB_COLLIDER_CAPSULE) {
+    const float ax = p[4] - p[0], ay = p[5] - p[1], az = p[6] - p[2];
+    const float l2 = fmaf(az, az, fmaf(ay, ay, ax * ax));
+    d.b = make_float4(ax, ay, az, l2 > 0.f ? 1.0f / l2 : 0.f);
+  } else if (c.kind == SB_COLLIDER_BOX) {
+    const double x = p[6], y = p[7], z = p[8], w = p[9];
+    const double n2 = ((x * x + y * y) + z * z) + w * w;
+    double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    if (n2 > 0) {
+      const double s = 2.0 / n2;
+      R[0][0] = 1.0 - s * (y * y + z * z); R[0][1] = s * (x * y - z * w); R[0][2] = s * (x * z + y * w);
+      R[1][0] = s * (x * y + z * w); R[1][1] = 1.0 - s * (x * x + z * z); R[1][2] = s * (y * z - x * w);
+      R[2][0] = s * (x * z - y * w); R[2][1] = s * (y * z + x * w); R[2][2] = 1.0 - s * (x * x + y * y);
+    }
+    d.a.w = 0.f;
+    d.b = make_float4((float)R[0][0], (float)R[1][0], (float)R[2][0], p[3]); // box axis k = column k of R
+    d.c = make_float4((float)R[0][1], (float)R[1][1], (float)R[2][1], p[4]);
+    d.d = make_float4((float)R[0][2], (float)R[1][2], (float)R[2][2], p[5]);
+  }
+  return d;
+}
+
 } // namespace sb
 
 using namespace sb;
@@ -134,8 +163,8 @@ struct sb_solver {
 
   float cur_dt = -1.f;
   bool prm_dirty = true;
-  float4 spheres[16];
-  int n_spheres = 0;
+  sb_collider colliders[SB_MAX_COLLIDERS];
+  int n_col = 0;
   std::map<uint64_t, cudaGraphExec_t> graphs;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
@@ -302,8 +331,12 @@ struct sb_solver {
     p.gx = prm.gravity[0]; p.gy = prm.gravity[1]; p.gz = prm.gravity[2];
     p.ground_y = prm.ground_y;
     p.use_ground = !(prm.flags & SB_FLAG_NO_GROUND);
-    p.n_spheres = n_spheres;
-    for (int s = 0; s < n_spheres; s++) p.spheres[s] = spheres[s];
+    p.n_col = n_col;
+    for (int s = 0; s < n_col; s++) {
+      p.col_kind[s] = colliders[s].kind;
+      p.col_fric[s] = colliders[s].friction;
+      p.col[s] = prepare_collider(colliders[s]);
+    }
     CK(cudaStreamSynchronize(stream)); // hprm may still be in flight from an earlier change
     *hprm = p;
     CK(cudaMemcpyAsync(dprm.p, hprm, sizeof(DevParams), cudaMemcpyHostToDevice, stream));
@@ -947,13 +980,36 @@ int sb_get_params(sb_handle h, sb_params *out) {
   return SB_OK;
 }
 
+int sb_set_colliders_ex(sb_handle h, const sb_collider *c, uint32_t n) {
+  NEED_HANDLE(h);
+  if (n > SB_MAX_COLLIDERS || (n && !c)) { h->err = "at most 16 colliders"; return SB_E_ARG; }
+  for (uint32_t k = 0; k < n; k++) {
+    const int np = c[k].kind == SB_COLLIDER_SPHERE ? 4 : c[k].kind == SB_COLLIDER_CAPSULE ? 7 : 10;
+    if (c[k].kind < SB_COLLIDER_SPHERE || c[k].kind > SB_COLLIDER_BOX) { h->err = "unknown collider kind"; return SB_E_ARG; }
+    if (!(c[k].friction >= 0.f && c[k].friction <= 1.f)) { h->err = "collider friction outside [0, 1]"; return SB_E_ARG; }
+    for (int j = 0; j < np; j++)
+      if (!std::isfinite(c[k].p[j])) { h->err = "collider is not finite"; return SB_E_ARG; }
+    const bool neg = c[k].kind == SB_COLLIDER_BOX ? (c[k].p[3] < 0.f || c[k].p[4] < 0.f || c[k].p[5] < 0.f) : c[k].p[3] < 0.f;
+    if (neg) { h->err = "collider radius / half extent is negative"; return SB_E_ARG; }
+  }
+  for (uint32_t k = 0; k < n; k++) h->colliders[k] = c[k];
+  h->n_col = (int)n;
+  h->prm_dirty = true;
+  return SB_OK;
+}
+
 int sb_set_colliders(sb_handle h, const float *s, uint32_t n) {
   NEED_HANDLE(h);
-  if (n > 16 || (n && !s)) { h->err = "at most 16 sphere colliders"; return SB_E_ARG; }
+  if (n > SB_MAX_COLLIDERS || (n && !s)) { h->err = "at most 16 sphere colliders"; return SB_E_ARG; }
   for (uint32_t k = 0; k < 4 * n; k++)
     if (!std::isfinite(s[k])) { h->err = "collider is not finite"; return SB_E_ARG; }
-  for (uint32_t k = 0; k < n; k++) h->spheres[k] = make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
-  h->n_spheres = (int)n;
+  for (uint32_t k = 0; k < n; k++) {
+    sb_collider c{};
+    c.kind = SB_COLLIDER_SPHERE;
+    for (int j = 0; j < 4; j++) c.p[j] = s[4 * k + j];
+    h->colliders[k] = c;
+  }
+  h->n_col = (int)n;
   h->prm_dirty = true;
   return SB_OK;
 }

@@ -14,6 +14,9 @@ import numpy as np
 from . import _abi
 from ._abi import SbError, SbInfo, SbMeshDesc, SbParams
 
+# sb_collider (include/softbody_b200.h): kind 0 sphere (centre, r) / 1 capsule (A, r, B) / 2 box (centre, half, quat)
+COLLIDER = np.dtype([("kind", np.int32), ("friction", np.float32), ("p", np.float32, 10)])
+
 
 def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
@@ -163,6 +166,11 @@ class SoftBody:
     def set_colliders(self, spheres_xyzr):
         s = np.ascontiguousarray(spheres_xyzr, dtype=np.float32).reshape(-1, 4)
         self._ck(self._lib.sb_set_colliders(self._h, _ptr(s) if len(s) else None, len(s)))
+
+    def set_colliders_ex(self, colliders):
+        """Mixed sphere / capsule / box colliders: an array of _abi.COLLIDER records (sb_collider)."""
+        c = np.ascontiguousarray(colliders, dtype=COLLIDER)
+        self._ck(self._lib.sb_set_colliders_ex(self._h, _ptr(c) if len(c) else None, len(c)))
 
     # -- the hot path ---------------------------------------------------------------
     def step(self, dt: float = 0.0, frames: int = 1):

@@ -15,8 +15,56 @@ def compliance(k):
     return 1.0 / k if k > 0 else -1.0
 
 
+def quat_matrix(q):
+    """Rotation matrix (box -> world) of the quaternion (x, y, z, w); zero quaternion = identity."""
+    x, y, z, w = (float(c) for c in q)
+    n = np.sqrt(x * x + y * y + z * z + w * w)
+    if n == 0:
+        return np.eye(3)
+    x, y, z, w = x / n, y / n, z / n, w / n
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def collide(x, xp, kind, fr, p):
+    """One collider on all points (sphere 0 / capsule 1 / box 2): textbook closest-point push-out, then the share
+    `fr` of the tangential motion since xp is removed.  Returns the new positions."""
+    x = x.copy()
+    if kind in (0, "sphere", 1, "capsule"):
+        r = p[3]
+        if kind in (0, "sphere"):
+            c = np.broadcast_to(p[:3], x.shape)
+        else:
+            a, b = p[:3], p[4:7]
+            ab = b - a
+            l2 = ab @ ab
+            t = np.clip(((x - a) @ ab) / l2, 0, 1) if l2 > 0 else np.zeros(len(x), x.dtype)
+            c = a + t[:, None] * ab
+        d = x - c
+        l = np.sqrt((d * d).sum(1))
+        hit = (l > 0) & (l < r)
+        n = np.zeros_like(x)
+        n[hit] = d[hit] / l[hit][:, None]
+        x[hit] = c[hit] + n[hit] * r
+    else:
+        c, half, R = p[:3], p[3:6], quat_matrix(p[6:10]).astype(x.dtype)
+        loc = (x - c) @ R  # components along the box axes (columns of R)
+        pen = half - np.abs(loc)
+        hit = (pen > 0).all(1)
+        k = np.argmin(pen, axis=1)
+        n = R.T[k]
+        sgn = np.where(loc[np.arange(len(x)), k] >= 0, 1.0, -1.0)
+        x[hit] += (sgn * pen[np.arange(len(x)), k])[hit][:, None] * n[hit]
+    if fr > 0:
+        m = x - xp
+        mt = m - (m * n).sum(1)[:, None] * n
+        x[hit] -= fr * mt[hit]
+    return x
+
+
 def simulate(x, v, w, edges, rest_len, tets, rest_vol6, *, dt, substeps, iterations, k_d, k_v, damping, friction,
-             gravity, ground_y, use_ground, batches, n_frames, spheres=(), dtype=np.float64):
+             gravity, ground_y, use_ground, batches, n_frames, spheres=(), colliders=(), dtype=np.float64):
     """batches: list of (kind, ids) with kind 'e' or 't'; ids vertex-disjoint within a batch."""
     x = x.astype(dtype).copy()
     v = v.astype(dtype).copy()
@@ -72,5 +120,7 @@ def simulate(x, v, w, edges, rest_len, tets, rest_vol6, *, dt, substeps, iterati
                 l = np.sqrt((d * d).sum(1))
                 inside = dyn & (l > 0) & (l < r)
                 x[inside] = c + d[inside] * (r / l[inside])[:, None]
+            for kind, fr, *p in colliders:
+                x[dyn] = collide(x[dyn], xp[dyn], kind, fr, np.asarray(p, dtype).ravel())
             v[dyn] = (x[dyn] - xp[dyn]) / h * max(0.0, 1 - h * damping)
     return x, v

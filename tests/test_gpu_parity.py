@@ -19,15 +19,18 @@ from softbodyunity_b200 import FLAG_FAST_MATH, FLAG_NO_GRAPH, FLAG_NO_GROUND, So
 pytestmark = pytest.mark.gpu
 
 
-def run_pair(pos, tets, tris, n_frames, spheres=None, inv_mass=None, **kw):
+def run_pair(pos, tets, tris, n_frames, spheres=None, inv_mass=None, colliders=None, **kw):
     sb = SoftBody(pos, tets, tris, inv_mass=inv_mass, **kw)
     if spheres is not None:
         sb.set_colliders(spheres)
+    if colliders is not None:
+        sb.set_colliders_ex(colliders)
     order, off = sb.schedule()
     m = orc.Model(pos, tets, inv_mass=inv_mass, density=kw.get("density", 1000.0), roles=sb.tet_roles())
     sb.step(frames=n_frames)
     x4, v4 = sb.get_state()
-    m.simulate(oracle_params(sb), n_frames=n_frames, order=order, batch_off=off, spheres=spheres, threads=8)
+    m.simulate(oracle_params(sb), n_frames=n_frames, order=order, batch_off=off, spheres=spheres, threads=8,
+               colliders=colliders)
     return sb, m, x4, v4
 
 
@@ -86,6 +89,34 @@ def test_colliders_pins_and_gravity_vector():
     assert np.array_equal(x4[pinned, :3], pos[pinned])
     d = np.linalg.norm(x4[:, :3] - sph[0, :3], axis=1)
     assert d.min() >= 0.2 - 1e-5
+
+
+def test_capsule_box_sphere_colliders_with_friction_are_bit_identical():
+    # a soft block impaled on a sphere, a degenerate capsule and an axis-aligned box falls onto a tilted box and a
+    # capsule; every collider moves vertices (checked with the oracle alone when the scene was set up)
+    pos, tets, tris = meshgen.block(12, 8, 12, spacing=0.05, origin=(-0.275, 0.45, -0.275))
+    q = np.array([0.0, 0.0, math.sin(0.15), math.cos(0.15)]) * 1.7  # about z, deliberately not normalised
+    cols = orc.colliders([
+        ("box", 0.3, -0.2, 0.3, 0.0, 0.15, 0.1, 0.3, *q),
+        ("capsule", 0.5, 0.1, 0.3, -0.3, 0.08, 0.35, 0.4, 0.3),
+        ("sphere", 0.2, 0.1, 0.6, 0.1, 0.08),
+        ("capsule", 0.0, -0.1, 0.65, -0.1, 0.06, -0.1, 0.65, -0.1),  # A == B: a sphere
+        ("box", 0.0, 0.0, 0.6, -0.15, 0.06, 0.05, 0.07, 0, 0, 0, 0),  # zero quaternion: axis aligned
+    ])
+    sb, m, x4, v4 = run_pair(pos, tets, tris, n_frames=40, colliders=cols, tile_cap=400, stiffness=3e4, friction=0.3)
+    assert bits_equal(x4, m.x4) and bits_equal(v4, m.v4)
+    d = np.linalg.norm(x4[:, :3] - cols[2]["p"][:3], axis=1)
+    assert d.min() >= 0.08 - 1e-5
+    fresh = orc.Model(pos, tets, roles=sb.tet_roles())
+    order, off = sb.schedule()
+    fresh.simulate(oracle_params(sb), n_frames=40, order=order, batch_off=off, threads=8)
+    assert np.abs(fresh.x4 - m.x4).max() > 1e-2, "colliders should change the outcome"
+    # replacing the list: sb_set_colliders (spheres, no friction) after sb_set_colliders_ex
+    sb.set_colliders(np.array([[0.0, 0.2, 0.0, 0.15]], np.float32))
+    sb.step(frames=3)
+    m.simulate(oracle_params(sb), n_frames=3, order=order, batch_off=off, spheres=np.array([[0.0, 0.2, 0.0, 0.15]], np.float32), threads=8)
+    x4, v4 = sb.get_state()
+    assert bits_equal(x4, m.x4) and bits_equal(v4, m.v4)
 
 
 def test_normals_match_and_surface_readback():

@@ -142,6 +142,97 @@ def test_sphere_collider_pushes_out():
     np.testing.assert_allclose(m.x4[0, :3] / 0.5, np.array([0.1, 0.2, 0.2]) / 0.3, rtol=1e-5)
 
 
+def _one_point(pos, cols, xp=None):
+    """Vertex 0 of a free tet placed at `pos` (having started the substep at xp), one finish stage, no forces."""
+    m = orc.Model(TET_POS + np.float32([50, 50, 50]), TET, inv_mass=np.ones(4, np.float32))
+    h = 0.01
+    start = np.asarray(pos if xp is None else xp, np.float32)
+    m.x4[0, :3] = start
+    m.v4[0, :3] = (np.asarray(pos, np.float32) - start) / np.float32(h)  # predict moves it from xp to pos
+    m.simulate(orc.params(dt=h, substeps=1, iterations=0, gravity=(0, 0, 0), flags=1), order=np.zeros(0, np.int32),
+               colliders=orc.colliders(cols))
+    return m.x4[0, :3].astype(np.float64)
+
+
+def test_capsule_collider_known_answers():
+    cap = [("capsule", 0.0, 0, 0, 0, 0.5, 2, 0, 0)]  # segment (0,0,0)-(2,0,0), radius 0.5
+    # beside the segment: out along the perpendicular
+    np.testing.assert_allclose(_one_point([1.0, 0.1, 0.0], cap), [1.0, 0.5, 0.0], atol=1e-6)
+    # beyond end B: out along the radius of the end cap
+    x = _one_point([2.1, 0.2, 0.0], cap)
+    assert abs(np.linalg.norm(x - [2, 0, 0]) - 0.5) < 1e-6 and x[0] > 2.0
+    # before end A (t clamps to 0)
+    x = _one_point([-0.2, 0.0, 0.3], cap)
+    assert abs(np.linalg.norm(x) - 0.5) < 1e-6 and x[0] < 0
+    # outside: untouched
+    p = np.float32([1.0, 0.6, 0.0])
+    assert np.array_equal(_one_point(p, cap), p.astype(np.float64))
+    # degenerate capsule (A == B) is a sphere
+    x = _one_point([0.1, 0.2, 0.2], [("capsule", 0.0, 0, 0, 0, 0.5, 0, 0, 0)])
+    y = _one_point([0.1, 0.2, 0.2], [("sphere", 0.0, 0, 0, 0, 0.5)])
+    assert np.array_equal(x, y)
+
+
+def test_box_collider_known_answers():
+    box = [("box", 0.0, 0, 0, 0, 1.0, 0.5, 2.0, 0, 0, 0, 1)]  # axis-aligned, half extents (1, .5, 2)
+    # nearest face is +y
+    np.testing.assert_allclose(_one_point([0.2, 0.3, 0.1], box), [0.2, 0.5, 0.1], atol=1e-6)
+    # nearest face is -x
+    np.testing.assert_allclose(_one_point([-0.9, 0.0, 0.0], box), [-1.0, 0.0, 0.0], atol=1e-6)
+    # outside in one axis only: untouched
+    p = np.float32([0.0, 0.6, 0.0])
+    assert np.array_equal(_one_point(p, box), p.astype(np.float64))
+    # a zero quaternion is the identity
+    z = [("box", 0.0, 0, 0, 0, 1.0, 0.5, 2.0, 0, 0, 0, 0)]
+    assert np.array_equal(_one_point([0.2, 0.3, 0.1], z), _one_point([0.2, 0.3, 0.1], box))
+    # rotated 90 degrees about z: the box's x axis is world y, so half extents are (.5, 1, 2) in the world;
+    # the quaternion need not be normalised
+    s = 2.0 * np.sqrt(0.5)
+    rot = [("box", 0.0, 0, 0, 0, 1.0, 0.5, 2.0, 0, 0, s, s)]
+    np.testing.assert_allclose(_one_point([0.3, 0.2, 0.1], rot), [0.5, 0.2, 0.1], atol=1e-6)
+    np.testing.assert_allclose(_one_point([0.0, -0.9, 0.1], rot), [0.0, -1.0, 0.1], atol=1e-6)
+    # translated centre
+    mv = [("box", 0.0, 5, 5, 5, 1.0, 1.0, 1.0, 0, 0, 0, 1)]
+    np.testing.assert_allclose(_one_point([5.0, 5.0, 5.75], mv), [5.0, 5.0, 6.0], atol=1e-6)
+
+
+def test_collider_friction_removes_tangential_motion():
+    # the point slid 0.4 along x and sank 0.1 into the box's top face during the substep
+    xp, pos = [0.0, 0.5, 0.0], [0.4, 0.4, 0.0]
+    for fr, ex in ((0.0, 0.4), (0.25, 0.3), (1.0, 0.0)):
+        x = _one_point(pos, [("box", fr, 0, 0, 0, 1.0, 0.5, 1.0, 0, 0, 0, 1)], xp=xp)
+        np.testing.assert_allclose(x, [ex, 0.5, 0.0], atol=1e-6)
+    # sphere: full friction leaves only the radial part of the motion
+    xp, pos = [0.0, 1.0, 0.0], [0.3, 0.8, 0.0]
+    x = _one_point(pos, [("sphere", 1.0, 0, 0, 0, 1.0)], xp=xp)
+    n = np.array(pos) / np.linalg.norm(pos)
+    m = x - np.array(xp)
+    assert abs(np.linalg.norm(np.cross(m, n))) < 1e-6  # what is left of the motion is along the normal
+    assert abs(np.linalg.norm(_one_point(pos, [("sphere", 0.0, 0, 0, 0, 1.0)], xp=xp)) - 1.0) < 1e-6
+
+
+def test_colliders_match_independent_numpy():
+    rng = np.random.default_rng(7)
+    pts = rng.uniform(-1.5, 1.5, (400, 3)).astype(np.float32)
+    xps = (pts + rng.normal(0, 0.05, pts.shape)).astype(np.float32)
+    q = rng.normal(size=4)
+    cols = [("sphere", 0.3, 0.2, -0.1, 0.3, 0.9), ("capsule", 0.5, -1, -1, -1, 0.4, 1, 0.5, 1),
+            ("box", 0.2, 0.1, 0.2, -0.3, 0.8, 0.6, 0.7, *q), ("box", 0.0, -0.8, 0.9, 0.5, 0.5, 0.5, 0.5, 0, 0, 0, 1)]
+    for col in cols:
+        got = np.array([_one_point(p, [col], xp=s) for p, s in zip(pts, xps)])
+        # np_xpbd works from the same fp32 start: predicted position = fma(h, v, xp) in fp32
+        h = np.float32(0.01)
+        v = (pts - xps) / h
+        pred = (xps.astype(np.float64) + np.float64(h) * v.astype(np.float64)).astype(np.float32)
+        want = np_xpbd.collide(pred.astype(np.float64), xps.astype(np.float64), col[0], col[1],
+                               np.asarray(col[2:], np.float64))
+        moved = np.abs(want - pred).max(1) > 0
+        assert moved.sum() > 10
+        # a point within rounding of a face / radius may be classified differently by the two: allow a few
+        bad = np.abs(got - want).max(1) > 1e-5
+        assert bad.sum() <= 2, (col[0], bad.sum())
+
+
 def test_normals_cube_and_sphere():
     pos, tets, tris = meshgen.block(5, spacing=0.25, origin=(0, 0, 0), jitter=0.0)
     m = orc.Model(pos, tets)
