@@ -193,9 +193,41 @@ int sb_read_normals(sb_handle h, float *dst_xyz, uint32_t n_verts);
 int sb_surface_vertices(sb_handle h, int32_t *ids, uint32_t capacity, uint32_t *n_surface);
 int sb_read_surface(sb_handle h, float *dst_pos_xyz, float *dst_nrm_xyz, uint32_t n_surface);
 
+/*
+ * Render mesh driven by the tets (Unity: the MeshFilter's surface mesh embedded in the simulated tet mesh).
+ * sb_skin_bind finds, for every render vertex, the tet that encloses its REST position (or the nearest one, with
+ * extrapolating weights) and its four barycentric weights (w0 = 1 - w1 - w2 - w3), on the host, once.
+ * sb_read_skinned evaluates sum_k w_k * x[tet vertex k] on the GPU (operation order: oracle's orc_skin) and, when
+ * dst_nrm_xyz is given, area-weighted normals over render_tris; either destination may be NULL.  Synchronises.
+ * sb_skin_bind also works on an sb_plan handle (binding only).
+ */
+int sb_skin_bind(sb_handle h, const float *render_pos_xyz, uint32_t n_render_verts, const int32_t *render_tris,
+                 uint32_t n_render_tris);
+int sb_skin_get_binding(sb_handle h, int32_t *tet_of, float *bary4, uint32_t n_render_verts);
+int sb_read_skinned(sb_handle h, float *dst_pos_xyz, float *dst_nrm_xyz, uint32_t n_render_verts);
+/* The binding alone, no handle: tets in the caller's vertex order, weights relative to tets[4 * tet_of[i] ..]. */
+int sb_skin_compute(const float *tet_pos_xyz, uint32_t n_verts, const int32_t *tets, uint32_t n_tets,
+                    const float *points_xyz, uint32_t n_points, int32_t *tet_of, float *bary4);
+
 /* Full state as float4 arrays in the caller's numbering: x4 = (x,y,z,inv_mass), v4 = (vx,vy,vz,0). */
 int sb_get_state(sb_handle h, float *x4, float *v4, uint32_t n_verts);
 int sb_set_state(sb_handle h, const float *x4, const float *v4, uint32_t n_verts);
+
+/*
+ * State snapshots for replay and regression vectors (.sbs: "SBSTATE1", version, vertex count, frame number, topology
+ * hash, sb_params, x4, v4, FNV-1a checksum; little endian).  sb_save_state / sb_load_state move a handle's state
+ * through such a file; loading checks the vertex count and the topology hash, restores the frame counter and, when
+ * apply_params != 0, the parameters.  A run resumed from a snapshot is bit-identical to the uninterrupted one.
+ * sb_state_write / sb_state_read are the file layer alone (no device; x4 == v4 == NULL reads the header only).
+ */
+int sb_save_state(sb_handle h, const char *path);
+int sb_load_state(sb_handle h, const char *path, int32_t apply_params);
+int sb_frames_done(sb_handle h, uint64_t *out); /* sb_step calls since creation or the frame of the loaded snapshot */
+int sb_state_write(const char *path, const float *x4, const float *v4, uint32_t n_verts, const sb_params *params,
+                   uint64_t frame, uint64_t topo_hash);
+int sb_state_read(const char *path, float *x4, float *v4, uint32_t capacity_verts, uint32_t *n_verts, sb_params *params,
+                  uint64_t *frame, uint64_t *topo_hash);
+uint64_t sb_topology_hash(uint32_t n_verts, const int32_t *tets, uint32_t n_tets);
 
 /* Same 16 doubles as the oracle's diagnostics (energy, volume, momenta, strain, NaN count, min y). */
 int sb_diagnostics(sb_handle h, double *out16);
@@ -294,6 +326,28 @@ int sb_debug_trace_pass(sb_handle h, uint32_t pass, unsigned long long *out, uin
 int sb_debug_verify_streams(sb_handle h, uint64_t *n_bad, uint64_t *wavefronts, uint64_t *wavefronts_ideal);
 
 const char *sb_last_error(sb_handle h); /* h may be NULL: last sb_create failure on this thread */
+
+/*
+ * Mesh ingest, host only (no device needed): the step BEFORE the path.  An sb_tetmesh owns positions, positively
+ * oriented tets and outward-wound boundary triangles; sb_tetmesh_desc points an sb_mesh_desc at them for sb_create
+ * (valid until sb_tetmesh_free).  Errors: negative sb_status, message via sb_ingest_last_error (per thread).
+ *   sb_tetmesh_from_surface  closed triangle surface (Unity Mesh.vertices / triangles) -> lattice of `spacing`-sized
+ *                            cells whose centre has non-zero winding number, five tets per cell
+ *   sb_tetmesh_from_arrays   caller's arrays; orientation fixed, boundary extracted when n_tris == 0
+ *   sb_tetmesh_load / save   TetGen <base>.node + .ele (+ .face) or Gmsh MSH 2.2 ASCII (.msh), by extension
+ */
+typedef struct sb_tetmesh *sb_tetmesh_handle;
+int sb_tetmesh_from_surface(const float *surf_pos_xyz, uint32_t n_verts, const int32_t *surf_tris, uint32_t n_tris,
+                            float spacing, sb_tetmesh_handle *out);
+int sb_tetmesh_from_arrays(const float *pos_xyz, uint32_t n_verts, const int32_t *tets, uint32_t n_tets,
+                           const int32_t *tris, uint32_t n_tris, sb_tetmesh_handle *out);
+int sb_tetmesh_load(const char *path, sb_tetmesh_handle *out);
+int sb_tetmesh_save(sb_tetmesh_handle m, const char *path);
+int sb_tetmesh_sizes(sb_tetmesh_handle m, uint32_t *n_verts, uint32_t *n_tets, uint32_t *n_tris);
+int sb_tetmesh_copy(sb_tetmesh_handle m, float *pos_xyz, int32_t *tets, int32_t *tris); /* any pointer may be NULL */
+int sb_tetmesh_desc(sb_tetmesh_handle m, sb_mesh_desc *desc);
+int sb_tetmesh_free(sb_tetmesh_handle m);
+const char *sb_ingest_last_error(void);
 
 #ifdef __cplusplus
 }

@@ -152,6 +152,19 @@ class Model:
         getattr(lib(), "orc_normals" + self.sfx)(C.c_int32(self.V), _p(self.x4), C.c_int32(len(tris)), _p(tris), _p(out))
         return out
 
+    def skin(self, tet_of, bary4, tris=None):
+        """Render vertices bound to the tets (caller's vertex order): positions (n,3) and, with tris, normals (n,3)."""
+        tet_of = np.ascontiguousarray(tet_of, np.int32)
+        bary4 = np.ascontiguousarray(bary4, np.float32).reshape(-1, 4)
+        out4 = np.zeros((len(tet_of), 4), self.dtype)
+        getattr(lib(), "orc_skin" + self.sfx)(_p(self.x4), _p(self.tets), C.c_int32(len(tet_of)), _p(tet_of), _p(bary4), _p(out4))
+        if tris is None:
+            return out4[:, :3].copy()
+        tris = np.ascontiguousarray(tris, np.int32).reshape(-1, 3)
+        nrm = np.empty((len(tet_of), 3), self.dtype)
+        getattr(lib(), "orc_normals" + self.sfx)(C.c_int32(len(tet_of)), _p(out4), C.c_int32(len(tris)), _p(tris), _p(nrm))
+        return out4[:, :3].copy(), nrm
+
     def diagnostics(self, gravity=(0.0, -9.81, 0.0)):
         assert self.dtype == np.float32
         g = np.asarray(gravity, np.float32)

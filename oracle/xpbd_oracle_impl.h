@@ -389,5 +389,22 @@ void FN(orc_normals)(int32_t V, const REAL *x4, int32_t F, const int32_t *tris, 
   }
 }
 
+/*
+ * Render mesh bound to the tets: out4[i] = sum_k w_k * x[tets[4*tet_of[i] + k]] with the four barycentric weights
+ * bary4[4i..] of render vertex i, as FMA(w3,x3, FMA(w2,x2, FMA(w1,x1, w0*x0))) per component; out4 is xyz0-strided
+ * so that orc_normals can run over it with the render triangles.
+ */
+void FN(orc_skin)(const REAL *x4, const int32_t *tets, int32_t n, const int32_t *tet_of, const float *bary4, REAL *out4) {
+  for (int32_t i = 0; i < n; i++) {
+    const int32_t *q = tets + 4 * (size_t)tet_of[i];
+    const float *w = bary4 + 4 * (size_t)i;
+    for (int k = 0; k < 3; k++)
+      out4[4 * (size_t)i + k] = FMA((REAL)w[3], x4[4 * (size_t)q[3] + k],
+                                    FMA((REAL)w[2], x4[4 * (size_t)q[2] + k],
+                                        FMA((REAL)w[1], x4[4 * (size_t)q[1] + k], (REAL)w[0] * x4[4 * (size_t)q[0] + k])));
+    out4[4 * (size_t)i + 3] = 0;
+  }
+}
+
 #undef CROSS
 #undef DOT3

@@ -24,6 +24,10 @@ EXPORTS = [
     "sb_set_stream", "sb_prepare", "sb_enqueue", "sb_halo_set", "sb_halo_pack", "sb_halo_unpack", "sb_lumped_inv_mass",
     "sb_halo_alloc", "sb_halo_connect", "sb_halo_error", "sb_ipc_export", "sb_ipc_open",
     "sb_dist_setup", "sb_dist_connect", "sb_dist_owned", "sb_dist_error", "sb_dist_layout",
+    "sb_skin_bind", "sb_skin_get_binding", "sb_read_skinned", "sb_skin_compute",
+    "sb_save_state", "sb_load_state", "sb_frames_done", "sb_state_write", "sb_state_read", "sb_topology_hash",
+    "sb_tetmesh_from_surface", "sb_tetmesh_from_arrays", "sb_tetmesh_load", "sb_tetmesh_save", "sb_tetmesh_sizes",
+    "sb_tetmesh_copy", "sb_tetmesh_desc", "sb_tetmesh_free", "sb_ingest_last_error",
 ]
 
 
@@ -137,6 +141,25 @@ def load():
         "sb_dist_owned": (C.c_int, [vp, vp, vp]),
         "sb_dist_error": (C.c_int, [vp, P(i32)]),
         "sb_dist_layout": (C.c_int, [vp, i32, i32, vp, vp, u32]),
+        "sb_skin_bind": (C.c_int, [vp, vp, u32, vp, u32]),
+        "sb_skin_get_binding": (C.c_int, [vp, vp, vp, u32]),
+        "sb_read_skinned": (C.c_int, [vp, vp, vp, u32]),
+        "sb_skin_compute": (C.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
+        "sb_save_state": (C.c_int, [vp, C.c_char_p]),
+        "sb_load_state": (C.c_int, [vp, C.c_char_p, i32]),
+        "sb_frames_done": (C.c_int, [vp, P(C.c_uint64)]),
+        "sb_state_write": (C.c_int, [C.c_char_p, vp, vp, u32, P(SbParams), C.c_uint64, C.c_uint64]),
+        "sb_state_read": (C.c_int, [C.c_char_p, vp, vp, u32, P(u32), P(SbParams), P(C.c_uint64), P(C.c_uint64)]),
+        "sb_topology_hash": (C.c_uint64, [u32, vp, u32]),
+        "sb_tetmesh_from_surface": (C.c_int, [vp, u32, vp, u32, f32, P(vp)]),
+        "sb_tetmesh_from_arrays": (C.c_int, [vp, u32, vp, u32, vp, u32, P(vp)]),
+        "sb_tetmesh_load": (C.c_int, [C.c_char_p, P(vp)]),
+        "sb_tetmesh_save": (C.c_int, [vp, C.c_char_p]),
+        "sb_tetmesh_sizes": (C.c_int, [vp, P(u32), P(u32), P(u32)]),
+        "sb_tetmesh_copy": (C.c_int, [vp, vp, vp, vp]),
+        "sb_tetmesh_desc": (C.c_int, [vp, P(SbMeshDesc)]),
+        "sb_tetmesh_free": (C.c_int, [vp]),
+        "sb_ingest_last_error": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsoftbody_b200.so")
-SOURCES = ["solver.cu", "plan.cpp"]
+SOURCES = ["solver.cu", "plan.cpp", "ingest.cpp"]
 DEPS = SOURCES + ["kernels.cuh", "plan.h", os.path.join("..", "..", "include", "softbody_b200.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -165,6 +165,16 @@ struct sb_solver {
   bool prm_dirty = true;
   sb_collider colliders[SB_MAX_COLLIDERS];
   int n_col = 0;
+  uint64_t frames_done = 0; // sb_step calls since creation / the last sb_load_state (stored in snapshots)
+  // render mesh bound to the tets (sb_skin_bind)
+  uint32_t skin_n = 0, skin_f = 0;
+  std::vector<int32_t> skin_tet;
+  std::vector<float> skin_bary;
+  DevBuf<uint4> skin_slots;
+  DevBuf<float4> skin_w, skin_x, skin_nrm;
+  DevBuf<uint32_t> skin_tri_off, skin_tri_ids;
+  DevBuf<int32_t> skin_tris;
+  DevBuf<float> skin_stage;
   std::map<uint64_t, cudaGraphExec_t> graphs;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
@@ -719,6 +729,52 @@ struct sb_solver {
     }
     CK(cudaStreamSynchronize(stream));
   }
+  // Render mesh: upload the binding (tet per render vertex + weights) and the CSR of its triangles for the normals.
+  void skin_upload(const int32_t *tris, uint32_t n, uint32_t nf) {
+    CK(cudaSetDevice(device));
+    std::vector<uint4> slots(n);
+    for (uint32_t i = 0; i < n; i++) {
+      const int32_t *q = &plan.tets[4 * (size_t)skin_tet[i]];
+      slots[i] = make_uint4(plan.inv[q[0]], plan.inv[q[1]], plan.inv[q[2]], plan.inv[q[3]]);
+    }
+    skin_slots.upload(slots, &dev_bytes);
+    std::vector<float4> w(n);
+    for (uint32_t i = 0; i < n; i++)
+      w[i] = make_float4(skin_bary[4 * (size_t)i], skin_bary[4 * (size_t)i + 1], skin_bary[4 * (size_t)i + 2], skin_bary[4 * (size_t)i + 3]);
+    skin_w.upload(w, &dev_bytes);
+    skin_x.alloc(n, &dev_bytes);
+    skin_nrm.alloc(n, &dev_bytes);
+    skin_stage.alloc(6 * (size_t)n, &dev_bytes);
+    std::vector<uint32_t> off((size_t)n + 1, 0), ids(3 * (size_t)nf);
+    for (size_t k = 0; k < 3 * (size_t)nf; k++) off[(size_t)tris[k] + 1]++;
+    for (uint32_t i = 0; i < n; i++) off[i + 1] += off[i];
+    {
+      std::vector<uint32_t> cur(off.begin(), off.end() - 1);
+      for (uint32_t f = 0; f < nf; f++) // ascending triangle id per vertex, as the oracle sums them
+        for (int j = 0; j < 3; j++) ids[cur[tris[3 * (size_t)f + j]]++] = f;
+    }
+    skin_tri_off.upload(off, &dev_bytes);
+    skin_tri_ids.upload(ids, &dev_bytes);
+    skin_tris.upload(std::vector<int32_t>(tris, tris + 3 * (size_t)nf), &dev_bytes);
+    skin_n = n;
+    skin_f = nf;
+  }
+  void read_skinned(float *dpos, float *dnrm) {
+    CK(cudaSetDevice(device));
+    const uint32_t n = skin_n;
+    k_skin<<<grid_for(n, 256), 256, 0, stream>>>(n, skin_slots.p, skin_w.p, x.p, skin_x.p);
+    if (dpos) {
+      k_gather_xyz<<<grid_for(n, 256), 256, 0, stream>>>(n, nullptr, skin_x.p, skin_stage.p);
+      CK(cudaMemcpyAsync(dpos, skin_stage.p, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    }
+    if (dnrm) {
+      k_normals<<<grid_for(n, 256), 256, 0, stream>>>(n, skin_tri_off.p, skin_tri_ids.p, skin_tris.p, skin_x.p, skin_nrm.p);
+      k_gather_xyz<<<grid_for(n, 256), 256, 0, stream>>>(n, nullptr, skin_nrm.p, skin_stage.p + 3 * (size_t)n);
+      CK(cudaMemcpyAsync(dnrm, skin_stage.p + 3 * (size_t)n, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(stream));
+  }
   void get_state(float *x4, float *v4) {
     CK(cudaSetDevice(device));
     const uint32_t V = plan.V;
@@ -1016,7 +1072,7 @@ int sb_set_colliders(sb_handle h, const float *s, uint32_t n) {
 
 int sb_step(sb_handle h, float dt) {
   NEED_DEVICE(h);
-  return guarded(h, [&]() -> int { h->step(dt); return SB_OK; });
+  return guarded(h, [&]() -> int { h->step(dt); h->frames_done++; return SB_OK; });
 }
 
 int sb_synchronize(sb_handle h) {
@@ -1064,6 +1120,96 @@ int sb_read_normals(sb_handle h, float *dst, uint32_t n) {
     for (size_t s = 0; s < ns; s++) std::memcpy(dst + 3 * (size_t)h->plan.surf_ids[s], tmp + 3 * s, 3 * sizeof(float));
     return SB_OK;
   });
+}
+
+// ---- render mesh bound to the tets ---------------------------------------------------------------------
+int sb_skin_bind(sb_handle h, const float *pos, uint32_t n, const int32_t *tris, uint32_t nf) {
+  NEED_HANDLE(h);
+  if (!n || !pos || (nf && !tris)) { h->err = "null or empty render mesh"; return SB_E_ARG; }
+  for (size_t k = 0; k < 3 * (size_t)nf; k++)
+    if (tris[k] < 0 || (uint32_t)tris[k] >= n) { h->err = "render triangle index out of range"; return SB_E_ARG; }
+  if (h->dist.ctl) { h->err = "a render mesh cannot be bound to one rank of a distributed mesh"; return SB_E_STATE; }
+  return guarded(h, [&]() -> int {
+    h->skin_tet.assign(n, 0);
+    h->skin_bary.assign(4 * (size_t)n, 0.f);
+    const int rc = sb_skin_compute(h->plan.pos.data(), h->plan.V, h->plan.tets.data(), h->plan.T, pos, n, h->skin_tet.data(),
+                                   h->skin_bary.data());
+    if (rc != SB_OK) {
+      h->skin_tet.clear();
+      h->skin_bary.clear();
+      h->skin_n = 0;
+      h->err = sb_ingest_last_error();
+      return rc;
+    }
+    if (h->on_device) h->skin_upload(tris, n, nf);
+    else { h->skin_n = n; h->skin_f = nf; }
+    return SB_OK;
+  });
+}
+
+int sb_skin_get_binding(sb_handle h, int32_t *tet_of, float *bary4, uint32_t n) {
+  NEED_HANDLE(h);
+  if (!h->skin_n) { h->err = "no render mesh bound (sb_skin_bind)"; return SB_E_STATE; }
+  if (n != h->skin_n) { h->err = "render vertex count mismatch"; return SB_E_ARG; }
+  if (tet_of) std::memcpy(tet_of, h->skin_tet.data(), (size_t)n * sizeof(int32_t));
+  if (bary4) std::memcpy(bary4, h->skin_bary.data(), 4 * (size_t)n * sizeof(float));
+  return SB_OK;
+}
+
+int sb_read_skinned(sb_handle h, float *dst_pos, float *dst_nrm, uint32_t n) {
+  NEED_DEVICE(h);
+  if (!h->skin_n) { h->err = "no render mesh bound (sb_skin_bind)"; return SB_E_STATE; }
+  if (n != h->skin_n) { h->err = "render vertex count mismatch"; return SB_E_ARG; }
+  if (!dst_pos && !dst_nrm) return SB_E_ARG;
+  return guarded(h, [&]() -> int { h->read_skinned(dst_pos, dst_nrm); return SB_OK; });
+}
+
+// ---- snapshots (file layout: ingest.cpp) ------------------------------------------------------------------
+int sb_save_state(sb_handle h, const char *path) {
+  NEED_DEVICE(h);
+  if (!path) return SB_E_ARG;
+  return guarded(h, [&]() -> int {
+    const uint32_t V = h->plan.V;
+    std::vector<float> x4(4 * (size_t)V), v4(4 * (size_t)V);
+    h->get_state(x4.data(), v4.data());
+    const int rc = sb_state_write(path, x4.data(), v4.data(), V, &h->prm, h->frames_done,
+                                  sb_topology_hash(V, h->plan.tets.data(), h->plan.T));
+    if (rc != SB_OK) h->err = sb_ingest_last_error();
+    return rc;
+  });
+}
+
+int sb_load_state(sb_handle h, const char *path, int32_t apply_params) {
+  NEED_DEVICE(h);
+  if (!path) return SB_E_ARG;
+  return guarded(h, [&]() -> int {
+    const uint32_t V = h->plan.V;
+    uint32_t n = 0;
+    uint64_t frame = 0, topo = 0;
+    sb_params p;
+    int rc = sb_state_read(path, nullptr, nullptr, 0, &n, &p, &frame, &topo);
+    if (rc == SB_OK && (n != V || topo != sb_topology_hash(V, h->plan.tets.data(), h->plan.T))) {
+      h->err = "snapshot belongs to a different mesh";
+      return SB_E_ARG;
+    }
+    std::vector<float> x4(4 * (size_t)V), v4(4 * (size_t)V);
+    if (rc == SB_OK) rc = sb_state_read(path, x4.data(), v4.data(), V, nullptr, nullptr, nullptr, nullptr);
+    if (rc != SB_OK) { h->err = sb_ingest_last_error(); return rc; }
+    if (apply_params) {
+      rc = sb_set_params(h, &p);
+      if (rc != SB_OK) return rc;
+    }
+    h->set_state(x4.data(), v4.data());
+    h->frames_done = frame;
+    return SB_OK;
+  });
+}
+
+int sb_frames_done(sb_handle h, uint64_t *out) {
+  NEED_HANDLE(h);
+  if (!out) return SB_E_ARG;
+  *out = h->frames_done;
+  return SB_OK;
 }
 
 int sb_get_state(sb_handle h, float *x4, float *v4, uint32_t n) {

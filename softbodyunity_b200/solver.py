@@ -285,6 +285,42 @@ class SoftBody:
             v4 = np.ascontiguousarray(v4, np.float32)
         self._ck(self._lib.sb_set_state(self._h, _buf_ptr(x4), _buf_ptr(v4), self.n_verts))
 
+    # -- render mesh bound to the tets -----------------------------------------------------
+    def skin_bind(self, render_pos, render_tris=None):
+        """Bind a render mesh to the tets at rest (host); works on a host_only handle too."""
+        rp = np.ascontiguousarray(render_pos, np.float32).reshape(-1, 3)
+        rt = None if render_tris is None else np.ascontiguousarray(render_tris, np.int32).reshape(-1, 3)
+        self._ck(self._lib.sb_skin_bind(self._h, _ptr(rp), len(rp), _ptr(rt), 0 if rt is None else len(rt)))
+        self.n_render = len(rp)
+
+    def skin_binding(self):
+        tet_of = np.empty(self.n_render, np.int32)
+        bary = np.empty((self.n_render, 4), np.float32)
+        self._ck(self._lib.sb_skin_get_binding(self._h, _ptr(tet_of), _ptr(bary), self.n_render))
+        return tet_of, bary
+
+    def read_skinned(self, normals=True):
+        """LateUpdate for an embedded render mesh: its vertices (and normals) from the current tets."""
+        pos = np.empty((self.n_render, 3), np.float32)
+        nrm = np.empty((self.n_render, 3), np.float32) if normals else None
+        self._ck(self._lib.sb_read_skinned(self._h, _ptr(pos), _ptr(nrm), self.n_render))
+        return (pos, nrm) if normals else pos
+
+    # -- snapshots ---------------------------------------------------------------------------
+    def save_state(self, path):
+        self._ck(self._lib.sb_save_state(self._h, str(path).encode()))
+
+    def load_state(self, path, apply_params=False):
+        self._ck(self._lib.sb_load_state(self._h, str(path).encode(), int(apply_params)))
+        if apply_params:
+            self._ck(self._lib.sb_get_params(self._h, C.byref(self._params)))
+
+    @property
+    def frames_done(self) -> int:
+        out = C.c_uint64()
+        self._ck(self._lib.sb_frames_done(self._h, C.byref(out)))
+        return out.value
+
     def diagnostics(self):
         out = np.zeros(16, np.float64)
         rc = self._lib.sb_diagnostics(self._h, _ptr(out))
