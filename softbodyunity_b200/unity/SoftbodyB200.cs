@@ -36,6 +36,45 @@ public struct SbMeshDesc          // sb_mesh_desc, 112 bytes
     public int reserved0;
 }
 
+[StructLayout(LayoutKind.Sequential)]
+public struct SbCollider          // sb_collider, 48 bytes: kind 0 sphere / 1 capsule / 2 box
+{
+    public int kind;
+    public float friction;
+    public float p0, p1, p2, p3, p4, p5, p6, p7, p8, p9;
+
+    public static SbCollider From(Collider c, float friction)   // world-space pose of a Unity collider
+    {
+        var t = c.transform;
+        var k = new SbCollider { friction = friction };
+        if (c is SphereCollider s)
+        {
+            var o = t.TransformPoint(s.center);
+            float r = s.radius * Mathf.Max(Mathf.Abs(t.lossyScale.x), Mathf.Abs(t.lossyScale.y), Mathf.Abs(t.lossyScale.z));
+            k.kind = 0; k.p0 = o.x; k.p1 = o.y; k.p2 = o.z; k.p3 = r;
+        }
+        else if (c is CapsuleCollider cap)
+        {
+            var axis = cap.direction == 0 ? Vector3.right : cap.direction == 1 ? Vector3.up : Vector3.forward;
+            float half = Mathf.Max(0f, cap.height * 0.5f - cap.radius);
+            var a = t.TransformPoint(cap.center - axis * half);
+            var b = t.TransformPoint(cap.center + axis * half);
+            k.kind = 1; k.p0 = a.x; k.p1 = a.y; k.p2 = a.z; k.p3 = cap.radius * Mathf.Abs(t.lossyScale.x);
+            k.p4 = b.x; k.p5 = b.y; k.p6 = b.z;
+        }
+        else if (c is BoxCollider box)
+        {
+            var o = t.TransformPoint(box.center);
+            var h = Vector3.Scale(box.size * 0.5f, t.lossyScale);
+            var q = t.rotation;
+            k.kind = 2; k.p0 = o.x; k.p1 = o.y; k.p2 = o.z; k.p3 = Mathf.Abs(h.x); k.p4 = Mathf.Abs(h.y); k.p5 = Mathf.Abs(h.z);
+            k.p6 = q.x; k.p7 = q.y; k.p8 = q.z; k.p9 = q.w;
+        }
+        else throw new NotSupportedException("sphere, capsule and box colliders only");
+        return k;
+    }
+}
+
 internal static class SbNative
 {
     const string Lib = "softbody_b200";
@@ -45,7 +84,18 @@ internal static class SbNative
     [DllImport(Lib)] public static extern int sb_destroy(IntPtr h);
     [DllImport(Lib)] public static extern int sb_set_params(IntPtr h, ref SbParams prm);
     [DllImport(Lib)] public static extern int sb_set_colliders(IntPtr h, float[] spheresXyzr, uint n);
+    [DllImport(Lib)] public static extern int sb_set_colliders_ex(IntPtr h, [In] SbCollider[] colliders, uint n);
     [DllImport(Lib)] public static extern int sb_step(IntPtr h, float dt);
+    // render mesh embedded in the tets, snapshots, mesh ingest (all optional for the hot path)
+    [DllImport(Lib)] public static extern int sb_skin_bind(IntPtr h, IntPtr renderPosXyz, uint nRenderVerts, int[] renderTris, uint nRenderTris);
+    [DllImport(Lib)] public static extern int sb_read_skinned(IntPtr h, IntPtr dstPosXyz, IntPtr dstNrmXyz, uint nRenderVerts);
+    [DllImport(Lib)] public static extern int sb_save_state(IntPtr h, string path);
+    [DllImport(Lib)] public static extern int sb_load_state(IntPtr h, string path, int applyParams);
+    [DllImport(Lib)] public static extern int sb_tetmesh_from_surface(IntPtr surfPosXyz, uint nVerts, int[] surfTris, uint nTris, float spacing, out IntPtr mesh);
+    [DllImport(Lib)] public static extern int sb_tetmesh_load(string path, out IntPtr mesh);
+    [DllImport(Lib)] public static extern int sb_tetmesh_desc(IntPtr mesh, out SbMeshDesc desc);
+    [DllImport(Lib)] public static extern int sb_tetmesh_free(IntPtr mesh);
+    [DllImport(Lib)] public static extern IntPtr sb_ingest_last_error();
     [DllImport(Lib)] public static extern int sb_read_positions(IntPtr h, IntPtr dstXyz, uint nVerts);
     [DllImport(Lib)] public static extern int sb_read_normals(IntPtr h, IntPtr dstXyz, uint nVerts);
     [DllImport(Lib)] public static extern IntPtr sb_last_error(IntPtr h);
@@ -116,6 +166,17 @@ public class SoftbodyB200 : MonoBehaviour
         nrmPin = GCHandle.Alloc(normals, GCHandleType.Pinned);
         mesh = GetComponent<MeshFilter>().mesh;
         mesh.MarkDynamic();
+    }
+
+    // Scene colliders the body should respond to (sphere / capsule / box), re-sent whenever they move.
+    public Collider[] sceneColliders;
+    public float colliderFriction = 0f;
+    public void PushColliders()
+    {
+        int n = sceneColliders == null ? 0 : Mathf.Min(sceneColliders.Length, 16);
+        var list = new SbCollider[Mathf.Max(n, 1)];
+        for (int i = 0; i < n; i++) list[i] = SbCollider.From(sceneColliders[i], colliderFriction);
+        Check(SbNative.sb_set_colliders_ex(handle, list, (uint)n), handle);
     }
 
     // the hot path: one native call per fixed tick
