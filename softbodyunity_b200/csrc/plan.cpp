@@ -678,6 +678,18 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
       if (cnt[c] >= hard - slack) soft[kind][(size_t)c / 64] |= 1ull << (c & 63);
       if (cnt[c] == hard) full[kind][(size_t)c / 64] |= 1ull << (c & 63);
     }
+    if (getenv("SB_PLAN_STATS")) { // debug: rounds against the lower bounds (capacity, valence)
+      std::vector<uint32_t> val((size_t)nv * 2, 0);
+      for (size_t i = 0; i < ne; i++) {
+        int32_t vs[4];
+        const int n = ent_verts(D, ents[i], vs);
+        for (int k = 0; k < n; k++) val[(size_t)local(vs[k]) * 2 + (ents[i] < 0)]++;
+      }
+      uint32_t mv[2] = {0, 0};
+      for (uint32_t v = 0; v < nv; v++) { mv[0] = std::max(mv[0], val[2 * v]); mv[1] = std::max(mv[1], val[2 * v + 1]); }
+      fprintf(stderr, "TILE %zu nv %u edges %zu tets %zu ecol %zu (cap %zu val %u) tcol %zu (cap %zu val %u)\n", t, nv, n_kind[0],
+              n_kind[1], ecount.size(), (n_kind[0] + cap_e - 1) / cap_e, mv[0], tcount.size(), (n_kind[1] + cap_t - 1) / cap_t, mv[1]);
+    }
     mask[0] = std::vector<uint64_t>();
     mask[1] = std::vector<uint64_t>();
     O.n_ecol = (uint32_t)ecount.size();

@@ -3,7 +3,7 @@
 There are no golden vectors in the reference (its mount is /root/reference/README.md:1 only), so these
 are REGRESSION PINS produced by this repo's own CPU oracle (oracle/xpbd_oracle.c) under the Gauss-Seidel
 order the planner exports; they pin the oracle, the planner's schedule and -- on a GPU -- the kernels
-against silent change.  Run from the repo root:  python tests/golden/make_golden.py
+against silent change.  Run from the repo root:  python tests/golden/make_golden.py [case ...]
 """
 import os
 import sys
@@ -29,19 +29,55 @@ CASES = {
 }
 
 
+def _uv_sphere(r, n_lat, n_lon, centre):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_ingest import uv_sphere
+    return uv_sphere(r, n_lat, n_lon, centre)
+
+
+def _ingested_sphere():
+    """Surface mesh -> tets through the ingest path; the surface itself is the render mesh."""
+    from softbodyunity_b200 import ingest
+    sp, st = _uv_sphere(0.25, 10, 20, (0.0, 0.5, 0.0))
+    pos, tets, tris = ingest.tetrahedralize_surface(sp, st, 0.07)
+    return pos, tets, tris, sp, st
+
+
+# sphere / capsule / box colliders with friction, a body made by the ingest path, an embedded render mesh
+CASES["ingested_sphere_on_colliders"] = dict(
+    gen=_ingested_sphere, plan=dict(tile_cap=128),
+    prm=dict(stiffness_distance=4.0e4, friction=0.25, substeps=5, iterations=6), frames=30,
+    colliders=[("box", 0.3, -0.15, 0.12, 0.0, 0.2, 0.1, 0.3, 0.0, 0.0, 0.2588190451, 0.9659258263),
+               ("capsule", 0.5, 0.05, 0.1, -0.3, 0.07, 0.3, 0.2, 0.3),
+               ("sphere", 0.1, 0.0, 0.5, 0.05, 0.06)])
+
+
 def main():
+    only = sys.argv[1:]
     for name, c in CASES.items():
-        pos, tets, tris = c["gen"]()
+        if only and name not in only:
+            continue
+        pos, tets, tris, *render = c["gen"]()
         kw = dict(c["prm"])
         sb = SoftBody(pos, tets, tris, host_only=True, **c["plan"],
                       **{{"stiffness_distance": "stiffness", "stiffness_volume": "volume_stiffness"}.get(k, k): v for k, v in kw.items()})
         order, off = sb.schedule()
         m = orc.Model(pos, tets, roles=sb.tet_roles())
-        m.simulate(orc.params(**kw), n_frames=c["frames"], order=order, batch_off=off)
+        extra = {}
+        cols = None
+        if "colliders" in c:
+            cols = orc.colliders(c["colliders"])
+            extra["colliders"] = cols
+        m.simulate(orc.params(**kw), n_frames=c["frames"], order=order, batch_off=off, colliders=cols)
         normals = m.normals(tris)
+        if render:
+            sb.skin_bind(*render)
+            tet_of, bary = sb.skin_binding()
+            skin_pos, skin_nrm = m.skin(tet_of, bary, render[1])
+            extra.update(render_pos=render[0], render_tris=render[1], skin_tet=tet_of, skin_bary=bary, skin_pos=skin_pos, skin_nrm=skin_nrm)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), pos=pos, tets=tets, tris=tris, order=order, batch_off=off, roles=sb.tet_roles(),
                             x4=m.x4, v4=m.v4, normals=normals, frames=c["frames"],
-                            plan=np.array(sorted(c["plan"].items()), dtype=object), prm=np.array(sorted(kw.items()), dtype=object))
+                            plan=np.array(sorted(c["plan"].items()), dtype=object), prm=np.array(sorted(kw.items()), dtype=object), **extra)
         print(name, pos.shape, tets.shape, "batches", len(off) - 1, "min y", float(m.x4[:, 1].min()))
 
 
