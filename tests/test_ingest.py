@@ -105,6 +105,21 @@ def test_sphere_and_torus_volumes(flip):
     assert is_watertight(f)
 
 
+def test_triangle_soup_with_split_vertices_gives_the_same_tets():
+    # Unity meshes split vertices at UV seams and hard edges: the surface is closed geometrically, not by index
+    sp, st = uv_sphere(0.6, 14, 28, centre=(0.1, 0.2, 0.3))
+    ref = ingest.tetrahedralize_surface(sp, st, 0.09)
+    soup_pos = sp[st].reshape(-1, 3)
+    soup_tri = np.arange(len(soup_pos), dtype=np.int32).reshape(-1, 3)
+    got = ingest.tetrahedralize_surface(soup_pos, soup_tri, 0.09)
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
+    # and every split copy binds like the vertex it copies
+    t_ref, b_ref = ingest.skin_binding(ref[0], ref[1], sp)
+    t_soup, b_soup = ingest.skin_binding(ref[0], ref[1], soup_pos)
+    assert np.array_equal(t_soup.reshape(-1, 3), t_ref[st]) and np.array_equal(b_soup.reshape(-1, 3, 4), b_ref[st])
+
+
 def test_two_components_and_bad_input():
     a, fa = uv_sphere(0.5, 12, 24, centre=(0, 0, 0))
     b, fb = uv_sphere(0.3, 12, 24, centre=(2, 0.1, 0))
