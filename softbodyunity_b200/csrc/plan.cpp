@@ -255,6 +255,70 @@ void attach_edges(Plan &P, bool enable) {
       P.edge_owner[e] = (int32_t)(pick >> 3);
     }
   }
+  // Augmentation.  The greedy pass leaves ~8 % of the edges of a lattice mesh without a tet although slots remain:
+  // an edge left over takes the slot of an edge that can move to another of its own tets (an augmenting path of
+  // length two in the edge -> slot matching).  Fewer free edges = fewer edge rounds per tile.
+  static const int augment = getenv("SB_ATTACH_AUGMENT") ? atoi(getenv("SB_ATTACH_AUGMENT")) : 1; // (0: A/B switch for benches)
+  if (augment) {
+    auto group_ok = [&](uint32_t t, uint32_t e) {
+      if (!P.n_ghost) return true;
+      return tet_cut[t] == (uint8_t)n_ghosts(&P.edges[2 * (size_t)e], 2);
+    };
+    // put edge e into a free compatible slot of one of its tets other than `not_t`
+    auto try_place = [&](uint32_t e, uint32_t not_t) -> bool {
+      for (uint32_t k = ioff[e]; k < ioff[e + 1]; k++) {
+        const uint32_t t = inc[k] >> 3, pk = inc[k] & 7;
+        if (t == not_t || !group_ok(t, e)) continue;
+        if (pair01[t] < 0) {
+          pair01[t] = (int8_t)pk; P.tet_e01[t] = (int32_t)e; P.edge_owner[e] = (int32_t)t;
+          return true;
+        }
+        if (pair23[t] < 0 && pair01[t] == (int8_t)(5 - pk)) {
+          pair23[t] = (int8_t)pk; P.tet_e23[t] = (int32_t)e; P.edge_owner[e] = (int32_t)t;
+          return true;
+        }
+      }
+      return false;
+    };
+    for (int sweep = 0; sweep < 2; sweep++)
+      for (uint32_t oi = 0; oi < E; oi++) {
+        const uint32_t e = by_inc[oi];
+        if (P.edge_owner[e] >= 0) continue;
+        if (P.n_ghost && n_ghosts(&P.edges[2 * (size_t)e], 2) == 2) continue;
+        if (try_place(e, 0xffffffffu)) continue; // a slot freed by an earlier move
+        for (uint32_t k = ioff[e]; k < ioff[e + 1] && P.edge_owner[e] < 0; k++) {
+          const uint32_t t = inc[k] >> 3, pk = inc[k] & 7;
+          if (!group_ok(t, e) || pair01[t] < 0) continue;
+          if (pair23[t] < 0) {
+            // t holds one edge e1 (not opposite to e): move e1 on, take its slot
+            const uint32_t e1 = (uint32_t)P.tet_e01[t];
+            pair01[t] = -1; P.tet_e01[t] = -1; P.edge_owner[e1] = -1;
+            if (try_place(e1, t)) {
+              pair01[t] = (int8_t)pk; P.tet_e01[t] = (int32_t)e; P.edge_owner[e] = (int32_t)t;
+            } else {
+              pair01[t] = (int8_t)0; // restored below
+              for (int q = 0; q < 6; q++)
+                if (te[6 * (size_t)t + q] == (int32_t)e1) pair01[t] = (int8_t)q;
+              P.tet_e01[t] = (int32_t)e1; P.edge_owner[e1] = (int32_t)t;
+            }
+          } else if (pair23[t] == (int8_t)(5 - pk) || pair01[t] == (int8_t)(5 - pk)) {
+            // t is full and one of its two edges is opposite to e: the OTHER one moves on and e takes its slot
+            const bool keep01 = pair01[t] == (int8_t)(5 - pk);
+            const uint32_t e_keep = (uint32_t)(keep01 ? P.tet_e01[t] : P.tet_e23[t]);
+            const uint32_t e_go = (uint32_t)(keep01 ? P.tet_e23[t] : P.tet_e01[t]);
+            const int8_t p_keep = keep01 ? pair01[t] : pair23[t], p_go = keep01 ? pair23[t] : pair01[t];
+            // free e_go's slot: the tet keeps e_keep as its (0,1) edge for the moment
+            pair01[t] = p_keep; P.tet_e01[t] = (int32_t)e_keep;
+            pair23[t] = -1; P.tet_e23[t] = -1; P.edge_owner[e_go] = -1;
+            if (try_place(e_go, t)) {
+              pair23[t] = (int8_t)pk; P.tet_e23[t] = (int32_t)e; P.edge_owner[e] = (int32_t)t;
+            } else {
+              pair23[t] = p_go; P.tet_e23[t] = (int32_t)e_go; P.edge_owner[e_go] = (int32_t)t;
+            }
+          }
+        }
+      }
+  }
   // roles: (a, b, c, d) with (a, b) the first attached edge and (c, d) the other two vertices in their
   // original relative order; if that permutation is odd, swap a and b
   for (uint32_t t = 0; t < T; t++) {
@@ -633,50 +697,212 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
     // Constraints are coloured in a scattered order (a fixed hash of the constraint id): colouring them in
     // id order, which is spatial order, fills the early colours from one corner of the tile and leaves
     // the last corner a long tail of nearly empty colours.
+    // First-fit is sensitive to that order: a tile whose colouring ends well above its lower bound
+    // max(valence, ceil(n / capacity)) is coloured again in other scattered orders and the best is kept
+    // (the slowest tile of a pass ends the pass, so the worst tiles matter most).
     std::vector<uint32_t> cord(ne);
-    std::iota(cord.begin(), cord.end(), 0u);
+    std::vector<uint32_t> try_col(ne), try_e, try_t;
+    size_t lower = 0;
     {
-      auto hash = [](uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; };
-      std::vector<uint64_t> key(ne);
-      for (size_t i = 0; i < ne; i++) key[i] = ((uint64_t)hash((uint32_t)ents[i]) << 32) | (uint32_t)i;
-      std::sort(key.begin(), key.end());
-      for (size_t i = 0; i < ne; i++) cord[i] = (uint32_t)key[i];
+      std::vector<uint32_t> val((size_t)nv * 2, 0);
+      for (size_t i = 0; i < ne; i++) {
+        int32_t vs[4];
+        const int n = ent_verts(D, ents[i], vs);
+        for (int k = 0; k < n; k++) val[(size_t)local(vs[k]) * 2 + (ents[i] < 0)]++;
+      }
+      uint32_t mv[2] = {0, 0};
+      for (uint32_t v = 0; v < nv; v++) { mv[0] = std::max(mv[0], val[2 * v]); mv[1] = std::max(mv[1], val[2 * v + 1]); }
+      lower = std::max<size_t>(mv[0], (n_kind[0] + cap_e - 1) / cap_e) + std::max<size_t>(mv[1], (n_kind[1] + cap_t - 1) / cap_t);
     }
-    for (size_t oi = 0; oi < ne; oi++) {
-      const size_t i = cord[oi];
-      int32_t vs[4];
-      const int n = ent_verts(D, ents[i], vs);
-      const int kind = ents[i] < 0;
-      const size_t W = words[kind];
-      uint64_t *M = mask[kind].data();
-      // first colour free at every vertex that is below the soft capacity; failing that, one below the
-      // hard capacity (the slack the soft limit left is what absorbs the stragglers); failing that, a new one
-      const uint32_t hard = kind ? cap_t : cap_e, slack = std::max(1u, hard / 32);
-      std::vector<uint32_t> &cnt = kind ? tcount : ecount;
-      auto first_free_colour = [&](const std::vector<uint64_t> &closed) {
-        for (size_t wd = 0; wd < W; wd++) {
-          uint64_t u = closed[wd];
-          for (int k = 0; k < n; k++) u |= M[(size_t)local(vs[k]) * W + wd];
-          if (~u) return (int)(wd * 64) + __builtin_ctzll(~u);
+    auto colour_once = [&](uint32_t seed, std::vector<uint32_t> &col_o, std::vector<uint32_t> &ecount_o, std::vector<uint32_t> &tcount_o) -> bool {
+      ecount_o.clear();
+      tcount_o.clear();
+      for (int k = 0; k < 2; k++) {
+        std::fill(mask[k].begin(), mask[k].end(), 0);
+        std::fill(full[k].begin(), full[k].end(), 0);
+        std::fill(soft[k].begin(), soft[k].end(), 0);
+      }
+      std::iota(cord.begin(), cord.end(), 0u);
+      {
+        auto hash = [](uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; };
+        std::vector<uint64_t> key(ne);
+        for (size_t i = 0; i < ne; i++) key[i] = ((uint64_t)hash((uint32_t)ents[i] ^ (seed * 0x9e3779b9u)) << 32) | (uint32_t)i;
+        std::sort(key.begin(), key.end());
+        for (size_t i = 0; i < ne; i++) cord[i] = (uint32_t)key[i];
+      }
+      for (size_t oi = 0; oi < ne; oi++) {
+        const size_t i = cord[oi];
+        int32_t vs[4];
+        const int n = ent_verts(D, ents[i], vs);
+        const int kind = ents[i] < 0;
+        const size_t W = words[kind];
+        uint64_t *M = mask[kind].data();
+        // first colour free at every vertex that is below the soft capacity; failing that, one below the
+        // hard capacity (the slack the soft limit left is what absorbs the stragglers); failing that, a new one
+        const uint32_t hard = kind ? cap_t : cap_e, slack = std::max(1u, hard / 32);
+        std::vector<uint32_t> &cnt = kind ? tcount_o : ecount_o;
+        auto first_free_colour = [&](const std::vector<uint64_t> &closed) {
+          for (size_t wd = 0; wd < W; wd++) {
+            uint64_t u = closed[wd];
+            for (int k = 0; k < n; k++) u |= M[(size_t)local(vs[k]) * W + wd];
+            if (~u) return (int)(wd * 64) + __builtin_ctzll(~u);
+          }
+          return -1;
+        };
+        const size_t k_target = (n_kind[kind] + (hard - slack) - 1) / (hard - slack);
+        int c = first_free_colour(soft[kind]);
+        if ((c < 0 || (size_t)c >= cnt.size()) && cnt.size() >= k_target) {
+          const int c2 = first_free_colour(full[kind]);
+          if (c2 >= 0 && (size_t)c2 < cnt.size()) c = c2;
         }
-        return -1;
+        if (c < 0) return false;
+        for (int k = 0; k < n; k++) M[(size_t)local(vs[k]) * W + (size_t)c / 64] |= 1ull << (c & 63);
+        col_o[i] = (uint32_t)c;
+        if ((size_t)c >= cnt.size()) cnt.resize(c + 1, 0);
+        ++cnt[c];
+        if (cnt[c] >= hard - slack) soft[kind][(size_t)c / 64] |= 1ull << (c & 63);
+        if (cnt[c] == hard) full[kind][(size_t)c / 64] |= 1ull << (c & 63);
+      }
+      return true;
+    };
+    {
+      static const int n_try = getenv("SB_COLOUR_TRIES") ? atoi(getenv("SB_COLOUR_TRIES")) : 1;
+      static const int try_margin = getenv("SB_COLOUR_MARGIN") ? atoi(getenv("SB_COLOUR_MARGIN")) : 2;
+      bool have = false;
+      for (int a = 0; a < std::max(1, n_try); a++) {
+        if (!colour_once((uint32_t)a, try_col, try_e, try_t)) {
+          if (a == 0) { O.err = "vertex valence needs more than 256 colours beyond the capacity bound"; return; }
+          continue;
+        }
+        if (!have || try_e.size() + try_t.size() < ecount.size() + tcount.size()) {
+          col.swap(try_col); ecount.swap(try_e); tcount.swap(try_t);
+          try_col.resize(ne);
+          have = true;
+        }
+        if (ecount.size() + tcount.size() <= lower + (size_t)try_margin) break; // close enough to the bound
+      }
+    }
+    // Stragglers.  First-fit leaves a tail of nearly empty colours (e.g. ... 124 103 86 48 21 2): every one of them
+    // costs the tile a full round trip (gather, project, scatter, barrier).  Empty the smallest colours into the room
+    // the others have left: a member moves to a colour where it conflicts with nobody, or with exactly one member
+    // that can itself move elsewhere (one Kempe step).  Colours that end up empty are dropped.
+    static const int recolour = getenv("SB_RECOLOUR") ? atoi(getenv("SB_RECOLOUR")) : 1; // (0: A/B switch for benches)
+    for (int kind = 0; kind < 2 && recolour; kind++) {
+      std::vector<uint32_t> &cnt = kind ? tcount : ecount;
+      const uint32_t K = (uint32_t)cnt.size(), hard = kind ? cap_t : cap_e;
+      if (K < 2) continue;
+      const uint32_t NONE = 0xffffffffu;
+      std::vector<uint32_t> owner((size_t)nv * K, NONE); // who holds colour c at local vertex v
+      std::vector<std::vector<uint32_t>> members(K);
+      auto verts_of = [&](uint32_t i, uint32_t *lv) {
+        int32_t vs[4];
+        const int n = ent_verts(D, ents[i], vs);
+        for (int k = 0; k < n; k++) lv[k] = local(vs[k]);
+        return n;
       };
-      const size_t k_target = (n_kind[kind] + (hard - slack) - 1) / (hard - slack);
-      int c = first_free_colour(soft[kind]);
-      if ((c < 0 || (size_t)c >= cnt.size()) && cnt.size() >= k_target) {
-        const int c2 = first_free_colour(full[kind]);
-        if (c2 >= 0 && (size_t)c2 < cnt.size()) c = c2;
+      for (size_t i = 0; i < ne; i++) {
+        if ((ents[i] < 0) != (kind != 0)) continue;
+        uint32_t lv[4];
+        const int n = verts_of((uint32_t)i, lv);
+        for (int k = 0; k < n; k++) owner[(size_t)lv[k] * K + col[i]] = (uint32_t)i;
+        members[col[i]].push_back((uint32_t)i);
       }
-      if (c < 0) {
-        O.err = "vertex valence needs more than 256 colours beyond the capacity bound";
-        return;
+      auto move = [&](uint32_t i, uint32_t to) {
+        uint32_t lv[4];
+        const int n = verts_of(i, lv);
+        for (int k = 0; k < n; k++) { owner[(size_t)lv[k] * K + col[i]] = NONE; owner[(size_t)lv[k] * K + to] = i; }
+        --cnt[col[i]];
+        ++cnt[to];
+        col[i] = to;
+      };
+      // conflicts of member i in colour c: distinct holders of c at i's vertices, ignoring `skip`; returns count (<= 4)
+      auto conflicts = [&](uint32_t i, uint32_t c, uint32_t skip, uint32_t *out) {
+        uint32_t lv[4];
+        const int n = verts_of(i, lv);
+        int m = 0;
+        for (int k = 0; k < n; k++) {
+          const uint32_t o = owner[(size_t)lv[k] * K + c];
+          if (o == NONE || o == skip) continue;
+          bool seen = false;
+          for (int j = 0; j < m; j++) seen |= out[j] == o;
+          if (!seen) out[m++] = o;
+        }
+        return m;
+      };
+      std::vector<uint32_t> by_size(K);
+      std::iota(by_size.begin(), by_size.end(), 0u);
+      std::stable_sort(by_size.begin(), by_size.end(), [&](uint32_t a, uint32_t b) { return cnt[a] < cnt[b]; });
+      std::vector<uint8_t> closed(K, 0); // colours being emptied (or already empty) take no new member
+      for (uint32_t src : by_size) {
+        if (cnt[src] == 0 || cnt[src] > hard / 2) continue;
+        // is there room elsewhere at all?
+        size_t room = 0;
+        for (uint32_t c = 0; c < K; c++)
+          if (c != src && !closed[c]) room += hard - cnt[c];
+        if (room < cnt[src]) continue;
+        closed[src] = 1;
+        std::vector<uint32_t> todo;
+        for (uint32_t i : members[src])
+          if (col[i] == src) todo.push_back(i);
+        for (uint32_t i : todo) {
+          uint32_t cf[4];
+          bool done = false;
+          for (uint32_t c = 0; c < K && !done; c++) { // a free seat
+            if (closed[c] || cnt[c] >= hard) continue;
+            if (conflicts(i, c, NONE, cf) == 0) { move(i, c); members[c].push_back(i); done = true; }
+          }
+          for (uint32_t c = 0; c < K && !done; c++) { // one Kempe step: the only conflicting member moves on
+            if (closed[c] || cnt[c] >= hard) continue;
+            if (conflicts(i, c, NONE, cf) != 1) continue;
+            const uint32_t x = cf[0];
+            for (uint32_t c2 = 0; c2 < K && !done; c2++) {
+              if (c2 == c || closed[c2] || cnt[c2] >= hard) continue;
+              uint32_t cf2[4];
+              if (conflicts(x, c2, NONE, cf2) != 0) continue;
+              move(x, c2); members[c2].push_back(x);
+              move(i, c); members[c].push_back(i);
+              done = true;
+            }
+          }
+          for (uint32_t c = 0; c < K && !done; c++) { // ... or the only two (the colour may be full: two leave, one joins)
+            if (closed[c]) continue;
+            if (conflicts(i, c, NONE, cf) != 2) continue;
+            const uint32_t x = cf[0], y = cf[1];
+            uint32_t cx = NONE;
+            for (uint32_t c2 = 0; c2 < K && cx == NONE; c2++) {
+              uint32_t cf2[4];
+              if (c2 != c && !closed[c2] && cnt[c2] < hard && conflicts(x, c2, NONE, cf2) == 0) cx = c2;
+            }
+            if (cx == NONE) continue;
+            const uint32_t from = col[x];
+            move(x, cx); // y must not collide with x in its new colour: evaluated after x has moved
+            uint32_t cy = NONE;
+            for (uint32_t c2 = 0; c2 < K && cy == NONE; c2++) {
+              uint32_t cf2[4];
+              if (c2 != c && !closed[c2] && cnt[c2] < hard && conflicts(y, c2, NONE, cf2) == 0) cy = c2;
+            }
+            if (cy == NONE) { move(x, from); continue; }
+            members[cx].push_back(x);
+            move(y, cy); members[cy].push_back(y);
+            move(i, c); members[c].push_back(i);
+            done = true;
+          }
+        }
+        if (cnt[src] != 0) closed[src] = 0; // not emptied: it stays a colour like any other
       }
-      for (int k = 0; k < n; k++) M[(size_t)local(vs[k]) * W + (size_t)c / 64] |= 1ull << (c & 63);
-      col[i] = (uint32_t)c;
-      if ((size_t)c >= cnt.size()) cnt.resize(c + 1, 0);
-      ++cnt[c];
-      if (cnt[c] >= hard - slack) soft[kind][(size_t)c / 64] |= 1ull << (c & 63);
-      if (cnt[c] == hard) full[kind][(size_t)c / 64] |= 1ull << (c & 63);
+      // drop the empty colours (order of the others kept)
+      std::vector<uint32_t> renum(K, NONE);
+      uint32_t nk = 0;
+      for (uint32_t c = 0; c < K; c++)
+        if (cnt[c]) renum[c] = nk++;
+      if (nk != K) {
+        for (size_t i = 0; i < ne; i++)
+          if ((ents[i] < 0) == (kind != 0)) col[i] = renum[col[i]];
+        std::vector<uint32_t> nc(nk);
+        for (uint32_t c = 0; c < K; c++)
+          if (cnt[c]) nc[renum[c]] = cnt[c];
+        cnt.swap(nc);
+      }
     }
     if (getenv("SB_PLAN_STATS")) { // debug: rounds against the lower bounds (capacity, valence)
       std::vector<uint32_t> val((size_t)nv * 2, 0);
@@ -687,6 +913,13 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
       }
       uint32_t mv[2] = {0, 0};
       for (uint32_t v = 0; v < nv; v++) { mv[0] = std::max(mv[0], val[2 * v]); mv[1] = std::max(mv[1], val[2 * v + 1]); }
+      if (t % 97 == 0) {
+        fprintf(stderr, "TCOUNT %zu:", t);
+        for (uint32_t c : tcount) fprintf(stderr, " %u", c);
+        fprintf(stderr, " | E:");
+        for (uint32_t c : ecount) fprintf(stderr, " %u", c);
+        fprintf(stderr, "\n");
+      }
       fprintf(stderr, "TILE %zu nv %u edges %zu tets %zu ecol %zu (cap %zu val %u) tcol %zu (cap %zu val %u)\n", t, nv, n_kind[0],
               n_kind[1], ecount.size(), (n_kind[0] + cap_e - 1) / cap_e, mv[0], tcount.size(), (n_kind[1] + cap_t - 1) / cap_t, mv[1]);
     }
