@@ -280,7 +280,7 @@ void attach_edges(Plan &P, bool enable) {
       }
       return false;
     };
-    for (int sweep = 0; sweep < 2; sweep++)
+    for (int sweep = 0; sweep < augment + 1; sweep++)
       for (uint32_t oi = 0; oi < E; oi++) {
         const uint32_t e = by_inc[oi];
         if (P.edge_owner[e] >= 0) continue;
@@ -739,7 +739,8 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
         uint64_t *M = mask[kind].data();
         // first colour free at every vertex that is below the soft capacity; failing that, one below the
         // hard capacity (the slack the soft limit left is what absorbs the stragglers); failing that, a new one
-        const uint32_t hard = kind ? cap_t : cap_e, slack = std::max(1u, hard / 32);
+        static const uint32_t slack_div = getenv("SB_SLACK_DIV") ? (uint32_t)atoi(getenv("SB_SLACK_DIV")) : 16u;
+        const uint32_t hard = kind ? cap_t : cap_e, slack = std::max(1u, hard / slack_div);
         std::vector<uint32_t> &cnt = kind ? tcount_o : ecount_o;
         auto first_free_colour = [&](const std::vector<uint64_t> &closed) {
           for (size_t wd = 0; wd < W; wd++) {
@@ -829,12 +830,16 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
         }
         return m;
       };
+      static const int rc_sweeps = getenv("SB_RC_SWEEPS") ? atoi(getenv("SB_RC_SWEEPS")) : 2;
+      static const int rc_frac = getenv("SB_RC_FRAC") ? atoi(getenv("SB_RC_FRAC")) : 75; // % of the capacity
+      std::vector<uint8_t> closed(K, 0); // colours being emptied (or already empty) take no new member
+      for (int sweep = 0; sweep < rc_sweeps; sweep++) {
       std::vector<uint32_t> by_size(K);
       std::iota(by_size.begin(), by_size.end(), 0u);
       std::stable_sort(by_size.begin(), by_size.end(), [&](uint32_t a, uint32_t b) { return cnt[a] < cnt[b]; });
-      std::vector<uint8_t> closed(K, 0); // colours being emptied (or already empty) take no new member
+      for (uint32_t c = 0; c < K; c++) closed[c] = cnt[c] == 0;
       for (uint32_t src : by_size) {
-        if (cnt[src] == 0 || cnt[src] > hard / 2) continue;
+        if (cnt[src] == 0 || cnt[src] > hard * (uint32_t)rc_frac / 100) continue;
         // is there room elsewhere at all?
         size_t room = 0;
         for (uint32_t c = 0; c < K; c++)
@@ -889,6 +894,7 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
           }
         }
         if (cnt[src] != 0) closed[src] = 0; // not emptied: it stays a colour like any other
+      }
       }
       // drop the empty colours (order of the others kept)
       std::vector<uint32_t> renum(K, NONE);
