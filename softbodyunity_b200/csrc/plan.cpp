@@ -1039,18 +1039,21 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
           std::vector<uint32_t> oc(n_oct);
           for (uint32_t o = 0; o < n_oct; o++) oc[o] = oct_cost(o, ~0u, 0);
           uint32_t rng = 0x9e3779b9u ^ (uint32_t)(t * 2654435761u) ^ (c * 40503u);
-          for (int sweep = 0; sweep < 6; sweep++) {
+          static const int ls_sweeps = getenv("SB_LS_SWEEPS") ? atoi(getenv("SB_LS_SWEEPS")) : 6;
+          static const int ls_tries = getenv("SB_LS_TRIES") ? atoi(getenv("SB_LS_TRIES")) : 24;
+          for (int sweep = 0; sweep < ls_sweeps; sweep++) {
             bool improved = false;
             for (uint32_t a = 0; a < n; a++) {
               const uint32_t oa = a / 8;
               if (oc[oa] <= (uint32_t)nvs) continue; // already conflict-free
-              for (int tries = 0; tries < 24; tries++) {
+              for (int tries = 0; tries < ls_tries; tries++) {
                 rng = rng * 1664525u + 1013904223u;
                 const uint32_t b = (uint32_t)(((uint64_t)(rng >> 8) * n) >> 24);
                 const uint32_t ob = b / 8;
                 if (ob == oa || b >= n || cls[a] != cls[b]) continue;
                 const uint32_t na = oct_cost(oa, a, b), nb = oct_cost(ob, b, a);
-                if (na + nb < oc[oa] + oc[ob]) {
+                static const int ls_plateau = getenv("SB_LS_PLATEAU") ? atoi(getenv("SB_LS_PLATEAU")) : 0;
+                if (na + nb < oc[oa] + oc[ob] || (ls_plateau && na + nb == oc[oa] + oc[ob] && na < oc[oa])) {
                   std::swap(tmp[a], tmp[b]);
                   for (int j = 0; j < 4; j++) std::swap(rr[(size_t)a * 4 + j], rr[(size_t)b * 4 + j]);
                   oc[oa] = na;
