@@ -261,3 +261,18 @@ def test_small_bodies_are_kept_whole_by_default():
     i = sb.info()
     assert i["n_tile_passes"] == 1 and i["tiles_in_pass"][0] == 6 and i["constraints_global"] == 0
     assert i["tile_cap"] == 2028 and i["block_threads"] == 256
+
+
+def test_rounds_stay_near_their_lower_bound():
+    """Planner quality pin (host only): the straggler recolouring and the augmented edge attachment keep a tile's
+    rounds within ~5 % of max(valence, ceil(n / capacity)) summed over both kinds; first-fit alone was ~19 % above."""
+    pos, tets, tris = meshgen.block(45, 45, 45, spacing=0.01)
+    sb = SoftBody(pos, tets, tris, host_only=True)
+    i = sb.info()
+    assert i["n_tilings"] == 4
+    assert i["edges_attached"] >= 0.985 * i["n_edges"]
+    rounds, n_tiles = sum(i["rounds_in_pass"]), sum(i["tiles_in_pass"])
+    assert rounds / n_tiles <= 14.0, rounds / n_tiles  # 13.1 today; 15.6 with first-fit and greedy attachment alone
+    assert sb.verify_streams() == 0
+    wf, ideal = sb.smem_model
+    assert wf / ideal < 1.75
