@@ -199,7 +199,7 @@ int sb_tetmesh_from_surface(const float *sp, uint32_t nv, const int32_t *st, uin
       // centre the lattice on the bounding box
       lo[k] = 0.5 * (lo[k] + hi[k]) - 0.5 * (double)n[k] * h;
     }
-    if ((double)n[0] * (double)n[1] * (double)n[2] > 4.0e9) return fail(SB_E_ARG, "spacing too small: more than 4e9 lattice cells");
+    if ((double)n[0] * (double)n[1] * (double)n[2] > 1.0e9) return fail(SB_E_ARG, "spacing too small: more than 1e9 lattice cells");
     const int64_t nx = n[0], ny = n[1], nz = n[2];
     // triangles bucketed by the (y, z) columns their projection overlaps
     std::vector<std::vector<uint32_t>> bucket((size_t)(ny * nz));
@@ -240,6 +240,13 @@ int sb_tetmesh_from_surface(const float *sp, uint32_t nv, const int32_t *st, uin
           cr.push_back({(w0 * a[0] + w1 * b[0] + w2 * c[0]) / area, sign});
         }
         if (cr.empty()) continue;
+        int total = 0;
+        for (const Crossing &q : cr) total += q.sign;
+        if (total != 0) { // a ray that enters a closed surface leaves it again
+          char msg[160];
+          std::snprintf(msg, sizeof msg, "the surface is not closed (a ray at y = %.6g, z = %.6g crosses it %+d times net)", py, pz, total);
+          return fail(SB_E_ARG, msg);
+        }
         std::sort(cr.begin(), cr.end(), [](const Crossing &p, const Crossing &q) { return p.x < q.x; });
         // winding number at a point = signed crossings of the ray beyond it
         int wind = 0;

@@ -1025,17 +1025,22 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
             // cost of octet o with the record at swap_pos replaced by the one at swap_with (swap_pos == ~0u: as is)
             uint32_t cost = 0;
             const uint32_t k0 = o * 8, k1 = std::min(n, k0 + 8);
+            static const int ls_pairs = getenv("SB_LS_PAIRS") ? atoi(getenv("SB_LS_PAIRS")) : 0;
             for (int j = 0; j < nvs; j++) {
               uint8_t cntb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
               uint8_t m = 0;
+              uint32_t pairs = 0;
               for (uint32_t k = k0; k < k1; k++) {
                 const uint32_t src = k == swap_pos ? swap_with : k;
-                m = std::max(m, ++cntb[rr[(size_t)src * 4 + j]]);
+                const uint8_t v = ++cntb[rr[(size_t)src * 4 + j]];
+                pairs += v - 1u; // records already on this residue: the sum is the number of conflicting pairs
+                m = std::max(m, v);
               }
-              cost += m;
+              cost += ls_pairs ? 32u * m + pairs : m;
             }
             return cost;
           };
+          static const int ls_pairs_on = getenv("SB_LS_PAIRS") ? atoi(getenv("SB_LS_PAIRS")) : 0;
           std::vector<uint32_t> oc(n_oct);
           for (uint32_t o = 0; o < n_oct; o++) oc[o] = oct_cost(o, ~0u, 0);
           uint32_t rng = 0x9e3779b9u ^ (uint32_t)(t * 2654435761u) ^ (c * 40503u);
@@ -1045,7 +1050,7 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
             bool improved = false;
             for (uint32_t a = 0; a < n; a++) {
               const uint32_t oa = a / 8;
-              if (oc[oa] <= (uint32_t)nvs) continue; // already conflict-free
+              if (oc[oa] <= (uint32_t)nvs * (ls_pairs_on ? 32u : 1u)) continue; // already conflict-free
               for (int tries = 0; tries < ls_tries; tries++) {
                 rng = rng * 1664525u + 1013904223u;
                 const uint32_t b = (uint32_t)(((uint64_t)(rng >> 8) * n) >> 24);

@@ -129,6 +129,10 @@ def test_two_components_and_bad_input():
     assert near_a.any() and near_b.any() and (near_a | near_b).all()
     with pytest.raises(SbError, match="spacing"):
         ingest.tetrahedralize_surface(a, fa, 0.0)
+    with pytest.raises(SbError, match="1e9 lattice cells"):
+        ingest.tetrahedralize_surface(a, fa, 1e-5)
+    with pytest.raises(SbError, match="not closed"):
+        ingest.tetrahedralize_surface(a, fa[a[fa].mean(1)[:, 0] < 0.3], 0.07)  # a hole on the +x side of the sphere
     with pytest.raises(SbError, match="out of range"):
         ingest.tetrahedralize_surface(a, fa + 1000, 0.1)
     with pytest.raises(SbError, match="inside"):
