@@ -258,14 +258,15 @@ void attach_edges(Plan &P, bool enable) {
   // Augmentation.  The greedy pass leaves ~8 % of the edges of a lattice mesh without a tet although slots remain:
   // an edge left over takes the slot of an edge that can move to another of its own tets (an augmenting path of
   // length two in the edge -> slot matching).  Fewer free edges = fewer edge rounds per tile.
-  static const int augment = getenv("SB_ATTACH_AUGMENT") ? atoi(getenv("SB_ATTACH_AUGMENT")) : 1; // (0: A/B switch for benches)
+  static const int augment = getenv("SB_ATTACH_AUGMENT") ? atoi(getenv("SB_ATTACH_AUGMENT")) : 1; // depth of the search (0: off, A/B switch for benches)
   if (augment) {
     auto group_ok = [&](uint32_t t, uint32_t e) {
       if (!P.n_ghost) return true;
       return tet_cut[t] == (uint8_t)n_ghosts(&P.edges[2 * (size_t)e], 2);
     };
-    // put edge e into a free compatible slot of one of its tets other than `not_t`
-    auto try_place = [&](uint32_t e, uint32_t not_t) -> bool {
+    // Put edge e into a slot of one of its tets other than `not_t`: a free compatible slot if there is one, else
+    // (depth > 0) the slot of an occupant that can itself be placed elsewhere -- an augmenting path, depth first.
+    std::function<bool(uint32_t, uint32_t, int)> place = [&](uint32_t e, uint32_t not_t, int depth) -> bool {
       for (uint32_t k = ioff[e]; k < ioff[e + 1]; k++) {
         const uint32_t t = inc[k] >> 3, pk = inc[k] & 7;
         if (t == not_t || !group_ok(t, e)) continue;
@@ -278,46 +279,39 @@ void attach_edges(Plan &P, bool enable) {
           return true;
         }
       }
-      return false;
-    };
-    for (int sweep = 0; sweep < augment + 1; sweep++)
-      for (uint32_t oi = 0; oi < E; oi++) {
-        const uint32_t e = by_inc[oi];
-        if (P.edge_owner[e] >= 0) continue;
-        if (P.n_ghost && n_ghosts(&P.edges[2 * (size_t)e], 2) == 2) continue;
-        if (try_place(e, 0xffffffffu)) continue; // a slot freed by an earlier move
-        for (uint32_t k = ioff[e]; k < ioff[e + 1] && P.edge_owner[e] < 0; k++) {
-          const uint32_t t = inc[k] >> 3, pk = inc[k] & 7;
-          if (!group_ok(t, e) || pair01[t] < 0) continue;
-          if (pair23[t] < 0) {
-            // t holds one edge e1 (not opposite to e): move e1 on, take its slot
-            const uint32_t e1 = (uint32_t)P.tet_e01[t];
-            pair01[t] = -1; P.tet_e01[t] = -1; P.edge_owner[e1] = -1;
-            if (try_place(e1, t)) {
-              pair01[t] = (int8_t)pk; P.tet_e01[t] = (int32_t)e; P.edge_owner[e] = (int32_t)t;
-            } else {
-              pair01[t] = (int8_t)0; // restored below
-              for (int q = 0; q < 6; q++)
-                if (te[6 * (size_t)t + q] == (int32_t)e1) pair01[t] = (int8_t)q;
-              P.tet_e01[t] = (int32_t)e1; P.edge_owner[e1] = (int32_t)t;
-            }
-          } else if (pair23[t] == (int8_t)(5 - pk) || pair01[t] == (int8_t)(5 - pk)) {
-            // t is full and one of its two edges is opposite to e: the OTHER one moves on and e takes its slot
-            const bool keep01 = pair01[t] == (int8_t)(5 - pk);
-            const uint32_t e_keep = (uint32_t)(keep01 ? P.tet_e01[t] : P.tet_e23[t]);
-            const uint32_t e_go = (uint32_t)(keep01 ? P.tet_e23[t] : P.tet_e01[t]);
-            const int8_t p_keep = keep01 ? pair01[t] : pair23[t], p_go = keep01 ? pair23[t] : pair01[t];
-            // free e_go's slot: the tet keeps e_keep as its (0,1) edge for the moment
-            pair01[t] = p_keep; P.tet_e01[t] = (int32_t)e_keep;
-            pair23[t] = -1; P.tet_e23[t] = -1; P.edge_owner[e_go] = -1;
-            if (try_place(e_go, t)) {
-              pair23[t] = (int8_t)pk; P.tet_e23[t] = (int32_t)e; P.edge_owner[e] = (int32_t)t;
-            } else {
-              pair23[t] = p_go; P.tet_e23[t] = (int32_t)e_go; P.edge_owner[e_go] = (int32_t)t;
-            }
-          }
+      if (depth <= 0) return false;
+      for (uint32_t k = ioff[e]; k < ioff[e + 1]; k++) {
+        const uint32_t t = inc[k] >> 3, pk = inc[k] & 7;
+        if (t == not_t || !group_ok(t, e) || pair01[t] < 0) continue;
+        if (pair23[t] < 0) {
+          // t holds one edge e1 (not opposite to e, or e would have fitted): e1 moves on, e takes its slot
+          const uint32_t e1 = (uint32_t)P.tet_e01[t];
+          const int8_t p1 = pair01[t];
+          pair01[t] = (int8_t)pk; P.tet_e01[t] = (int32_t)e; P.edge_owner[e] = (int32_t)t; // (so that e1 cannot come back here)
+          P.edge_owner[e1] = -1;
+          if (place(e1, t, depth - 1)) return true;
+          pair01[t] = p1; P.tet_e01[t] = (int32_t)e1; P.edge_owner[e1] = (int32_t)t; P.edge_owner[e] = -1;
+        } else if (pair23[t] == (int8_t)(5 - pk) || pair01[t] == (int8_t)(5 - pk)) {
+          // t is full and one of its two edges is opposite to e: the OTHER one moves on and e takes its slot
+          const bool keep01 = pair01[t] == (int8_t)(5 - pk);
+          const uint32_t e_keep = (uint32_t)(keep01 ? P.tet_e01[t] : P.tet_e23[t]);
+          const uint32_t e_go = (uint32_t)(keep01 ? P.tet_e23[t] : P.tet_e01[t]);
+          const int8_t p_keep = keep01 ? pair01[t] : pair23[t], p_go = keep01 ? pair23[t] : pair01[t];
+          pair01[t] = p_keep; P.tet_e01[t] = (int32_t)e_keep;
+          pair23[t] = (int8_t)pk; P.tet_e23[t] = (int32_t)e; P.edge_owner[e] = (int32_t)t;
+          P.edge_owner[e_go] = -1;
+          if (place(e_go, t, depth - 1)) return true;
+          pair23[t] = p_go; P.tet_e23[t] = (int32_t)e_go; P.edge_owner[e_go] = (int32_t)t; P.edge_owner[e] = -1;
         }
       }
+      return false;
+    };
+    for (uint32_t oi = 0; oi < E; oi++) {
+      const uint32_t e = by_inc[oi];
+      if (P.edge_owner[e] >= 0) continue;
+      if (P.n_ghost && n_ghosts(&P.edges[2 * (size_t)e], 2) == 2) continue;
+      place(e, 0xffffffffu, augment);
+    }
   }
   // roles: (a, b, c, d) with (a, b) the first attached edge and (c, d) the other two vertices in their
   // original relative order; if that permutation is odd, swap a and b
