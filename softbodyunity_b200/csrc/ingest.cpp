@@ -173,7 +173,8 @@ int sb_tetmesh_from_arrays(const float *pos_xyz, uint32_t V, const int32_t *tets
     if (!F) boundary_faces(m->tets, m->tris);
     *out = m;
     return SB_OK;
-  } catch (const std::bad_alloc &) { return fail(SB_E_NOMEM, "out of memory"); }
+  } catch (const std::bad_alloc &) { return fail(SB_E_NOMEM, "out of memory");
+  } catch (const std::exception &e) { return fail(SB_E_ARG, e.what()); }
 }
 
 int sb_tetmesh_from_surface(const float *sp, uint32_t nv, const int32_t *st, uint32_t nt, float spacing,
@@ -288,7 +289,8 @@ int sb_tetmesh_from_surface(const float *sp, uint32_t nv, const int32_t *st, uin
     boundary_faces(m->tets, m->tris);
     *out = m;
     return SB_OK;
-  } catch (const std::bad_alloc &) { return fail(SB_E_NOMEM, "out of memory"); }
+  } catch (const std::bad_alloc &) { return fail(SB_E_NOMEM, "out of memory");
+  } catch (const std::exception &e) { return fail(SB_E_ARG, e.what()); }
 }
 
 // ---- render mesh -> tets ------------------------------------------------------------------------------
@@ -394,7 +396,8 @@ int sb_skin_compute(const float *tet_pos_xyz, uint32_t V, const int32_t *tets, u
       bary4[4 * (size_t)i] = (float)(1.0 - ((double)b1 + (double)b2 + (double)b3));
     }
     return SB_OK;
-  } catch (const std::bad_alloc &) { return fail(SB_E_NOMEM, "out of memory"); }
+  } catch (const std::bad_alloc &) { return fail(SB_E_NOMEM, "out of memory");
+  } catch (const std::exception &e) { return fail(SB_E_ARG, e.what()); }
 }
 
 // ---- files ---------------------------------------------------------------------------------------------------
@@ -417,6 +420,12 @@ std::string strip_ext(const std::string &p, std::string *ext) {
   return p.substr(0, dot);
 }
 
+// a count read from a header cannot exceed the bytes of its file (every entry takes several): guards the resize
+long long file_bytes(const std::string &path) {
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  return f ? (long long)f.tellg() : 0;
+}
+
 // TetGen: <base>.node + <base>.ele (+ optional <base>.face)
 int load_tetgen(const std::string &base, sb_tetmesh &m) {
   std::ifstream fn(base + ".node"), fe(base + ".ele");
@@ -426,7 +435,7 @@ int load_tetgen(const std::string &base, sb_tetmesh &m) {
   long long np = 0, dim = 0, nattr = 0, nmark = 0;
   if (!next_data_line(fn, line)) return fail(SB_E_ARG, ".node: empty file");
   { std::istringstream s(line); s >> np >> dim >> nattr >> nmark; }
-  if (np <= 0 || dim != 3) return fail(SB_E_ARG, ".node: expected '<points> 3 <attrs> <markers>'");
+  if (np <= 0 || np > 0x7fffffffLL || np > file_bytes(base + ".node") || dim != 3) return fail(SB_E_ARG, ".node: expected '<points> 3 <attrs> <markers>'");
   std::map<long long, int32_t> id_of;
   m.pos.resize(3 * (size_t)np);
   for (long long i = 0; i < np; i++) {
@@ -440,7 +449,7 @@ int load_tetgen(const std::string &base, sb_tetmesh &m) {
   long long ne = 0, npt = 0;
   if (!next_data_line(fe, line)) return fail(SB_E_ARG, ".ele: empty file");
   { std::istringstream s(line); s >> ne >> npt; }
-  if (ne <= 0 || (npt != 4 && npt != 10)) return fail(SB_E_ARG, ".ele: expected '<tets> 4|10 <attrs>'");
+  if (ne <= 0 || ne > 0x7fffffffLL || ne > file_bytes(base + ".ele") || (npt != 4 && npt != 10)) return fail(SB_E_ARG, ".ele: expected '<tets> 4|10 <attrs>'");
   m.tets.resize(4 * (size_t)ne);
   for (long long t = 0; t < ne; t++) {
     if (!next_data_line(fe, line)) return fail(SB_E_ARG, ".ele: fewer tets than the header says");
@@ -457,6 +466,7 @@ int load_tetgen(const std::string &base, sb_tetmesh &m) {
   if (ff && next_data_line(ff, line)) {
     long long nf = 0;
     { std::istringstream s(line); s >> nf; }
+    if (nf < 0 || nf > 0x7fffffffLL) return fail(SB_E_ARG, ".face: bad face count");
     for (long long f = 0; f < nf; f++) {
       if (!next_data_line(ff, line)) return fail(SB_E_ARG, ".face: fewer faces than the header says");
       std::istringstream s(line);
@@ -491,7 +501,7 @@ int load_msh(const std::string &path, sb_tetmesh &m) {
     } else if (line == "$Nodes") {
       long long nn = 0;
       in >> nn;
-      if (nn <= 0) return fail(SB_E_ARG, ".msh: no nodes");
+      if (nn <= 0 || nn > 0x7fffffffLL || nn > file_bytes(path)) return fail(SB_E_ARG, ".msh: no nodes");
       m.pos.resize(3 * (size_t)nn);
       for (long long i = 0; i < nn; i++) {
         long long id; double x, y, z;
@@ -502,6 +512,7 @@ int load_msh(const std::string &path, sb_tetmesh &m) {
     } else if (line == "$Elements") {
       long long ne = 0;
       in >> ne;
+      if (!in || ne < 0) return fail(SB_E_ARG, ".msh: bad element count");
       std::getline(in, line);
       for (long long e = 0; e < ne; e++) {
         if (!std::getline(in, line)) return fail(SB_E_ARG, ".msh: fewer elements than the header says");
@@ -562,7 +573,8 @@ int sb_tetmesh_load(const char *path, sb_tetmesh_handle *out) {
     if (m->tris.empty()) boundary_faces(m->tets, m->tris);
     *out = m;
     return SB_OK;
-  } catch (const std::bad_alloc &) { return fail(SB_E_NOMEM, "out of memory"); }
+  } catch (const std::bad_alloc &) { return fail(SB_E_NOMEM, "out of memory");
+  } catch (const std::exception &e) { return fail(SB_E_ARG, e.what()); }
 }
 
 int sb_tetmesh_save(sb_tetmesh_handle m, const char *path) {

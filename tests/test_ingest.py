@@ -292,3 +292,43 @@ def test_skin_follows_affine_motion_in_the_oracle_and_binds_through_a_plan_handl
     assert np.abs(moved - (sp.astype(np.float64) @ A.T + [0.3, -0.2, 0.1])).max() < 2e-6
     with pytest.raises(SbError):
         sb.read_skinned()  # no device behind an sb_plan handle
+
+
+def test_parsers_survive_garbage(tmp_path):
+    """Truncated, mutated and random files give an error code, never a crash or an exception across the ABI."""
+    pos, tets, tris = meshgen.block(4, 4, 4)
+    good = {}
+    for name in ("g.msh", "g.node"):
+        ingest.save_mesh(tmp_path / name, pos, tets, tris)
+    for f in ("g.msh", "g.node", "g.ele", "g.face"):
+        good[f] = (tmp_path / f).read_bytes()
+    ingest.write_state(tmp_path / "g.sbs", np.zeros((64, 4), np.float32), np.zeros((64, 4), np.float32), default_params())
+    good["g.sbs"] = (tmp_path / "g.sbs").read_bytes()
+    rng = np.random.default_rng(11)
+    outcomes = {"ok": 0, "error": 0}
+    for trial in range(120):
+        f = ("g.msh", "g.node", "g.ele", "g.sbs")[trial % 4]
+        raw = bytearray(good[f])
+        kind = trial % 3
+        if kind == 0:
+            raw = raw[:int(rng.integers(0, len(raw)))]
+        elif kind == 1:
+            for _ in range(8):
+                raw[int(rng.integers(0, len(raw)))] = int(rng.integers(32, 127))
+        else:
+            k = int(rng.integers(0, max(1, len(raw) - 40)))
+            raw[k:k + 20] = b"99999999999999999999"  # absurd counts / ids
+        # siblings of a TetGen set stay intact
+        for g in ("g.node", "g.ele", "g.face"):
+            (tmp_path / g.replace("g.", "t.")).write_bytes(good[g])
+        target = tmp_path / f.replace("g.", "t.")
+        target.write_bytes(bytes(raw))
+        try:
+            if f.endswith(".sbs"):
+                ingest.read_state(target)
+            else:
+                ingest.load_mesh(target)
+            outcomes["ok"] += 1
+        except SbError:
+            outcomes["error"] += 1
+    assert outcomes["error"] > 40 and outcomes["ok"] + outcomes["error"] == 120
