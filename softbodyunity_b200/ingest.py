@@ -5,6 +5,7 @@ after the substep path.  Reference: NOT IN MOUNT
 ones.  Nothing here needs a GPU.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -104,6 +105,8 @@ def read_state(path):
     lib = _abi.load()
     n, fr, th, p = C.c_uint32(), C.c_uint64(), C.c_uint64(), SbParams()
     _ck(lib.sb_state_read(str(path).encode(), None, None, 0, C.byref(n), C.byref(p), C.byref(fr), C.byref(th)))
+    if os.path.getsize(path) < 88 + 32 * n.value:
+        raise SbError(_abi.SB_E_ARG, "snapshot is truncated")
     x = np.empty((n.value, 4), np.float32)
     v = np.empty((n.value, 4), np.float32)
     _ck(lib.sb_state_read(str(path).encode(), _ptr(x), _ptr(v), n.value, None, None, None, None))
