@@ -85,3 +85,21 @@ def test_snapshot_resume_is_bit_identical(tmp_path):
     c = SoftBody(pos2, tets2, tris2)
     with pytest.raises(SbError, match="different mesh"):
         c.load_state(snap)
+
+
+def test_replay_tool_between_two_snapshots(tmp_path):
+    import subprocess
+    import sys
+    import os
+    pos, tets, tris = meshgen.sphere(10, spacing=0.05)
+    ingest.save_mesh(tmp_path / "body.msh", pos, tets, tris)
+    p, t, f = ingest.load_mesh(tmp_path / "body.msh")
+    sb = SoftBody(p, t, f, stiffness=6e4, damping=0.2, substeps=6, iterations=4)
+    sb.step(frames=5)
+    sb.save_state(tmp_path / "a.sbs")
+    sb.step(frames=8)
+    sb.save_state(tmp_path / "b.sbs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "replay.py"), "--mesh", str(tmp_path / "body.msh"),
+                        "--from", str(tmp_path / "a.sbs"), "--to", str(tmp_path / "b.sbs")], capture_output=True, text=True)
+    assert r.returncode == 0 and "0 position words and 0 velocity words differ" in r.stdout, r.stdout + r.stderr
