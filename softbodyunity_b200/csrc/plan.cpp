@@ -541,14 +541,59 @@ bool grid_tilings(const Plan &P, uint32_t cap, int n_tilings, std::vector<Tiling
         T.part[v] = (int32_t)cell;
         count[cell]++;
       }
-      // compact the non-empty boxes
+      for (size_t c = 0; c < count.size(); c++)
+        if (count[c] > cap) ok = false;
+      // Rims.  A shifted tiling ends in slices of boxes (1/4, 1/2, 3/4 of a box thick, and their products at the
+      // edges and corners): a quarter of its tiles hold a few hundred vertices, take a CTA slot each and run
+      // valence-many nearly empty rounds.  Small boxes are merged with a face neighbour while the union stays
+      // within the cap: a union of boxes of one tiling keeps every element that was interior to one of them (and
+      // gains those that crossed the plane between them).
+      static const int merge_rims = getenv("SB_MERGE_RIMS") ? atoi(getenv("SB_MERGE_RIMS")) : 1;
+      static const int merge_pct = getenv("SB_MERGE_PCT") ? atoi(getenv("SB_MERGE_PCT")) : 100;
+      uint32_t biggest = 0;
+      for (uint32_t c : count) biggest = std::max(biggest, c);
+      const uint32_t limit = (uint32_t)((uint64_t)std::min(cap, biggest) * (uint32_t)merge_pct / 100);
+      std::vector<uint32_t> root(count.size());
+      std::iota(root.begin(), root.end(), 0u);
+      if (ok && s > 0 && merge_rims) {
+        auto find = [&](uint32_t c) {
+          while (root[c] != c) c = root[c] = root[root[c]];
+          return c;
+        };
+        std::vector<uint32_t> size(count.begin(), count.end());
+        std::vector<uint32_t> small;
+        for (uint32_t c = 0; c < (uint32_t)count.size(); c++)
+          if (count[c] && count[c] <= limit / 2) small.push_back(c);
+        std::stable_sort(small.begin(), small.end(), [&](uint32_t a, uint32_t b) { return count[a] < count[b]; });
+        for (int sweep = 0; sweep < 3; sweep++)
+          for (uint32_t c : small) {
+            const uint32_t r = find(c);
+            if (size[r] > limit / 2) continue; // grown enough
+            const int cx = (int)(c % (uint32_t)m[0]), cy = (int)(c / (uint32_t)m[0] % (uint32_t)m[1]), cz = (int)(c / ((uint32_t)m[0] * (uint32_t)m[1]));
+            uint32_t best = 0xffffffffu, best_size = 0;
+            static const int D6[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+            for (const auto &d : D6) {
+              const int x = cx + d[0], y = cy + d[1], z = cz + d[2];
+              if (x < 0 || y < 0 || z < 0 || x >= m[0] || y >= m[1] || z >= m[2]) continue;
+              const uint32_t q0 = (uint32_t)x + (uint32_t)m[0] * ((uint32_t)y + (uint32_t)m[1] * (uint32_t)z);
+              if (!count[q0]) continue;
+              const uint32_t q = find(q0);
+              if (q == r || size[q] + size[r] > limit) continue;
+              if (best == 0xffffffffu || size[q] < best_size) { best = q; best_size = size[q]; }
+            }
+            if (best == 0xffffffffu) continue;
+            const uint32_t keep = std::min(r, best), gone = std::max(r, best); // deterministic: the lower cell index names the tile
+            root[gone] = keep;
+            size[keep] = size[r] + size[best];
+          }
+        for (uint32_t c = 0; c < (uint32_t)count.size(); c++) root[c] = find(c);
+      }
+      // compact the non-empty tiles
       std::vector<int32_t> remap(count.size(), -1);
       uint32_t nt = 0;
-      for (size_t c = 0; c < count.size(); c++) {
-        if (count[c] > cap) ok = false;
-        if (count[c]) remap[c] = (int32_t)nt++;
-      }
-      for (uint32_t v = 0; v < V; v++) T.part[v] = remap[T.part[v]];
+      for (size_t c = 0; c < count.size(); c++)
+        if (count[c] && root[c] == c) remap[c] = (int32_t)nt++;
+      for (uint32_t v = 0; v < V; v++) T.part[v] = remap[root[T.part[v]]];
       T.n_tiles = nt;
     }
     if (ok) return true;
@@ -604,7 +649,8 @@ inline int ent_verts(const DevTopo &D, int32_t ent, int32_t *vs) {
 // `in` whose vertices all lie in one tile are consumed; the rest go to `out`.
 std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_t> &part, uint32_t n_tiles,
                        const std::vector<uint32_t> *contig_off, const std::vector<int32_t> &in,
-                       std::vector<int32_t> &out, TilePass &TP, int threads, uint32_t bt_opt, uint32_t width, int n_sm) {
+                       std::vector<int32_t> &out, TilePass &TP, int threads, uint32_t bt_opt, uint32_t width, int n_sm,
+                       const std::vector<int32_t> *box0 = nullptr) {
   // 1. classify and bucket by tile (stable)
   std::vector<uint64_t> toff((size_t)n_tiles + 1, 0);
   std::vector<int32_t> owner(in.size());
@@ -1151,9 +1197,12 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
     } else {
       TP.tile_verts.insert(TP.tile_verts.end(), O.verts.begin(), O.verts.end());
       TP.vert_off.push_back((uint32_t)TP.tile_verts.size());
-      // maximal runs of consecutive device ids: {first device id, first local id}, closed by {0, n}
+      // maximal runs of consecutive device ids: {first device id, first local id}, closed by {0, n}.  A run never
+      // crosses a box of the unshifted tiling (box0): those boxes are the units a mesh spread over several GPUs is
+      // cut along, and a run is read and written in the memory of the rank that owns its first vertex.
       for (uint32_t k = 0; k < O.n_verts; k++)
-        if (k == 0 || O.verts[k] != O.verts[k - 1] + 1) TP.runs.push_back({O.verts[k], k});
+        if (k == 0 || O.verts[k] != O.verts[k - 1] + 1 || (box0 && (*box0)[O.verts[k]] != (*box0)[O.verts[k - 1]]))
+          TP.runs.push_back({O.verts[k], k});
       TP.runs.push_back({0u, O.n_verts});
       TP.run_off.push_back((uint32_t)TP.runs.size());
     }
@@ -1620,7 +1669,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
       TilePass TP;
       // every tiling runs with the CTA width chosen for the unshifted one (whole boxes only)
       err = build_pass(P, D, dpart[s], tilings[s].n_tiles, s == 0 ? &tile_off : nullptr, assigned[s], next, TP, threads,
-                       s == 0 ? bt_opt : P.passes[P.passes.size() - (size_t)s].bt, width, opt.n_sm);
+                       s == 0 ? bt_opt : P.passes[P.passes.size() - (size_t)s].bt, width, opt.n_sm, s == 0 ? nullptr : &dpart[0]);
       if (!err.empty()) return err;
       work.insert(work.end(), next.begin(), next.end()); // empty by construction
       P.passes.push_back(std::move(TP));

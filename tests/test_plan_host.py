@@ -275,4 +275,7 @@ def test_rounds_stay_near_their_lower_bound():
     assert rounds / n_tiles <= 14.0, rounds / n_tiles  # 13.1 today; 15.6 with first-fit and greedy attachment alone
     assert sb.verify_streams() == 0
     wf, ideal = sb.smem_model
-    assert wf / ideal < 1.75
+    assert wf / ideal < 1.85  # (the merged rim tiles lowered the conflict-free count more than the total)
+    # rim merging: a shifted tiling has fewer tiles than its (n + 1)^3 boxes and no tile heavier than a full box
+    assert all(t < 216 for t in i["tiles_in_pass"][1:4]) and i["tiles_in_pass"][0] == 125
+    assert max(i["max_colours_in_pass"][1:4]) <= i["max_colours_in_pass"][0] + 1
