@@ -502,6 +502,14 @@ struct sb_solver {
       while (r + 1 < D.n_ranks && dev >= D.slab_lo[r + 1]) r++;
       return r;
     };
+    // a tile reads and writes each of its runs in the memory of the rank that owns the run's first vertex: no run
+    // may cross a slab boundary (the planner never lets a run cross a box of the unshifted tiling)
+    for (const TilePass &tp : plan.passes)
+      for (uint32_t t = 0; t < tp.n_tiles() && !tp.contiguous && !tp.run_off.empty(); t++)
+        for (uint32_t r = tp.run_off[t]; r + 1 < tp.run_off[t + 1]; r++) {
+          const uint32_t first = tp.runs[r].x, len = tp.runs[r + 1].y - tp.runs[r].y;
+          if (len && owner_of(first) != owner_of(first + len - 1)) throw std::string("a vertex run crosses a slab boundary");
+        }
     // this rank's tiles of every pass: those with most of their vertices in its slab (ties: the lower rank),
     // heaviest first, dealt to the SMs in a snake like the single-GPU launch order.  (Dealing a spanning tile
     // to the less loaded of its ranks instead was measured slower: more of its runs become remote.)
