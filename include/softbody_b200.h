@@ -333,12 +333,17 @@ const char *sb_last_error(sb_handle h); /* h may be NULL: last sb_create failure
  * (valid until sb_tetmesh_free).  Errors: negative sb_status, message via sb_ingest_last_error (per thread).
  *   sb_tetmesh_from_surface  closed triangle surface (Unity Mesh.vertices / triangles) -> lattice of `spacing`-sized
  *                            cells whose centre has non-zero winding number, five tets per cell
+ *   sb_tetmesh_snap_to_surface  optional second step: the staircase boundary of that lattice pulled onto the surface
  *   sb_tetmesh_from_arrays   caller's arrays; orientation fixed, boundary extracted when n_tris == 0
  *   sb_tetmesh_load / save   TetGen <base>.node + .ele (+ .face) or Gmsh MSH 2.2 ASCII (.msh), by extension
  */
 typedef struct sb_tetmesh *sb_tetmesh_handle;
 int sb_tetmesh_from_surface(const float *surf_pos_xyz, uint32_t n_verts, const int32_t *surf_tris, uint32_t n_tris,
                             float spacing, sb_tetmesh_handle *out);
+/* Boundary vertices of m moved onto the surface where it is nearer than max_dist and no tet at the vertex shrinks
+   below 30 % of its lattice volume (ingest.cpp); *n_moved (may be NULL) counts them. */
+int sb_tetmesh_snap_to_surface(sb_tetmesh_handle m, const float *surf_pos_xyz, uint32_t n_verts, const int32_t *surf_tris,
+                               uint32_t n_tris, float max_dist, uint32_t *n_moved);
 int sb_tetmesh_from_arrays(const float *pos_xyz, uint32_t n_verts, const int32_t *tets, uint32_t n_tets,
                            const int32_t *tris, uint32_t n_tris, sb_tetmesh_handle *out);
 int sb_tetmesh_load(const char *path, sb_tetmesh_handle *out);

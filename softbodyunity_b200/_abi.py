@@ -26,7 +26,7 @@ EXPORTS = [
     "sb_dist_setup", "sb_dist_connect", "sb_dist_owned", "sb_dist_error", "sb_dist_layout",
     "sb_skin_bind", "sb_skin_get_binding", "sb_read_skinned", "sb_skin_compute",
     "sb_save_state", "sb_load_state", "sb_frames_done", "sb_state_write", "sb_state_read", "sb_topology_hash",
-    "sb_tetmesh_from_surface", "sb_tetmesh_from_arrays", "sb_tetmesh_load", "sb_tetmesh_save", "sb_tetmesh_sizes",
+    "sb_tetmesh_from_surface", "sb_tetmesh_snap_to_surface", "sb_tetmesh_from_arrays", "sb_tetmesh_load", "sb_tetmesh_save", "sb_tetmesh_sizes",
     "sb_tetmesh_copy", "sb_tetmesh_desc", "sb_tetmesh_free", "sb_ingest_last_error",
 ]
 
@@ -153,6 +153,7 @@ def load():
         "sb_topology_hash": (C.c_uint64, [u32, vp, u32]),
         "sb_tetmesh_from_surface": (C.c_int, [vp, u32, vp, u32, f32, P(vp)]),
         "sb_tetmesh_from_arrays": (C.c_int, [vp, u32, vp, u32, vp, u32, P(vp)]),
+        "sb_tetmesh_snap_to_surface": (C.c_int, [vp, vp, u32, vp, u32, f32, P(u32)]),
         "sb_tetmesh_load": (C.c_int, [C.c_char_p, P(vp)]),
         "sb_tetmesh_save": (C.c_int, [vp, C.c_char_p]),
         "sb_tetmesh_sizes": (C.c_int, [vp, P(u32), P(u32), P(u32)]),

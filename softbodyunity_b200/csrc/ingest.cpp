@@ -293,6 +293,175 @@ int sb_tetmesh_from_surface(const float *sp, uint32_t nv, const int32_t *st, uin
   } catch (const std::exception &e) { return fail(SB_E_ARG, e.what()); }
 }
 
+// ---- boundary vertices onto the surface -----------------------------------------------------------------------
+
+namespace {
+
+// closest point of triangle abc to p (Ericson, Real-Time Collision Detection 5.1.5), in double
+void closest_on_triangle(const double *p, const double *a, const double *b, const double *c, double *out) {
+  double ab[3], ac[3], ap[3];
+  for (int k = 0; k < 3; k++) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; ap[k] = p[k] - a[k]; }
+  auto dot = [](const double *u, const double *v) { return u[0] * v[0] + u[1] * v[1] + u[2] * v[2]; };
+  const double d1 = dot(ab, ap), d2 = dot(ac, ap);
+  if (d1 <= 0 && d2 <= 0) { for (int k = 0; k < 3; k++) out[k] = a[k]; return; }
+  double bp[3];
+  for (int k = 0; k < 3; k++) bp[k] = p[k] - b[k];
+  const double d3 = dot(ab, bp), d4 = dot(ac, bp);
+  if (d3 >= 0 && d4 <= d3) { for (int k = 0; k < 3; k++) out[k] = b[k]; return; }
+  const double vc = d1 * d4 - d3 * d2;
+  if (vc <= 0 && d1 >= 0 && d3 <= 0) {
+    const double v = d1 / (d1 - d3);
+    for (int k = 0; k < 3; k++) out[k] = a[k] + v * ab[k];
+    return;
+  }
+  double cp[3];
+  for (int k = 0; k < 3; k++) cp[k] = p[k] - c[k];
+  const double d5 = dot(ab, cp), d6 = dot(ac, cp);
+  if (d6 >= 0 && d5 <= d6) { for (int k = 0; k < 3; k++) out[k] = c[k]; return; }
+  const double vb = d5 * d2 - d1 * d6;
+  if (vb <= 0 && d2 >= 0 && d6 <= 0) {
+    const double w = d2 / (d2 - d6);
+    for (int k = 0; k < 3; k++) out[k] = a[k] + w * ac[k];
+    return;
+  }
+  const double va = d3 * d6 - d5 * d4;
+  if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
+    const double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+    for (int k = 0; k < 3; k++) out[k] = b[k] + w * (c[k] - b[k]);
+    return;
+  }
+  const double den = 1.0 / (va + vb + vc), v = vb * den, w = vc * den;
+  for (int k = 0; k < 3; k++) out[k] = a[k] + ab[k] * v + ac[k] * w;
+}
+
+} // namespace
+
+/*
+ * The lattice of sb_tetmesh_from_surface does not conform to the surface it fills: its boundary is a staircase up
+ * to half a cell inside or outside.  This moves every boundary vertex of the tet mesh to the closest point of the
+ * surface when that point is nearer than max_dist (half the lattice spacing is the natural choice), unless the move
+ * would shrink a tet at the vertex below 30 % of the volume it had in the lattice (the vertex then stays).  Returns the number of
+ * vertices moved through *n_moved (may be NULL).
+ */
+int sb_tetmesh_snap_to_surface(sb_tetmesh_handle m, const float *sp, uint32_t nv, const int32_t *st, uint32_t nt, float max_dist,
+                               uint32_t *n_moved) {
+  if (!m || !sp || !st || !nv || !nt) return fail(SB_E_ARG, "null or empty argument");
+  if (!(max_dist > 0) || !std::isfinite(max_dist)) return fail(SB_E_ARG, "max_dist must be positive");
+  try {
+    for (size_t i = 0; i < 3 * (size_t)nt; i++)
+      if (st[i] < 0 || (uint32_t)st[i] >= nv) return fail(SB_E_ARG, "surface triangle index out of range");
+    const size_t V = m->pos.size() / 3, T = m->tets.size() / 4;
+    // boundary vertices and the tets at each of them
+    std::vector<uint8_t> on_boundary(V, 0);
+    for (int32_t i : m->tris) on_boundary[i] = 1;
+    std::vector<uint32_t> toff(V + 1, 0), tlist(4 * T);
+    for (size_t i = 0; i < 4 * T; i++) toff[(size_t)m->tets[i] + 1]++;
+    for (size_t v = 0; v < V; v++) toff[v + 1] += toff[v];
+    {
+      std::vector<uint32_t> cur(toff.begin(), toff.end() - 1);
+      for (size_t t = 0; t < T; t++)
+        for (int j = 0; j < 4; j++) tlist[cur[m->tets[4 * t + j]]++] = (uint32_t)t;
+    }
+    // uniform grid over the surface triangles, cells of max_dist: a query looks at the 27 cells around it
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (uint32_t i = 0; i < nv; i++)
+      for (int k = 0; k < 3; k++) {
+        const double p = sp[3 * (size_t)i + k];
+        if (!std::isfinite(p)) return fail(SB_E_ARG, "surface vertex is not finite");
+        lo[k] = std::min(lo[k], p); hi[k] = std::max(hi[k], p);
+      }
+    double cell = max_dist;
+    int64_t g[3];
+    for (;;) {
+      double cells = 1;
+      for (int k = 0; k < 3; k++) { g[k] = std::max<int64_t>(1, (int64_t)std::ceil((hi[k] - lo[k]) / cell) + 1); cells *= (double)g[k]; }
+      if (cells <= 32.0e6) break;
+      cell *= 1.5;
+    }
+    const int64_t reach = (int64_t)std::ceil(max_dist / cell);
+    auto cell_of = [&](double p, int k) { return std::min<int64_t>(g[k] - 1, std::max<int64_t>(0, (int64_t)std::floor((p - lo[k]) / cell))); };
+    std::vector<uint32_t> off((size_t)(g[0] * g[1] * g[2]) + 1, 0), items;
+    for (int phase = 0; phase < 2; phase++) {
+      for (uint32_t t = 0; t < nt; t++) {
+        int64_t c0[3], c1[3];
+        for (int k = 0; k < 3; k++) {
+          double tl = 1e300, th = -1e300;
+          for (int j = 0; j < 3; j++) { const double p = sp[3 * (size_t)st[3 * (size_t)t + j] + k]; tl = std::min(tl, p); th = std::max(th, p); }
+          c0[k] = cell_of(tl, k); c1[k] = cell_of(th, k);
+        }
+        for (int64_t z = c0[2]; z <= c1[2]; z++)
+          for (int64_t y = c0[1]; y <= c1[1]; y++)
+            for (int64_t x = c0[0]; x <= c1[0]; x++) {
+              const size_t c = (size_t)((z * g[1] + y) * g[0] + x);
+              if (phase == 0) off[c + 1]++;
+              else items[off[c]++] = t;
+            }
+      }
+      if (phase == 0) {
+        for (size_t c = 0; c + 1 < off.size(); c++) off[c + 1] += off[c];
+        items.resize(off.back());
+      } else {
+        for (size_t c = off.size() - 1; c > 0; c--) off[c] = off[c - 1];
+        off[0] = 0;
+      }
+    }
+    auto vol6 = [&](size_t t, size_t moved_v, const double *np) {
+      double q[4][3];
+      for (int j = 0; j < 4; j++) {
+        const size_t v = (size_t)m->tets[4 * t + j];
+        for (int k = 0; k < 3; k++) q[j][k] = v == moved_v ? np[k] : (double)m->pos[3 * v + k];
+      }
+      return det6(q[0], q[1], q[2], q[3]);
+    };
+    std::vector<double> vol0(T); // volumes before any vertex moves: the bound is relative to these
+    {
+      const double none[3] = {0, 0, 0};
+      for (size_t t = 0; t < T; t++) vol0[t] = vol6(t, (size_t)-1, none);
+    }
+    uint32_t moved = 0;
+    for (size_t v = 0; v < V; v++) {
+      if (!on_boundary[v]) continue;
+      const double p[3] = {m->pos[3 * v], m->pos[3 * v + 1], m->pos[3 * v + 2]};
+      double best[3] = {0, 0, 0}, best_d2 = (double)max_dist * max_dist;
+      bool found = false;
+      const int64_t c[3] = {cell_of(p[0], 0), cell_of(p[1], 1), cell_of(p[2], 2)};
+      for (int64_t z = std::max<int64_t>(0, c[2] - reach); z <= std::min(g[2] - 1, c[2] + reach); z++)
+        for (int64_t y = std::max<int64_t>(0, c[1] - reach); y <= std::min(g[1] - 1, c[1] + reach); y++)
+          for (int64_t x = std::max<int64_t>(0, c[0] - reach); x <= std::min(g[0] - 1, c[0] + reach); x++) {
+            const size_t cc = (size_t)((z * g[1] + y) * g[0] + x);
+            for (uint32_t k = off[cc]; k < off[cc + 1]; k++) {
+              const uint32_t t = items[k];
+              double a[3], b[3], cq[3], q[3];
+              for (int j = 0; j < 3; j++) {
+                a[j] = sp[3 * (size_t)st[3 * (size_t)t] + j];
+                b[j] = sp[3 * (size_t)st[3 * (size_t)t + 1] + j];
+                cq[j] = sp[3 * (size_t)st[3 * (size_t)t + 2] + j];
+              }
+              closest_on_triangle(p, a, b, cq, q);
+              const double d2 = (q[0] - p[0]) * (q[0] - p[0]) + (q[1] - p[1]) * (q[1] - p[1]) + (q[2] - p[2]) * (q[2] - p[2]);
+              if (d2 < best_d2) { best_d2 = d2; best[0] = q[0]; best[1] = q[1]; best[2] = q[2]; found = true; }
+            }
+          }
+      if (!found || best_d2 == 0) continue;
+      // the float the vertex becomes must keep every tet at it well shaped: all the way, else part of the way
+      for (int step = 4; step >= 1; step--) {
+        const double f = 0.25 * step;
+        const double np[3] = {(double)(float)(p[0] + f * (best[0] - p[0])), (double)(float)(p[1] + f * (best[1] - p[1])),
+                              (double)(float)(p[2] + f * (best[2] - p[2]))};
+        bool ok = true;
+        for (uint32_t k = toff[v]; k < toff[v + 1] && ok; k++) ok = vol6(tlist[k], v, np) > 0.3 * vol0[tlist[k]];
+        if (!ok) continue;
+        for (int k = 0; k < 3; k++) m->pos[3 * v + k] = (float)np[k];
+        moved++;
+        break;
+      }
+    }
+    if (n_moved) *n_moved = moved;
+    return SB_OK;
+  } catch (const std::bad_alloc &) { return fail(SB_E_NOMEM, "out of memory");
+  } catch (const std::exception &e) { return fail(SB_E_ARG, e.what()); }
+}
+
 // ---- render mesh -> tets ------------------------------------------------------------------------------
 
 int sb_skin_compute(const float *tet_pos_xyz, uint32_t V, const int32_t *tets, uint32_t T, const float *pts_xyz, uint32_t n,

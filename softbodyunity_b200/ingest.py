@@ -37,12 +37,20 @@ def _take(handle):
         lib.sb_tetmesh_free(handle)
 
 
-def tetrahedralize_surface(surf_pos, surf_tris, spacing):
-    """Closed triangle surface -> lattice tet mesh of the enclosed volume (cells of size `spacing`)."""
+def tetrahedralize_surface(surf_pos, surf_tris, spacing, snap=False):
+    """Closed triangle surface -> lattice tet mesh of the enclosed volume (cells of size `spacing`).
+    snap=True (or a distance) then pulls the staircase boundary onto the surface (default reach: one spacing)."""
     sp = np.ascontiguousarray(surf_pos, np.float32).reshape(-1, 3)
     st = np.ascontiguousarray(surf_tris, np.int32).reshape(-1, 3)
+    lib = _abi.load()
     h = C.c_void_p()
-    _ck(_abi.load().sb_tetmesh_from_surface(_ptr(sp), len(sp), _ptr(st), len(st), float(spacing), C.byref(h)))
+    _ck(lib.sb_tetmesh_from_surface(_ptr(sp), len(sp), _ptr(st), len(st), float(spacing), C.byref(h)))
+    if snap:
+        reach = float(spacing) if snap is True else float(snap)
+        rc = lib.sb_tetmesh_snap_to_surface(h, _ptr(sp), len(sp), _ptr(st), len(st), reach, None)
+        if rc != 0:
+            lib.sb_tetmesh_free(h)
+            _ck(rc)
     return _take(h)
 
 

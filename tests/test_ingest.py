@@ -105,6 +105,36 @@ def test_sphere_and_torus_volumes(flip):
     assert is_watertight(f)
 
 
+def test_snapping_pulls_the_staircase_boundary_onto_the_surface():
+    sp, st = uv_sphere(1.0, 32, 64)
+    p0, t0, f0 = ingest.tetrahedralize_surface(sp, st, 0.1)
+    p1, t1, f1 = ingest.tetrahedralize_surface(sp, st, 0.1, snap=True)
+    assert np.array_equal(t0, t1) and np.array_equal(f0, f1)  # topology untouched
+    b = np.unique(f0)
+    inner = np.setdiff1d(np.arange(len(p0)), b)
+    assert np.array_equal(p0[inner], p1[inner])  # only boundary vertices move
+    dev0 = np.sqrt(((np.linalg.norm(p0[b], axis=1) - 1) ** 2).mean())
+    dev1 = np.sqrt(((np.linalg.norm(p1[b], axis=1) - 1) ** 2).mean())
+    assert dev1 < 0.5 * dev0, (dev0, dev1)
+    v0, v1 = tet_volumes(p0, t0), tet_volumes(p1, t1)
+    assert (v1 > 0.29 * v0).all()  # no tet collapses
+    assert abs(v1.sum() / (4 / 3 * np.pi) - 1) < abs(v0.sum() / (4 / 3 * np.pi) - 1)  # and the volume is closer
+    # a lattice that already lies on the surface stays put
+    pos, tets, tris = meshgen.block(6, 6, 6, spacing=0.2, origin=(0, 0, 0), jitter=0.0)
+    cs, ct = surface_of(pos, tris)
+    a = ingest.tetrahedralize_surface(cs, ct, 0.1)
+    b2 = ingest.tetrahedralize_surface(cs, ct, 0.1, snap=True)
+    assert np.abs(a[0] - b2[0]).max() < 1e-6
+    # the snapped body plans and steps (oracle, a few frames resting on the ground)
+    q = p1.copy()
+    q[:, 1] -= q[:, 1].min() - 0.01  # lowest vertex 1 cm above the ground plane
+    sb = SoftBody(q, t1, f1, host_only=True)
+    order, off = sb.schedule()
+    m = orc.Model(q, t1, roles=sb.tet_roles())
+    m.simulate(orc.params(stiffness_distance=1e5), n_frames=5, order=order, batch_off=off, threads=4)
+    assert np.isfinite(m.x4).all() and m.x4[:, 1].min() >= 0.0
+
+
 def test_triangle_soup_with_split_vertices_gives_the_same_tets():
     # Unity meshes split vertices at UV seams and hard edges: the surface is closed geometrically, not by index
     sp, st = uv_sphere(0.6, 14, 28, centre=(0.1, 0.2, 0.3))
