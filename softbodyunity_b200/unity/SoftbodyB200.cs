@@ -92,6 +92,7 @@ internal static class SbNative
     [DllImport(Lib)] public static extern int sb_save_state(IntPtr h, string path);
     [DllImport(Lib)] public static extern int sb_load_state(IntPtr h, string path, int applyParams);
     [DllImport(Lib)] public static extern int sb_tetmesh_from_surface(IntPtr surfPosXyz, uint nVerts, int[] surfTris, uint nTris, float spacing, out IntPtr mesh);
+    [DllImport(Lib)] public static extern int sb_tetmesh_snap_to_surface(IntPtr mesh, IntPtr surfPosXyz, uint nVerts, int[] surfTris, uint nTris, float maxDist, out uint nMoved);
     [DllImport(Lib)] public static extern int sb_tetmesh_load(string path, out IntPtr mesh);
     [DllImport(Lib)] public static extern int sb_tetmesh_desc(IntPtr mesh, out SbMeshDesc desc);
     [DllImport(Lib)] public static extern int sb_tetmesh_free(IntPtr mesh);
