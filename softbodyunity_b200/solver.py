@@ -115,6 +115,25 @@ class SoftBody:
         i = self.info()
         self.n_edges, self.n_surface = i["n_edges"], i["n_surface_verts"]
 
+    # -- from the formats either side of the path (ingest.py) ---------------------------------
+    @classmethod
+    def from_surface(cls, surf_pos, surf_tris, spacing, snap=True, bind=True, **kw):
+        """Body from a closed surface mesh (a Unity `Mesh`): lattice tets of `spacing`, boundary snapped onto the
+        surface, and -- with bind -- the surface itself bound as the render mesh (read_skinned)."""
+        from . import ingest
+        pos, tets, tris = ingest.tetrahedralize_surface(surf_pos, surf_tris, spacing, snap=snap)
+        sb = cls(pos, tets, tris, **kw)
+        if bind:
+            sb.skin_bind(surf_pos, surf_tris)
+        return sb
+
+    @classmethod
+    def from_file(cls, path, **kw):
+        """Body from a TetGen (.node/.ele) or Gmsh (.msh) tet mesh."""
+        from . import ingest
+        pos, tets, tris = ingest.load_mesh(path)
+        return cls(pos, tets, tris, **kw)
+
     # -- lifecycle ---------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None) and self._h.value:

@@ -362,3 +362,18 @@ def test_parsers_survive_garbage(tmp_path):
         except SbError:
             outcomes["error"] += 1
     assert outcomes["error"] > 40 and outcomes["ok"] + outcomes["error"] == 120
+
+
+def test_softbody_from_surface_and_from_file(tmp_path):
+    sp, st = uv_sphere(0.3, 12, 24, centre=(0, 0.5, 0))
+    sb = SoftBody.from_surface(sp, st, 0.06, host_only=True, tile_cap=256)
+    assert sb.n_render == len(sp) and sb.verify_streams() == 0
+    tet_of, b = sb.skin_binding()
+    assert np.abs(b.sum(1) - 1).max() < 1e-5 and b.min() > -0.6  # snapped boundary: the render vertices sit on or near it
+    pos, tets, tris = ingest.tetrahedralize_surface(sp, st, 0.06, snap=True)
+    ingest.save_mesh(tmp_path / "s.msh", pos, tets, tris)
+    sb2 = SoftBody.from_file(tmp_path / "s.msh", host_only=True, tile_cap=256)
+    assert (sb2.n_verts, sb2.n_tets) == (sb.n_verts, sb.n_tets)
+    o1, f1 = sb.schedule()
+    o2, f2 = sb2.schedule()
+    assert np.array_equal(o1, o2) and np.array_equal(f1, f2)
