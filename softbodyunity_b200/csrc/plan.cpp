@@ -519,15 +519,27 @@ bool grid_tilings(const Plan &P, uint32_t cap, int n_tilings, std::vector<Tiling
     // fine-grid ("atom") coordinates: boxes of every tiling are unions of atoms
     std::vector<int32_t> atom(3 * (size_t)V);
     atom_key.resize(V);
+    // Order of the atoms inside a box of the unshifted tiling: z-major, but as a snake (every other row of x runs
+    // backwards, every other slice of rows runs backwards in y).  The part of a shifted box that falls into one
+    // unshifted box is a product of prefixes / suffixes of the atom ranges; in plain z-major order it is one run of
+    // device ids per (z, y) row, in the snake two consecutive rows join where the snake turns: half the runs
+    // (bulk copies) per tile.
+    static const int snake = getenv("SB_ATOM_SNAKE") ? atoi(getenv("SB_ATOM_SNAKE")) : 1;
     for (uint32_t v = 0; v < V; v++) {
-      uint32_t key = 0;
+      uint32_t sub[3];
       for (int k = 2; k >= 0; k--) {
         const double f = ext[k] > 0 ? ((double)P.pos[3 * (size_t)v + k] - lo[k]) / wa[k] * n_tilings : 0.0;
         const int a = std::min(n[k] * n_tilings - 1, std::max(0, (int)std::floor(f)));
         atom[3 * (size_t)v + k] = a;
-        key = key * (uint32_t)n_tilings + (uint32_t)(a % n_tilings);
+        sub[k] = (uint32_t)(a % n_tilings);
       }
-      atom_key[v] = key;
+      const uint32_t nt_ = (uint32_t)n_tilings;
+      uint32_t zi = sub[2], yi = sub[1], xi = sub[0];
+      if (snake) {
+        if (zi & 1u) yi = nt_ - 1 - yi;
+        if ((zi * nt_ + yi) & 1u) xi = nt_ - 1 - xi;
+      }
+      atom_key[v] = (zi * nt_ + yi) * nt_ + xi;
     }
     for (int s = 0; s < n_tilings && ok; s++) {
       const int m[3] = {n[0] + (s > 0), n[1] + (s > 0), n[2] + (s > 0)};
@@ -687,6 +699,23 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
   }
   const uint32_t cap_e = 2 * width * bt, cap_t = width * bt;
 
+  // A tile of a shifted tiling stages ALL the vertices of its boxes, not only those its constraints of this pass
+  // touch: a vertex whose constraints all went to other tilings would otherwise split a run of device ids in two
+  // (measured: 66 runs per tile instead of the ~30 the geometry gives).  No other tile of the pass touches a vertex
+  // of this tile's boxes, so loading it and storing it back unchanged is safe.
+  static const int whole_boxes = getenv("SB_WHOLE_BOXES") ? atoi(getenv("SB_WHOLE_BOXES")) : 1;
+  std::vector<uint32_t> mem_off, mem_list;
+  if (box0 && whole_boxes && !contig_off) {
+    mem_off.assign((size_t)n_tiles + 1, 0);
+    for (uint32_t d = 0; d < P.V; d++)
+      if (part[d] >= 0) mem_off[(size_t)part[d] + 1]++;
+    for (uint32_t t = 0; t < n_tiles; t++) mem_off[t + 1] += mem_off[t];
+    mem_list.resize(mem_off[n_tiles]);
+    std::vector<uint32_t> cur(mem_off.begin(), mem_off.end() - 1);
+    for (uint32_t d = 0; d < P.V; d++)
+      if (part[d] >= 0) mem_list[cur[part[d]]++] = d; // ascending device id inside a tile
+  }
+
   // 2. per tile: local numbering, capacity-limited greedy colouring, rounds
   std::vector<TileOut> outs(n_tiles);
   int nt = std::max(1, threads);
@@ -702,16 +731,20 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
       nv = (*contig_off)[t + 1] - base;
     } else {
       if (loc.size() != P.V) loc.assign(P.V, 0xffffffffu);
-      for (size_t i = 0; i < ne; i++) {
-        int32_t vs[4];
-        int n = ent_verts(D, ents[i], vs);
-        for (int k = 0; k < n; k++)
-          if (loc[vs[k]] == 0xffffffffu) {
-            loc[vs[k]] = 0;
-            O.verts.push_back((uint32_t)vs[k]);
-          }
+      if (!mem_off.empty()) {
+        if (ne) O.verts.assign(mem_list.begin() + mem_off[t], mem_list.begin() + mem_off[t + 1]);
+      } else {
+        for (size_t i = 0; i < ne; i++) {
+          int32_t vs[4];
+          int n = ent_verts(D, ents[i], vs);
+          for (int k = 0; k < n; k++)
+            if (loc[vs[k]] == 0xffffffffu) {
+              loc[vs[k]] = 0;
+              O.verts.push_back((uint32_t)vs[k]);
+            }
+        }
+        std::sort(O.verts.begin(), O.verts.end());
       }
-      std::sort(O.verts.begin(), O.verts.end());
       nv = (uint32_t)O.verts.size();
       for (uint32_t k = 0; k < nv; k++) loc[O.verts[k]] = k;
     }
@@ -1205,6 +1238,12 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
           TP.runs.push_back({O.verts[k], k});
       TP.runs.push_back({0u, O.n_verts});
       TP.run_off.push_back((uint32_t)TP.runs.size());
+      if (getenv("SB_PLAN_STATS") && t == n_tiles / 2) {
+        fprintf(stderr, "RUNS tile %u nv %u:", t, O.n_verts);
+        const size_t r0 = TP.run_off[TP.run_off.size() - 2], r1 = TP.runs.size() - 1;
+        for (size_t r = r0; r < r1; r++) fprintf(stderr, " %u+%u", TP.runs[r].x, TP.runs[r + 1].y - TP.runs[r].y);
+        fprintf(stderr, "\n");
+      }
     }
     TP.max_ecol = std::max(TP.max_ecol, O.n_ecol);
     TP.max_tcol = std::max(TP.max_tcol, O.n_tcol);
