@@ -410,7 +410,8 @@ def main():
                        "tile_passes": info["n_tile_passes"], "tiles_in_pass": info["tiles_in_pass"][:info["n_tile_passes"]],
                        "tile_cap": info["tile_cap"], "block_threads": info["block_threads"], "round_width": info["round_width"],
                        "edges_attached": info["edges_attached"], "rounds_per_sweep": sum(info["rounds_in_pass"][:info["n_tile_passes"]]),
-                       "planner": {k: os.environ[k] for k in ("SB_RECOLOUR", "SB_ATTACH_AUGMENT", "SB_MERGE_RIMS") if k in os.environ} or "defaults",
+                       "runs_per_sweep": sum(info["runs_in_pass"][:info["n_tile_passes"]]),
+                       "planner": {k: os.environ[k] for k in ("SB_RECOLOUR", "SB_ATTACH_AUGMENT", "SB_MERGE_RIMS", "SB_WHOLE_BOXES", "SB_ATOM_SNAKE") if k in os.environ} or "defaults",
                        "rounds_per_tile": [round(r / max(1, t), 1) for r, t in zip(info["rounds_in_pass"][:info["n_tile_passes"]],
                                                                                   info["tiles_in_pass"][:info["n_tile_passes"]])],
                        "l2": "no flush: per-step working set (constraint streams + state) %.0f MB exceeds the 126 MB L2" %

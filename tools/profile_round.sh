@@ -8,7 +8,7 @@ python bench.py --steps 20 --warmup 3 --kernel-breakdown > $out/bench_${tag}.jso
 python bench.py --steps 20 --warmup 3 --kernel-breakdown --fast-math --no-cpu-baseline > $out/bench_${tag}_fast.json 2>> $out/bench_${tag}.err
 python bench.py --impl reference --steps 5 --warmup 3 > $out/bench_${tag}_reference.json 2>> $out/bench_${tag}.err
 # planner A/B on the same box: every host-side switch off / on (rim merge, recolouring, augmented attachment), and the body batch
-python tools/ab_plan.py --variants "SB_MERGE_RIMS=0 SB_RECOLOUR=0 SB_ATTACH_AUGMENT=0;SB_MERGE_RIMS=0;" > $out/ab_plan_${tag}.log 2>&1
+python tools/ab_plan.py --variants "SB_MERGE_RIMS=0 SB_WHOLE_BOXES=0 SB_ATOM_SNAKE=0 SB_RECOLOUR=0 SB_ATTACH_AUGMENT=0;SB_MERGE_RIMS=0 SB_WHOLE_BOXES=0 SB_ATOM_SNAKE=0;SB_WHOLE_BOXES=0 SB_ATOM_SNAKE=0;SB_MERGE_RIMS=0;" > $out/ab_plan_${tag}.log 2>&1
 python tools/ab_plan.py --bodies 1184 --variants "" > $out/ab_bodies_${tag}.log 2>&1
 # launch list of a short run of the same command (cold-cache, serialised: compare shares)
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/plain_${tag}.log 2>&1 &&
