@@ -74,14 +74,23 @@ def bytes_per_substep(n_verts, n_edges, n_tets, iterations):
     return B_PREDICT + iterations * b_iter + B_FINISH
 
 
-def measured_traffic():
-    """DRAM bytes per tile-pass launch (mean of the captured launches) from the committed ncu capture (profiles/), or None."""
+def measured_traffic(info=None):
+    """DRAM bytes per tile-pass launch (mean of the captured launches) from the newest committed ncu capture
+    (profiles/*_traffic.json), or (None, reason): a capture of another plan (rounds per sweep / tiles per pass differ
+    from what runs now) is refused rather than quoted."""
     try:
         files = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
-        ls = json.load(open(os.path.join(ROOT, "profiles", files[-1])))["launches"]
+        doc = json.load(open(os.path.join(ROOT, "profiles", files[-1])))
+        ls = doc["launches"]
+        if info is not None:
+            np_ = info["n_tile_passes"]
+            want = {"rounds_per_sweep": int(sum(info["rounds_in_pass"][:np_])), "tiles_in_pass": [int(t) for t in info["tiles_in_pass"][:np_]]}
+            have = {k: doc.get(k) for k in want}
+            if have != want:
+                return None, f"{files[-1]} is of another plan ({have} captured, {want} running): not quoted"
         return sum(d["dram_read_bytes"] + d["dram_write_bytes"] for d in ls) / len(ls), files[-1]
-    except Exception:
-        return None, None
+    except Exception as e:
+        return None, f"no usable capture under profiles/ ({type(e).__name__})"
 
 
 def peaks():
@@ -148,14 +157,14 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons)}
 
 
-def cpu_oracle_rate(pos, tets, order, off, substeps, iterations, threads, reps, roles=None):
+def cpu_oracle_rate(pos, tets, sched, substeps, iterations, threads, reps, roles=None):
     """vertex-substeps/s of the CPU oracle on `reps` steps of `substeps` substeps each."""
     from oracle import xpbd_oracle as orc
     m = orc.Model(pos, tets, roles=roles)
     p = orc.params(dt=(1.0 / 60.0) * substeps / 10.0, substeps=substeps, iterations=iterations)
-    m.simulate(p, n_frames=1, order=order, batch_off=off, threads=threads)  # touch memory
+    m.simulate(p, n_frames=1, threads=threads, **sched)  # touch memory
     t0 = time.perf_counter()
-    m.simulate(p, n_frames=reps, order=order, batch_off=off, threads=threads)
+    m.simulate(p, n_frames=reps, threads=threads, **sched)
     dt = time.perf_counter() - t0
     return len(pos) * substeps * reps / dt, dt
 
@@ -168,7 +177,7 @@ def run_reference(args, rank, world):
     from softbodyunity_b200 import SoftBody
     pos, tets, tris, name = workload(args)
     plan = SoftBody(pos, tets, tris, host_only=True)  # only the Gauss-Seidel order (colour schedule) is taken from it
-    order, off = plan.schedule()
+    sched = plan.schedule_kw()
     info = plan.info()
     threads = os.cpu_count() or 1
     from oracle import xpbd_oracle as orc
@@ -176,10 +185,10 @@ def run_reference(args, rank, world):
     sub = 1  # one step of this arm = ONE substep (iterations sweeps) of the workload: bounded sample
     p = orc.params(dt=(1.0 / 60.0) / args.substeps, substeps=sub, iterations=args.iterations)
     for _ in range(args.warmup):
-        m.simulate(p, n_frames=1, order=order, batch_off=off, threads=threads)
+        m.simulate(p, n_frames=1, threads=threads, **sched)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        m.simulate(p, n_frames=1, order=order, batch_off=off, threads=threads)
+        m.simulate(p, n_frames=1, threads=threads, **sched)
     dt = time.perf_counter() - t0
     val = len(pos) * sub * args.steps / dt
     out = {
@@ -196,24 +205,40 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
+def state_checksum(x4_owned, world, dist, torch):
+    """Order-independent checksum of the positions (sum of the 32-bit words of x4, high and low halves apart),
+    over all ranks: the same mesh stepped the same number of frames gives the same value on any number of GPUs."""
+    w = np.ascontiguousarray(x4_owned, np.float32).view(np.uint32).astype(np.int64)
+    t = torch.tensor([int((w >> 16).sum()), int((w & 0xffff).sum())], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return "%x-%x" % (int(t[0].item()), int(t[1].item()))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="block", choices=["block", "sphere", "bodies", "partitioned", "dist"])
-    ap.add_argument("--n", "--size", dest="n", type=int, default=100)
+    ap.add_argument("--workload", default=None, choices=["block", "sphere", "bodies", "partitioned", "dist", "replicas"],
+                    help="default: block (1 M vertices) on one GPU; on N > 1 GPUs `dist`, ONE 200^3 = 8 M-vertex block over all of them")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=None)
     ap.add_argument("--substeps", type=int, default=10)
     ap.add_argument("--iterations", type=int, default=10)
     ap.add_argument("--fast-math", action="store_true")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--dag", action="store_true", help="persistent tile-DAG kernel (one launch per substep)")
+    ap.add_argument("--no-snake", action="store_true", help="A/B: same pass order in every iteration")
+    ap.add_argument("--no-fuse", action="store_true", help="A/B: one launch per tile pass, separate predict / finish kernels")
+    ap.add_argument("--slabs", action="store_true", help="A/B (dist): ranks as slabs of the default box order, not compact blocks")
     ap.add_argument("--tile-cap", type=int, default=0)
     ap.add_argument("--later-tile-cap", type=int, default=0)
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--round-width", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bodies", action="store_true", help="skip the secondary 4096-body measurement (BASELINE.json configs[3])")
+    ap.add_argument("--bodies-n", type=int, default=4096)
     ap.add_argument("--kernel-breakdown", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -221,6 +246,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload is None:
+        # N > 1: the path that SHARDS -- one mesh spread over the GPUs (BASELINE.json configs[4]), strong scaling
+        args.workload = "block" if world == 1 else "dist"
+    if args.workload == "replicas":  # (round 1's N > 1 default: one independent 1 M body per GPU)
+        args.workload, replicas = "block", True
+    else:
+        replicas = False
+    if args.n is None:
+        args.n = {"block": 100, "sphere": 58, "bodies": args.bodies_n, "dist": 200, "partitioned": 200}[args.workload]
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -239,24 +273,27 @@ def main():
         clocks.start()  # nvidia-smi takes a moment to come up; samples are windowed by timestamp
     from softbodyunity_b200 import FLAG_FAST_MATH, SoftBody
     pos, tets, tris, name = workload(args, rank, world)
-    flags = (FLAG_FAST_MATH if args.fast_math else 0) | (16 if args.no_pdl else 0) | (32 if args.dag else 0)
+    flags = ((FLAG_FAST_MATH if args.fast_math else 0) | (16 if args.no_pdl else 0) | (32 if args.dag else 0) |
+             (64 if args.no_snake else 0) | (128 if args.no_fuse else 0))
     kw = dict(substeps=args.substeps, iterations=args.iterations, flags=flags, tile_cap=args.tile_cap,
               later_tile_cap=args.later_tile_cap, block_threads=args.block_threads, round_width=args.round_width)
-    part_mesh = None
+    shared = None      # a body shared by all ranks (one mesh over the GPUs)
     if args.workload == "partitioned" and world > 1:
         from softbodyunity_b200.partition import PartitionedBody, connect_peers, slab_partition
-        (part_mesh,) = slab_partition(pos, tets, tris, world, only_rank=rank)
+        (part,) = slab_partition(pos, tets, tris, world, only_rank=rank)
         V_global, T_global = len(pos), len(tets)
         del pos, tets, tris
-        body = PartitionedBody(part_mesh, device=local, **kw)
-        connect_peers(body, local)     # CUDA IPC handles travel over torch.distributed once; the data path is P2P stores
-        sb = body.sb
+        shared = PartitionedBody(part, device=local, **kw)
+        connect_peers(shared, local)     # CUDA IPC handles travel over torch.distributed once; the data path is P2P stores
+        sb = shared.sb
     elif args.workload == "dist" and world > 1:
         from softbodyunity_b200.dist import DistBody
         V_global, T_global = len(pos), len(tets)
-        body = DistBody(pos, tets, tris, device=local, **kw)
-        sb = body.sb
-        part_mesh = body
+        if args.slabs:
+            kw["dist_ranks"] = 0
+        shared = DistBody(pos, tets, tris, device=local, **kw)
+        kw.pop("dist_ranks", None)
+        sb = shared.sb
     else:
         sb = SoftBody(pos, tets, tris, device=local, **kw)
     info = sb.info()
@@ -283,16 +320,26 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def timed_frames(body, steps, warmup):
+        """device time (ms, max over ranks) of `steps` frames after `warmup` frames, barrier + synchronize both sides"""
+        body.step(frames=warmup)
+        body.synchronize()
+        barrier()
+        t = body.time_frames(steps)
+        barrier()
+        return max_over_ranks(t)
+
     # ---- device-resident throughput ---------------------------------------------------
     clocks.mark_begin()
-    sb.step(frames=args.warmup)
-    sb.synchronize()
-    barrier()
-    ms = sb.time_frames(args.steps)
-    barrier()
-    ms = max_over_ranks(ms)
+    ms = timed_frames(sb, args.steps, args.warmup)
+    checksum = None
+    if shared is not None and args.workload == "dist":
+        x4o = sb.unpack_frame(sb.read_packed())[0]
+        checksum = state_checksum(x4o, world, dist, torch)
+    elif args.workload == "dist":  # the same mesh on one GPU: the value every N must reproduce
+        checksum = state_checksum(sb.get_state()[0], 1, dist, torch)
     # keep the GPU under the same load until the sampler has seen it (untimed)
-    if part_mesh is not None:
+    if shared is not None:
         # ranks that share one mesh must issue the SAME number of frames: a count from the reduced time, not a clock
         sb.step(frames=max(2, int(600.0 / max(ms / args.steps, 1e-3))))
         sb.synchronize()
@@ -303,125 +350,167 @@ def main():
             sb.synchronize()
     clocks.mark_end()
     clk = clocks.stop() if rank == 0 else None
-    V_all = V if world == 1 else int(round(sum_over_ranks(V)))
-    value = V_all * args.substeps * args.steps / (ms * 1e-3)
-
-    if part_mesh is not None:
-        # strong scaling of ONE mesh: report the device-timed figure only (the host-buffer protocol of the
-        # single-body e2e leg would have to re-send ghosts as well; not measured for this workload)
+    if shared is not None:
+        V_all = V_global
         if sb.halo_error() or sb.dist_error():
             raise SystemExit("bench.py: a wait for a peer GPU timed out")
-        if rank == 0:
-            print(json.dumps({
-                "metric": METRIC, "value": V_global * args.substeps * args.steps / (ms * 1e-3), "unit": "vertex-substeps/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": name, "n_verts": V_global, "n_tets": T_global,
-                           "own_verts_rank0": int(part_mesh.owned.sum()) if args.workload == "dist" else V,
-                           "tiles_rank0": part_mesh.tiles if args.workload == "dist" else None,
-                           "ghost_verts_rank0": info["n_ghost_verts"], "constraints_cut_rank0": info["constraints_cut"],
-                           "math": "fast" if args.fast_math else "exact (bit-identical to CPU oracle)",
-                           "tile_passes": info["n_tile_passes"], "build_seconds": info["build_seconds"]},
-                "e2e": None, "gpu_launches": info["launches_per_frame"] * args.steps, "clocks": clk}), flush=True)
-        dist.destroy_process_group()
-        return
+    else:
+        V_all = V if world == 1 else int(round(sum_over_ranks(V)))
+    value = V_all * args.substeps * args.steps / (ms * 1e-3)
 
-    # ---- end to end through the C ABI with host buffers ---------------------------------
-    x4 = torch.empty((V, 4), dtype=torch.float32).pin_memory()
-    v4 = torch.empty((V, 4), dtype=torch.float32).pin_memory()
-    out_pos = torch.empty((V, 3), dtype=torch.float32).pin_memory()
-    out_sp = torch.empty((max(ns, 1), 3), dtype=torch.float32).pin_memory()
-    out_sn = torch.empty((max(ns, 1), 3), dtype=torch.float32).pin_memory()
-    sb.get_state(x4, v4)
+    # ---- end to end through the C ABI with HOST buffers, one packed copy each way -------------------
+    # every step: H2D of the step's input state (x4 + v4 of the vertices this rank owns) from pinned memory, sb_step,
+    # D2H of the frame (state + surface positions + surface normals) into pinned memory; sb_read_packed synchronises
+    e2e = None
+    if args.workload != "partitioned" or shared is None:
+        n_own, ns_own, b_in, b_out = sb.packed_sizes()
+        host = torch.empty(b_out, dtype=torch.uint8).pin_memory()
+        sb.read_packed(host)
 
-    def e2e_step():
-        sb.set_state(x4, v4)            # H2D: this step's input state from pinned host memory
-        sb.step()
-        sb.positions(out_pos)           # D2H: all positions (mesh write-back)
-        if ns:
-            sb.read_surface(out_sp, out_sn)  # D2H: surface positions + normals
-        sb.get_state(x4, v4)            # D2H: state handed back to the host for the next call
+        def e2e_step():
+            sb.write_packed(host)   # H2D (the first b_in bytes: x4 | v4)
+            sb.step()
+            sb.read_packed(host)    # D2H: x4 | v4 | surface xyz | surface normals
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    h2d = 2 * V * 16
-    d2h = V * 12 + 2 * ns * 12 + 2 * V * 16
-    e2e_val = V_all * args.substeps * args.steps / e2e_s
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": V_all * args.substeps * args.steps / e2e_s, "unit": "vertex-substeps/s",
+               "h2d_bytes_per_step": int(sum_over_ranks(b_in)), "d2h_bytes_per_step": int(sum_over_ranks(b_out)),
+               "ms_per_step": 1e3 * e2e_s / args.steps,
+               "protocol": "sb_write_packed (x4 | v4 from pinned host memory) -> sb_step -> sb_read_packed (x4 | v4 | surface xyz | "
+                           "surface normals into pinned host memory), one copy and one synchronisation each way"
+                           + (", every rank its own vertices" if shared is not None else "")}
+        if shared is not None and sb.dist_error():
+            raise SystemExit("bench.py: a wait for a peer GPU timed out")
 
-    # ---- roofline of the dominant kernel (first tile pass), timed alone --------------------
+    # ---- roofline of the dominant kernel ------------------------------------------------------------
     hbm, peak_src = peaks()
-    B_sub = bytes_per_substep(V, E, T, args.iterations)
+    B_sub = bytes_per_substep(V_all if shared is not None else V, E, T, args.iterations)
     roof = None
     breakdown = None
-    if info["n_tile_passes"] > 0:
-        # dominant kernel = the tile pass (k_tile_rounds; n_pass launches per sweep).  Average launch duration
-        # measured live: the device-timed step minus the per-vertex kernels, divided by the pass launches in it.
+    if shared is not None:
+        # whole-step figure only (sb_time_kernel would run launches the peers do not run)
+        ach = value * B_sub / 1e9
+        roof = {"bound": "hbm", "kernel": "k_tile_rounds (whole step, all ranks)", "achieved": ach, "peak": hbm * world, "unit": "GB/s",
+                "frac": ach / (hbm * world), "traffic": None, "traffic_source": "not captured for the multi-GPU run (ncu is a one-GPU tool here)",
+                "peak_source": peak_src + " x n_gpus", "bytes_per_vertex_substep": B_sub,
+                "launch_ms": ms / args.steps / max(1, info["launches_per_frame"]),
+                "launch_ms_source": "device-timed step / launches in it (max over ranks)"}
+    elif info["n_tile_passes"] > 0:
         n_pass = info["n_tile_passes"]
-        # algorithmic bytes of one sweep (12 E + 20 T + 32 V), shared out over its n_pass launches;
-        # the positions a pass re-reads from L2 are this design's overhead, not algorithmic traffic
-        launch_bytes = (12.0 * E + 20.0 * T + 32.0 * V) / n_pass
+        # The frame program (sb_frame_program): consecutive occurrences of a pass share one launch, and predict /
+        # collide + velocity update run inside the tile launches at the substep boundaries, so the tile launches
+        # carry the whole algorithmic traffic of the step (S * (64 + I * (12 E + 20 T + 32 V) / V + 64)
+        # per vertex) minus what separate per-vertex kernels, if any, carry (64 B per vertex each).
+        prog = sb.frame_program()
+        n_launch = int((prog[:, 0] == 2).sum())
+        n_pred, n_fin, n_nrm = int((prog[:, 0] == 0).sum()), int((prog[:, 0] == 1).sum()), int((prog[:, 0] == 6).sum())
         t_pred, t_fin, t_nrm = sb.time_kernel(0, 30), sb.time_kernel(1, 30), sb.time_kernel(2, 30)
-        n_launch = args.substeps * args.iterations * n_pass
         step_ms = ms / args.steps
-        k_ms = (step_ms - args.substeps * (t_pred + t_fin) - t_nrm) / n_launch
+        k_ms = (step_ms - n_pred * t_pred - n_fin * t_fin - n_nrm * t_nrm) / n_launch
+        launch_bytes = (B_sub * V * args.substeps - 64.0 * V * (n_pred + n_fin)) / n_launch
         alone_ms = sb.time_kernel(16, reps=30)
         ach = launch_bytes / (k_ms * 1e-3) / 1e9
-        traffic, traffic_src = measured_traffic()
-        roof = {"bound": "hbm", "kernel": "k_tile_rounds (%d tile passes per sweep)" % n_pass, "achieved": ach, "peak": hbm, "unit": "GB/s",
+        traffic, traffic_src = measured_traffic(info)
+        roof = {"bound": "hbm", "kernel": "k_tile_rounds (%d tile passes per sweep, %d launches per step)" % (n_pass, n_launch),
+                "achieved": ach, "peak": hbm, "unit": "GB/s",
                 "frac": ach / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_launch": launch_bytes,
-                "launch_ms": k_ms, "launch_ms_source": "(device-timed step - per-vertex kernels) / tile-pass launches in the step",
-                "launches_per_step": n_launch, "share_of_step": k_ms * n_launch / step_ms,
+                "launch_ms": k_ms, "launch_ms_source": "(device-timed step - separate per-vertex kernels) / tile-pass launches in the step; "
+                                                       "bytes_per_launch = algorithmic bytes of the step the tile launches carry / their number",
+                "launches_per_step": n_launch, "separate_vertex_kernels_per_step": n_pred + n_fin,
+                "share_of_step": k_ms * n_launch / step_ms,
                 "pass0_alone_ms": alone_ms,
                 "step_achieved": V * args.substeps * args.steps / (ms * 1e-3) * B_sub / 1e9,
                 "step_frac": V * args.substeps * args.steps / (ms * 1e-3) * B_sub / 1e9 / hbm,
                 "bytes_per_vertex_substep": B_sub}
         if args.kernel_breakdown:
-            breakdown = {"predict_ms": sb.time_kernel(0, 30), "finish_ms": sb.time_kernel(1, 30),
-                         "normals_ms": sb.time_kernel(2, 30)}
+            breakdown = {"predict_ms": t_pred, "finish_ms": t_fin, "normals_ms": t_nrm}
             for p in range(info["n_tile_passes"]):
                 breakdown[f"pass{p}_ms"] = sb.time_kernel(16 + p, 30)
             if info["n_global_batches"]:
                 breakdown["global_ms"] = sb.time_kernel(32, 30)
 
-    # ---- CPU baseline: the oracle on the host cores, bounded sample, rank 0 ------------------
+    # ---- CPU baseline: the oracle on the host cores, bounded sample, rank 0 at N = 1 ------------------
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
-        order, off = sb.schedule()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        rate, secs = cpu_oracle_rate(pos, tets, order, off, 1, args.iterations, threads, reps=max(1, min(10, args.substeps)),
+        rate, secs = cpu_oracle_rate(pos, tets, sb.schedule_kw(), 1, args.iterations, threads, reps=max(1, min(10, args.substeps)),
                                      roles=sb.tet_roles())
         cpu = {"value": rate, "unit": "vertex-substeps/s", "cores": threads, "kind": "port",
                "sample": f"{max(1, min(10, args.substeps))} substeps x {args.iterations} iterations of the same mesh and colour order "
                          f"({secs:.1f} s); CPU oracle (C, OpenMP over colour batches), not the reference C# solver (not in the mount)"}
 
+    own_rank0 = int(shared.owned.sum()) if (shared is not None and args.workload == "dist") else V
+    tiles_rank0 = shared.tiles if (shared is not None and args.workload == "dist") else None
+    launches = info["launches_per_frame"]
+    del sb, shared
+    import gc
+    gc.collect()
+
+    # ---- secondary: BASELINE.json configs[3], 4096 independent 2 k-vertex bodies sharded over the ranks --------
+    bodies = None
+    if not args.no_bodies and args.workload in ("block", "dist"):
+        from softbodyunity_b200 import meshgen
+        from softbodyunity_b200.shard import shard_range
+        lo, hi = shard_range(args.bodies_n, rank, world)
+        bp, bt_, bf = meshgen.bodies(hi - lo, dims=(13, 13, 12), spacing=0.02, base_height=0.004, seed=1234 + rank)
+        bsb = SoftBody(bp, bt_, bf, device=local, substeps=args.substeps, iterations=args.iterations, flags=flags & ~32)
+        bsteps = max(2, args.steps // 4)
+        bms = timed_frames(bsb, bsteps, 3)
+        bi = bsb.info()
+        bV = int(round(sum_over_ranks(bi["n_verts"])))
+        bval = bV * args.substeps * bsteps / (bms * 1e-3)
+        bB = bytes_per_substep(bi["n_verts"], bi["n_edges"], bi["n_tets"], args.iterations)
+        bodies = {"workload": f"{args.bodies_n} independent 2028-vertex bodies sharded over {world} rank(s), no communication "
+                              f"(BASELINE.json configs[3]), S={args.substeps} I={args.iterations}",
+                  "value": bval, "unit": "vertex-substeps/s", "scaling": "strong", "n_verts": bV, "steps": bsteps, "ms_per_step": bms / bsteps,
+                  "launches_per_step": bi["launches_per_frame"], "bodies_rank0": hi - lo,
+                  "roofline_frac": bval * bB / 1e9 / (hbm * world), "bytes_per_vertex_substep": bB, "build_seconds": bi["build_seconds"]}
+        del bsb
+
     if rank == 0:
+        cfg = {"workload": name + (" per GPU, independent bodies, no communication" if replicas and world > 1 else ""),
+               "n_verts": V_all if world > 1 and not replicas else V, "n_edges": E, "n_tets": T,
+               "math": "fast" if args.fast_math else "exact (bit-identical to CPU oracle)",
+               "tile_passes": info["n_tile_passes"], "tiles_in_pass": info["tiles_in_pass"][:info["n_tile_passes"]],
+               "tile_cap": info["tile_cap"], "block_threads": info["block_threads"], "round_width": info["round_width"],
+               "edges_attached": info["edges_attached"], "rounds_per_sweep": sum(info["rounds_in_pass"][:info["n_tile_passes"]]),
+               "runs_per_sweep": sum(info["runs_in_pass"][:info["n_tile_passes"]]),
+               "order": "same pass order every iteration" if args.no_snake else "snake: odd iterations run the tile passes backwards",
+               "launches": "one per pass occurrence, separate predict / finish" if args.no_fuse else
+                           "consecutive occurrences of a pass fused; predict / finish inside the tile launches at substep boundaries",
+               "planner": {k: os.environ[k] for k in ("SB_RECOLOUR", "SB_ATTACH_AUGMENT", "SB_MERGE_RIMS", "SB_WHOLE_BOXES", "SB_ATOM_SNAKE") if k in os.environ} or "defaults",
+               "rounds_per_tile": [round(r / max(1, t), 1) for r, t in zip(info["rounds_in_pass"][:info["n_tile_passes"]],
+                                                                          info["tiles_in_pass"][:info["n_tile_passes"]])],
+               "l2": "no flush: per-step working set (constraint streams + state) %.0f MB exceeds the 126 MB L2" %
+                     ((8.0 * E + 16.0 * T + 48.0 * (V_all if world > 1 and not replicas else V)) / 1e6),
+               "build_seconds": info["build_seconds"]}
+        if world > 1 and args.workload in ("dist", "partitioned"):
+            cfg.update(own_verts_rank0=own_rank0, tiles_rank0=tiles_rank0,
+                       comm="NVLink peer memory (CUDA IPC): tiles read / write their vertex runs in the owner's HBM; epoch words "
+                            "order the zone tiles of neighbouring ranks; no collective on the data path (NCCL: rendezvous, timing)"
+                            if args.workload == "dist" else "ghost vertices + P2P halo kernels twice per sweep",
+                       partition="slabs of the box order" if args.slabs else "compact blocks of boxes (recursive bisection)")
         out = {
             "metric": METRIC, "value": value, "unit": "vertex-substeps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.workload == "bodies" else "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name + (" per GPU, independent bodies, no communication" if world > 1 and args.workload != "bodies" else ""),
-                       "n_verts": V, "n_edges": E, "n_tets": T, "math": "fast" if args.fast_math else "exact (bit-identical to CPU oracle)",
-                       "tile_passes": info["n_tile_passes"], "tiles_in_pass": info["tiles_in_pass"][:info["n_tile_passes"]],
-                       "tile_cap": info["tile_cap"], "block_threads": info["block_threads"], "round_width": info["round_width"],
-                       "edges_attached": info["edges_attached"], "rounds_per_sweep": sum(info["rounds_in_pass"][:info["n_tile_passes"]]),
-                       "runs_per_sweep": sum(info["runs_in_pass"][:info["n_tile_passes"]]),
-                       "planner": {k: os.environ[k] for k in ("SB_RECOLOUR", "SB_ATTACH_AUGMENT", "SB_MERGE_RIMS", "SB_WHOLE_BOXES", "SB_ATOM_SNAKE") if k in os.environ} or "defaults",
-                       "rounds_per_tile": [round(r / max(1, t), 1) for r, t in zip(info["rounds_in_pass"][:info["n_tile_passes"]],
-                                                                                  info["tiles_in_pass"][:info["n_tile_passes"]])],
-                       "l2": "no flush: per-step working set (constraint streams + state) %.0f MB exceeds the 126 MB L2" %
-                             ((8.0 * E + 16.0 * T + 48.0 * V) / 1e6),
-                       "build_seconds": info["build_seconds"]},
-            "e2e": {"value": e2e_val, "unit": "vertex-substeps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / args.steps},
-            "gpu_launches": info["launches_per_frame"] * args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak" if (replicas and world > 1) else "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "e2e": e2e, "gpu_launches": launches * args.steps,
             "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }
+        if checksum is not None:
+            out["state_checksum"] = {"after_frames": args.warmup + args.steps, "x4_words_hi_lo": checksum,
+                                     "meaning": "sum of the 32-bit words of every vertex's (x, y, z, 1/m), high and low halves; the same for any "
+                                                "number of GPUs (the execution order is the plan's), and for `--workload dist` on one GPU with the same plan"}
+        if bodies is not None:
+            out["bodies"] = bodies
         if breakdown:
             out["kernel_breakdown_ms"] = breakdown
         print(json.dumps(out), flush=True)

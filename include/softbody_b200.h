@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SB_ABI_VERSION 2u
+#define SB_ABI_VERSION 3u
 
 typedef struct sb_solver *sb_handle;
 
@@ -58,6 +58,13 @@ typedef enum sb_status {
                                 constraint records) runs under this pass's tail: 8.8 -> 8.5 ms per frame at 1 M vertices */
 #define SB_FLAG_DAG 32       /* run all tile passes of a substep as ONE persistent kernel over the tile dependency graph
                                 (single-GPU meshes planned as balanced shifted tilings; ignored otherwise) */
+#define SB_FLAG_NO_SNAKE 64  /* run the tile passes of every iteration in the same order.  By default odd iterations of a
+                                substep run them backwards (a symmetric Gauss-Seidel sweep): the last pass of one iteration
+                                and the first of the next then work on the same tiles and share one launch */
+#define SB_FLAG_NO_FUSE 128  /* one launch per tile pass and separate predict / finish kernels.  By default consecutive
+                                occurrences of a pass are one launch that keeps the positions in shared memory, and
+                                predict / collide + velocity update run inside the tile launches at the substep
+                                boundaries (same arithmetic, same order: the results do not depend on this flag) */
 
 /*
  * Solver parameters (the inspector fields).  Names per BASELINE.json:5; units,
@@ -106,7 +113,9 @@ typedef struct sb_mesh_desc {
   int32_t n_ghost_verts;    /* partitioned meshes: the LAST n_ghost_verts vertices are ghost copies of vertices
                                another rank owns (never integrated here; constraints among ghosts are dropped) */
   uint32_t n_edges;         /* entries of `edges` (ignored when edges == NULL) */
-  int32_t reserved[1];      /* must be 0 */
+  int32_t dist_ranks;       /* 0, or the number of GPUs (2..8) the mesh will be spread over with sb_dist_setup: the
+                               boxes of the unshifted tiling are then cut into that many compact blocks and numbered
+                               block by block (fewer tiles straddle two GPUs than with slabs of the default order) */
 } sb_mesh_desc; /* 112 bytes */
 
 /* Sizes and build statistics, for logs, benches and the byte model. */
@@ -209,6 +218,19 @@ int sb_read_skinned(sb_handle h, float *dst_pos_xyz, float *dst_nrm_xyz, uint32_
 int sb_skin_compute(const float *tet_pos_xyz, uint32_t n_verts, const int32_t *tets, uint32_t n_tets,
                     const float *points_xyz, uint32_t n_points, int32_t *tet_of, float *bary4);
 
+/*
+ * One frame in one buffer, one copy and one synchronisation each way (what a per-frame host loop should use):
+ *   sb_read_packed  -> [ x4 of n_verts | v4 of n_verts | xyz of n_surface surface vertices | their normals ]
+ *   sb_write_packed <- [ x4 of n_verts | v4 of n_verts ]
+ * n_verts / n_surface are all vertices / surface vertices in ascending vertex id -- or, on one rank of a distributed
+ * mesh (sb_dist_setup), the ones that rank owns, ascending vertex id (sb_dist_owned marks them).  sb_packed_sizes
+ * gives the counts and the two buffer sizes in bytes (32 n_verts, 32 n_verts + 24 n_surface).  Pinned host memory
+ * makes the copies asynchronous to the host until the call's final synchronisation.
+ */
+int sb_packed_sizes(sb_handle h, uint32_t *n_verts, uint32_t *n_surface, uint64_t *bytes_in, uint64_t *bytes_out);
+int sb_read_packed(sb_handle h, void *dst, uint64_t bytes);
+int sb_write_packed(sb_handle h, const void *src, uint64_t bytes);
+
 /* Full state as float4 arrays in the caller's numbering: x4 = (x,y,z,inv_mass), v4 = (vx,vy,vz,0). */
 int sb_get_state(sb_handle h, float *x4, float *v4, uint32_t n_verts);
 int sb_set_state(sb_handle h, const float *x4, const float *v4, uint32_t n_verts);
@@ -253,6 +275,19 @@ int sb_get_topology(sb_handle h, int32_t *edges_2E, float *rest_len_E, float *re
  * ("re-run under the same colour ordering", BASELINE.json:5).
  */
 int sb_get_schedule(sb_handle h, int64_t *n_order, int32_t *order, int32_t *n_batches, int64_t *batch_off);
+/*
+ * The same for the iterations 1, 3, 5 ... of a substep (sb_get_schedule: iterations 0, 2, 4 ...): the tile passes in
+ * reverse order unless SB_FLAG_NO_SNAKE / SB_FLAG_DAG is set or the plan has constraints outside the tile passes,
+ * in which case it equals sb_get_schedule.  A CPU replay alternates the two orders within every substep.
+ */
+int sb_get_schedule_odd(sb_handle h, int64_t *n_order, int32_t *order, int32_t *n_batches, int64_t *batch_off);
+/*
+ * The launches of one frame at the current parameters, 6 int32 per launch: kind (0 predict, 1 finish, 2 tile pass,
+ * 3 global batches, 4 constraint group, 5 exchange, 6 normals, 7 tile DAG), arg (pass / group / phase), segments,
+ * repetitions per segment, predict-before, finish-after.  *n_launches receives the count; ops6 may be NULL.
+ * sb_enqueue(h, SB_OP_LAUNCH, i) enqueues launch i alone (drivers that interleave several handles on one stream).
+ */
+int sb_frame_program(sb_handle h, int32_t *n_launches, int32_t *ops6, uint32_t capacity);
 
 /* For tile pass `pass`: per caller vertex, the tile that stages it, or -1 (tile_of may be NULL). */
 int sb_get_tiles(sb_handle h, uint32_t pass, int32_t *tile_of, uint32_t *n_tiles);
@@ -283,6 +318,7 @@ int sb_time_kernel(sb_handle h, int32_t which, int32_t reps, float *avg_ms);
 #define SB_OP_HALO_SEND 5 /* arg: list id; the two halves of an exchange, for several ranks driven from one stream */
 #define SB_OP_HALO_RECV 6
 #define SB_OP_PASS 7 /* arg: tile pass index (one launch; for drivers that interleave several handles on one stream) */
+#define SB_OP_LAUNCH 8 /* arg: index into sb_frame_program (one launch of the frame as sb_step would issue it) */
 int sb_set_stream(sb_handle h, void *stream);
 int sb_prepare(sb_handle h, float dt); /* pushes parameters for this dt; synchronises */
 int sb_enqueue(sb_handle h, int32_t op, int32_t arg);
@@ -306,8 +342,10 @@ int sb_lumped_inv_mass(const float *pos_xyz, uint32_t n_verts, const int32_t *te
  *   sb_dist_connect  (once per peer) gives the peer's two addresses; when all peers are connected the handle is live.
  * sb_step then runs this rank's tiles; a tile reads and writes each of its vertex runs in the memory of the rank that
  * owns the run, and kernels of neighbouring ranks order themselves through an epoch word.  All ranks must issue the
- * same sequence of steps.  Positions / state read back from a rank are valid for the vertices sb_dist_owned marks.
- * Surface normals are not computed in this mode.
+ * same sequence of steps (and hold the same flags: the launch sequence must be the same everywhere).  Positions /
+ * state read back from a rank are valid for the vertices sb_dist_owned marks; sb_read_packed carries exactly those.
+ * Surface normals: each rank computes them for the surface vertices it owns (triangles that reach into a
+ * neighbour's slab read the neighbour's positions over NVLink).  sb_time_kernel is refused on such a handle.
  */
 int sb_dist_setup(sb_handle h, int32_t rank, int32_t n_ranks, void **x_base_out, void **ctl_base_out);
 int sb_dist_connect(sb_handle h, int32_t peer, void *peer_x, void *peer_ctl);

@@ -124,10 +124,16 @@ class Model:
         return np.concatenate([np.arange(self.E, dtype=np.int32),
                                (np.arange(self.T, dtype=np.int64) | 0x80000000).astype(np.uint32).view(np.int32)])
 
-    def simulate(self, prm: OrcParams, n_frames=1, order=None, batch_off=None, spheres=None, threads=1, colliders=None):
+    def simulate(self, prm: OrcParams, n_frames=1, order=None, batch_off=None, spheres=None, threads=1, colliders=None,
+                 order_odd=None, batch_off_odd=None):
+        """order / batch_off: the Gauss-Seidel order of the iterations 0, 2, 4 ... of every substep; order_odd /
+        batch_off_odd: that of the iterations 1, 3, 5 ... (None: the same order again)."""
         order = self.natural_order() if order is None else np.ascontiguousarray(order, np.int32)
         nb = 0 if batch_off is None else len(batch_off) - 1
         boff = None if batch_off is None else np.ascontiguousarray(batch_off, np.int64)
+        odd = None if order_odd is None else np.ascontiguousarray(order_odd, np.int32)
+        nb_odd = 0 if batch_off_odd is None else len(batch_off_odd) - 1
+        boff_odd = None if batch_off_odd is None else np.ascontiguousarray(batch_off_odd, np.int64)
         if colliders is not None:
             assert spheres is None
             sph = np.ascontiguousarray(colliders, COLLIDER)
@@ -137,11 +143,11 @@ class Model:
             sph["p"][:, :4] = s4
         else:
             sph = None
-        rc = getattr(lib(), "orc_simulate" + self.sfx)(
+        rc = getattr(lib(), "orc_simulate2" + self.sfx)(
             C.c_int32(self.V), _p(self.x4), _p(self.v4), C.c_int32(self.E), _p(self.edges), _p(self.rest_len),
             C.c_int32(self.T), _p(self.roles), _p(self.rest_vol6), C.byref(prm), C.c_int64(len(order)), _p(order),
-            C.c_int32(nb), _p(boff), C.c_int32(0 if sph is None else len(sph)), _p(sph), C.c_int32(n_frames),
-            C.c_int32(threads))
+            C.c_int32(nb), _p(boff), C.c_int64(0 if odd is None else len(odd)), _p(odd), C.c_int32(nb_odd), _p(boff_odd),
+            C.c_int32(0 if sph is None else len(sph)), _p(sph), C.c_int32(n_frames), C.c_int32(threads))
         if rc != 0:
             raise ValueError(f"orc_simulate failed: {rc}")
         return self.x4, self.v4

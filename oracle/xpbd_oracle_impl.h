@@ -300,41 +300,59 @@ static inline void FN(apply_entry)(REAL *x4, int32_t ent, const int32_t *edges, 
  * constraints; with threads > 1 each run is an OpenMP parallel-for (the result
  * does not depend on the thread count because runs are independent sets).
  * Pass n_batches = 0 for plain sequential order.
+ *
+ * orc_simulate2: iterations 0, 2, 4 ... of every substep follow `order`, iterations
+ * 1, 3, 5 ... follow `order_odd` (NULL: `order` again).  The product sweeps its tile
+ * passes forwards and backwards alternately (a symmetric Gauss-Seidel sweep), so that the
+ * last pass of one iteration and the first of the next work on the same tiles.
  */
-int FN(orc_simulate)(int32_t V, REAL *x4, REAL *v4, int32_t E, const int32_t *edges,
-                     const REAL *rest_len, int32_t T, const int32_t *tets, const REAL *rest_vol6,
-                     const orc_params *p, int64_t n_order, const int32_t *order, int32_t n_batches,
-                     const int64_t *batch_off, int32_t n_col, const orc_collider *colliders,
-                     int32_t n_frames, int32_t threads) {
+static void FN(run_order)(REAL *x4, int64_t n_order, const int32_t *order, int32_t n_batches, const int64_t *batch_off,
+                          int par, int threads, const int32_t *edges, const REAL *rest_len, const int32_t *tets,
+                          const REAL *rest_vol6, const FN(step_consts) *c) {
+  (void)threads;
+  if (!par) {
+    for (int64_t k = 0; k < n_order; k++) FN(apply_entry)(x4, order[k], edges, rest_len, tets, rest_vol6, c);
+  } else {
+    for (int32_t b = 0; b < n_batches; b++) {
+      int64_t lo = batch_off[b], hi = batch_off[b + 1];
+#pragma omp parallel for schedule(static) num_threads(threads) if (hi - lo > 2048)
+      for (int64_t k = lo; k < hi; k++) FN(apply_entry)(x4, order[k], edges, rest_len, tets, rest_vol6, c);
+    }
+  }
+}
+
+int FN(orc_simulate2)(int32_t V, REAL *x4, REAL *v4, int32_t E, const int32_t *edges,
+                      const REAL *rest_len, int32_t T, const int32_t *tets, const REAL *rest_vol6,
+                      const orc_params *p, int64_t n_order, const int32_t *order, int32_t n_batches,
+                      const int64_t *batch_off, int64_t n_order_odd, const int32_t *order_odd, int32_t n_batches_odd,
+                      const int64_t *batch_off_odd, int32_t n_col, const orc_collider *colliders,
+                      int32_t n_frames, int32_t threads) {
   if (V < 0 || p->substeps <= 0 || p->iterations < 0 || !(p->dt > 0) || n_col < 0 || n_col > 16) return -1;
   orc_prepared cols[16];
   for (int s = 0; s < n_col; s++) {
     if (colliders[s].kind < 0 || colliders[s].kind > 2) return -1;
     orc_prepare_collider(colliders + s, cols + s);
   }
+  if (!order_odd) { order_odd = order; n_order_odd = n_order; n_batches_odd = n_batches; batch_off_odd = batch_off; }
   for (int64_t k = 0; k < n_order; k++) {
     int32_t id = order[k] & 0x7fffffff;
     if (order[k] >= 0 ? id >= E : id >= T) return -2;
   }
-  (void)threads;
+  for (int64_t k = 0; k < n_order_odd; k++) {
+    int32_t id = order_odd[k] & 0x7fffffff;
+    if (order_odd[k] >= 0 ? id >= E : id >= T) return -2;
+  }
   FN(step_consts) c = FN(make_consts)(p);
   REAL *xp = (REAL *)malloc(sizeof(REAL) * 3 * (size_t)(V > 0 ? V : 1));
   if (!xp) return -3;
-  const int par = threads > 1 && n_batches > 0;
+  const int par = threads > 1 && n_batches > 0, par_odd = threads > 1 && n_batches_odd > 0;
   for (int f = 0; f < n_frames; f++) {
     for (int s = 0; s < p->substeps; s++) {
 #pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1)
       for (int32_t i = 0; i < V; i++) FN(predict_one)(x4 + 4 * (size_t)i, xp + 3 * (size_t)i, v4 + 4 * (size_t)i, &c);
       for (int it = 0; it < p->iterations; it++) {
-        if (!par) {
-          for (int64_t k = 0; k < n_order; k++) FN(apply_entry)(x4, order[k], edges, rest_len, tets, rest_vol6, &c);
-        } else {
-          for (int32_t b = 0; b < n_batches; b++) {
-            int64_t lo = batch_off[b], hi = batch_off[b + 1];
-#pragma omp parallel for schedule(static) num_threads(threads) if (hi - lo > 2048)
-            for (int64_t k = lo; k < hi; k++) FN(apply_entry)(x4, order[k], edges, rest_len, tets, rest_vol6, &c);
-          }
-        }
+        if (it & 1) FN(run_order)(x4, n_order_odd, order_odd, n_batches_odd, batch_off_odd, par_odd, threads, edges, rest_len, tets, rest_vol6, &c);
+        else FN(run_order)(x4, n_order, order, n_batches, batch_off, par, threads, edges, rest_len, tets, rest_vol6, &c);
       }
 #pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1)
       for (int32_t i = 0; i < V; i++)
@@ -343,6 +361,15 @@ int FN(orc_simulate)(int32_t V, REAL *x4, REAL *v4, int32_t E, const int32_t *ed
   }
   free(xp);
   return 0;
+}
+
+int FN(orc_simulate)(int32_t V, REAL *x4, REAL *v4, int32_t E, const int32_t *edges,
+                     const REAL *rest_len, int32_t T, const int32_t *tets, const REAL *rest_vol6,
+                     const orc_params *p, int64_t n_order, const int32_t *order, int32_t n_batches,
+                     const int64_t *batch_off, int32_t n_col, const orc_collider *colliders,
+                     int32_t n_frames, int32_t threads) {
+  return FN(orc_simulate2)(V, x4, v4, E, edges, rest_len, T, tets, rest_vol6, p, n_order, order, n_batches, batch_off, 0, NULL,
+                           0, NULL, n_col, colliders, n_frames, threads);
 }
 
 /*

@@ -12,14 +12,16 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 SB_OK, SB_E_ARG, SB_E_CUDA, SB_E_NCCL, SB_E_NAN, SB_E_STATE, SB_E_NOMEM = 0, -1, -2, -3, -4, -5, -6
 FLAG_NO_GROUND, FLAG_FAST_MATH, FLAG_NO_GRAPH, FLAG_NO_NORMALS, FLAG_NO_PDL, FLAG_DAG = 1, 2, 4, 8, 16, 32
-ABI_VERSION = 2
+FLAG_NO_SNAKE, FLAG_NO_FUSE = 64, 128
+ABI_VERSION = 3
 COLLIDER_SPHERE, COLLIDER_CAPSULE, COLLIDER_BOX, MAX_COLLIDERS = 0, 1, 2, 16
 
 EXPORTS = [
     "sb_abi_check", "sb_default_params", "sb_create", "sb_plan", "sb_destroy", "sb_set_params",
     "sb_get_params", "sb_set_colliders", "sb_set_colliders_ex", "sb_step", "sb_synchronize", "sb_read_positions",
     "sb_read_normals", "sb_surface_vertices", "sb_read_surface", "sb_get_state", "sb_set_state",
-    "sb_diagnostics", "sb_get_info", "sb_get_topology", "sb_get_tet_roles", "sb_get_schedule", "sb_get_tiles",
+    "sb_packed_sizes", "sb_read_packed", "sb_write_packed",
+    "sb_diagnostics", "sb_get_info", "sb_get_topology", "sb_get_tet_roles", "sb_get_schedule", "sb_get_schedule_odd", "sb_frame_program", "sb_get_tiles",
     "sb_time_frames", "sb_time_kernel", "sb_debug_trace_pass", "sb_debug_verify_streams", "sb_last_error",
     "sb_set_stream", "sb_prepare", "sb_enqueue", "sb_halo_set", "sb_halo_pack", "sb_halo_unpack", "sb_lumped_inv_mass",
     "sb_halo_alloc", "sb_halo_connect", "sb_halo_error", "sb_ipc_export", "sb_ipc_open",
@@ -48,7 +50,7 @@ class SbMeshDesc(C.Structure):
         ("density", C.c_float), ("device", C.c_int32), ("tile_cap", C.c_int32),
         ("max_tile_passes", C.c_int32), ("block_threads", C.c_int32),
         ("later_tile_cap", C.c_int32), ("host_threads", C.c_int32), ("round_width", C.c_int32),
-        ("attach_edges", C.c_int32), ("tilings", C.c_int32), ("n_ghost_verts", C.c_int32), ("n_edges", C.c_uint32), ("reserved", C.c_int32 * 1),
+        ("attach_edges", C.c_int32), ("tilings", C.c_int32), ("n_ghost_verts", C.c_int32), ("n_edges", C.c_uint32), ("dist_ranks", C.c_int32),
     ]
 
 
@@ -113,10 +115,15 @@ def load():
         "sb_read_surface": (C.c_int, [vp, vp, vp, u32]),
         "sb_get_state": (C.c_int, [vp, vp, vp, u32]),
         "sb_set_state": (C.c_int, [vp, vp, vp, u32]),
+        "sb_packed_sizes": (C.c_int, [vp, P(u32), P(u32), P(C.c_uint64), P(C.c_uint64)]),
+        "sb_read_packed": (C.c_int, [vp, vp, C.c_uint64]),
+        "sb_write_packed": (C.c_int, [vp, vp, C.c_uint64]),
         "sb_diagnostics": (C.c_int, [vp, vp]),
         "sb_get_info": (C.c_int, [vp, P(SbInfo)]),
         "sb_get_topology": (C.c_int, [vp, vp, vp, vp, vp]),
         "sb_get_schedule": (C.c_int, [vp, P(C.c_int64), vp, P(i32), vp]),
+        "sb_get_schedule_odd": (C.c_int, [vp, P(C.c_int64), vp, P(i32), vp]),
+        "sb_frame_program": (C.c_int, [vp, P(i32), vp, u32]),
         "sb_get_tiles": (C.c_int, [vp, u32, vp, P(u32)]),
         "sb_time_frames": (C.c_int, [vp, i32, f32, P(f32)]),
         "sb_time_kernel": (C.c_int, [vp, i32, i32, P(f32)]),

@@ -1422,7 +1422,7 @@ void lumped_inv_mass_into(const float *pos, uint32_t V, const int32_t *tets, uin
   std::copy(tmp.inv_mass.begin(), tmp.inv_mass.end(), out);
 }
 
-void Plan::export_schedule(std::vector<int32_t> &order, std::vector<int64_t> &batch_off) const {
+void Plan::export_schedule(std::vector<int32_t> &order, std::vector<int64_t> &batch_off, bool reverse) const {
   order.clear();
   batch_off.clear();
   batch_off.push_back(0);
@@ -1430,7 +1430,8 @@ void Plan::export_schedule(std::vector<int32_t> &order, std::vector<int64_t> &ba
     if ((int64_t)order.size() > batch_off.back()) batch_off.push_back((int64_t)order.size());
   };
   for (int group = 0; group < 2; group++) {
-  for (const TilePass &TP : passes) {
+  for (size_t pi = 0; pi < passes.size(); pi++) {
+    const TilePass &TP = passes[reverse ? passes.size() - 1 - pi : pi];
     if (TP.group != group) continue;
     const uint32_t nt = TP.n_tiles();
     // start of every colour of every tile inside TP.ents
@@ -1584,6 +1585,71 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   P.n_tilings = (uint32_t)n_tilings;
 
   std::vector<uint32_t> tile_off;
+  std::vector<uint32_t> block_first_tile; // dist_ranks + 1 when the boxes were numbered block by block
+  if (n_tilings >= 2 && opt.dist_ranks >= 2 && tilings[0].n_tiles >= (uint32_t)opt.dist_ranks) {
+    // One mesh over several GPUs: cut the boxes of the unshifted tiling into dist_ranks compact blocks by recursive
+    // coordinate bisection of their centroids (weights = vertex counts; the cut runs along the longest axis of the
+    // part, ties ordered by the other two axes so that a cut through a layer of boxes stays one piece) and number
+    // the boxes block by block: every rank then owns one range of device ids, and the surface between ranks -- the
+    // tiles that straddle two GPUs -- is that of a block, not of a slab of the default x-fastest order.
+    Tiling &T0 = tilings[0];
+    const uint32_t nt = T0.n_tiles, K = (uint32_t)opt.dist_ranks;
+    std::vector<double> cen(3 * (size_t)nt, 0.0);
+    std::vector<uint64_t> wgt(nt, 0);
+    for (uint32_t v = 0; v < P.V; v++) {
+      const uint32_t t = (uint32_t)T0.part[v];
+      for (int k = 0; k < 3; k++) cen[3 * (size_t)t + k] += P.pos[3 * (size_t)v + k];
+      wgt[t]++;
+    }
+    for (uint32_t t = 0; t < nt; t++)
+      for (int k = 0; k < 3; k++) cen[3 * (size_t)t + k] /= (double)std::max<uint64_t>(1, wgt[t]);
+    std::vector<uint32_t> idx(nt), block(nt, 0);
+    std::iota(idx.begin(), idx.end(), 0u);
+    std::function<void(size_t, size_t, uint32_t, uint32_t)> split = [&](size_t lo, size_t hi, uint32_t k, uint32_t first) {
+      if (k <= 1) {
+        for (size_t i = lo; i < hi; i++) block[idx[i]] = first;
+        return;
+      }
+      double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+      for (size_t i = lo; i < hi; i++)
+        for (int c = 0; c < 3; c++) {
+          mn[c] = std::min(mn[c], cen[3 * (size_t)idx[i] + c]);
+          mx[c] = std::max(mx[c], cen[3 * (size_t)idx[i] + c]);
+        }
+      int ax[3] = {2, 1, 0}; // ties between equal extents: z first (the slowest axis of the box order)
+      std::stable_sort(ax, ax + 3, [&](int a, int b) { return mx[a] - mn[a] > mx[b] - mn[b]; });
+      // box centroids of one layer differ by the jitter of their vertices: compare them on a coarse grid
+      const double q = std::max(1e-30, (mx[ax[0]] - mn[ax[0]]) * 1e-4);
+      auto key = [&](uint32_t t, int c) { return std::floor((cen[3 * (size_t)t + c] - mn[c]) / q); };
+      std::sort(idx.begin() + (ptrdiff_t)lo, idx.begin() + (ptrdiff_t)hi, [&](uint32_t a, uint32_t b) {
+        for (int j = 0; j < 3; j++) {
+          const double ka = key(a, ax[j]), kb = key(b, ax[j]);
+          if (ka != kb) return ka < kb;
+        }
+        return a < b;
+      });
+      const uint32_t kl = k / 2;
+      uint64_t total = 0, acc = 0;
+      for (size_t i = lo; i < hi; i++) total += wgt[idx[i]];
+      size_t cut = lo;
+      while (cut < hi && (acc + wgt[idx[cut]] / 2) * k <= total * kl) acc += wgt[idx[cut++]];
+      cut = std::min(std::max(cut, lo + kl), hi - (k - kl)); // at least one box per block
+      split(lo, cut, kl, first);
+      split(cut, hi, k - kl, first + kl);
+    };
+    split(0, nt, K, 0);
+    // new box ids: by block, old order inside a block
+    std::vector<uint32_t> order(nt), newid(nt);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return block[a] < block[b]; });
+    block_first_tile.assign((size_t)K + 1, nt);
+    for (uint32_t i = 0; i < nt; i++) {
+      newid[order[i]] = i;
+      block_first_tile[block[order[i]]] = std::min(block_first_tile[block[order[i]]], i);
+    }
+    for (uint32_t r = K; r-- > 0;) block_first_tile[r] = std::min(block_first_tile[r], block_first_tile[r + 1]);
+    for (uint32_t v = 0; v < P.V; v++) T0.part[v] = (int32_t)newid[(uint32_t)T0.part[v]];
+  }
   if (n_tilings >= 2) {
     // device numbering: tiles of tiling 0 are contiguous, ascending caller id inside a tile
     const Tiling &T0 = tilings[0];
@@ -1600,6 +1666,11 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     });
     P.inv.resize(P.V);
     for (uint32_t d = 0; d < P.V; d++) P.inv[P.perm[d]] = d;
+    if (!block_first_tile.empty()) {
+      P.dist_ranks = (uint32_t)opt.dist_ranks;
+      P.dist_slab_lo.resize(block_first_tile.size());
+      for (size_t r = 0; r < block_first_tile.size(); r++) P.dist_slab_lo[r] = tile_off[block_first_tile[r]];
+    }
   } else if (max_passes > 0) {
     tile_off = tile_vertices(P, cap, opt.n_sm);
   } else {

@@ -37,6 +37,10 @@ struct PlanOptions {
   int round_width = 0;      // 16-byte record words per thread per round: 1 or 2 (0 = 1)
   int compounds = -1;       // attach edges to tets (-1 = auto: on unless the mesh is one rank of a partition, 0 off, 1 on)
   int tilings = 0;          // 0 = auto; 1 = hierarchical passes only; N >= 2 = N balanced shifted tilings
+  int dist_ranks = 0;       // >= 2: the mesh will be spread over this many GPUs (sb_dist_setup): the boxes of the unshifted
+                            // tiling are cut into that many compact blocks (recursive bisection of the box grid, weighted by
+                            // vertex count) and numbered block by block, so that every rank's vertices are one range of
+                            // device ids and few tiles straddle two ranks
 };
 
 // One shared-memory tile pass: every tile is a vertex-disjoint set of vertices
@@ -128,11 +132,14 @@ struct Plan {
   std::vector<GlobalBatch> gbatches;
   // options actually used
   uint32_t tile_cap = 0, round_width = 1, n_tilings = 1;
+  uint32_t dist_ranks = 0;            // blocks the boxes of tiling 0 were numbered by (PlanOptions::dist_ranks), or 0
+  std::vector<uint32_t> dist_slab_lo; // dist_ranks + 1: first device id of every block
   bool dag_ok = false; // the passes are exactly the balanced tilings (one group, no leftovers): DAG kernel usable
   double build_seconds = 0;
 
-  // The equivalent sequential order of one iteration (see sb_get_schedule).
-  void export_schedule(std::vector<int32_t> &order, std::vector<int64_t> &batch_off) const;
+  // The equivalent sequential order of one iteration (see sb_get_schedule); reverse: the tile passes last to first
+  // (the order of the odd iterations of a substep, sb_get_schedule_odd).
+  void export_schedule(std::vector<int32_t> &order, std::vector<int64_t> &batch_off, bool reverse = false) const;
 };
 
 struct MeshInput {

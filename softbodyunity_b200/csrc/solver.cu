@@ -148,6 +148,11 @@ struct sb_solver {
   DevBuf<uint32_t> dist_ctl;
   bool dist_on = false;
   uint32_t dist_connected = 0; // bit p: peer p connected
+  // the vertices / surface vertices a packed frame carries: all of them, or (distributed) the ones this rank owns,
+  // ascending caller id either way
+  DevBuf<uint32_t> own_slot, own_surf;
+  uint32_t n_own = 0, n_own_surf = 0;
+  DevBuf<float4> pack_buf;
   DevBuf<int2> g_edges;
   DevBuf<float> g_elen;
   DevBuf<int4> g_tets;
@@ -283,7 +288,7 @@ struct sb_solver {
       pb.order.upload(tp.launch_order, &dev_bytes);
       pb.dev = PassDev{pb.order.p, pb.vert_off.p, tp.contiguous ? nullptr : pb.tile_verts.p, use_runs ? pb.run_off.p : nullptr,
                        use_runs ? pb.runs.p : nullptr, pb.rounds.p, reinterpret_cast<const uint4 *>(pb.stream.p),
-                       pb.aux.p, tp.n_tiles(), pos_bytes, nullptr};
+                       pb.aux.p, tp.n_tiles(), pos_bytes, nullptr, nullptr, 1u, 1u, 0u, 0u, nullptr, nullptr, 0u};
       pb.grid = tp.n_tiles();
       pb.bt = tp.bt;
       pb.width = tp.width;
@@ -304,8 +309,9 @@ struct sb_solver {
 
   template <bool FAST, int BT, int W16>
   static void set_attr_one(uint32_t smem) {
-    CK(cudaFuncSetAttribute(k_tile_rounds<FAST, BT, W16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if constexpr (!FAST) CK(cudaFuncSetAttribute(k_tile_rounds<FAST, BT, W16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_tile_rounds<FAST, BT, W16, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_tile_rounds<FAST, BT, W16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if constexpr (!FAST) CK(cudaFuncSetAttribute(k_tile_rounds<FAST, BT, W16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   template <bool FAST>
   static void set_attr_math(uint32_t smem) {
@@ -362,7 +368,7 @@ struct sb_solver {
   }
 
   template <bool FAST, int BT, int W16>
-  void launch_tile_cfg(const PassBufs &pb, cudaStream_t s) {
+  void launch_tile_cfg(const PassBufs &pb, const PassDev &dev, cudaStream_t s) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(pb.grid);
     cfg.blockDim = dim3(BT);
@@ -374,27 +380,40 @@ struct sb_solver {
     cfg.attrs = attr;
     cfg.numAttrs = (prm.flags & SB_FLAG_NO_PDL) ? 0 : 1;
     if constexpr (!FAST) {
-      if (pb.dev.trace) {
-        CK(cudaLaunchKernelEx(&cfg, k_tile_rounds<FAST, BT, W16, true>, pb.dev, x.p, (const DevParams *)dprm.p));
+      if (dev.trace) {
+        CK(cudaLaunchKernelEx(&cfg, k_tile_rounds<FAST, BT, W16, true, false>, dev, x.p, (const DevParams *)dprm.p));
         return;
       }
     }
-    CK(cudaLaunchKernelEx(&cfg, k_tile_rounds<FAST, BT, W16>, pb.dev, x.p, (const DevParams *)dprm.p));
+    if (dev.n_seg > 1 || dev.reps > 1 || dev.pre || dev.post)
+      CK(cudaLaunchKernelEx(&cfg, k_tile_rounds<FAST, BT, W16, false, true>, dev, x.p, (const DevParams *)dprm.p));
+    else
+      CK(cudaLaunchKernelEx(&cfg, k_tile_rounds<FAST, BT, W16, false, false>, dev, x.p, (const DevParams *)dprm.p));
   }
   template <bool FAST, int W16>
-  void launch_tile_w(const PassBufs &pb, cudaStream_t s) {
+  void launch_tile_w(const PassBufs &pb, const PassDev &dev, cudaStream_t s) {
     switch (pb.bt) {
-      case 32: launch_tile_cfg<FAST, 32, W16>(pb, s); break;
-      case 64: launch_tile_cfg<FAST, 64, W16>(pb, s); break;
-      case 128: launch_tile_cfg<FAST, 128, W16>(pb, s); break;
-      default: launch_tile_cfg<FAST, 256, W16>(pb, s); break;
+      case 32: launch_tile_cfg<FAST, 32, W16>(pb, dev, s); break;
+      case 64: launch_tile_cfg<FAST, 64, W16>(pb, dev, s); break;
+      case 128: launch_tile_cfg<FAST, 128, W16>(pb, dev, s); break;
+      default: launch_tile_cfg<FAST, 256, W16>(pb, dev, s); break;
     }
   }
+  // One launch of tile pass `pb`: n_seg segments (substeps) of `reps` repetitions of every tile's rounds, with the
+  // substep boundaries between segments -- and predict before / finish after, if asked -- done on the tiles.
   template <bool FAST>
-  void launch_tile(const PassBufs &pb, cudaStream_t s) {
-    if (!pb.grid || pb.empty) return;
-    if (pb.width == 2) launch_tile_w<FAST, 2>(pb, s);
-    else launch_tile_w<FAST, 1>(pb, s);
+  void launch_tile(const PassBufs &pb, cudaStream_t s, uint32_t n_seg = 1, uint32_t reps = 1, bool pre = false, bool post = false) {
+    if (pb.empty && !(pre || post || n_seg > 1)) return;
+    if (!pb.grid) {
+      // distributed: this rank has no tile in the pass, but its epoch moves with every launch of the sequence
+      if (dist_on && !pb.empty) k_dist_bump<<<1, 32, 0, s>>>(dist_dev.p);
+      return;
+    }
+    PassDev dev = pb.dev;
+    dev.n_seg = n_seg; dev.reps = reps; dev.pre = pre; dev.post = post;
+    dev.v = v.p; dev.xp = xp.p;
+    if (pb.width == 2) launch_tile_w<FAST, 2>(pb, dev, s);
+    else launch_tile_w<FAST, 1>(pb, dev, s);
   }
   // ---- persistent tile-DAG kernel -----------------------------------------------------
   template <bool FAST, int BT, int W16>
@@ -466,6 +485,22 @@ struct sb_solver {
     if (fast()) dag_dispatch<true>(true, s);
     else dag_dispatch<false>(true, s);
   }
+  // sticky error words of the multi-GPU waits (epoch of a peer, halo sequence number): 1 if any timed out
+  int dist_error_word() {
+    uint32_t e = 0, bad = 0;
+    if (dist.ctl) {
+      CK(cudaMemcpyAsync(&e, dist_ctl.p + 2, sizeof e, cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      bad |= e;
+    }
+    for (auto &kv : links)
+      if (kv.second.ctl_recv.p) {
+        CK(cudaMemcpyAsync(&e, kv.second.ctl_recv.p + 2, sizeof e, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        bad |= e;
+      }
+    return (int)bad;
+  }
   int dag_error() {
     if (!dag_ready) return 0;
     uint32_t e = 0;
@@ -475,8 +510,9 @@ struct sb_solver {
   }
 
   // ---- one mesh over several GPUs ------------------------------------------------------
-  // Host-only part: the slab of the device numbering a rank owns and the tiles of every pass it runs.
-  void dist_layout(int rank, int n_ranks, DistDev &D, std::vector<std::vector<uint32_t>> &tiles) const {
+  // Host-only part: the slab of the device numbering a rank owns, the tiles of every pass it runs (zone tiles first)
+  // and how many of them are zone tiles.
+  void dist_layout(int rank, int n_ranks, DistDev &D, std::vector<std::vector<uint32_t>> &tiles, std::vector<uint32_t> &n_zone) const {
     if (n_ranks < 2 || n_ranks > SB_MAX_RANKS || rank < 0 || rank >= n_ranks) throw std::string("rank / n_ranks out of range (2..8 ranks)");
     if (!plan.dag_ok) throw std::string("a distributed mesh must be planned as balanced shifted tilings (one big component, no ghosts, nothing left over)");
     const TilePass &t0 = plan.passes[0];
@@ -484,18 +520,23 @@ struct sb_solver {
     D = DistDev{};
     D.n_ranks = (uint32_t)n_ranks;
     D.rank = (uint32_t)rank;
-    // slabs: consecutive tiles of the unshifted tiling (consecutive device ids), equal vertex counts
-    uint32_t prev_tile = 0;
-    for (int r = 1; r < n_ranks; r++) {
-      const uint64_t target = (uint64_t)plan.V * r / n_ranks;
-      uint32_t tile = (uint32_t)(std::lower_bound(t0.vert_off.begin(), t0.vert_off.end() - 1, (uint32_t)target) - t0.vert_off.begin());
-      tile = std::max(tile, prev_tile + 1);
-      tile = std::min(tile, t0.n_tiles() - (uint32_t)(n_ranks - r));
-      D.slab_lo[r] = t0.vert_off[tile];
-      prev_tile = tile;
+    if (plan.dist_ranks == (uint32_t)n_ranks) {
+      // the planner numbered the boxes of the unshifted tiling rank by rank (blocks of boxes, PlanOptions::dist_ranks)
+      for (int r = 0; r <= n_ranks; r++) D.slab_lo[r] = plan.dist_slab_lo[r];
+    } else {
+      // slabs: consecutive tiles of the unshifted tiling (consecutive device ids), equal vertex counts
+      uint32_t prev_tile = 0;
+      for (int r = 1; r < n_ranks; r++) {
+        const uint64_t target = (uint64_t)plan.V * r / n_ranks;
+        uint32_t tile = (uint32_t)(std::lower_bound(t0.vert_off.begin(), t0.vert_off.end() - 1, (uint32_t)target) - t0.vert_off.begin());
+        tile = std::max(tile, prev_tile + 1);
+        tile = std::min(tile, t0.n_tiles() - (uint32_t)(n_ranks - r));
+        D.slab_lo[r] = t0.vert_off[tile];
+        prev_tile = tile;
+      }
+      D.slab_lo[0] = 0;
+      D.slab_lo[n_ranks] = plan.V;
     }
-    D.slab_lo[0] = 0;
-    D.slab_lo[n_ranks] = plan.V;
     for (int r = n_ranks + 1; r <= SB_MAX_RANKS; r++) D.slab_lo[r] = plan.V;
     auto owner_of = [&](uint32_t dev) {
       uint32_t r = 0;
@@ -510,39 +551,99 @@ struct sb_solver {
           const uint32_t first = tp.runs[r].x, len = tp.runs[r + 1].y - tp.runs[r].y;
           if (len && owner_of(first) != owner_of(first + len - 1)) throw std::string("a vertex run crosses a slab boundary");
         }
-    // this rank's tiles of every pass: those with most of their vertices in its slab (ties: the lower rank),
-    // heaviest first, dealt to the SMs in a snake like the single-GPU launch order.  (Dealing a spanning tile
+    // Who runs a tile: the rank that owns most of its vertices (ties: the lower rank).  (Dealing a spanning tile
     // to the less loaded of its ranks instead was measured slower: more of its runs become remote.)
-    tiles.assign(plan.passes.size(), {});
-    for (size_t k = 0; k < plan.passes.size(); k++) {
+    const size_t np = plan.passes.size();
+    std::vector<std::vector<uint8_t>> runner(np);
+    std::vector<std::vector<uint32_t>> tile_of(np, std::vector<uint32_t>(plan.V, 0xffffffffu));
+    for (size_t k = 0; k < np; k++) {
       const TilePass &tp = plan.passes[k];
-      std::vector<uint32_t> &mine = tiles[k];
+      runner[k].assign(tp.n_tiles(), 0xff);
       for (uint32_t t = 0; t < tp.n_tiles(); t++) {
         const uint32_t a = tp.vert_off[t], b = tp.vert_off[t + 1];
-        if (a == b || tp.rounds[t].y + tp.rounds[t].z == 0) continue;
+        if (a == b) continue;
         uint32_t cnt[SB_MAX_RANKS] = {0};
-        if (tp.contiguous) cnt[owner_of(a)] = b - a;
-        else
-          for (uint32_t i = a; i < b; i++) cnt[owner_of(tp.tile_verts[i])]++;
+        if (tp.contiguous) {
+          cnt[owner_of(a)] = b - a;
+          for (uint32_t i = a; i < b; i++) tile_of[k][i] = t;
+        } else {
+          for (uint32_t i = a; i < b; i++) {
+            cnt[owner_of(tp.tile_verts[i])]++;
+            tile_of[k][tp.tile_verts[i]] = t;
+          }
+        }
         uint32_t best = 0;
         for (uint32_t r = 1; r < D.n_ranks; r++)
           if (cnt[r] > cnt[best]) best = r;
-        if (best == D.rank) mine.push_back(t);
+        runner[k][t] = (uint8_t)best;
+      }
+    }
+    // Zone: a tile with a vertex that some tile of ANOTHER pass, run by ANOTHER rank, holds as well.  Everything else
+    // is interior: all its vertices are touched by this rank's tiles only, in every pass.  (A tile with a run in a
+    // peer's memory is a zone tile: the pass-0 tile of that run belongs to the peer.)
+    std::vector<std::vector<uint8_t>> in_zone(np);
+    for (size_t k = 0; k < np; k++) in_zone[k].assign(plan.passes[k].n_tiles(), 0);
+    uint32_t nbr = 0;
+    for (uint32_t d = 0; d < plan.V; d++) {
+      uint32_t ranks = 0;
+      for (size_t k = 0; k < np; k++)
+        if (tile_of[k][d] != 0xffffffffu) ranks |= 1u << runner[k][tile_of[k][d]];
+      if (ranks & (ranks - 1)) { // more than one rank touches this vertex
+        for (size_t k = 0; k < np; k++)
+          if (tile_of[k][d] != 0xffffffffu) in_zone[k][tile_of[k][d]] = 1;
+        if (ranks >> rank & 1u) nbr |= ranks;
+      }
+    }
+    D.nbr_mask = nbr & ~(1u << rank);
+    // this rank's tiles of every pass: zone tiles first, each part heaviest first and dealt to the SMs in a snake
+    // like the single-GPU launch order
+    tiles.assign(np, {});
+    n_zone.assign(np, 0);
+    for (size_t k = 0; k < np; k++) {
+      const TilePass &tp = plan.passes[k];
+      std::vector<uint32_t> part[2];
+      for (uint32_t t = 0; t < tp.n_tiles(); t++) {
+        if (runner[k][t] != (uint8_t)rank) continue;
+        const bool has_rounds = tp.rounds[t].y + tp.rounds[t].z != 0;
+        if (!has_rounds && !tp.contiguous) continue; // (a contiguous pass may carry the vertex stages: every tile runs)
+        part[in_zone[k][t] ? 0 : 1].push_back(t);
       }
       auto work = [&](uint32_t t) { return ((uint64_t)(tp.rounds[t].y + tp.rounds[t].z) << 32) | (uint32_t)(tp.ent_off[t + 1] - tp.ent_off[t]); };
-      std::stable_sort(mine.begin(), mine.end(), [&](uint32_t a, uint32_t b) { return work(a) > work(b); });
       const size_t layer = (size_t)std::max(1, n_sm);
-      for (size_t lo = layer; lo < mine.size(); lo += 2 * layer) std::reverse(mine.begin() + lo, mine.begin() + std::min(mine.size(), lo + layer));
+      for (auto &mine : part) {
+        std::stable_sort(mine.begin(), mine.end(), [&](uint32_t a, uint32_t b) { return work(a) > work(b); });
+        for (size_t lo = layer; lo < mine.size(); lo += 2 * layer) std::reverse(mine.begin() + lo, mine.begin() + std::min(mine.size(), lo + layer));
+      }
+      n_zone[k] = (uint32_t)part[0].size();
+      tiles[k] = part[0];
+      tiles[k].insert(tiles[k].end(), part[1].begin(), part[1].end());
     }
   }
   void dist_setup(int rank, int n_ranks) {
     if (halo_active()) throw std::string("halo lists and the peer-memory distribution are alternatives");
     std::vector<std::vector<uint32_t>> tiles;
-    dist_layout(rank, n_ranks, dist, tiles);
+    std::vector<uint32_t> n_zone;
+    dist_layout(rank, n_ranks, dist, tiles, n_zone);
     for (size_t k = 0; k < plan.passes.size(); k++) {
       passes[k].order.upload(tiles[k], &dev_bytes);
       passes[k].dev.order = passes[k].order.p;
+      passes[k].dev.n_zone = n_zone[k];
       passes[k].grid = (uint32_t)tiles[k].size();
+    }
+    {
+      std::vector<uint32_t> slots, surf;
+      const uint32_t lo = dist.slab_lo[rank], hi = dist.slab_lo[rank + 1];
+      for (uint32_t c = 0; c < plan.V; c++)
+        if (plan.inv[c] >= lo && plan.inv[c] < hi) slots.push_back(plan.inv[c]);
+      for (size_t s = 0; s < plan.surf_ids.size(); s++) {
+        const uint32_t d = plan.inv[plan.surf_ids[s]];
+        if (d >= lo && d < hi) surf.push_back((uint32_t)s);
+      }
+      n_own = (uint32_t)slots.size();
+      n_own_surf = (uint32_t)surf.size();
+      own_slot.upload(slots, &dev_bytes);
+      own_surf.upload(surf, &dev_bytes);
+      pack_buf.release();
     }
     dist_ctl.alloc(4 + SB_MAX_RANKS, &dev_bytes);
     CK(cudaMemset(dist_ctl.p, 0, (4 + SB_MAX_RANKS) * sizeof(uint32_t)));
@@ -567,9 +668,9 @@ struct sb_solver {
     }
   }
 
-  void launch_pass(size_t k, cudaStream_t s) {
-    if (fast()) launch_tile<true>(passes[k], s);
-    else launch_tile<false>(passes[k], s);
+  void launch_pass(size_t k, cudaStream_t s, uint32_t n_seg = 1, uint32_t reps = 1, bool pre = false, bool post = false) {
+    if (fast()) launch_tile<true>(passes[k], s, n_seg, reps, pre, post);
+    else launch_tile<false>(passes[k], s, n_seg, reps, pre, post);
   }
   void launch_global(cudaStream_t s, int group = -1) {
     for (const GlobalBatch &b : plan.gbatches) {
@@ -623,45 +724,166 @@ struct sb_solver {
   }
   void launch_normals(cudaStream_t s) {
     const uint32_t ns = (uint32_t)plan.surf_ids.size();
-    if (!ns || (prm.flags & SB_FLAG_NO_NORMALS) || dist_on) return; // (distributed: normals are the caller's, from the gathered positions)
+    if (!ns || (prm.flags & SB_FLAG_NO_NORMALS)) return;
+    if (dist_on) { // the surface vertices this rank owns; a launch of the epoch sequence on every rank
+      if (n_own_surf) k_normals_dist<<<grid_for(n_own_surf, 256), 256, 0, s>>>(n_own_surf, own_surf.p, surf_tri_off.p, surf_tri_ids.p, tris_dev.p, nrm.p, dist_dev.p);
+      else k_dist_bump<<<1, 32, 0, s>>>(dist_dev.p);
+      return;
+    }
     k_normals<<<grid_for(ns, 256), 256, 0, s>>>(ns, surf_tri_off.p, surf_tri_ids.p, tris_dev.p, x.p, nrm.p);
   }
 
-  uint32_t launches_per_frame() const {
-    uint32_t per_iter = 0;
-    for (auto &pb : passes) per_iter += pb.dev.n_tiles && !pb.empty ? 1 : 0;
-    for (auto &b : plan.gbatches) per_iter += b.cnt ? 1 : 0;
-    for (auto &kv : links) {
-      auto hl = halo.find(kv.first);
-      if (hl == halo.end() || !hl->second.n) continue;
-      per_iter += (kv.second.peer_buf ? 1 : 0) + (kv.second.recv.p ? 1 : 0); // one send and one receive kernel per sweep
+  // ---- the frame program ---------------------------------------------------------------
+  //
+  // One frame = substeps x { predict, iterations x sweep, finish } + normals, as a flat list of launches.
+  //
+  // Snake: the tile passes of a sweep are independent sets of constraints in SOME order; iteration 0, 2, 4 ... of a
+  // substep runs them forwards (pass 0, 1, ... n-1), iteration 1, 3, ... backwards (a symmetric Gauss-Seidel sweep),
+  // so the last pass of one iteration and the first of the next are the SAME pass, on the same tiles.
+  // Fusion: consecutive occurrences of one pass become one launch that keeps the tiles' positions in shared memory:
+  // within a substep the rounds are simply repeated (`reps`); across a substep boundary (possible when the pass is a
+  // contiguous one, whose tiles partition the vertices) the launch also carries collide + velocity update + predict of
+  // the tile's own vertices (`n_seg` segments), so that no separate per-vertex kernel runs there.  The first launch
+  // of a frame predicts (`pre`) and the last one finishes (`post`) in the same way.  With 4 tilings and 10 iterations
+  // that is 30 launches per substep instead of 42, and a batch of bodies that fit one tile each runs a whole frame
+  // (substeps x iterations sweeps) in ONE launch.
+  // The order is what sb_get_schedule / sb_get_schedule_odd export, and the oracle replays exactly that.
+  struct Launch {
+    enum Kind { PREDICT, FINISH, PASS, GLOBAL, GROUP, EXCHANGE, NORMALS, DAG } kind;
+    int arg = 0;                  // pass index / constraint group / exchange phase
+    uint32_t n_seg = 1, reps = 1; // PASS
+    bool pre = false, post = false;
+  };
+  // every constraint sits in a tile pass of group 0: any pass order is a Gauss-Seidel order, and passes can be fused
+  bool pure() const {
+    if (!plan.gbatches.empty() || plan.n_ghost || plan.passes.empty()) return false;
+    for (const TilePass &tp : plan.passes)
+      if (tp.group != 0) return false;
+    return true;
+  }
+  bool snake() const { return pure() && !(prm.flags & (SB_FLAG_NO_SNAKE | SB_FLAG_DAG)) && !halo_active(); }
+  bool fuse() const { return pure() && !(prm.flags & (SB_FLAG_NO_FUSE | SB_FLAG_DAG)) && !halo_active(); }
+
+  std::vector<Launch> program() const {
+    std::vector<Launch> L;
+    const int S = prm.substeps, I = prm.iterations;
+    auto simple = [&](Launch::Kind k, int arg = 0) { Launch l; l.kind = k; l.arg = arg; L.push_back(l); };
+    const bool want_normals = !plan.surf_ids.empty() && !(prm.flags & SB_FLAG_NO_NORMALS);
+    if (use_dag() || halo_active() || !pure()) {
+      for (int ss = 0; ss < S; ss++) {
+        simple(Launch::PREDICT);
+        if (use_dag()) simple(Launch::DAG);
+        else
+          for (int it = 0; it < I; it++) {
+            simple(Launch::GROUP, 0);
+            if (halo_active()) simple(Launch::EXCHANGE, 0);
+            simple(Launch::GROUP, 1);
+            if (halo_active()) simple(Launch::EXCHANGE, 1);
+          }
+        simple(Launch::FINISH);
+      }
+      if (want_normals) simple(Launch::NORMALS);
+      return L;
     }
-    uint32_t n = (uint32_t)prm.substeps * (2 + (use_dag() ? 1u : (uint32_t)prm.iterations * per_iter));
-    if (!plan.surf_ids.empty() && !(prm.flags & SB_FLAG_NO_NORMALS) && !dist_on) n++;
+    std::vector<int> live; // passes that hold constraints
+    for (size_t k = 0; k < plan.passes.size(); k++)
+      if (plan.passes[k].n_edges + plan.passes[k].n_tets) live.push_back((int)k);
+    const bool sn = snake(), fu = fuse();
+    auto contiguous = [&](int k) { return plan.passes[k].contiguous; };
+    // a pass launch under construction: reps of every segment (substep) it spans
+    struct Open { int pass = -1; std::vector<uint32_t> seg; bool pre = false; } open;
+    auto flush = [&](bool post) {
+      if (open.pass < 0) return;
+      // the kernel runs segments of equal length: split where the repetition count changes; a split falls on a
+      // substep boundary of a contiguous pass, so the halves carry it as finish (post) and predict (pre)
+      size_t lo = 0;
+      while (lo < open.seg.size()) {
+        size_t hi = lo + 1;
+        while (hi < open.seg.size() && open.seg[hi] == open.seg[lo]) hi++;
+        Launch l;
+        l.kind = Launch::PASS; l.arg = open.pass;
+        l.n_seg = (uint32_t)(hi - lo); l.reps = open.seg[lo];
+        l.pre = lo == 0 ? open.pre : true;
+        l.post = hi == open.seg.size() ? post : true;
+        L.push_back(l);
+        lo = hi;
+      }
+      open = Open();
+    };
+    for (int ss = 0; ss < S; ss++) {
+      bool first_of_substep = true;
+      auto occurrence = [&](int k) {
+        if (first_of_substep) {
+          first_of_substep = false;
+          // substep boundary: finish of the previous substep (none before the first), predict of this one
+          if (fu && open.pass == k && contiguous(k)) { open.seg.push_back(1); return; } // carried inside the launch
+          const bool had = open.pass >= 0 || ss > 0;
+          if (fu && open.pass >= 0 && contiguous(open.pass)) flush(true);
+          else { flush(false); if (had) simple(Launch::FINISH); }
+          if (fu && contiguous(k)) { open.pass = k; open.seg = {1}; open.pre = true; return; }
+          simple(Launch::PREDICT);
+          open.pass = k; open.seg = {1}; open.pre = false;
+          return;
+        }
+        if (fu && open.pass == k) { open.seg.back()++; return; }
+        flush(false);
+        open.pass = k; open.seg = {1}; open.pre = false;
+      };
+      if (live.empty() || I == 0) { // nothing to project: the per-vertex kernels alone
+        flush(false);
+        simple(Launch::PREDICT);
+        simple(Launch::FINISH);
+        continue;
+      }
+      for (int it = 0; it < I; it++) {
+        if (sn && (it & 1)) for (size_t j = live.size(); j-- > 0;) occurrence(live[j]);
+        else for (int k : live) occurrence(k);
+      }
+    }
+    if (open.pass >= 0) {
+      if (fu && contiguous(open.pass)) flush(true);
+      else { flush(false); simple(Launch::FINISH); }
+    }
+    if (want_normals) simple(Launch::NORMALS);
+    return L;
+  }
+
+  void run_launch(const Launch &l, cudaStream_t s) {
+    switch (l.kind) {
+      case Launch::PREDICT: launch_predict(s); break;
+      case Launch::FINISH: launch_finish(s); break;
+      case Launch::PASS: launch_pass((size_t)l.arg, s, l.n_seg, l.reps, l.pre, l.post); break;
+      case Launch::GLOBAL: launch_global(s, l.arg); break;
+      case Launch::GROUP: launch_group(l.arg, s); break;
+      case Launch::EXCHANGE: exchange(l.arg, s); break;
+      case Launch::NORMALS: launch_normals(s); break;
+      case Launch::DAG: launch_dag(s); break;
+    }
+  }
+
+  uint32_t launches_per_frame() const {
+    uint32_t n = 0;
+    for (const Launch &l : program()) {
+      if (l.kind == Launch::GROUP) {
+        for (size_t k = 0; k < passes.size(); k++) n += plan.passes[k].group == l.arg && passes[k].grid && !passes[k].empty;
+        for (auto &b : plan.gbatches) n += b.cnt && b.group == l.arg;
+      } else if (l.kind == Launch::EXCHANGE) {
+        for (auto &kv : links) {
+          auto hl = halo.find(kv.first);
+          if (hl == halo.end() || !hl->second.n) continue;
+          // phase 0: list 1 sends, list 0 receives; phase 1 the other way round
+          const bool sends = kv.first == (l.arg == 0 ? 1 : 0);
+          n += sends ? (kv.second.peer_buf ? 1 : 0) : (kv.second.recv.p ? 1 : 0);
+        }
+      } else {
+        n++;
+      }
+    }
     return n;
   }
 
   void enqueue_frame(cudaStream_t s) {
-    for (int ss = 0; ss < prm.substeps; ss++) {
-      launch_predict(s);
-      if (use_dag()) {
-        launch_dag(s);
-        launch_finish(s);
-        continue;
-      }
-      for (int it = 0; it < prm.iterations; it++) {
-        if (halo_active()) {
-          launch_group(0, s);
-          exchange(0, s);
-          launch_group(1, s);
-          exchange(1, s);
-        } else {
-          for (int g = 0; g < 2; g++) launch_group(g, s);
-        }
-      }
-      launch_finish(s);
-    }
-    launch_normals(s);
+    for (const Launch &l : program()) run_launch(l, s);
     CK(cudaGetLastError());
   }
 
@@ -810,6 +1032,34 @@ struct sb_solver {
     CK(cudaStreamSynchronize(stream));
   }
 
+  // ---- one frame in one buffer (sb_read_packed / sb_write_packed) --------------------------------------
+  uint32_t packed_verts() const { return dist.ctl ? n_own : plan.V; }
+  uint32_t packed_surf() const { return dist.ctl ? n_own_surf : (uint32_t)plan.surf_ids.size(); }
+  size_t packed_bytes(bool with_surface) const { return 32 * (size_t)packed_verts() + (with_surface ? 24 * (size_t)packed_surf() : 0); }
+  float4 *pack_staging() {
+    const size_t need = (packed_bytes(true) + 15) / 16;
+    if (pack_buf.n < need) pack_buf.alloc(need, &dev_bytes);
+    return pack_buf.p;
+  }
+  void read_packed(void *dst) {
+    CK(cudaSetDevice(device));
+    const uint32_t n = packed_verts(), ns = packed_surf();
+    float4 *st = pack_staging();
+    k_pack_frame<<<grid_for((size_t)n + ns, 256), 256, 0, stream>>>(n, dist.ctl ? own_slot.p : inv.p, ns, dist.ctl ? own_surf.p : nullptr,
+                                                                 surf_slot.p, x.p, v.p, nrm.p, st);
+    CK(cudaGetLastError());
+    d2h(dst, st, packed_bytes(true));
+  }
+  void write_packed(const void *src) {
+    CK(cudaSetDevice(device));
+    const uint32_t n = packed_verts();
+    float4 *st = pack_staging();
+    CK(cudaMemcpyAsync(st, src, packed_bytes(false), cudaMemcpyHostToDevice, stream));
+    k_unpack_state<<<grid_for(n, 256), 256, 0, stream>>>(n, dist.ctl ? own_slot.p : inv.p, st, x.p, v.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(stream)); // the host buffer belongs to the caller again when this returns
+  }
+
   void diagnostics(double *out) {
     CK(cudaSetDevice(device));
     if (!d_edges.p && plan.E) {
@@ -857,6 +1107,7 @@ struct sb_solver {
 
   float time_kernel(int which, int reps) {
     CK(cudaSetDevice(device));
+    if (dist.ctl) throw std::string("sb_time_kernel on a distributed handle would run launches the peers do not run (the epochs would part)");
     if (cur_dt < 0) refresh_params(prm.dt);
     const size_t nb = plan.V * sizeof(float4);
     // save state in the staging buffers plus one temporary
@@ -969,7 +1220,7 @@ static int create_impl(const sb_mesh_desc *mesh, const sb_params *params, sb_han
   *out = nullptr;
   g_create_error.clear();
   if (!mesh) { g_create_error = "mesh is NULL"; return SB_E_ARG; }
-  if (mesh->reserved[0] != 0) { g_create_error = "reserved fields must be 0"; return SB_E_ARG; }
+  if (mesh->dist_ranks != 0 && (mesh->dist_ranks < 2 || mesh->dist_ranks > SB_MAX_RANKS)) { g_create_error = "dist_ranks must be 0 or 2..8"; return SB_E_ARG; }
   if (mesh->attach_edges < 0 || mesh->attach_edges > 2) { g_create_error = "attach_edges must be 0, 1 or 2"; return SB_E_ARG; }
   sb_params dp;
   sb_default_params(&dp);
@@ -991,6 +1242,7 @@ static int create_impl(const sb_mesh_desc *mesh, const sb_params *params, sb_han
     opt.round_width = mesh->round_width;
     opt.compounds = mesh->attach_edges == 0 ? -1 : mesh->attach_edges == 1 ? 1 : 0;
     opt.tilings = mesh->tilings;
+    opt.dist_ranks = mesh->dist_ranks;
     if (device) {
       int ndev = 0;
       CK(cudaGetDeviceCount(&ndev));
@@ -1089,6 +1341,7 @@ int sb_synchronize(sb_handle h) {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     if (h->dag_error()) { h->err = "tile DAG: a dependency wait timed out"; return SB_E_STATE; }
+    if (h->dist_error_word()) { h->err = "a wait for a peer GPU timed out: the state is invalid"; return SB_E_STATE; }
     return SB_OK;
   });
 }
@@ -1096,7 +1349,11 @@ int sb_synchronize(sb_handle h) {
 int sb_read_positions(sb_handle h, float *dst, uint32_t n) {
   NEED_DEVICE(h);
   if (!dst || n != h->plan.V) { h->err = "dst is NULL or n_verts mismatch"; return SB_E_ARG; }
-  return guarded(h, [&]() -> int { h->read_positions(dst); return SB_OK; });
+  return guarded(h, [&]() -> int {
+    h->read_positions(dst);
+    if (h->dist_error_word()) { h->err = "a wait for a peer GPU timed out: the state is invalid"; return SB_E_STATE; }
+    return SB_OK;
+  });
 }
 
 int sb_surface_vertices(sb_handle h, int32_t *ids, uint32_t capacity, uint32_t *n_surface) {
@@ -1223,13 +1480,42 @@ int sb_frames_done(sb_handle h, uint64_t *out) {
 int sb_get_state(sb_handle h, float *x4, float *v4, uint32_t n) {
   NEED_DEVICE(h);
   if (n != h->plan.V) { h->err = "n_verts mismatch"; return SB_E_ARG; }
-  return guarded(h, [&]() -> int { h->get_state(x4, v4); return SB_OK; });
+  return guarded(h, [&]() -> int {
+    h->get_state(x4, v4);
+    if (h->dist_error_word()) { h->err = "a wait for a peer GPU timed out: the state is invalid"; return SB_E_STATE; }
+    return SB_OK;
+  });
 }
 
 int sb_set_state(sb_handle h, const float *x4, const float *v4, uint32_t n) {
   NEED_DEVICE(h);
   if (n != h->plan.V) { h->err = "n_verts mismatch"; return SB_E_ARG; }
   return guarded(h, [&]() -> int { h->set_state(x4, v4); return SB_OK; });
+}
+
+int sb_packed_sizes(sb_handle h, uint32_t *n_verts, uint32_t *n_surface, uint64_t *bytes_in, uint64_t *bytes_out) {
+  NEED_DEVICE(h);
+  if (n_verts) *n_verts = h->packed_verts();
+  if (n_surface) *n_surface = h->packed_surf();
+  if (bytes_in) *bytes_in = h->packed_bytes(false);
+  if (bytes_out) *bytes_out = h->packed_bytes(true);
+  return SB_OK;
+}
+
+int sb_read_packed(sb_handle h, void *dst, uint64_t bytes) {
+  NEED_DEVICE(h);
+  if (!dst || bytes != h->packed_bytes(true)) { h->err = "dst is NULL or the size is not sb_packed_sizes' bytes_out"; return SB_E_ARG; }
+  return guarded(h, [&]() -> int {
+    h->read_packed(dst);
+    if (h->dist_error_word()) { h->err = "a wait for a peer GPU timed out: the state is invalid"; return SB_E_STATE; }
+    return SB_OK;
+  });
+}
+
+int sb_write_packed(sb_handle h, const void *src, uint64_t bytes) {
+  NEED_DEVICE(h);
+  if (!src || bytes != h->packed_bytes(false)) { h->err = "src is NULL or the size is not sb_packed_sizes' bytes_in"; return SB_E_ARG; }
+  return guarded(h, [&]() -> int { h->write_packed(src); return SB_OK; });
 }
 
 int sb_diagnostics(sb_handle h, double *out16) {
@@ -1308,16 +1594,41 @@ int sb_get_topology(sb_handle h, int32_t *edges, float *rest_len, float *rest_vo
   return SB_OK;
 }
 
-int sb_get_schedule(sb_handle h, int64_t *n_order, int32_t *order, int32_t *n_batches, int64_t *batch_off) {
+static int schedule_impl(sb_handle h, bool odd, int64_t *n_order, int32_t *order, int32_t *n_batches, int64_t *batch_off) {
   NEED_HANDLE(h);
   return guarded(h, [&]() -> int {
     std::vector<int32_t> ord;
     std::vector<int64_t> off;
-    h->plan.export_schedule(ord, off);
+    h->plan.export_schedule(ord, off, odd && h->snake());
     if (n_order) *n_order = (int64_t)ord.size();
     if (n_batches) *n_batches = (int32_t)off.size() - 1;
     if (order) std::memcpy(order, ord.data(), ord.size() * sizeof(int32_t));
     if (batch_off) std::memcpy(batch_off, off.data(), off.size() * sizeof(int64_t));
+    return SB_OK;
+  });
+}
+
+int sb_get_schedule(sb_handle h, int64_t *n_order, int32_t *order, int32_t *n_batches, int64_t *batch_off) {
+  return schedule_impl(h, false, n_order, order, n_batches, batch_off);
+}
+int sb_get_schedule_odd(sb_handle h, int64_t *n_order, int32_t *order, int32_t *n_batches, int64_t *batch_off) {
+  return schedule_impl(h, true, n_order, order, n_batches, batch_off);
+}
+
+int sb_frame_program(sb_handle h, int32_t *n_launches, int32_t *ops6, uint32_t capacity) {
+  NEED_HANDLE(h);
+  if (!n_launches) return SB_E_ARG;
+  return guarded(h, [&]() -> int {
+    const std::vector<sb_solver::Launch> L = h->program();
+    *n_launches = (int32_t)L.size();
+    if (ops6) {
+      if (capacity < L.size()) throw std::string("capacity too small");
+      for (size_t i = 0; i < L.size(); i++) {
+        int32_t *o = ops6 + 6 * i;
+        o[0] = (int32_t)L[i].kind; o[1] = L[i].arg; o[2] = (int32_t)L[i].n_seg; o[3] = (int32_t)L[i].reps;
+        o[4] = L[i].pre; o[5] = L[i].post;
+      }
+    }
     return SB_OK;
   });
 }
@@ -1496,6 +1807,12 @@ int sb_enqueue(sb_handle h, int32_t op, int32_t arg) {
         if (arg < 0 || (size_t)arg >= h->passes.size()) throw std::string("no such tile pass");
         h->launch_pass((size_t)arg, h->stream);
         break;
+      case SB_OP_LAUNCH: {
+        const std::vector<sb_solver::Launch> L = h->program();
+        if (arg < 0 || (size_t)arg >= L.size()) throw std::string("no such launch in the frame program");
+        h->run_launch(L[(size_t)arg], h->stream);
+        break;
+      }
       default: throw std::string("unknown op");
     }
     CK(cudaGetLastError());
@@ -1624,7 +1941,8 @@ int sb_dist_layout(sb_handle h, int32_t rank, int32_t n_ranks, uint8_t *owned_V,
   return guarded(h, [&]() -> int {
     DistDev D;
     std::vector<std::vector<uint32_t>> tiles;
-    h->dist_layout(rank, n_ranks, D, tiles);
+    std::vector<uint32_t> n_zone;
+    h->dist_layout(rank, n_ranks, D, tiles, n_zone);
     if (owned_V) {
       std::memset(owned_V, 0, h->plan.V);
       for (uint32_t d = D.slab_lo[rank]; d < D.slab_lo[rank + 1]; d++) owned_V[h->plan.perm[d]] = 1;

@@ -11,17 +11,16 @@ from typing import List
 
 import numpy as np
 
-from ._abi import FLAG_NO_NORMALS
 from .solver import SoftBody, ipc_export, ipc_open
 
-OP_PREDICT, OP_FINISH, OP_PASS = 0, 2, 7
+OP_LAUNCH = 8
 
 
 class DistBody:
     def __init__(self, pos, tets, surf_tris=None, *, device=0, **solver_kw):
         import torch.distributed as dist
         self.rank, self.n_ranks = dist.get_rank(), dist.get_world_size()
-        solver_kw["flags"] = solver_kw.get("flags", 0) | FLAG_NO_NORMALS
+        solver_kw.setdefault("dist_ranks", self.n_ranks)  # boxes numbered block by block: compact ranks
         self.sb = SoftBody(pos, tets, surf_tris, device=device, **solver_kw)
         xb, cb = self.sb.dist_setup(self.rank, self.n_ranks)
         everyone = [None] * self.n_ranks
@@ -35,21 +34,31 @@ class DistBody:
     def step(self, dt: float = 0.0, frames: int = 1):
         self.sb.step(dt, frames=frames)
 
-    def gather_state(self):
-        """(x4, v4) of the whole mesh on every rank: each rank contributes the vertices it owns."""
+    def read_frame(self):
+        """This rank's share of a frame in one copy (sb_read_packed): (ids, x4, v4, surface ids, positions, normals)
+        of the vertices / surface vertices it owns, ascending vertex id."""
+        x4, v4, sp, sn = self.sb.unpack_frame(self.sb.read_packed())
+        surf = self.sb.surface_vertices()
+        return np.nonzero(self.owned)[0], x4, v4, surf[self.owned[surf]], sp, sn
+
+    def gather_state(self, with_surface=False):
+        """(x4, v4) of the whole mesh on every rank: each rank contributes the vertices it owns (and, with_surface,
+        the normals of the whole surface, (n_verts, 3), zero off the surface)."""
         import torch.distributed as dist
-        x4, v4 = self.sb.get_state()
         parts = [None] * self.n_ranks
-        dist.all_gather_object(parts, (np.nonzero(self.owned)[0], x4[self.owned], v4[self.owned]))
-        X, U = np.zeros_like(x4), np.zeros_like(v4)
-        for ids, xs, vs in parts:
-            X[ids], U[ids] = xs, vs
-        return X, U
+        dist.all_gather_object(parts, self.read_frame())
+        n = len(self.owned)
+        X, U, N = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32), np.zeros((n, 3), np.float32)
+        for ids, xs, vs, sids, sp, sn in parts:
+            X[ids], U[ids], N[sids] = xs, vs, sn
+        if self.sb.dist_error():
+            raise RuntimeError("a wait for a peer GPU timed out: the state is invalid")
+        return (X, U, N) if with_surface else (X, U)
 
 
 class VirtualRanks:
     def __init__(self, pos, tets, surf_tris, n_ranks, stream_ptr, **solver_kw):
-        solver_kw["flags"] = solver_kw.get("flags", 0) | FLAG_NO_NORMALS
+        solver_kw.setdefault("dist_ranks", n_ranks)
         self.ranks: List[SoftBody] = [SoftBody(pos, tets, surf_tris, stream=stream_ptr, **solver_kw) for _ in range(n_ranks)]
         addr = [sb.dist_setup(r, n_ranks) for r, sb in enumerate(self.ranks)]
         for r, sb in enumerate(self.ranks):
@@ -62,26 +71,21 @@ class VirtualRanks:
     def step(self, dt: float = 0.0, frames: int = 1):
         """One stream: the ranks' launches are interleaved kernel by kernel (a rank's kernel waits for its
         peers' previous kernel, which must therefore already be in the stream ahead of it)."""
-        p = self.ranks[0].params
-        n_pass = self.ranks[0].info()["n_tile_passes"]
+        n_launches = len(self.ranks[0].frame_program())  # the same program on every rank
         for sb in self.ranks:
             sb.prepare(dt)
         for _ in range(frames):
-            for _ in range(p.substeps):
+            for i in range(n_launches):
                 for sb in self.ranks:
-                    sb.enqueue(OP_PREDICT)
-                for _ in range(p.iterations):
-                    for k in range(n_pass):
-                        for sb in self.ranks:
-                            sb.enqueue(OP_PASS, k)
-                for sb in self.ranks:
-                    sb.enqueue(OP_FINISH)
+                    sb.enqueue(OP_LAUNCH, i)
 
-    def gather_state(self):
-        X = U = None
+    def gather_state(self, with_surface=False):
+        n = len(self.owned[0])
+        X, U, N = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32), np.zeros((n, 3), np.float32)
         for sb, own in zip(self.ranks, self.owned):
-            x4, v4 = sb.get_state()
-            if X is None:
-                X, U = np.zeros_like(x4), np.zeros_like(v4)
-            X[own], U[own] = x4[own], v4[own]
-        return X, U
+            x4, v4, sp, sn = sb.unpack_frame(sb.read_packed())  # the vertices this rank owns, one copy
+            surf = sb.surface_vertices()
+            X[own], U[own], N[surf[own[surf]]] = x4, v4, sn
+            if sb.dist_error():
+                raise RuntimeError("a wait for a peer timed out: the state is invalid")
+        return (X, U, N) if with_surface else (X, U)

@@ -81,7 +81,8 @@ class SoftBody:
                  stiffness=math.inf, volume_stiffness=math.inf, damping=0.0, friction=0.0,
                  substeps=10, iterations=10, dt=1.0 / 60.0, gravity=(0.0, -9.81, 0.0), ground_y=0.0,
                  flags=0, tile_cap=0, max_tile_passes=-1, block_threads=0, later_tile_cap=0,
-                 host_threads=0, round_width=0, attach_edges=0, tilings=0, n_ghost_verts=0, stream=None, host_only=False):
+                 host_threads=0, round_width=0, attach_edges=0, tilings=0, n_ghost_verts=0, dist_ranks=0, stream=None,
+                 host_only=False):
         self._lib = _abi.load()
         self._h = C.c_void_p()
         pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
@@ -103,6 +104,7 @@ class SoftBody:
         d.later_tile_cap, d.host_threads = later_tile_cap, host_threads
         d.round_width, d.attach_edges, d.tilings = round_width, attach_edges, tilings
         d.n_ghost_verts = n_ghost_verts
+        d.dist_ranks = dist_ranks
         self._params = default_params(
             dt=dt, substeps=substeps, iterations=iterations, stiffness_distance=stiffness,
             stiffness_volume=volume_stiffness, damping=damping, friction=friction, gravity=gravity,
@@ -223,7 +225,7 @@ class SoftBody:
         self._ck(self._lib.sb_halo_unpack(self._h, list_id, C.c_void_p(src_device_ptr)))
 
     # -- halo exchange over peer memory ------------------------------------------------
-    OP_EXCHANGE, OP_HALO_SEND, OP_HALO_RECV = 4, 5, 6
+    OP_EXCHANGE, OP_HALO_SEND, OP_HALO_RECV, OP_PASS, OP_LAUNCH = 4, 5, 6, 7, 8
 
     def halo_alloc(self, list_id: int) -> int:
         """Allocates this rank's receive buffer for a registered list; returns its device address."""
@@ -304,6 +306,32 @@ class SoftBody:
             v4 = np.ascontiguousarray(v4, np.float32)
         self._ck(self._lib.sb_set_state(self._h, _buf_ptr(x4), _buf_ptr(v4), self.n_verts))
 
+    # -- one frame in one buffer ------------------------------------------------------------
+    def packed_sizes(self):
+        """(n_verts, n_surface, bytes_in, bytes_out) of sb_write_packed / sb_read_packed (owned vertices on one rank of
+        a distributed mesh)."""
+        n, ns, bi, bo = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.sb_packed_sizes(self._h, C.byref(n), C.byref(ns), C.byref(bi), C.byref(bo)))
+        return n.value, ns.value, bi.value, bo.value
+
+    def read_packed(self, out=None):
+        """LateUpdate in one copy: a uint8 buffer [x4 | v4 | surface xyz | surface normals]; see unpack_frame."""
+        n, ns, bi, bo = self.packed_sizes()
+        out = np.empty(bo, np.uint8) if out is None else out
+        self._ck(self._lib.sb_read_packed(self._h, _buf_ptr(out), bo))
+        return out
+
+    def write_packed(self, buf):
+        n, ns, bi, bo = self.packed_sizes()
+        self._ck(self._lib.sb_write_packed(self._h, _buf_ptr(buf), bi))
+
+    def unpack_frame(self, buf):
+        """Views into a packed frame: x4 (n,4), v4 (n,4), surface positions (ns,3), surface normals (ns,3)."""
+        n, ns, bi, bo = self.packed_sizes()
+        f = np.asarray(buf).view(np.uint8).reshape(-1)[:bo].view(np.float32)
+        return (f[:4 * n].reshape(n, 4), f[4 * n:8 * n].reshape(n, 4), f[8 * n:8 * n + 3 * ns].reshape(ns, 3),
+                f[8 * n + 3 * ns:8 * n + 6 * ns].reshape(ns, 3))
+
     # -- render mesh bound to the tets -----------------------------------------------------
     def skin_bind(self, render_pos, render_tris=None):
         """Bind a render mesh to the tets at rest (host); works on a host_only handle too."""
@@ -377,14 +405,34 @@ class SoftBody:
         self._ck(self._lib.sb_get_tet_roles(self._h, None, _ptr(e01), _ptr(e23)))
         return e01, e23
 
-    def schedule(self):
-        """(order, batch_off): the Gauss-Seidel order of one iteration (see sb_get_schedule)."""
+    def schedule(self, odd=False):
+        """(order, batch_off): the Gauss-Seidel order of the iterations 0, 2, 4 ... of a substep (sb_get_schedule),
+        or with odd=True of the iterations 1, 3, 5 ... (sb_get_schedule_odd: the tile passes backwards, unless the
+        snake is off)."""
+        fn = self._lib.sb_get_schedule_odd if odd else self._lib.sb_get_schedule
         n, nb = C.c_int64(), C.c_int32()
-        self._ck(self._lib.sb_get_schedule(self._h, C.byref(n), None, C.byref(nb), None))
+        self._ck(fn(self._h, C.byref(n), None, C.byref(nb), None))
         order = np.empty(n.value, np.int32)
         off = np.empty(nb.value + 1, np.int64)
-        self._ck(self._lib.sb_get_schedule(self._h, C.byref(n), _ptr(order), C.byref(nb), _ptr(off)))
+        self._ck(fn(self._h, C.byref(n), _ptr(order), C.byref(nb), _ptr(off)))
         return order, off
+
+    def schedule_kw(self):
+        """The whole Gauss-Seidel order as the keyword arguments of the oracle's Model.simulate."""
+        order, off = self.schedule()
+        order_odd, off_odd = self.schedule(odd=True)
+        return dict(order=order, batch_off=off, order_odd=order_odd, batch_off_odd=off_odd)
+
+    LAUNCH_KINDS = ("predict", "finish", "pass", "global", "group", "exchange", "normals", "dag")
+
+    def frame_program(self):
+        """The launches of one frame at the current parameters: (n, 6) int32 rows of
+        (kind, arg, segments, repetitions, predict-before, finish-after); see sb_frame_program."""
+        n = C.c_int32()
+        self._ck(self._lib.sb_frame_program(self._h, C.byref(n), None, 0))
+        ops = np.zeros((n.value, 6), np.int32)
+        self._ck(self._lib.sb_frame_program(self._h, C.byref(n), _ptr(ops), n.value))
+        return ops
 
     def tiles(self, p: int):
         n = C.c_uint32()

@@ -33,7 +33,7 @@ public struct SbMeshDesc          // sb_mesh_desc, 112 bytes
     public float density;
     public int device, tileCap, maxTilePasses, blockThreads, laterTileCap, hostThreads, roundWidth, attachEdges, tilings, nGhostVerts;
     public uint nEdges;
-    public int reserved0;
+    public int distRanks;
 }
 
 [StructLayout(LayoutKind.Sequential)]
@@ -144,7 +144,7 @@ public class SoftbodyB200 : MonoBehaviour
     {
         uint ver, sp, sd, si;
         SbNative.sb_abi_check(out ver, out sp, out sd, out si);
-        if (ver != 2 || sp != Marshal.SizeOf(typeof(SbParams)) || sd != Marshal.SizeOf(typeof(SbMeshDesc)))
+        if (ver != 3 || sp != Marshal.SizeOf(typeof(SbParams)) || sd != Marshal.SizeOf(typeof(SbMeshDesc)))
             throw new InvalidOperationException("softbody_b200 ABI mismatch");
         SbNative.sb_default_params(out prm);
         FillParams();

@@ -62,20 +62,21 @@ def main():
         sb = SoftBody(pos, tets, tris, host_only=True, **c["plan"],
                       **{{"stiffness_distance": "stiffness", "stiffness_volume": "volume_stiffness"}.get(k, k): v for k, v in kw.items()})
         order, off = sb.schedule()
+        order_odd, off_odd = sb.schedule(odd=True)  # the tile passes backwards: iterations 1, 3, 5 ... of a substep
         m = orc.Model(pos, tets, roles=sb.tet_roles())
         extra = {}
         cols = None
         if "colliders" in c:
             cols = orc.colliders(c["colliders"])
             extra["colliders"] = cols
-        m.simulate(orc.params(**kw), n_frames=c["frames"], order=order, batch_off=off, colliders=cols)
+        m.simulate(orc.params(**kw), n_frames=c["frames"], order=order, batch_off=off, order_odd=order_odd, batch_off_odd=off_odd, colliders=cols)
         normals = m.normals(tris)
         if render:
             sb.skin_bind(*render)
             tet_of, bary = sb.skin_binding()
             skin_pos, skin_nrm = m.skin(tet_of, bary, render[1])
             extra.update(render_pos=render[0], render_tris=render[1], skin_tet=tet_of, skin_bary=bary, skin_pos=skin_pos, skin_nrm=skin_nrm)
-        np.savez_compressed(os.path.join(HERE, name + ".npz"), pos=pos, tets=tets, tris=tris, order=order, batch_off=off, roles=sb.tet_roles(),
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), pos=pos, tets=tets, tris=tris, order=order, batch_off=off, order_odd=order_odd, batch_off_odd=off_odd, roles=sb.tet_roles(),
                             x4=m.x4, v4=m.v4, normals=normals, frames=c["frames"],
                             plan=np.array(sorted(c["plan"].items()), dtype=object), prm=np.array(sorted(kw.items()), dtype=object), **extra)
         print(name, pos.shape, tets.shape, "batches", len(off) - 1, "min y", float(m.x4[:, 1].min()))

@@ -1,6 +1,6 @@
 """One mesh over several ranks through peer memory (sb_dist_*): virtual ranks on ONE GPU run the same kernels, peer
 pointers and epoch words as the multi-GPU path, and must reproduce the single-handle run -- and therefore the oracle
--- bit for bit, because the execution order IS the single-GPU order."""
+-- bit for bit, because the execution order IS the single-GPU order.  (Real GPUs: tests/test_multigpu.py.)"""
 import numpy as np
 import pytest
 
@@ -12,31 +12,36 @@ from softbodyunity_b200.dist import VirtualRanks
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("n_ranks,kw", [(2, dict(tile_cap=256)), (3, dict(tile_cap=200, block_threads=32)),
-                                         (4, dict(tile_cap=300, flags=16))])
+                                         (4, dict(tile_cap=300, flags=16)), (8, dict(tile_cap=160, iterations=5)),
+                                         (2, dict(tile_cap=256, flags=128)), (4, dict(tile_cap=256, dist_ranks=0))])
 def test_virtual_ranks_over_peer_memory_match_one_gpu_and_the_oracle(n_ranks, kw):
     import torch
     pos, tets, tris = meshgen.block(14, 12, 26, spacing=0.05, origin=(0, 0.02, 0))
-    one = SoftBody(pos, tets, tris, substeps=5, iterations=6, **kw)
+    kw = dict(dict(substeps=5, iterations=6, dist_ranks=n_ranks), **kw)
+    # one GPU, default numbering of the boxes: how the boxes of the unshifted tiling are numbered (block by block for
+    # the ranks, dist_ranks) changes neither the colouring nor the passes, so the results are the same bits
+    one = SoftBody(pos, tets, tris, **{k: v for k, v in kw.items() if k != "dist_ranks"})
     one.step(frames=6)
     x1, v1 = one.get_state()
     stream = torch.cuda.Stream()
-    vr = VirtualRanks(pos, tets, tris, n_ranks, stream.cuda_stream, substeps=5, iterations=6, **kw)
+    vr = VirtualRanks(pos, tets, tris, n_ranks, stream.cuda_stream, **kw)
     owned = np.stack(vr.owned)
     assert (owned.sum(0) == 1).all(), "every vertex has exactly one owner"
-    info = one.info()
-    for k in range(info["n_tile_passes"]):  # every non-empty tile of every pass runs on exactly one rank
+    info = vr.ranks[0].info()
+    for k in range(info["n_tile_passes"]):  # a tile of a pass runs on exactly one rank (pass 0: every tile runs)
         assert sum(t[k] for t in vr.tiles) <= info["tiles_in_pass"][k]
-        assert all(t[k] > 0 for t in vr.tiles)
+    assert sum(t[0] for t in vr.tiles) == info["tiles_in_pass"][0]
     vr.step(frames=6)
     stream.synchronize()
-    X, U = vr.gather_state()
+    X, U, N = vr.gather_state(with_surface=True)
     assert not any(sb.dist_error() for sb in vr.ranks)
     assert bits_equal(X, x1) and bits_equal(U[:, :3], v1[:, :3])
-    order, off = one.schedule()
-    m = orc.Model(pos, tets, roles=one.tet_roles())
-    m.simulate(oracle_params(one), n_frames=6, order=order, batch_off=off, threads=8)
+    m = orc.Model(pos, tets, roles=vr.ranks[0].tet_roles())
+    m.simulate(oracle_params(one), n_frames=6, threads=8, **vr.ranks[0].schedule_kw())
     assert m.x4[:, 1].min() == 0.0
-    assert bits_equal(X, m.x4)
+    assert bits_equal(X, m.x4) and bits_equal(U[:, :3], m.v4[:, :3])
+    ids = one.surface_vertices()
+    assert bits_equal(N[ids], m.normals(tris)[ids])
 
 
 @pytest.mark.gpu
@@ -45,3 +50,28 @@ def test_dist_setup_rejects_what_it_cannot_split():
     sb = SoftBody(pos, tets, tris)  # one tile: not a tiled mesh
     with pytest.raises(Exception):
         sb.dist_setup(0, 2)
+    pos, tets, tris = meshgen.block(14, 12, 26, spacing=0.05)
+    sb = SoftBody(pos, tets, tris, tile_cap=256)
+    sb.dist_setup(0, 2)
+    with pytest.raises(Exception):
+        sb.time_kernel(16, 2)  # a launch the peers do not run would part the epochs
+
+
+@pytest.mark.gpu
+def test_packed_frame_is_the_separate_read_backs_in_one_copy():
+    pos, tets, tris = meshgen.sphere(12, spacing=0.05)
+    sb = SoftBody(pos, tets, tris, tile_cap=400)
+    sb.step(frames=3)
+    n, ns, b_in, b_out = sb.packed_sizes()
+    assert (n, ns, b_in, b_out) == (len(pos), sb.n_surface, 32 * len(pos), 32 * len(pos) + 24 * sb.n_surface)
+    buf = sb.read_packed()
+    x4, v4, sp, sn = sb.unpack_frame(buf)
+    X, U = sb.get_state()
+    SP, SN = sb.read_surface()
+    assert bits_equal(x4, X) and bits_equal(v4, U) and bits_equal(sp, SP) and bits_equal(sn, SN)
+    # state in through the same door: a second body continues from the packed state bit for bit
+    other = SoftBody(pos, tets, tris, tile_cap=400)
+    other.write_packed(buf)
+    sb.step(frames=2)
+    other.step(frames=2)
+    assert bits_equal(sb.get_state()[0], other.get_state()[0]) and bits_equal(sb.get_state()[1], other.get_state()[1])

@@ -33,10 +33,13 @@ def test_oracle_and_planner_reproduce_the_fixture(path):
     sb = SoftBody(z["pos"], z["tets"], z["tris"], host_only=True, **plan, **{ALIAS.get(k, k): v for k, v in prm.items()})
     order, off = sb.schedule()
     assert np.array_equal(order, z["order"]) and np.array_equal(off, z["batch_off"]), "the planner's schedule changed"
+    order_odd, off_odd = sb.schedule(odd=True)
+    assert np.array_equal(order_odd, z["order_odd"]) and np.array_equal(off_odd, z["batch_off_odd"]), "the planner's schedule changed"
     m = orc.Model(z["pos"], z["tets"], roles=z["roles"])
     assert np.array_equal(sb.tet_roles(), z["roles"]), "the planner's tet roles changed"
     cols = z["colliders"] if "colliders" in z else None
-    m.simulate(orc.params(**prm), n_frames=int(z["frames"]), order=z["order"], batch_off=z["batch_off"], colliders=cols)
+    m.simulate(orc.params(**prm), n_frames=int(z["frames"]), order=z["order"], batch_off=z["batch_off"], order_odd=z["order_odd"],
+               batch_off_odd=z["batch_off_odd"], colliders=cols)
     assert bits_equal(m.x4, z["x4"]) and bits_equal(m.v4, z["v4"])
     assert bits_equal(m.normals(z["tris"]), z["normals"])
     if "render_pos" in z:  # the body came out of the ingest path and carries an embedded render mesh

@@ -19,14 +19,14 @@ def test_surface_to_tets_to_steps_to_skinned_render_mesh():
     sb.skin_bind(sp, st)
     tet_of, b = sb.skin_binding()
     m = orc.Model(p, t, roles=sb.tet_roles())
-    order, off = sb.schedule()
+    sched = sb.schedule_kw()
     pos0, nrm0 = sb.read_skinned()
     ref0, rn0 = m.skin(tet_of, b, st)
     assert bits_equal(pos0, ref0) and bits_equal(nrm0, rn0)
     assert np.abs(pos0 - sp).max() < 1e-6
     for frames in (5, 20):
         sb.step(frames=frames)
-        m.simulate(oracle_params(sb), n_frames=frames, order=order, batch_off=off, threads=8)
+        m.simulate(oracle_params(sb), n_frames=frames, threads=8, **sched)
         pos, nrm = sb.read_skinned()
         ref, rn = m.skin(tet_of, b, st)
         assert bits_equal(sb.get_state()[0], m.x4)
@@ -76,8 +76,7 @@ def test_snapshot_resume_is_bit_identical(tmp_path):
     # the file is what ingest.read_state reads; it matches the oracle at frame 7
     s = ingest.read_state(snap)
     m = orc.Model(pos, tets, roles=a.tet_roles())
-    order, off = a.schedule()
-    m.simulate(oracle_params(a), n_frames=7, order=order, batch_off=off, threads=8)
+    m.simulate(oracle_params(a), n_frames=7, threads=8, **a.schedule_kw())
     assert s["frame"] == 7 and bits_equal(s["x4"], m.x4) and bits_equal(s["v4"], m.v4)
     assert s["topo_hash"] == ingest.topology_hash(len(pos), tets)
     # a snapshot of another mesh is refused

@@ -25,11 +25,11 @@ def run_pair(pos, tets, tris, n_frames, spheres=None, inv_mass=None, colliders=N
         sb.set_colliders(spheres)
     if colliders is not None:
         sb.set_colliders_ex(colliders)
-    order, off = sb.schedule()
+    sched = sb.schedule_kw()
     m = orc.Model(pos, tets, inv_mass=inv_mass, density=kw.get("density", 1000.0), roles=sb.tet_roles())
     sb.step(frames=n_frames)
     x4, v4 = sb.get_state()
-    m.simulate(oracle_params(sb), n_frames=n_frames, order=order, batch_off=off, spheres=spheres, threads=8,
+    m.simulate(oracle_params(sb), n_frames=n_frames, spheres=spheres, threads=8, **sched,
                colliders=colliders)
     return sb, m, x4, v4
 
@@ -108,13 +108,13 @@ def test_capsule_box_sphere_colliders_with_friction_are_bit_identical():
     d = np.linalg.norm(x4[:, :3] - cols[2]["p"][:3], axis=1)
     assert d.min() >= 0.08 - 1e-5
     fresh = orc.Model(pos, tets, roles=sb.tet_roles())
-    order, off = sb.schedule()
-    fresh.simulate(oracle_params(sb), n_frames=40, order=order, batch_off=off, threads=8)
+    sched = sb.schedule_kw()
+    fresh.simulate(oracle_params(sb), n_frames=40, threads=8, **sched)
     assert np.abs(fresh.x4 - m.x4).max() > 1e-2, "colliders should change the outcome"
     # replacing the list: sb_set_colliders (spheres, no friction) after sb_set_colliders_ex
     sb.set_colliders(np.array([[0.0, 0.2, 0.0, 0.15]], np.float32))
     sb.step(frames=3)
-    m.simulate(oracle_params(sb), n_frames=3, order=order, batch_off=off, spheres=np.array([[0.0, 0.2, 0.0, 0.15]], np.float32), threads=8)
+    m.simulate(oracle_params(sb), n_frames=3, spheres=np.array([[0.0, 0.2, 0.0, 0.15]], np.float32), threads=8, **sched)
     x4, v4 = sb.get_state()
     assert bits_equal(x4, m.x4) and bits_equal(v4, m.v4)
 
@@ -144,11 +144,11 @@ def test_graph_and_direct_launch_agree_and_params_update():
     xb, vb = b.get_state()
     assert bits_equal(xa, xb) and bits_equal(va, vb)
     # oracle through the same parameter changes
-    order, off = a.schedule()
+    sched = a.schedule_kw()
     m = orc.Model(pos, tets, roles=a.tet_roles())
-    m.simulate(orc.params(substeps=10, iterations=10), n_frames=3, order=order, batch_off=off)
-    m.simulate(orc.params(substeps=4, iterations=7, damping=1.0), n_frames=3, order=order, batch_off=off)
-    m.simulate(orc.params(dt=0.005, substeps=4, iterations=7, damping=1.0), n_frames=2, order=order, batch_off=off)
+    m.simulate(orc.params(substeps=10, iterations=10), n_frames=3, **sched)
+    m.simulate(orc.params(substeps=4, iterations=7, damping=1.0), n_frames=3, **sched)
+    m.simulate(orc.params(dt=0.005, substeps=4, iterations=7, damping=1.0), n_frames=2, **sched)
     assert bits_equal(xa, m.x4) and bits_equal(va, m.v4)
 
 
@@ -182,12 +182,12 @@ def test_energy_and_volume_drift_track_the_oracle():
     # BASELINE.json:5: "energy and volume drift must match"; sampled every 10 frames over 100 frames
     pos, tets, tris = meshgen.sample_cube(7, centre_height=0.8, jitter=0.05)
     sb = SoftBody(pos, tets, tris, stiffness=1e5, substeps=5, iterations=4)
-    order, off = sb.schedule()
+    sched = sb.schedule_kw()
     m = orc.Model(pos, tets, roles=sb.tet_roles())
     p = oracle_params(sb)
     for _ in range(10):
         sb.step(frames=10)
-        m.simulate(p, n_frames=10, order=order, batch_off=off)
+        m.simulate(p, n_frames=10, **sched)
         d, r = sb.diagnostics()["raw"], m.diagnostics()
         e_gpu, e_ref = d[0] + d[1], r[0] + r[1]
         assert abs(e_gpu - e_ref) <= 1e-9 * max(1.0, abs(e_ref))
@@ -213,9 +213,9 @@ def test_large_mesh_properties():
     d0 = sb.diagnostics()
     sb.step(frames=2)
     x4, v4 = sb.get_state()
-    order, off = sb.schedule()
+    sched = sb.schedule_kw()
     m = orc.Model(pos, tets, roles=sb.tet_roles())
-    m.simulate(oracle_params(sb), n_frames=2, order=order, batch_off=off, threads=16)
+    m.simulate(oracle_params(sb), n_frames=2, threads=16, **sched)
     assert ulp_diff_count(x4, m.x4) == 0
     sb.step(frames=8)
     d1 = sb.diagnostics()
@@ -223,3 +223,36 @@ def test_large_mesh_properties():
     # 10 sweeps per substep do not converge a 100-layer stack: it compresses a few percent on impact
     assert abs(d1["volume"] - d0["volume"]) / d0["volume"] < 0.05
     assert d1["rms_strain"] < 0.1  # (the bottom cells of the under-converged stack do collapse on impact)
+
+
+@pytest.mark.parametrize("S,I", [(3, 4), (2, 5), (4, 1), (1, 6), (3, 2)])
+@pytest.mark.parametrize("flags", [0, 128, 64, 64 | 128, 16, 4])
+def test_snake_order_and_fused_launches_match_the_oracle(S, I, flags):
+    # default: odd iterations run the passes backwards and consecutive occurrences of a pass share a launch that
+    # also carries the substep boundary (finish + predict on the tile); 128 = no fusion, 64 = no snake,
+    # 16 = no PDL, 4 = no graph.  Every variant is bit-identical to the oracle replaying ITS order, and fusion
+    # never changes a bit.
+    pos, tets, tris = meshgen.block(13, 11, 10, spacing=0.05, origin=(0, 0.001, 0))
+    kw = dict(tile_cap=256, substeps=S, iterations=I, friction=0.3, damping=0.2, stiffness=5e4)
+    sb, m, x4, v4 = run_pair(pos, tets, tris, n_frames=7, spheres=np.array([[0.3, 0.1, 0.25, 0.2]], np.float32), flags=flags, **kw)
+    assert bits_equal(x4, m.x4) and bits_equal(v4, m.v4)  # (ground, a sphere collider inside the block, friction, damping)
+    if flags == 0:
+        other = SoftBody(pos, tets, tris, flags=128, **kw)
+        other.set_colliders(np.array([[0.3, 0.1, 0.25, 0.2]], np.float32))
+        other.step(frames=7)
+        xo, vo = other.get_state()
+        assert bits_equal(x4, xo) and bits_equal(v4, vo)
+        assert len(sb.frame_program()) < len(other.frame_program())
+
+
+def test_a_batch_of_bodies_runs_a_frame_in_one_launch():
+    pos, tets, tris = meshgen.bodies(60, dims=(7, 6, 5), spacing=0.04, base_height=0.01)
+    sb, m, x4, v4 = run_pair(pos, tets, tris, n_frames=8, tile_cap=512, substeps=4, iterations=5, friction=0.2)
+    prog = sb.frame_program()
+    assert len(prog) == 2 and tuple(prog[0]) == (2, 0, 4, 5, 1, 1) and prog[1][0] == 6
+    assert m.x4[:, 1].min() == 0.0 and bits_equal(x4, m.x4) and bits_equal(v4, m.v4)
+    # pinned vertices and a tile without constraints ride through the vertex stages too
+    w = np.asarray(sb.topology()[3]).copy()
+    w[::17] = 0.0
+    sb2, m2, x2, v2 = run_pair(pos, tets, tris, n_frames=5, inv_mass=w, tile_cap=512, substeps=3, iterations=2)
+    assert bits_equal(x2, m2.x4) and bits_equal(v2, m2.v4)

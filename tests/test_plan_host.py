@@ -32,7 +32,7 @@ def test_struct_layouts_match_the_header():
     lib = _abi.load()
     v, a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
     assert lib.sb_abi_check(C.byref(v), C.byref(a), C.byref(b), C.byref(c)) == 0
-    assert (v.value, a.value, b.value) == (2, 48, 112)
+    assert (v.value, a.value, b.value) == (3, 48, 112)
     assert c.value == C.sizeof(_abi.SbInfo)
     assert C.sizeof(orc.OrcParams) == 48  # the oracle takes the same parameter block
     p = _abi.SbParams()
@@ -279,3 +279,91 @@ def test_rounds_stay_near_their_lower_bound():
     # rim merging: a shifted tiling has fewer tiles than its (n + 1)^3 boxes and no tile heavier than a full box
     assert all(t < 216 for t in i["tiles_in_pass"][1:4]) and i["tiles_in_pass"][0] == 125
     assert max(i["max_colours_in_pass"][1:4]) <= i["max_colours_in_pass"][0] + 1
+
+
+# ---- the frame program: snake order and fused launches (host-only handles) ---------------------------------------
+
+def _program(sb):
+    return [tuple(int(v) for v in row) for row in sb.frame_program()]
+
+
+def test_frame_program_fuses_passes_and_carries_the_substep_boundaries():
+    from softbodyunity_b200 import FLAG_NO_FUSE, FLAG_NO_NORMALS, FLAG_NO_SNAKE
+    pos, tets, tris = meshgen.block(14, 12, 11, spacing=0.05)
+    sb = SoftBody(pos, tets, tris, host_only=True, tile_cap=256, substeps=10, iterations=10, flags=FLAG_NO_NORMALS)
+    info = sb.info()
+    assert info["n_tilings"] == 4 and info["n_tile_passes"] == 4 and info["n_global_batches"] == 0
+    prog = _program(sb)
+    # kind 2 = tile pass only: predict / finish ride inside the pass-0 launches
+    assert {p[0] for p in prog} == {2}
+    assert len(prog) == 10 * 30 + 1
+    # every occurrence of every pass is there: substeps x iterations of each
+    for k in range(4):
+        assert sum(p[2] * p[3] for p in prog if p[1] == k) == 100
+    assert prog[0] == (2, 0, 1, 1, 1, 0) and prog[-1] == (2, 0, 1, 1, 0, 1)   # predict before the first, finish after the last
+    assert prog[1:4] == [(2, 1, 1, 1, 0, 0), (2, 2, 1, 1, 0, 0), (2, 3, 1, 2, 0, 0)]  # 0 1 2 (33) 2 1 (00) ...
+    assert sum(1 for p in prog if p[2] == 2) == 9                              # the substep boundaries inside launches
+    # neighbours never repeat a pass (else they would have been fused)
+    assert all(a[1] != b[1] for a, b in zip(prog, prog[1:]))
+    # odd iteration counts end a substep on the last pass: the boundary falls between two launches
+    sb.set_params(iterations=3)
+    prog = _program(sb)
+    kinds = [p[0] for p in prog]
+    # finish is a kernel of its own there (pass 3 is not a contiguous pass), predict rides in the next pass-0 launch
+    assert kinds.count(0) == 0 and kinds.count(1) == 10 and sum(p[4] for p in prog) == 10 and sum(p[5] for p in prog) == 0
+    # no fusion: the classic sequence
+    sb.set_params(iterations=10, flags=FLAG_NO_NORMALS | FLAG_NO_FUSE)
+    prog = _program(sb)
+    assert len(prog) == 10 * 42 and all(p[2:] == (1, 1, 0, 0) for p in prog)
+    seq = [p[1] for p in prog if p[0] == 2][:8]
+    assert seq == [0, 1, 2, 3, 3, 2, 1, 0]
+    sb.set_params(flags=FLAG_NO_NORMALS | FLAG_NO_FUSE | FLAG_NO_SNAKE)
+    assert [p[1] for p in _program(sb) if p[0] == 2][:8] == [0, 1, 2, 3, 0, 1, 2, 3]
+
+
+def test_odd_schedule_is_the_even_one_with_the_passes_reversed():
+    from softbodyunity_b200 import FLAG_NO_SNAKE
+    pos, tets, tris = meshgen.block(14, 12, 11, spacing=0.05)
+    sb = SoftBody(pos, tets, tris, host_only=True, tile_cap=256)
+    (o0, b0), (o1, b1) = sb.schedule(), sb.schedule(odd=True)
+    assert len(o0) == len(o1) and np.array_equal(np.sort(o0), np.sort(o1)) and not np.array_equal(o0, o1)
+    info = sb.info()
+    cons = [int(c) for c in info["constraints_in_pass"][:4]]
+    # blocks of the even order, reversed, are the odd order
+    cuts = np.cumsum([0] + cons)
+    blocks = [o0[cuts[k]:cuts[k + 1]] for k in range(4)]
+    assert np.array_equal(np.concatenate(blocks[::-1]), o1)
+    sb.set_params(flags=FLAG_NO_SNAKE)
+    assert np.array_equal(sb.schedule(odd=True)[0], o0)
+
+
+def test_a_batch_of_small_bodies_is_one_launch_per_frame():
+    from softbodyunity_b200 import FLAG_NO_NORMALS
+    pos, tets, tris = meshgen.bodies(12, dims=(6, 5, 5), spacing=0.04)
+    sb = SoftBody(pos, tets, tris, host_only=True, tile_cap=512, substeps=5, iterations=6, flags=FLAG_NO_NORMALS)
+    assert _program(sb) == [(2, 0, 5, 6, 1, 1)]
+
+
+def test_dist_layout_zones_and_compact_blocks():
+    # ranks as compact blocks (dist_ranks) and the zone property: an interior tile's vertices are touched by tiles of
+    # the same rank only, in every pass
+    pos, tets, tris = meshgen.block(16, 16, 16, spacing=0.05)
+    for n_ranks in (2, 4, 8):
+        sb = SoftBody(pos, tets, tris, host_only=True, dist_ranks=n_ranks, tile_cap=200)
+        n_pass = sb.info()["n_tile_passes"]
+        owned = np.stack([sb.dist_layout(r, n_ranks)[0] for r in range(n_ranks)])
+        assert (owned.sum(0) == 1).all()
+        counts = owned.sum(1)
+        assert counts.max() <= 1.35 * counts.min(), counts  # balanced up to the granularity of a box
+        # compact: a block of a 16^3 cube cut 2 x 2 x 2 has 3 inner faces, a slab of the x-fastest order would have 2 full ones
+        runner = []  # per pass: rank that runs each tile
+        for k in range(n_pass):
+            run_k = np.full(sb.info()["tiles_in_pass"][k], -1)
+            for r in range(n_ranks):
+                run_k[sb.dist_layout(r, n_ranks, k)[1]] = r
+            runner.append(run_k)
+        tile_of = [sb.tiles(k)[0] for k in range(n_pass)]
+        ranks_at = np.stack([np.where(tile_of[k] >= 0, runner[k][np.maximum(tile_of[k], 0)], -1) for k in range(n_pass)])
+        # every rank of a 2-rank split has tiles in every pass (the advisor's empty-pass case is covered by k_dist_bump)
+        mixed = np.array([len(set(c[c >= 0])) > 1 for c in ranks_at.T])
+        assert mixed.any() and not mixed.all()

@@ -20,11 +20,11 @@ for name, (gen, kw) in cases.items():
         k = dict(substeps=1, iterations=1)
         k.update(kw); k.update(extra)
         sb = SoftBody(pos, tets, tris, **k)
-        order, off = sb.schedule()
+        sched = sb.schedule_kw()
         m = orc.Model(pos, tets, roles=sb.tet_roles())
         sb.step(frames=1)
         x4, v4 = sb.get_state()
-        m.simulate(oracle_params(sb), n_frames=1, order=order, batch_off=off, threads=1)
+        m.simulate(oracle_params(sb), n_frames=1, threads=1, **sched)
         badv = np.nonzero((x4.view(np.uint32) != m.x4.view(np.uint32)).any(1))[0]
         msg = f"{name:8s} {label:11s}: {len(badv)} of {len(pos)} vertices differ, max |dx| {np.abs(x4 - m.x4).max():.3e}"
         if len(badv):

@@ -12,15 +12,18 @@ python tools/ab_plan.py --variants "SB_MERGE_RIMS=0 SB_WHOLE_BOXES=0 SB_ATOM_SNA
 python tools/ab_plan.py --bodies 1184 --variants "" > $out/ab_bodies_${tag}.log 2>&1
 # launch list of a short run of the same command (cold-cache, serialised: compare shares)
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/plain_${tag}.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 1400 -c 900 --csv --log-file $out/launches_${tag}.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 1000 -c 700 --csv --log-file $out/launches_${tag}.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/ncu_launch_${tag}.log 2>&1
 python tools/launch_summary.py $out/launches_${tag}.csv $out/${tag}_launches.md > /dev/null
-python tools/profile_step.py > $out/plain2_${tag}.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_tile_rounds -s 8 -c 4 -o $out/prof_${tag} \
-    python tools/profile_step.py > $out/ncu_full_${tag}.log 2>&1
+# one ncu --set full capture of ALL tile launches of one frame of 2 substeps x 10 iterations (61 launches: single, double
+# and substep-boundary ones in the proportions of the bench), second frame
+PS="--substeps 2 --iterations 10 --frames 2 --info-out $out/${tag}_plan_info.json"
+python tools/profile_step.py $PS > $out/plain2_${tag}.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_tile_rounds -s 61 -c 61 -f -o $out/prof_${tag} \
+    python tools/profile_step.py $PS > $out/ncu_full_${tag}.log 2>&1
 tail -2 $out/ncu_full_${tag}.log
 python tools/ncu_summary.py $out/prof_${tag}.ncu-rep $out/${tag}_ncu_tile_rounds.md > /dev/null
-python tools/traffic_json.py $out/prof_${tag}.ncu-rep $out/${tag}_traffic.json "${tag}"
+python tools/traffic_json.py $out/prof_${tag}.ncu-rep $out/${tag}_traffic.json "${tag}" $out/${tag}_plan_info.json
 for f in bench_${tag}.json bench_${tag}_fast.json bench_${tag}_reference.json; do python - $out/$f <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])

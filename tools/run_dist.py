@@ -1,5 +1,5 @@
-"""torchrun entry: ONE block over all ranks through peer memory (sb_dist_*); rank 0 checks the gathered state
-against the CPU oracle replaying the single-GPU order (bitwise) and prints the time per frame.
+"""torchrun entry: ONE block over all ranks through peer memory (sb_dist_*); rank 0 checks the gathered state and the
+surface normals against the CPU oracle replaying the plan's order (bitwise) and prints the time per frame.
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 tools/run_dist.py --dims 40 40 80 --frames 6
 """
 import argparse, os, sys, time
@@ -11,6 +11,11 @@ import torch.distributed as dist
 ap = argparse.ArgumentParser()
 ap.add_argument("--dims", type=int, nargs=3, default=[40, 40, 80])
 ap.add_argument("--frames", type=int, default=6)
+ap.add_argument("--substeps", type=int, default=10)
+ap.add_argument("--iterations", type=int, default=10)
+ap.add_argument("--flags", type=int, default=0)
+ap.add_argument("--tile-cap", type=int, default=0)
+ap.add_argument("--slabs", action="store_true", help="ranks as slabs of the default box order instead of compact blocks")
 ap.add_argument("--no-check", action="store_true")
 a = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
@@ -20,32 +25,31 @@ from softbodyunity_b200 import meshgen
 from softbodyunity_b200.dist import DistBody
 
 pos, tets, tris = meshgen.block(*a.dims, spacing=0.02, origin=(0.0, 0.004, 0.0), seed=5)
-body = DistBody(pos, tets, tris, device=local)
+kw = dict(substeps=a.substeps, iterations=a.iterations, flags=a.flags, tile_cap=a.tile_cap)
+if a.slabs:
+    kw["dist_ranks"] = 0
+body = DistBody(pos, tets, tris, device=local, **kw)
 print(f"[rank {rank}] owns {int(body.owned.sum())} of {len(pos)} vertices, tiles per pass {body.tiles}", flush=True)
 torch.cuda.synchronize(); dist.barrier()
-t0 = time.perf_counter()
-body.step(frames=a.frames)
+body.step(frames=a.frames)          # first call: includes the graph capture
 body.sb.synchronize(); dist.barrier()
-dt = time.perf_counter() - t0
-torch.cuda.synchronize(); dist.barrier()
-t1 = time.perf_counter()
-body.step(frames=a.frames)
-body.sb.synchronize(); dist.barrier()
-dt2 = time.perf_counter() - t1
-if rank == 0:
-    print(f"second call: {1e3 * dt2 / a.frames:.2f} ms/frame", flush=True)
-X, U = body.gather_state()
+ms = body.sb.time_frames(a.frames)  # CUDA events on the solver's stream
+t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+X, U, N = body.gather_state(with_surface=True)
 err = body.sb.dist_error()
 if rank == 0:
-    print(f"world {world}: V={len(pos)} frames={a.frames} {1e3 * dt / a.frames:.2f} ms/frame (first call: includes graph capture)  peer wait timed out: {err}")
+    print(f"world {world}: V={len(pos)} {a.substeps}x{a.iterations} frames={a.frames} {float(t.item()) / a.frames:.3f} ms/frame (device-timed, max over ranks)  "
+          f"launches/frame {body.sb.info()['launches_per_frame']}  peer wait timed out: {err}")
     if not a.no_check:
         from oracle import xpbd_oracle as orc
-        order, off = body.sb.schedule()
         p = body.sb.params
         ref = orc.Model(pos, tets, roles=body.sb.tet_roles())
-        ref.simulate(orc.params(dt=p.dt, substeps=p.substeps, iterations=p.iterations), n_frames=2 * a.frames, order=order, batch_off=off, threads=os.cpu_count())
-        same = np.array_equal(X.view(np.uint32), ref.x4.view(np.uint32)) and np.array_equal(U[:, :3].view(np.uint32), ref.v4[:, :3].view(np.uint32))
-        print("bit-identical to the CPU oracle (single-GPU order):", same, " min y", float(X[:, 1].min()))
+        ref.simulate(orc.params(dt=p.dt, substeps=p.substeps, iterations=p.iterations), n_frames=2 * a.frames, threads=os.cpu_count(), **body.sb.schedule_kw())
+        ids = body.sb.surface_vertices()
+        same = (np.array_equal(X.view(np.uint32), ref.x4.view(np.uint32)) and np.array_equal(U[:, :3].view(np.uint32), ref.v4[:, :3].view(np.uint32))
+                and np.array_equal(N[ids].view(np.uint32), ref.normals(tris)[ids].view(np.uint32)))
+        print("bit-identical to the CPU oracle (state and surface normals):", same, " min y", float(X[:, 1].min()))
         if not same:
             print("max |dx|", float(np.abs(X[:, :3] - ref.x4[:, :3]).max()))
 dist.destroy_process_group()

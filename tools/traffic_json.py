@@ -1,5 +1,5 @@
 """DRAM bytes and duration per launch from an .ncu-rep -> profiles/<tag>_traffic.json (read by bench.py).
-Usage: traffic_json.py <rep> <out.json> [note]"""
+Usage: traffic_json.py <rep> <out.json> [note] [plan-info.json written by profile_step.py --info-out]"""
 import csv, io, json, subprocess, sys
 rep, out = sys.argv[1], sys.argv[2]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -13,6 +13,10 @@ def val(r, key):
 launches = [{"kernel": r[ix["Kernel Name"]][:60], "grid": r[ix["launch__grid_size"]],
              "dram_read_bytes": val(r, "dram__bytes_read.sum"), "dram_write_bytes": val(r, "dram__bytes_write.sum"),
              "duration_us": val(r, "gpu__time_duration.sum")} for r in data]
-json.dump({"source": "ncu --set full --clock-control none, tools/profile_step.py (1 M block in ground contact, 2nd frame)"
-                     + (", " + sys.argv[3] if len(sys.argv) > 3 else ""), "launches": launches}, open(out, "w"), indent=1)
+doc = {"source": "ncu --set full --clock-control none, tools/profile_step.py (1 M block in ground contact, 2nd frame)"
+                 + (", " + sys.argv[3] if len(sys.argv) > 3 else ""), "launches": launches}
+if len(sys.argv) > 4:
+    plan = json.load(open(sys.argv[4]))
+    doc.update(rounds_per_sweep=plan["rounds_per_sweep"], tiles_in_pass=plan["tiles_in_pass"], substeps=plan["substeps"], iterations=plan["iterations"])
+json.dump(doc, open(out, "w"), indent=1)
 print(json.dumps(launches[0]))
