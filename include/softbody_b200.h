@@ -104,8 +104,10 @@ typedef struct sb_mesh_desc {
   int32_t block_threads;    /* threads per tile CTA (32, 64, 128 or 256); 0 = auto per pass */
   int32_t later_tile_cap;   /* max vertices per tile in passes after the first; 0 = auto */
   int32_t host_threads;     /* threads for the host-side build; 0 = auto */
-  int32_t round_width;      /* 16-byte constraint-record words per thread per round (1 or 2): a round = one colour of
-                               2 * width * block_threads edges or width * block_threads tets; 0 = auto (1) */
+  int32_t round_width;      /* 16-byte constraint-record words per thread per round: a round = one colour of 2 * width *
+                               block_threads free edges or of block_threads compounds.  1: a compound is one tet with its
+                               attached edges; 2: a bi-tet, two tets that share a face with up to four attached edges
+                               (sb_get_tet_mates).  0 = auto: 2, except for one rank of a partition with ghosts (1) */
   int32_t attach_edges;     /* 0 = auto, 1 = on, 2 = off: project each edge right after a tet that contains it, from the
                                registers holding the tet's vertices (the tet's vertex ROLES are then an even permutation
                                of the caller's order, see sb_get_tet_roles).  Auto: on */
@@ -263,6 +265,13 @@ int sb_get_info(sb_handle h, sb_info *out);
  * Identity / -1 when attach_edges is off.  Any pointer may be NULL.
  */
 int sb_get_tet_roles(sb_handle h, int32_t *tets_4T, int32_t *edge01_T, int32_t *edge23_T);
+/*
+ * Bi-tets (round_width 2, the default): tets are projected in pairs that share a face, by one thread that keeps the
+ * shared vertices in registers.  mate_T[t] = the tet paired with t or -1; lead_T[t] = 1 for a single tet or the first
+ * tet of a pair (projected first, with its attached edges; then its mate with its own).  The roles of a pair are
+ * A = (a, s0, s1, s2), B = (b, s1, s0, s2).  Either pointer may be NULL.
+ */
+int sb_get_tet_mates(sb_handle h, int32_t *mate_T, int32_t *lead_T);
 
 /* Derived topology in the caller's numbering (any pointer may be NULL). */
 int sb_get_topology(sb_handle h, int32_t *edges_2E, float *rest_len_E, float *rest_vol6_T, float *inv_mass_V);

@@ -21,7 +21,7 @@ EXPORTS = [
     "sb_get_params", "sb_set_colliders", "sb_set_colliders_ex", "sb_step", "sb_synchronize", "sb_read_positions",
     "sb_read_normals", "sb_surface_vertices", "sb_read_surface", "sb_get_state", "sb_set_state",
     "sb_packed_sizes", "sb_read_packed", "sb_write_packed",
-    "sb_diagnostics", "sb_get_info", "sb_get_topology", "sb_get_tet_roles", "sb_get_schedule", "sb_get_schedule_odd", "sb_frame_program", "sb_get_tiles",
+    "sb_diagnostics", "sb_get_info", "sb_get_topology", "sb_get_tet_roles", "sb_get_tet_mates", "sb_get_schedule", "sb_get_schedule_odd", "sb_frame_program", "sb_get_tiles",
     "sb_time_frames", "sb_time_kernel", "sb_debug_trace_pass", "sb_debug_verify_streams", "sb_last_error",
     "sb_set_stream", "sb_prepare", "sb_enqueue", "sb_halo_set", "sb_halo_pack", "sb_halo_unpack", "sb_lumped_inv_mass",
     "sb_halo_alloc", "sb_halo_connect", "sb_halo_error", "sb_ipc_export", "sb_ipc_open",
@@ -129,6 +129,7 @@ def load():
         "sb_time_kernel": (C.c_int, [vp, i32, i32, P(f32)]),
         "sb_debug_trace_pass": (C.c_int, [vp, u32, vp, u32]),
         "sb_get_tet_roles": (C.c_int, [vp, vp, vp, vp]),
+        "sb_get_tet_mates": (C.c_int, [vp, vp, vp]),
         "sb_debug_verify_streams": (C.c_int, [vp, vp, vp, vp]),
         "sb_last_error": (C.c_char_p, [vp]),
         "sb_set_stream": (C.c_int, [vp, vp]),

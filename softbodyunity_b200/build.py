@@ -28,16 +28,31 @@ def stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles the library if it is stale.  Safe with several processes at once (torchrun: every rank imports the
+    package): one of them builds under a file lock, into a temporary file that is renamed into place; the others wait
+    for the lock and find the library fresh."""
     if not force and not stale():
         return LIB
-    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lpthread"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libsoftbody_b200.so")
-    if verbose:
-        sys.stderr.write(r.stdout + r.stderr)
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not stale():
+                return LIB  # another process built it while this one waited
+            tmp = f"{LIB}.tmp.{os.getpid()}"
+            cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+                ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lpthread"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("nvcc failed building libsoftbody_b200.so")
+            os.replace(tmp, LIB)
+            if verbose:
+                sys.stderr.write(r.stdout + r.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

@@ -169,6 +169,8 @@ void attach_edges(Plan &P, bool enable) {
   P.tet_e23.assign(T, -1);
   P.edge_owner.assign(E, -1);
   P.edges_attached = 0;
+  P.tet_mate.assign(T, -1);
+  P.tet_lead.assign(T, 1);
   if (!enable || !T || !E) return;
   // first edge of every vertex a in the sorted list (a < b)
   std::vector<uint32_t> first((size_t)P.V + 1, 0);
@@ -328,6 +330,278 @@ void attach_edges(Plan &P, bool enable) {
     if (inversions & 1) std::swap(perm[0], perm[1]);
     for (int j = 0; j < 4; j++) P.tet_roles[4 * (size_t)t + j] = P.tets[4 * (size_t)t + perm[j]];
     P.edges_attached += 1 + (pair23[t] >= 0);
+  }
+}
+
+// ---- bi-tets ---------------------------------------------------------------------------------------------
+//
+// Two tets that share a face have five vertices between them.  A thread that projects both keeps the three shared
+// vertices in registers: 5 loads + 5 stores of shared memory for two tets instead of 8 + 8, half the records, rounds
+// and barriers.  The pair is one COMPOUND: tet A = (a, s0, s1, s2), tet B = (b, s1, s0, s2) -- the apex first, the
+// shared face in the cyclic order that makes both an even permutation of the caller's tets (A and B lie on opposite
+// sides of the face, hence the swap) -- and up to four edges ride along, between the roles (0,1) and (2,3) of each:
+//   A: (a, s0) and (s1, s2)      B: (b, s1) and (s0, s2)
+// Rotating the face (s0 -> s1 -> s2 -> s0) keeps the parities, so a pair offers three such slot sets and the
+// attachment below picks the rotation that fits the edges it wants to place.  The kernel projects A, its edges, B,
+// its edges, in this order; the exported schedule says the same.
+//
+// tet_mate[t] = partner or -1; tet_lead[t] = 1 for a single tet or the A of a pair, 0 for a B.
+void pair_and_attach(Plan &P, int threads, bool attach) {
+  static const int pr[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+  const uint32_t T = P.T, E = P.E, V = P.V;
+  P.tet_roles = P.tets;
+  P.tet_e01.assign(T, -1);
+  P.tet_e23.assign(T, -1);
+  P.edge_owner.assign(E, -1);
+  P.edges_attached = 0;
+  P.tet_mate.assign(T, -1);
+  P.tet_lead.assign(T, 1);
+  if (!T) return;
+  // ---- face neighbours through the tets around each tet's vertices ----
+  std::vector<uint32_t> voff((size_t)V + 1, 0), vt(4 * (size_t)T);
+  for (size_t i = 0; i < 4 * (size_t)T; i++) voff[(size_t)P.tets[i] + 1]++;
+  for (uint32_t v = 0; v < V; v++) voff[v + 1] += voff[v];
+  {
+    std::vector<uint32_t> cur(voff.begin(), voff.end() - 1);
+    for (uint32_t t = 0; t < T; t++)
+      for (int j = 0; j < 4; j++) vt[cur[P.tets[4 * (size_t)t + j]]++] = t; // ascending tet id per vertex
+  }
+  std::vector<int32_t> nb(4 * (size_t)T, -1); // nb[4 t + j] = the tet across the face opposite vertex j
+  parallel_for(T, threads, 4096, [&](size_t t, int) {
+    const int32_t *q = &P.tets[4 * t];
+    for (int j = 0; j < 4; j++) {
+      const int32_t x = q[(j + 1) & 3], y = q[(j + 2) & 3], z = q[(j + 3) & 3];
+      for (uint32_t k = voff[x]; k < voff[(size_t)x + 1]; k++) {
+        const uint32_t u = vt[k];
+        if (u == t) continue;
+        const int32_t *r = &P.tets[4 * (size_t)u];
+        const bool hy = r[0] == y || r[1] == y || r[2] == y || r[3] == y;
+        const bool hz = r[0] == z || r[1] == z || r[2] == z || r[3] == z;
+        if (hy && hz) { nb[4 * t + j] = (int32_t)u; break; }
+      }
+    }
+  });
+  vt = std::vector<uint32_t>();
+  // The pair pattern for (A = t, apex index ja; B = u): the shared face in the cyclic order that makes (a, s0, s1, s2)
+  // an even permutation of A; usable when (b, s1, s0, s2) is then an even permutation of B (always, in a
+  // consistently oriented mesh).
+  auto pattern = [&](uint32_t t, int ja, uint32_t u, int32_t *out5) -> bool { // out5 = a, s0, s1, s2, b
+    const int32_t *q = &P.tets[4 * (size_t)t], *r = &P.tets[4 * (size_t)u];
+    int32_t s[3];
+    int n = 0;
+    for (int j = 0; j < 4; j++)
+      if (j != ja) s[n++] = q[j];
+    if (ja & 1) std::swap(s[1], s[2]); // moving the apex to the front is ja transpositions
+    int jb = -1;
+    for (int j = 0; j < 4; j++)
+      if (r[j] != s[0] && r[j] != s[1] && r[j] != s[2]) jb = jb < 0 ? j : 4;
+    if (jb < 0 || jb > 3) return false;
+    const int32_t want[4] = {r[jb], s[1], s[0], s[2]};
+    int idx[4];
+    for (int k = 0; k < 4; k++) {
+      idx[k] = -1;
+      for (int j = 0; j < 4; j++)
+        if (r[j] == want[k]) idx[k] = j;
+      if (idx[k] < 0) return false;
+    }
+    int inv = 0;
+    for (int x = 0; x < 4; x++)
+      for (int y = x + 1; y < 4; y++) inv += idx[x] > idx[y];
+    if (inv & 1) return false;
+    out5[0] = q[ja]; out5[1] = s[0]; out5[2] = s[1]; out5[3] = s[2]; out5[4] = r[jb];
+    return true;
+  };
+  // ---- greedy matching on the face-adjacency graph: a tet takes the free neighbour that has the fewest free
+  // neighbours itself (ties: the lowest id); sequential, hence independent of the thread count ----
+  static const int pairs_on = getenv("SB_BITETS") ? atoi(getenv("SB_BITETS")) : 1;
+  std::vector<int8_t> apex_of(T, -1); // for a leader with a mate: index of its apex in the caller's tet
+  if (pairs_on && !P.n_ghost) {
+    auto free_deg = [&](uint32_t u) {
+      int d = 0;
+      for (int j = 0; j < 4; j++) d += nb[4 * (size_t)u + j] >= 0 && P.tet_mate[nb[4 * (size_t)u + j]] < 0;
+      return d;
+    };
+    for (uint32_t t = 0; t < T; t++) {
+      if (P.tet_mate[t] >= 0) continue;
+      int best_j = -1, best_d = 99;
+      for (int j = 0; j < 4; j++) {
+        const int32_t u = nb[4 * (size_t)t + j];
+        if (u < 0 || P.tet_mate[u] >= 0) continue;
+        int32_t five[5];
+        if (!pattern(t, j, (uint32_t)u, five)) continue;
+        const int d = free_deg((uint32_t)u);
+        if (d < best_d || (d == best_d && u < nb[4 * (size_t)t + best_j])) { best_d = d; best_j = j; }
+      }
+      if (best_j < 0) continue;
+      const uint32_t u = (uint32_t)nb[4 * (size_t)t + best_j];
+      P.tet_mate[t] = (int32_t)u;
+      P.tet_mate[u] = (int32_t)t;
+      P.tet_lead[u] = 0;
+      apex_of[t] = (int8_t)best_j;
+    }
+  }
+  nb = std::vector<int32_t>();
+  for (uint32_t t = 0; t < T; t++) P.tets_paired += P.tet_mate[t] >= 0;
+  // ---- edges -> compounds ----
+  std::vector<uint32_t> first((size_t)V + 1, 0);
+  for (uint32_t e = 0; e < E; e++) first[(size_t)P.edges[2 * (size_t)e] + 1]++;
+  for (uint32_t v = 0; v < V; v++) first[v + 1] += first[v];
+  auto edge_id = [&](int32_t a, int32_t b) -> int32_t {
+    if (a > b) std::swap(a, b);
+    uint32_t lo = first[a], hi = first[(size_t)a + 1];
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) / 2;
+      if (P.edges[2 * (size_t)mid + 1] < b) lo = mid + 1;
+      else hi = mid;
+    }
+    return lo < first[(size_t)a + 1] && P.edges[2 * (size_t)lo + 1] == b ? (int32_t)lo : -1;
+  };
+  // local edges of an owner (a leader): single tet: its six vertex pairs; pair: 0..2 (a, s_j), 3..5 (b, s_j),
+  // 6..8 the face edge opposite s_j
+  auto local_edges = [&](uint32_t t, int32_t (*ab)[2]) -> int {
+    if (P.tet_mate[t] < 0) {
+      for (int k = 0; k < 6; k++) { ab[k][0] = P.tets[4 * (size_t)t + pr[k][0]]; ab[k][1] = P.tets[4 * (size_t)t + pr[k][1]]; }
+      return 6;
+    }
+    int32_t f[5];
+    pattern(t, apex_of[t], (uint32_t)P.tet_mate[t], f);
+    for (int j = 0; j < 3; j++) {
+      ab[j][0] = f[0]; ab[j][1] = f[1 + j];
+      ab[3 + j][0] = f[4]; ab[3 + j][1] = f[1 + j];
+      ab[6 + j][0] = f[1 + (j + 1) % 3]; ab[6 + j][1] = f[1 + (j + 2) % 3];
+    }
+    return 9;
+  };
+  // slot sets: a compound may hold any subset of ONE of its options
+  static const uint16_t opt_single[3] = {(1 << 0) | (1 << 5), (1 << 1) | (1 << 4), (1 << 2) | (1 << 3)};
+  uint16_t opt_pair[3];
+  for (int i = 0; i < 3; i++) opt_pair[i] = (uint16_t)((1 << i) | (1 << (3 + (i + 1) % 3)) | (1 << (6 + i)) | (1 << (6 + (i + 1) % 3)));
+  auto feasible = [&](uint32_t t, uint16_t mask) {
+    const uint16_t *o = P.tet_mate[t] < 0 ? opt_single : opt_pair;
+    return (mask & ~o[0]) == 0 || (mask & ~o[1]) == 0 || (mask & ~o[2]) == 0;
+  };
+  // incidence: edge -> (owner, local edge)
+  std::vector<uint32_t> ioff((size_t)E + 1, 0);
+  for (uint32_t t = 0; t < T && attach; t++) {
+    if (!P.tet_lead[t]) continue;
+    int32_t ab[9][2];
+    const int n = local_edges(t, ab);
+    for (int k = 0; k < n; k++) {
+      const int32_t e = edge_id(ab[k][0], ab[k][1]);
+      if (e >= 0) ioff[(size_t)e + 1]++;
+    }
+  }
+  uint32_t max_inc = 0;
+  for (uint32_t e = 0; e < E; e++) {
+    max_inc = std::max(max_inc, ioff[e + 1]);
+    ioff[e + 1] += ioff[e];
+  }
+  std::vector<uint64_t> inc(ioff[E]); // owner * 16 + local edge
+  {
+    std::vector<uint32_t> cur(ioff.begin(), ioff.end() - 1);
+    for (uint32_t t = 0; t < T && attach; t++) {
+      if (!P.tet_lead[t]) continue;
+      int32_t ab[9][2];
+      const int n = local_edges(t, ab);
+      for (int k = 0; k < n; k++) {
+        const int32_t e = edge_id(ab[k][0], ab[k][1]);
+        if (e >= 0) inc[cur[e]++] = (uint64_t)t * 16u + (uint32_t)k;
+      }
+    }
+  }
+  std::vector<uint32_t> by_inc(E);
+  {
+    std::vector<uint32_t> cnt((size_t)max_inc + 2, 0);
+    for (uint32_t e = 0; e < E; e++) cnt[(size_t)(ioff[e + 1] - ioff[e]) + 1]++;
+    for (uint32_t k = 0; k <= max_inc; k++) cnt[k + 1] += cnt[k];
+    for (uint32_t e = 0; e < E; e++) by_inc[cnt[ioff[e + 1] - ioff[e]]++] = e;
+  }
+  std::vector<uint16_t> taken(T, 0);
+  std::vector<int8_t> slot_of(E, -1); // local edge the edge occupies in its owner (edge_owner = the LEADER here)
+  auto put = [&](uint32_t e, uint32_t t, int l) { taken[t] |= (uint16_t)(1u << l); P.edge_owner[e] = (int32_t)t; slot_of[e] = (int8_t)l; };
+  auto drop = [&](uint32_t e) { taken[P.edge_owner[e]] &= (uint16_t)~(1u << slot_of[e]); P.edge_owner[e] = -1; slot_of[e] = -1; };
+  static const int augment = getenv("SB_ATTACH_AUGMENT") ? atoi(getenv("SB_ATTACH_AUGMENT")) : 1;
+  // Put edge e into a compound other than `not_t`: where it fits as things are, else (depth > 0) in the place of an
+  // occupant that can itself move elsewhere (an augmenting path in the edge -> slot matching, depth first).
+  std::function<bool(uint32_t, uint32_t, int)> place = [&](uint32_t e, uint32_t not_t, int depth) -> bool {
+    for (uint32_t k = ioff[e]; k < ioff[e + 1]; k++) {
+      const uint32_t t = (uint32_t)(inc[k] >> 4);
+      const int l = (int)(inc[k] & 15);
+      if (t == not_t) continue;
+      if (feasible(t, (uint16_t)(taken[t] | (1u << l)))) { put(e, t, l); return true; }
+    }
+    if (depth <= 0) return false;
+    for (uint32_t k = ioff[e]; k < ioff[e + 1]; k++) {
+      const uint32_t t = (uint32_t)(inc[k] >> 4);
+      const int l = (int)(inc[k] & 15);
+      if (t == not_t) continue;
+      int32_t ab[9][2];
+      const int n = local_edges(t, ab);
+      for (int l1 = 0; l1 < n; l1++) {
+        if (!(taken[t] >> l1 & 1)) continue;
+        if (!feasible(t, (uint16_t)((taken[t] & ~(1u << l1)) | (1u << l)))) continue;
+        const int32_t e1 = edge_id(ab[l1][0], ab[l1][1]);
+        drop((uint32_t)e1);
+        put(e, t, l); // (so that e1 cannot come back here)
+        if (place((uint32_t)e1, t, depth - 1)) return true;
+        drop(e);
+        put((uint32_t)e1, t, l1);
+      }
+    }
+    return false;
+  };
+  for (uint32_t oi = 0; oi < E && attach; oi++) place(by_inc[oi], 0xffffffffu, 0);
+  if (augment && attach)
+    for (uint32_t oi = 0; oi < E; oi++)
+      if (P.edge_owner[by_inc[oi]] < 0) place(by_inc[oi], 0xffffffffu, augment);
+  // ---- roles and attached edges per tet ----
+  for (uint32_t t = 0; t < T; t++) {
+    if (!P.tet_lead[t]) continue;
+    int32_t ab[9][2];
+    const int n = local_edges(t, ab);
+    auto held = [&](int l) -> int32_t { return (taken[t] >> l & 1) ? edge_id(ab[l][0], ab[l][1]) : -1; };
+    if (P.tet_mate[t] < 0) {
+      if (!taken[t]) continue;
+      int k0 = -1;
+      for (int k = 0; k < 6 && k0 < 0; k++)
+        if (taken[t] >> k & 1) k0 = k;
+      // roles: (a, b, c, d) with (a, b) the first attached edge and (c, d) the other two vertices in their
+      // original relative order; if that permutation is odd, swap a and b
+      const int i0 = pr[k0][0], i1 = pr[k0][1];
+      int perm[4] = {i0, i1, -1, -1};
+      int at = 2;
+      for (int j = 0; j < 4; j++)
+        if (j != i0 && j != i1) perm[at++] = j;
+      int inversions = 0;
+      for (int x = 0; x < 4; x++)
+        for (int y = x + 1; y < 4; y++) inversions += perm[x] > perm[y];
+      if (inversions & 1) std::swap(perm[0], perm[1]);
+      for (int j = 0; j < 4; j++) P.tet_roles[4 * (size_t)t + j] = P.tets[4 * (size_t)t + perm[j]];
+      P.tet_e01[t] = held(k0);
+      P.tet_e23[t] = held(5 - k0);
+      (void)n;
+    } else {
+      const uint32_t u = (uint32_t)P.tet_mate[t];
+      int rot = 0;
+      for (int i = 2; i >= 0; i--)
+        if ((taken[t] & ~opt_pair[i]) == 0) rot = i;
+      int32_t f[5];
+      pattern(t, apex_of[t], u, f);
+      const int32_t s0 = f[1 + rot], s1 = f[1 + (rot + 1) % 3], s2 = f[1 + (rot + 2) % 3];
+      int32_t *ra = &P.tet_roles[4 * (size_t)t], *rb = &P.tet_roles[4 * (size_t)u];
+      ra[0] = f[0]; ra[1] = s0; ra[2] = s1; ra[3] = s2;
+      rb[0] = f[4]; rb[1] = s1; rb[2] = s0; rb[3] = s2;
+      P.tet_e01[t] = held(rot);                    // (a, s0)
+      P.tet_e23[t] = held(6 + rot);                // (s1, s2): the face edge opposite s0
+      P.tet_e01[u] = held(3 + (rot + 1) % 3);      // (b, s1)
+      P.tet_e23[u] = held(6 + (rot + 1) % 3);      // (s0, s2): the face edge opposite s1
+    }
+  }
+  // edge_owner: the tet whose roles carry the edge
+  for (uint32_t e = 0; e < E; e++) P.edge_owner[e] = -1;
+  for (uint32_t t = 0; t < T; t++) {
+    if (P.tet_e01[t] >= 0) { P.edge_owner[P.tet_e01[t]] = (int32_t)t; P.edges_attached++; }
+    if (P.tet_e23[t] >= 0) { P.edge_owner[P.tet_e23[t]] = (int32_t)t; P.edges_attached++; }
   }
 }
 
@@ -634,7 +908,7 @@ struct TileOut {
   uint32_t n_ecol = 0, n_tcol = 0, n_verts = 0;
   std::vector<uint32_t> stream;  // words: edge rounds, then tet rounds
   std::vector<float> aux;        // per tet round
-  std::vector<uint8_t> has01, has23; // per tet colour
+  std::vector<uint8_t> flags;        // per tet colour: bit 0 some (0,1) edge attached, 1 some (2,3) edge, 2 some mate, 3 / 4 some edge of a mate
   std::vector<int32_t> ents;     // processing order
   std::vector<uint32_t> col_cnt; // per colour, edge colours first
   uint64_t n_edges = 0, n_tets = 0;
@@ -644,9 +918,10 @@ struct TileOut {
 struct DevTopo {
   std::vector<int32_t> edges; // 2E device ids, roles (a,b) as in the canonical list
   std::vector<int32_t> tets;  // 4T device ids, roles as given
+  std::vector<int32_t> apex;  // T: for the first tet of a bi-tet, the device id of its mate's apex (the fifth vertex), else -1
 };
 
-inline int ent_verts(const DevTopo &D, int32_t ent, int32_t *vs) {
+inline int ent_verts(const DevTopo &D, int32_t ent, int32_t *vs, bool with_mate = true) {
   if (ent >= 0) {
     vs[0] = D.edges[2 * (size_t)ent];
     vs[1] = D.edges[2 * (size_t)ent + 1];
@@ -654,6 +929,10 @@ inline int ent_verts(const DevTopo &D, int32_t ent, int32_t *vs) {
   }
   const int32_t *q = &D.tets[4 * (size_t)(ent & 0x7fffffff)];
   vs[0] = q[0]; vs[1] = q[1]; vs[2] = q[2]; vs[3] = q[3];
+  if (with_mate && !D.apex.empty() && D.apex[ent & 0x7fffffff] >= 0) { // a bi-tet: the mate rides with its leader
+    vs[4] = D.apex[ent & 0x7fffffff];
+    return 5;
+  }
   return 4;
 }
 
@@ -667,7 +946,7 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
   std::vector<uint64_t> toff((size_t)n_tiles + 1, 0);
   std::vector<int32_t> owner(in.size());
   parallel_for(in.size(), threads, 1 << 16, [&](size_t i, int) {
-    int32_t vs[4];
+    int32_t vs[5];
     int n = ent_verts(D, in[i], vs);
     int32_t p = part[vs[0]];
     for (int k = 1; k < n; k++)
@@ -694,10 +973,17 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
   uint32_t bt = bt_opt;
   if (!bt) { // by the fullest tile: partial tiles at the rim of a tiling must not talk the pass into narrow CTAs
     uint64_t per_tile = 0;
-    for (uint32_t t = 0; t < n_tiles; t++) per_tile = std::max<uint64_t>(per_tile, toff[t + 1] - toff[t]);
-    bt = per_tile < 1600 * width ? 64u : per_tile < 6400 * width ? 128u : 256u;
+    for (uint32_t t = 0; t < n_tiles; t++) {
+      uint64_t w = 0; // in single constraints: a bi-tet counts as two tets
+      for (uint64_t i = toff[t]; i < toff[t + 1]; i++) w += (tent[i] < 0 && !D.apex.empty() && D.apex[tent[i] & 0x7fffffff] >= 0) ? 2 : 1;
+      per_tile = std::max<uint64_t>(per_tile, w);
+    }
+    bt = per_tile < 1600 ? 64u : per_tile < 6400 ? 128u : 256u;
   }
-  const uint32_t cap_e = 2 * width * bt, cap_t = width * bt;
+  // a round: 2 * width * bt free edges, or bt compounds (width 1: a tet with its attached edges in one 16-byte
+  // word; width 2: a bi-tet -- or a single tet -- with its attached edges in two words)
+  const uint32_t cap_e = 2 * width * bt, cap_t = bt;
+  const bool bitet = width == 2;
 
   // A tile of a shifted tiling stages ALL the vertices of its boxes, not only those its constraints of this pass
   // touch: a vertex whose constraints all went to other tilings would otherwise split a run of device ids in two
@@ -735,7 +1021,7 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
         if (ne) O.verts.assign(mem_list.begin() + mem_off[t], mem_list.begin() + mem_off[t + 1]);
       } else {
         for (size_t i = 0; i < ne; i++) {
-          int32_t vs[4];
+          int32_t vs[5];
           int n = ent_verts(D, ents[i], vs);
           for (int k = 0; k < n; k++)
             if (loc[vs[k]] == 0xffffffffu) {
@@ -779,7 +1065,7 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
     {
       std::vector<uint32_t> val((size_t)nv * 2, 0);
       for (size_t i = 0; i < ne; i++) {
-        int32_t vs[4];
+        int32_t vs[5];
         const int n = ent_verts(D, ents[i], vs);
         for (int k = 0; k < n; k++) val[(size_t)local(vs[k]) * 2 + (ents[i] < 0)]++;
       }
@@ -805,7 +1091,7 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
       }
       for (size_t oi = 0; oi < ne; oi++) {
         const size_t i = cord[oi];
-        int32_t vs[4];
+        int32_t vs[5];
         const int n = ent_verts(D, ents[i], vs);
         const int kind = ents[i] < 0;
         const size_t W = words[kind];
@@ -869,20 +1155,20 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
       std::vector<uint32_t> owner((size_t)nv * K, NONE); // who holds colour c at local vertex v
       std::vector<std::vector<uint32_t>> members(K);
       auto verts_of = [&](uint32_t i, uint32_t *lv) {
-        int32_t vs[4];
+        int32_t vs[5];
         const int n = ent_verts(D, ents[i], vs);
         for (int k = 0; k < n; k++) lv[k] = local(vs[k]);
         return n;
       };
       for (size_t i = 0; i < ne; i++) {
         if ((ents[i] < 0) != (kind != 0)) continue;
-        uint32_t lv[4];
+        uint32_t lv[5];
         const int n = verts_of((uint32_t)i, lv);
         for (int k = 0; k < n; k++) owner[(size_t)lv[k] * K + col[i]] = (uint32_t)i;
         members[col[i]].push_back((uint32_t)i);
       }
       auto move = [&](uint32_t i, uint32_t to) {
-        uint32_t lv[4];
+        uint32_t lv[5];
         const int n = verts_of(i, lv);
         for (int k = 0; k < n; k++) { owner[(size_t)lv[k] * K + col[i]] = NONE; owner[(size_t)lv[k] * K + to] = i; }
         --cnt[col[i]];
@@ -891,7 +1177,7 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
       };
       // conflicts of member i in colour c: distinct holders of c at i's vertices, ignoring `skip`; returns count (<= 4)
       auto conflicts = [&](uint32_t i, uint32_t c, uint32_t skip, uint32_t *out) {
-        uint32_t lv[4];
+        uint32_t lv[5];
         const int n = verts_of(i, lv);
         int m = 0;
         for (int k = 0; k < n; k++) {
@@ -923,7 +1209,7 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
         for (uint32_t i : members[src])
           if (col[i] == src) todo.push_back(i);
         for (uint32_t i : todo) {
-          uint32_t cf[4];
+          uint32_t cf[5];
           bool done = false;
           for (uint32_t c = 0; c < K && !done; c++) { // a free seat
             if (closed[c] || cnt[c] >= hard) continue;
@@ -935,7 +1221,7 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
             const uint32_t x = cf[0];
             for (uint32_t c2 = 0; c2 < K && !done; c2++) {
               if (c2 == c || closed[c2] || cnt[c2] >= hard) continue;
-              uint32_t cf2[4];
+              uint32_t cf2[5];
               if (conflicts(x, c2, NONE, cf2) != 0) continue;
               move(x, c2); members[c2].push_back(x);
               move(i, c); members[c].push_back(i);
@@ -948,7 +1234,7 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
             const uint32_t x = cf[0], y = cf[1];
             uint32_t cx = NONE;
             for (uint32_t c2 = 0; c2 < K && cx == NONE; c2++) {
-              uint32_t cf2[4];
+              uint32_t cf2[5];
               if (c2 != c && !closed[c2] && cnt[c2] < hard && conflicts(x, c2, NONE, cf2) == 0) cx = c2;
             }
             if (cx == NONE) continue;
@@ -956,7 +1242,7 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
             move(x, cx); // y must not collide with x in its new colour: evaluated after x has moved
             uint32_t cy = NONE;
             for (uint32_t c2 = 0; c2 < K && cy == NONE; c2++) {
-              uint32_t cf2[4];
+              uint32_t cf2[5];
               if (c2 != c && !closed[c2] && cnt[c2] < hard && conflicts(y, c2, NONE, cf2) == 0) cy = c2;
             }
             if (cy == NONE) { move(x, from); continue; }
@@ -986,7 +1272,7 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
     if (getenv("SB_PLAN_STATS")) { // debug: rounds against the lower bounds (capacity, valence)
       std::vector<uint32_t> val((size_t)nv * 2, 0);
       for (size_t i = 0; i < ne; i++) {
-        int32_t vs[4];
+        int32_t vs[5];
         const int n = ent_verts(D, ents[i], vs);
         for (int k = 0; k < n; k++) val[(size_t)local(vs[k]) * 2 + (ents[i] < 0)]++;
       }
@@ -1029,32 +1315,36 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
       for (uint32_t c = 0; c < ncol; c++) {
         const uint32_t lo = coff[c], n = coff[c + 1] - coff[c];
         const bool tet = c >= O.n_ecol;
-        const int nvs = tet ? 4 : 2;
-        auto second_edge = [&](int32_t e) { return tet && P.tet_e23[e & 0x7fffffff] >= 0; };
+        const int nvs = tet ? (bitet ? 5 : 4) : 2;
+        // first class: compounds that run the longer code (a mate; else a second attached edge), so that the warps
+        // behind them skip it
+        auto second_edge = [&](int32_t e) {
+          return tet && (bitet ? P.tet_mate[e & 0x7fffffff] >= 0 : P.tet_e23[e & 0x7fffffff] >= 0);
+        };
         if (tet) std::stable_partition(O.ents.begin() + lo, O.ents.begin() + lo + n, second_edge);
         if (n < 16) continue;
-        std::vector<uint8_t> res((size_t)n * 4);
+        std::vector<uint8_t> res((size_t)n * 5, 8); // bank group (local id mod 8) per vertex slot; 8 = no such vertex
         for (uint32_t k = 0; k < n; k++) {
-          int32_t vs[4];
-          ent_verts(D, O.ents[lo + k], vs);
-          for (int j = 0; j < nvs; j++) res[(size_t)k * 4 + j] = (uint8_t)(local(vs[j]) & 7u);
+          int32_t vs[5];
+          const int nv_k = ent_verts(D, O.ents[lo + k], vs);
+          for (int j = 0; j < nv_k; j++) res[(size_t)k * 5 + j] = (uint8_t)(local(vs[j]) & 7u);
         }
         uint32_t n_first = 0;
         while (n_first < n && second_edge(O.ents[lo + n_first])) n_first++;
         tmp.clear();
         tmp.reserve(n);
         cls.clear();
-        uint8_t used[4] = {0, 0, 0, 0};
+        uint8_t used[5] = {0, 0, 0, 0, 0};
         // greedy octets, class by class; the octet that straddles the class boundary keeps its residues
         for (int pass = 0; pass < 2; pass++) {
           const uint32_t k0 = pass ? n_first : 0, k1 = pass ? n : n_first;
           for (auto &bk : bucket) bk.clear();
-          for (uint32_t k = k0; k < k1; k++) bucket[res[(size_t)k * 4]].push_back(k);
+          for (uint32_t k = k0; k < k1; k++) bucket[res[(size_t)k * 5]].push_back(k);
           for (auto &bk : bucket) std::reverse(bk.begin(), bk.end()); // pop_back takes ascending ids first
           uint32_t left = k1 - k0;
           while (left) {
             const uint32_t pos = (uint32_t)tmp.size() & 7u;
-            if (pos == 0) used[0] = used[1] = used[2] = used[3] = 0;
+            if (pos == 0) used[0] = used[1] = used[2] = used[3] = used[4] = 0;
             // prefer the bucket whose slot-0 residue is still free in this octet
             int b = -1;
             for (int r = 0; r < 8; r++) {
@@ -1073,12 +1363,12 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
             for (size_t q = 0; q < 12 && q < B.size(); q++) {
               const uint32_t k = B[B.size() - 1 - q];
               int conf = 0;
-              for (int j = 1; j < nvs; j++) conf += used[j] >> res[(size_t)k * 4 + j] & 1;
+              for (int j = 1; j < nvs; j++) conf += used[j] >> res[(size_t)k * 5 + j] & 1;
               if (conf < pick_conf) { pick_conf = conf; pick = B.size() - 1 - q; if (!conf) break; }
             }
             const uint32_t k = B[pick];
             B.erase(B.begin() + (ptrdiff_t)pick);
-            for (int j = 0; j < nvs; j++) used[j] |= (uint8_t)(1u << res[(size_t)k * 4 + j]);
+            for (int j = 0; j < nvs; j++) used[j] |= (uint8_t)(1u << res[(size_t)k * 5 + j]);
             tmp.push_back(O.ents[lo + k]);
             cls.push_back((uint8_t)pass);
             left--;
@@ -1088,11 +1378,11 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
         // count (per octet and vertex slot: the largest number of records in one bank group)
         {
           const uint32_t n_oct = (n + 7) / 8;
-          std::vector<uint8_t> rr((size_t)n * 4);
+          std::vector<uint8_t> rr((size_t)n * 5, 8);
           for (uint32_t k = 0; k < n; k++) {
-            int32_t vs[4];
-            ent_verts(D, tmp[k], vs);
-            for (int j = 0; j < nvs; j++) rr[(size_t)k * 4 + j] = (uint8_t)(local(vs[j]) & 7u);
+            int32_t vs[5];
+            const int nv_k = ent_verts(D, tmp[k], vs);
+            for (int j = 0; j < nv_k; j++) rr[(size_t)k * 5 + j] = (uint8_t)(local(vs[j]) & 7u);
           }
           auto oct_cost = [&](uint32_t o, uint32_t swap_pos, uint32_t swap_with) {
             // cost of octet o with the record at swap_pos replaced by the one at swap_with (swap_pos == ~0u: as is)
@@ -1105,7 +1395,8 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
               uint32_t pairs = 0;
               for (uint32_t k = k0; k < k1; k++) {
                 const uint32_t src = k == swap_pos ? swap_with : k;
-                const uint8_t v = ++cntb[rr[(size_t)src * 4 + j]];
+                if (rr[(size_t)src * 5 + j] > 7) continue; // a single tet among bi-tets: no fifth vertex
+                const uint8_t v = ++cntb[rr[(size_t)src * 5 + j]];
                 pairs += v - 1u; // records already on this residue: the sum is the number of conflicting pairs
                 m = std::max(m, v);
               }
@@ -1133,7 +1424,7 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
                 static const int ls_plateau = getenv("SB_LS_PLATEAU") ? atoi(getenv("SB_LS_PLATEAU")) : 0;
                 if (na + nb < oc[oa] + oc[ob] || (ls_plateau && na + nb == oc[oa] + oc[ob] && na < oc[oa])) {
                   std::swap(tmp[a], tmp[b]);
-                  for (int j = 0; j < 4; j++) std::swap(rr[(size_t)a * 4 + j], rr[(size_t)b * 4 + j]);
+                  for (int j = 0; j < 5; j++) std::swap(rr[(size_t)a * 5 + j], rr[(size_t)b * 5 + j]);
                   oc[oa] = na;
                   oc[ob] = nb;
                   improved = true;
@@ -1152,33 +1443,50 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
     const uint32_t round_words = 4 * width * bt;
     O.stream.assign((size_t)ncol * round_words, 0u);
     O.aux.assign((size_t)O.n_tcol * width * bt, std::numeric_limits<float>::quiet_NaN());
-    O.has01.assign(O.n_tcol, 0);
-    O.has23.assign(O.n_tcol, 0);
+    O.flags.assign(O.n_tcol, 0);
     for (uint32_t c = 0; c < ncol; c++) {
       const bool tet = c >= O.n_ecol;
       uint32_t *rw = O.stream.data() + (size_t)c * round_words;
       for (uint32_t k = 0; k < O.col_cnt[c]; k++) {
-        int32_t vs[4];
+        int32_t vs[5];
         const int32_t e = O.ents[coff[c] + k];
-        ent_verts(D, e, vs);
+        const int nv_k = ent_verts(D, e, vs);
         uint32_t thr, sub;
-        round_slot(k, tet ? width : 2 * width, thr, sub);
+        round_slot(k, tet ? 1 : 2 * width, thr, sub);
         if (!tet) {
           uint32_t *r = rw + (size_t)thr * 4 * width + 2 * sub;
           r[0] = local(vs[0]) | (local(vs[1]) << 16);
           r[1] = f2u(P.rest_len[e]);
         } else {
-          uint32_t *r = rw + (size_t)thr * 4 * width + 4 * sub;
+          uint32_t *r = rw + (size_t)thr * 4 * width;
           const int32_t id = e & 0x7fffffff, e01 = P.tet_e01[id], e23 = P.tet_e23[id];
+          const uint32_t qnan = 0x7fc00000u;
           r[0] = local(vs[0]) | (local(vs[1]) << 16);
           r[1] = local(vs[2]) | (local(vs[3]) << 16);
           r[2] = f2u(P.rest_vol6[id]);
-          r[3] = e01 >= 0 ? f2u(P.rest_len[e01]) : 0x7fc00000u;
-          O.aux[(size_t)(c - O.n_ecol) * width * bt + (size_t)thr * width + sub] =
+          r[3] = e01 >= 0 ? f2u(P.rest_len[e01]) : qnan;
+          O.aux[(size_t)(c - O.n_ecol) * width * bt + (size_t)thr * width] =
               e23 >= 0 ? P.rest_len[e23] : std::numeric_limits<float>::quiet_NaN();
           O.n_edges += (e01 >= 0) + (e23 >= 0);
-          if (e01 >= 0) O.has01[c - O.n_ecol] = 1;
-          if (e23 >= 0) O.has23[c - O.n_ecol] = 1;
+          uint8_t &fl = O.flags[c - O.n_ecol];
+          if (e01 >= 0) fl |= 1;
+          if (e23 >= 0) fl |= 2;
+          if (bitet) {
+            // second word: the mate B = (b, s1, s0, s2) on the registers (4, 2, 1, 3): its apex, its rest volume, the
+            // rest lengths of its attached edges (b, s1) and (s0, s2); a NaN volume = no mate
+            const int32_t mate = nv_k == 5 ? P.tet_mate[id] : -1;
+            r[4] = mate >= 0 ? local(vs[4]) : 0u;
+            r[5] = mate >= 0 ? f2u(P.rest_vol6[mate]) : qnan;
+            r[6] = mate >= 0 && P.tet_e01[mate] >= 0 ? f2u(P.rest_len[P.tet_e01[mate]]) : qnan;
+            r[7] = mate >= 0 && P.tet_e23[mate] >= 0 ? f2u(P.rest_len[P.tet_e23[mate]]) : qnan;
+            if (mate >= 0) {
+              fl |= 4;
+              if (P.tet_e01[mate] >= 0) fl |= 8;
+              if (P.tet_e23[mate] >= 0) fl |= 16;
+              O.n_edges += (P.tet_e01[mate] >= 0) + (P.tet_e23[mate] >= 0);
+              O.n_tets++;
+            }
+          }
         }
       }
       (tet ? O.n_tets : O.n_edges) += O.col_cnt[c];
@@ -1211,14 +1519,8 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
     TileOut &O = outs[t];
     TP.rounds.push_back({(uint32_t)(TP.stream.size() / 4), O.n_ecol, O.n_tcol, (uint32_t)TP.aux.size()});
     TP.aux.insert(TP.aux.end(), O.aux.begin(), O.aux.end());
-    if (TP.col_has01.size() < O.n_tcol) {
-      TP.col_has01.resize(O.n_tcol, 0);
-      TP.col_has23.resize(O.n_tcol, 0);
-    }
-    for (uint32_t c = 0; c < O.n_tcol; c++) {
-      TP.col_has01[c] |= O.has01[c];
-      TP.col_has23[c] |= O.has23[c];
-    }
+    if (TP.col_flags.size() < O.n_tcol) TP.col_flags.resize(O.n_tcol, 0);
+    for (uint32_t c = 0; c < O.n_tcol; c++) TP.col_flags[c] |= O.flags[c];
     TP.stream.insert(TP.stream.end(), O.stream.begin(), O.stream.end());
     TP.ents.insert(TP.ents.end(), O.ents.begin(), O.ents.end());
     TP.ent_off.push_back(TP.ents.size());
@@ -1279,7 +1581,7 @@ uint32_t next_parts(const Plan &P, const DevTopo &D, const std::vector<int32_t> 
   std::vector<uint64_t> votes;
   votes.reserve(cut.size() * 4);
   for (int32_t ent : cut) {
-    int32_t vs[4];
+    int32_t vs[5];
     int n = ent_verts(D, ent, vs);
     for (int i = 0; i < n; i++)
       for (int j = 0; j < n; j++)
@@ -1342,25 +1644,29 @@ uint32_t next_parts(const Plan &P, const DevTopo &D, const std::vector<int32_t> 
 
 std::string global_colouring(Plan &P, const DevTopo &D, const std::vector<int32_t> &rest_in) {
   if (rest_in.empty()) return "";
-  // a tet that ends up here brings its attached edges along as plain edges
-  std::vector<int32_t> rest;
+  // a tet that ends up here brings its attached edges along as plain edges, and its mate (bi-tets) as a plain tet
+  std::vector<int32_t> rest, tets_in;
   rest.reserve(rest_in.size());
   for (int32_t ent : rest_in)
     if (ent >= 0) rest.push_back(ent);
   for (int32_t ent : rest_in)
     if (ent < 0) {
-      const int32_t id = ent & 0x7fffffff;
-      if (P.tet_e01[id] >= 0) rest.push_back(P.tet_e01[id]);
-      if (P.tet_e23[id] >= 0) rest.push_back(P.tet_e23[id]);
+      tets_in.push_back(ent);
+      const int32_t mate = P.tet_mate.empty() ? -1 : P.tet_mate[ent & 0x7fffffff];
+      if (mate >= 0) tets_in.push_back((int32_t)(0x80000000u | (uint32_t)mate));
     }
-  for (int32_t ent : rest_in)
-    if (ent < 0) rest.push_back(ent);
+  for (int32_t ent : tets_in) {
+    const int32_t id = ent & 0x7fffffff;
+    if (P.tet_e01[id] >= 0) rest.push_back(P.tet_e01[id]);
+    if (P.tet_e23[id] >= 0) rest.push_back(P.tet_e23[id]);
+  }
+  for (int32_t ent : tets_in) rest.push_back(ent);
   std::vector<Mask128> me(P.V), mt(P.V);
   std::vector<uint8_t> col(rest.size());
   std::vector<uint32_t> ecount, tcount;
   for (size_t i = 0; i < rest.size(); i++) {
-    int32_t vs[4];
-    int n = ent_verts(D, rest[i], vs);
+    int32_t vs[5];
+    int n = ent_verts(D, rest[i], vs, false);
     bool tet = rest[i] < 0;
     std::vector<Mask128> &M = tet ? mt : me;
     Mask128 u;
@@ -1392,8 +1698,8 @@ std::string global_colouring(Plan &P, const DevTopo &D, const std::vector<int32_
   for (size_t c = 0; c < tcount.size(); c++) P.gbatches.push_back({true, tof[c], tcount[c], 0});
   std::vector<uint32_t> ecur(eoff.begin(), eoff.end() - 1), tcur(tof.begin(), tof.end() - 1);
   for (size_t i = 0; i < rest.size(); i++) {
-    int32_t vs[4];
-    ent_verts(D, rest[i], vs);
+    int32_t vs[5];
+    ent_verts(D, rest[i], vs, false);
     if (rest[i] >= 0) {
       uint32_t k = ecur[col[i]]++;
       P.g_edges[k] = {vs[0], vs[1]};
@@ -1454,21 +1760,37 @@ void Plan::export_schedule(std::vector<int32_t> &order, std::vector<int64_t> &ba
         }
         close();
         if (!kind) continue;
-        // the edges attached to this colour's tets: a thread projects tet, edge (0,1), edge (2,3) in a row;
-        // records of one colour are vertex-disjoint, so "all tets, all (0,1) edges, all (2,3) edges" is the
-        // same computation written as independent batches
-        for (int which = 0; which < 2; which++) {
-          const std::vector<int32_t> &att = which ? tet_e23 : tet_e01;
-          for (uint32_t t = 0; t < nt; t++) {
-            const uint32_t nk = TP.col_off[t + 1] - TP.col_off[t] - TP.n_ecol[t];
-            if (c >= nk) continue;
-            const uint32_t j = TP.col_off[t] + TP.n_ecol[t] + c;
-            for (uint32_t k = 0; k < TP.col_cnt[j]; k++) {
-              const int32_t e = att[TP.ents[cstart[j] + k] & 0x7fffffff];
-              if (e >= 0) order.push_back(e);
+        // the edges attached to this colour's tets: a thread projects tet, edge (0,1), edge (2,3) in a row -- and then
+        // the tet's mate and its two edges (bi-tets); records of one colour are vertex-disjoint, so "all tets, all
+        // (0,1) edges, all (2,3) edges, all mates, ..." is the same computation written as independent batches
+        for (int half = 0; half < 2; half++) {
+          if (half) { // the mates
+            for (uint32_t t = 0; t < nt; t++) {
+              const uint32_t nk = TP.col_off[t + 1] - TP.col_off[t] - TP.n_ecol[t];
+              if (c >= nk) continue;
+              const uint32_t j = TP.col_off[t] + TP.n_ecol[t] + c;
+              for (uint32_t k = 0; k < TP.col_cnt[j]; k++) {
+                const int32_t m = TP.width == 2 ? tet_mate[TP.ents[cstart[j] + k] & 0x7fffffff] : -1;
+                if (m >= 0) order.push_back((int32_t)(0x80000000u | (uint32_t)m));
+              }
             }
+            close();
           }
-          close();
+          for (int which = 0; which < 2; which++) {
+            const std::vector<int32_t> &att = which ? tet_e23 : tet_e01;
+            for (uint32_t t = 0; t < nt; t++) {
+              const uint32_t nk = TP.col_off[t + 1] - TP.col_off[t] - TP.n_ecol[t];
+              if (c >= nk) continue;
+              const uint32_t j = TP.col_off[t] + TP.n_ecol[t] + c;
+              for (uint32_t k = 0; k < TP.col_cnt[j]; k++) {
+                int32_t id = TP.ents[cstart[j] + k] & 0x7fffffff;
+                if (half) id = TP.width == 2 ? tet_mate[id] : -1;
+                const int32_t e = id >= 0 ? att[id] : -1;
+                if (e >= 0) order.push_back(e);
+              }
+            }
+            close();
+          }
         }
       }
     }
@@ -1537,7 +1859,11 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     lumped_inv_mass(P, in.density);
   }
   lap("edges, masses");
-  attach_edges(P, opt.compounds != 0);
+  // round_width 2 (the default for a mesh that is not one rank of a partition): tets in face-sharing pairs
+  if (opt.round_width < 0 || opt.round_width > 2) return "round_width must be 1 or 2";
+  const bool bitets = !P.n_ghost && (opt.round_width == 2 || (opt.round_width == 0 && opt.compounds != 0));
+  if (bitets) pair_and_attach(P, threads, opt.compounds != 0);
+  else attach_edges(P, opt.compounds != 0);
   lap("attach edges");
   rest_values(P, threads);
   err = build_surface(P);
@@ -1552,8 +1878,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   P.tile_cap = cap;
   const uint32_t bt_opt = opt.block_threads > 0 ? (uint32_t)opt.block_threads : 0u;
   if (bt_opt && bt_opt != 32 && bt_opt != 64 && bt_opt != 128 && bt_opt != 256) return "block_threads must be 32, 64, 128 or 256";
-  if (opt.round_width < 0 || opt.round_width > 2) return "round_width must be 1 or 2";
-  const uint32_t width = opt.round_width > 0 ? (uint32_t)opt.round_width : 1u;
+  const uint32_t width = bitets ? 2u : 1u;
   P.round_width = width;
   int max_passes = opt.max_tile_passes < 0 ? 6 : std::min(opt.max_tile_passes, 8);
 
@@ -1684,6 +2009,34 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   D.tets.resize(4 * (size_t)P.T);
   parallel_for(2 * (size_t)P.E, threads, 1 << 18, [&](size_t i, int) { D.edges[i] = (int32_t)P.inv[P.edges[i]]; });
   parallel_for(4 * (size_t)P.T, threads, 1 << 18, [&](size_t i, int) { D.tets[i] = (int32_t)P.inv[P.tet_roles[i]]; });
+  if (P.tets_paired && n_tilings >= 2) {
+    // a bi-tet that no tiling holds in one box (its five vertices span more than an element does: small boxes) is
+    // split back into its two tets -- their roles and attached edges are valid on their own -- rather than left over
+    uint64_t split = 0;
+    for (uint32_t t = 0; t < P.T; t++) {
+      if (!P.tet_lead[t] || P.tet_mate[t] < 0) continue;
+      const int32_t u = P.tet_mate[t];
+      const int32_t five[5] = {P.tet_roles[4 * (size_t)t], P.tet_roles[4 * (size_t)t + 1], P.tet_roles[4 * (size_t)t + 2],
+                               P.tet_roles[4 * (size_t)t + 3], P.tet_roles[4 * (size_t)u]};
+      bool somewhere = false;
+      for (int s2 = 0; s2 < n_tilings && !somewhere; s2++) {
+        bool in = true;
+        for (int k = 1; k < 5; k++) in &= tilings[s2].part[five[k]] == tilings[s2].part[five[0]];
+        somewhere = in;
+      }
+      if (!somewhere) {
+        P.tet_mate[t] = P.tet_mate[u] = -1;
+        P.tet_lead[u] = 1;
+        split += 2;
+      }
+    }
+    P.tets_paired -= split;
+  }
+  if (P.tets_paired) {
+    D.apex.assign(P.T, -1);
+    for (uint32_t t = 0; t < P.T; t++)
+      if (P.tet_lead[t] && P.tet_mate[t] >= 0) D.apex[t] = (int32_t)P.inv[P.tet_roles[4 * (size_t)P.tet_mate[t]]]; // role 0 of B is its apex
+  }
   std::vector<float> dev_pos(3 * (size_t)P.V);
   for (uint32_t d = 0; d < P.V; d++)
     for (int k = 0; k < 3; k++) dev_pos[3 * (size_t)d + k] = P.pos[3 * (size_t)P.perm[d] + k];
@@ -1706,7 +2059,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     std::vector<uint8_t> mask(cons.size());
     parallel_for(mask.size(), threads, 1 << 16, [&](size_t i, int) {
       const int32_t ent = cons[i];
-      int32_t vs[4];
+      int32_t vs[5];
       const int n = ent_verts(D, ent, vs);
       uint8_t m = 0;
       for (int s = 0; s < n_tilings; s++) {
@@ -1737,8 +2090,13 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
       const int32_t ent = cons[i];
       const int kind = ent < 0;
       // tets weigh more than edges in the kernels, and carry their attached edges
-      const uint64_t wgt = kind ? 5 + 2 * ((P.tet_e01[ent & 0x7fffffff] >= 0) + (P.tet_e23[ent & 0x7fffffff] >= 0)) : 2;
-      int32_t vs[4];
+      uint64_t wgt = 2;
+      if (kind) {
+        const int32_t ta = ent & 0x7fffffff, tb = P.tet_mate[ta];
+        wgt = 5 + 2 * ((P.tet_e01[ta] >= 0) + (P.tet_e23[ta] >= 0));
+        if (tb >= 0) wgt += 5 + 2 * ((P.tet_e01[tb] >= 0) + (P.tet_e23[tb] >= 0));
+      }
+      int32_t vs[5];
       const int n = ent_verts(D, ent, vs);
       int best = -1;
       uint32_t best_deg = 0, best_sum = 0;
@@ -1830,7 +2188,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
         std::vector<uint8_t> seen(P.V, 0);
         size_t nvr = 0;
         for (int32_t ent : work) {
-          int32_t vs[4];
+          int32_t vs[5];
           int n = ent_verts(D, ent, vs);
           for (int j = 0; j < n; j++)
             if (!seen[vs[j]]) { seen[vs[j]] = 1; nvr++; }
@@ -1870,6 +2228,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   for (size_t i = 0; i < (size_t)P.E + P.T; i++) {
     const int32_t ent = i < P.E ? (int32_t)i : (int32_t)(0x80000000u | (uint32_t)(i - P.E));
     if (i < P.E && P.edge_owner[i] >= 0) continue; // rides with its tet
+    if (i >= P.E && !P.tet_lead[i - P.E]) continue;  // rides with its mate
     int ng = 0, n;
     if (ent >= 0) {
       n = 2;

@@ -74,7 +74,8 @@ struct TilePass {
                                       // the SMs in a snake so that every SM's single wave of CTAs weighs the same
   std::vector<uint32_t> stream;     // 32-bit words; every round starts 16-byte aligned
   std::vector<float> aux;           // per tet round: width * bt floats (L23 of the compound, NaN if none)
-  std::vector<uint8_t> col_has01, col_has23; // per tet colour index: some tile attaches a (0,1) / (2,3) edge there
+  std::vector<uint8_t> col_flags;   // per tet colour index: bit 0 some tile attaches a (0,1) edge there, 1 a (2,3) edge, 2 a mate
+                                    // (bi-tets), 3 / 4 a (0,1) / (2,3) edge of a mate: the batches the exported schedule has
   uint32_t bt = 64, width = 1;      // CTA threads and 16-byte words per thread per round of this pass
   // schedule bookkeeping (host only): per tile, constraints in processing order
   std::vector<uint64_t> ent_off;    // n_tiles + 1 offsets into ents
@@ -110,6 +111,9 @@ struct Plan {
   std::vector<int32_t> tet_roles; // 4T: tets[t] in the role order the projection uses (an even permutation)
   std::vector<int32_t> tet_e01, tet_e23; // T: edge attached to roles (0,1) / (2,3) of the tet, or -1
   std::vector<int32_t> edge_owner;       // E: tet the edge is attached to, or -1 (projected in an edge round)
+  std::vector<int32_t> tet_mate;         // T: the tet this one forms a bi-tet with (they share a face), or -1
+  std::vector<uint8_t> tet_lead;         // T: 1 for a single tet or the first tet (A) of a bi-tet, 0 for its second (B)
+  uint64_t tets_paired = 0;
   uint64_t edges_attached = 0;
   std::vector<float> rest_len;  // E
   std::vector<float> rest_vol6; // T

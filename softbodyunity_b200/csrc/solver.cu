@@ -1548,8 +1548,7 @@ int sb_get_info(sb_handle h, sb_info *o) {
   uint32_t nb = 0;
   for (size_t k = 0; k < P.passes.size(); k++) {
     nb += P.passes[k].max_ecol + P.passes[k].max_tcol;
-    for (uint8_t f : P.passes[k].col_has01) nb += f;
-    for (uint8_t f : P.passes[k].col_has23) nb += f;
+    for (uint8_t f : P.passes[k].col_flags) nb += (uint32_t)__builtin_popcount(f);
     if (k < 8) {
       o->tiles_in_pass[k] = P.passes[k].n_tiles();
       o->max_colours_in_pass[k] = P.passes[k].max_ecol + P.passes[k].max_tcol;
@@ -1581,6 +1580,16 @@ int sb_get_tet_roles(sb_handle h, int32_t *tets_4T, int32_t *edge01_T, int32_t *
   if (tets_4T) std::memcpy(tets_4T, P.tet_roles.data(), P.tet_roles.size() * sizeof(int32_t));
   if (edge01_T) std::memcpy(edge01_T, P.tet_e01.data(), P.tet_e01.size() * sizeof(int32_t));
   if (edge23_T) std::memcpy(edge23_T, P.tet_e23.data(), P.tet_e23.size() * sizeof(int32_t));
+  return SB_OK;
+}
+
+int sb_get_tet_mates(sb_handle h, int32_t *mate_T, int32_t *lead_T) {
+  NEED_HANDLE(h);
+  const Plan &P = h->plan;
+  for (uint32_t t = 0; t < P.T; t++) {
+    if (mate_T) mate_T[t] = P.tet_mate[t];
+    if (lead_T) lead_T[t] = P.tet_lead[t];
+  }
   return SB_OK;
 }
 
@@ -1676,14 +1685,22 @@ int sb_debug_verify_streams(sb_handle h, uint64_t *n_bad, uint64_t *wavefronts, 
         const uint32_t *rw = tp.stream.data() + ((size_t)meta.x * 4 + (size_t)c * 4 * W * bt);
         // shared-memory model: one LDS.128 per vertex slot and sub-record; a quarter-warp (8 lanes) costs as
         // many wavefronts as its most crowded 16-byte bank group holds distinct addresses
-        for (uint32_t sub = 0; sub < (tet ? W : 2 * W); sub++)
-          for (uint32_t slot = 0; slot < (tet ? 4u : 2u); slot++)
+        const bool bitet = W == 2;
+        const uint32_t n_sub = tet ? 1u : 2 * W, n_slot = tet ? (bitet ? 5u : 4u) : 2u;
+        auto vid = [&](const uint32_t *r, uint32_t slot) -> uint32_t { // local vertex id in a record's vertex slot
+          if (!tet) return slot ? r[0] >> 16 : r[0] & 0xffffu;
+          if (slot == 4) return r[4] & 0xffffu;
+          const uint32_t wd = r[slot / 2];
+          return slot & 1 ? wd >> 16 : wd & 0xffffu;
+        };
+        for (uint32_t sub = 0; sub < n_sub; sub++)
+          for (uint32_t slot = 0; slot < n_slot; slot++)
             for (uint32_t o = 0; o < bt; o += 8) {
               uint32_t ids[8], nid = 0, mult[8] = {0, 0, 0, 0, 0, 0, 0, 0};
               for (uint32_t l = 0; l < 8; l++) {
-                const uint32_t *r = rw + (size_t)(o + l) * 4 * W + (tet ? 4 : 2) * sub;
-                const uint32_t wd = r[tet ? slot / 2 : 0];
-                const uint32_t id = tet ? (slot & 1 ? wd >> 16 : wd & 0xffffu) : (slot ? wd >> 16 : wd & 0xffffu);
+                const uint32_t *r = rw + (size_t)(o + l) * 4 * W + (tet ? 0 : 2 * sub);
+                if (slot == 4 && r[5] == 0x7fc00000u) continue; // no mate: no fifth access
+                const uint32_t id = vid(r, slot);
                 bool dup = false;
                 for (uint32_t q = 0; q < nid; q++) dup |= ids[q] == id;
                 if (!dup) { ids[nid++] = id; mult[id & 7]++; }
@@ -1691,14 +1708,13 @@ int sb_debug_verify_streams(sb_handle h, uint64_t *n_bad, uint64_t *wavefronts, 
               uint32_t m = 0;
               for (uint32_t q = 0; q < 8; q++) m = std::max(m, mult[q]);
               wf += m;
-              wf_ideal += 1;
+              wf_ideal += nid ? 1 : 0;
             }
         uint32_t seen = 0;
         for (uint32_t thr = 0; thr < bt; thr++)
-          for (uint32_t sub = 0; sub < (tet ? W : 2 * W); sub++) {
-            const uint32_t *r = rw + (size_t)thr * 4 * W + (tet ? 4 : 2) * sub;
-            const uint32_t subs = tet ? W : 2 * W;
-            const uint32_t k = 8u * subs * (thr / 8u) + 8u * sub + (thr & 7u); // inverse of round_slot
+          for (uint32_t sub = 0; sub < n_sub; sub++) {
+            const uint32_t *r = rw + (size_t)thr * 4 * W + (tet ? 0 : 2 * sub);
+            const uint32_t k = 8u * n_sub * (thr / 8u) + 8u * sub + (thr & 7u); // inverse of round_slot
             const bool pad = (r[0] & 0xffffu) == (r[0] >> 16);
             if (k >= cnt) { bad += !pad; continue; }
             if (pad) { bad++; continue; }
@@ -1714,19 +1730,36 @@ int sb_debug_verify_streams(sb_handle h, uint64_t *n_bad, uint64_t *wavefronts, 
               const int32_t id = ent & 0x7fffffff;
               const int32_t *q = &P.tet_roles[4 * (size_t)id];
               const uint32_t l[4] = {r[0] & 0xffffu, r[0] >> 16, r[1] & 0xffffu, r[1] >> 16};
-              bool ok = std::memcmp(&r[2], &P.rest_vol6[id], 4) == 0;
+              bool ok = std::memcmp(&r[2], &P.rest_vol6[id], 4) == 0 && P.tet_lead[id];
               for (int j = 0; j < 4; j++) ok = ok && P.perm[dev_id(l[j])] == (uint32_t)q[j];
               // attached edges: rest lengths in the record / aux stream, and they do join roles (0,1) / (2,3)
-              const float a23 = tp.aux[(size_t)meta.w + (size_t)(c - meta.y) * W * bt + (size_t)thr * W + sub];
-              const int32_t e01 = P.tet_e01[id], e23 = P.tet_e23[id];
-              auto joins = [&](int32_t e, int32_t u, int32_t v) {
+              const float a23 = tp.aux[(size_t)meta.w + (size_t)(c - meta.y) * W * bt + (size_t)thr * W];
+              auto joins = [&](int32_t e, int32_t owner, int32_t u, int32_t v) {
                 return (P.edges[2 * (size_t)e] == std::min(u, v)) && (P.edges[2 * (size_t)e + 1] == std::max(u, v)) &&
-                       P.edge_owner[e] == id;
+                       P.edge_owner[e] == owner;
               };
-              if (e01 >= 0) ok = ok && std::memcmp(&r[3], &P.rest_len[e01], 4) == 0 && joins(e01, q[0], q[1]);
-              else ok = ok && r[3] == 0x7fc00000u;
-              if (e23 >= 0) ok = ok && std::memcmp(&a23, &P.rest_len[e23], 4) == 0 && joins(e23, q[2], q[3]);
-              else ok = ok && a23 != a23;
+              auto slot_ok = [&](int32_t e, int32_t owner, uint32_t bits, int32_t u, int32_t v) {
+                if (e >= 0) return std::memcmp(&bits, &P.rest_len[e], 4) == 0 && joins(e, owner, u, v);
+                return bits == 0x7fc00000u;
+              };
+              uint32_t a23b; std::memcpy(&a23b, &a23, 4);
+              ok = ok && slot_ok(P.tet_e01[id], id, r[3], q[0], q[1]);
+              ok = ok && (P.tet_e23[id] >= 0 ? slot_ok(P.tet_e23[id], id, a23b, q[2], q[3]) : a23 != a23);
+              const int32_t mate = P.tet_mate[id];
+              if (bitet) {
+                if (mate >= 0) {
+                  // the mate runs on the registers (4, 2, 1, 3): its roles must be (p4, p2, p1, p3)
+                  const int32_t *m = &P.tet_roles[4 * (size_t)mate];
+                  const uint32_t lm[4] = {r[4] & 0xffffu, l[2], l[1], l[3]};
+                  for (int j = 0; j < 4; j++) ok = ok && P.perm[dev_id(lm[j])] == (uint32_t)m[j];
+                  ok = ok && std::memcmp(&r[5], &P.rest_vol6[mate], 4) == 0 && !P.tet_lead[mate] && P.tet_mate[mate] == id;
+                  ok = ok && slot_ok(P.tet_e01[mate], mate, r[6], m[0], m[1]) && slot_ok(P.tet_e23[mate], mate, r[7], m[2], m[3]);
+                } else {
+                  ok = ok && r[5] == 0x7fc00000u && r[6] == 0x7fc00000u && r[7] == 0x7fc00000u;
+                }
+              } else {
+                ok = ok && mate < 0;
+              }
               bad += !ok;
             }
           }

@@ -399,6 +399,13 @@ class SoftBody:
         self._ck(self._lib.sb_get_tet_roles(self._h, _ptr(roles), None, None))
         return roles
 
+    def tet_mates(self):
+        """(mate, lead): the tet each tet forms a bi-tet with (or -1), and 1 for a single tet or the first tet of a pair."""
+        mate = np.empty(self.n_tets, np.int32)
+        lead = np.empty(self.n_tets, np.int32)
+        self._ck(self._lib.sb_get_tet_mates(self._h, _ptr(mate), _ptr(lead)))
+        return mate, lead
+
     def attached_edges(self):
         e01 = np.empty(self.n_tets, np.int32)
         e23 = np.empty(self.n_tets, np.int32)

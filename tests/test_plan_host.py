@@ -249,7 +249,10 @@ def test_attached_edges_and_tet_roles():
     assert np.array_equal(np.sort(roles[has23][:, 2:], 1), edges[e23[has23]])
     att = np.concatenate([e01[has01], e23[has23]])
     assert len(np.unique(att)) == len(att) == sb.info()["edges_attached"]
-    assert (~has01 & has23).sum() == 0  # the (2,3) slot is only used after the (0,1) slot
+    # single compounds (round_width=1): the (2,3) slot is only used after the (0,1) slot
+    one = SoftBody(pos, tets, tris, host_only=True, tile_cap=200, round_width=1)
+    f01, f23 = one.attached_edges()
+    assert ((f01 < 0) & (f23 >= 0)).sum() == 0 and one.info()["round_width"] == 1
     # switched off: identity roles, nothing attached
     off = SoftBody(pos, tets, tris, host_only=True, tile_cap=200, attach_edges=2)
     assert np.array_equal(off.tet_roles(), tets) and off.info()["edges_attached"] == 0
@@ -267,7 +270,7 @@ def test_rounds_stay_near_their_lower_bound():
     """Planner quality pin (host only): the straggler recolouring and the augmented edge attachment keep a tile's
     rounds within ~5 % of max(valence, ceil(n / capacity)) summed over both kinds; first-fit alone was ~19 % above."""
     pos, tets, tris = meshgen.block(45, 45, 45, spacing=0.01)
-    sb = SoftBody(pos, tets, tris, host_only=True)
+    sb = SoftBody(pos, tets, tris, host_only=True, round_width=1)
     i = sb.info()
     assert i["n_tilings"] == 4
     assert i["edges_attached"] >= 0.985 * i["n_edges"]
@@ -276,6 +279,11 @@ def test_rounds_stay_near_their_lower_bound():
     assert sb.verify_streams() == 0
     wf, ideal = sb.smem_model
     assert wf / ideal < 1.85  # (the merged rim tiles lowered the conflict-free count more than the total)
+    # bi-tets (the default): two thirds of the rounds, three quarters of the shared-memory load wavefronts
+    bi = SoftBody(pos, tets, tris, host_only=True)
+    j = bi.info()
+    assert j["round_width"] == 2 and j["edges_attached"] >= 0.975 * j["n_edges"] and bi.verify_streams() == 0
+    assert sum(j["rounds_in_pass"]) <= 0.72 * rounds and bi.smem_model[0] <= 0.8 * wf
     # rim merging: a shifted tiling has fewer tiles than its (n + 1)^3 boxes and no tile heavier than a full box
     assert all(t < 216 for t in i["tiles_in_pass"][1:4]) and i["tiles_in_pass"][0] == 125
     assert max(i["max_colours_in_pass"][1:4]) <= i["max_colours_in_pass"][0] + 1
@@ -367,3 +375,35 @@ def test_dist_layout_zones_and_compact_blocks():
         # every rank of a 2-rank split has tiles in every pass (the advisor's empty-pass case is covered by k_dist_bump)
         mixed = np.array([len(set(c[c >= 0])) > 1 for c in ranks_at.T])
         assert mixed.any() and not mixed.all()
+
+
+def test_bitets_pair_tets_across_a_face_on_fixed_registers():
+    # default plan: tets in face-sharing pairs; the second tet (B) runs on the registers (4, 2, 1, 3) of the first (A)
+    pos, tets, tris = meshgen.block(12, 11, 10, spacing=0.1, jitter=0.1, seed=3)
+    sb = SoftBody(pos, tets, tris, host_only=True, tile_cap=300)
+    assert sb.info()["round_width"] == 2 and sb.verify_streams() == 0
+    roles = sb.tet_roles()
+    mate, lead = sb.tet_mates()
+    paired = mate >= 0
+    assert paired.mean() > 0.94                                  # a greedy matching pairs nearly every tet of a lattice (a few are split again: tile_cap 300 makes small boxes)
+    assert (mate[mate[paired]] == np.nonzero(paired)[0]).all()   # mutual
+    assert (lead[paired] != lead[mate[paired]]).all() and lead[~paired].all()
+    A = np.nonzero(paired & (lead == 1))[0]
+    B = mate[A]
+    ra, rb = roles[A], roles[B]
+    assert (rb[:, 1] == ra[:, 2]).all() and (rb[:, 2] == ra[:, 1]).all() and (rb[:, 3] == ra[:, 3]).all()
+    assert (rb[:, 0] != ra[:, 0]).all()
+    # both stay even permutations of the caller's tets (checked by the volume sign in test_attached_edges_and_tet_roles)
+    edges = sb.topology()[0]
+    e01, e23 = sb.attached_edges()
+    att = np.concatenate([e01[e01 >= 0], e23[e23 >= 0]])
+    assert len(att) > 0.9 * len(edges)  # (a small block is mostly boundary: 1.39 edges per tet against 1.22 inside)
+    # the schedule still covers every constraint exactly once per iteration
+    order, off = sb.schedule()
+    ids = np.where(order < 0, (order & 0x7fffffff) + len(edges), order)
+    assert len(ids) == len(edges) + len(tets) and len(np.unique(ids)) == len(ids)
+    # and the batches are independent sets
+    for b in range(len(off) - 1):
+        seg = order[off[b]:off[b + 1]]
+        vs = np.concatenate([roles[seg[seg < 0] & 0x7fffffff].ravel(), edges[seg[seg >= 0]].ravel()])
+        assert len(np.unique(vs)) == len(vs)
