@@ -276,7 +276,10 @@ struct sb_solver {
       pb.stream.upload(tp.stream, &dev_bytes);
       pb.aux.upload(tp.aux, &dev_bytes);
       const uint32_t pos_bytes = (tp.max_tile_verts * 16u + 127u) & ~127u;
-      pb.smem = pos_bytes + 16u; // positions + the mbarrier their bulk copies complete on
+      // positions + the mbarrier their bulk copies complete on + the ring of constraint records (16-byte words) and
+      // aux floats the asynchronous copies fill, SB_PREFETCH rounds deep (kernels.cuh)
+      const uint32_t ring_depth = tp.width == 2 ? 2u : 4u;
+      pb.smem = pos_bytes + 16u + ring_depth * tp.bt * tp.width * 20u;
       if (pb.smem > (uint32_t)prop.sharedMemPerBlockOptin) throw std::string("tile_cap exceeds the shared memory of this device");
       // bulk copies per run pay off when runs are long; else threads gather vertex by vertex
       const bool use_runs = !tp.contiguous && !tp.tile_verts.empty() &&
