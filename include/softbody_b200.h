@@ -107,7 +107,8 @@ typedef struct sb_mesh_desc {
   int32_t round_width;      /* 16-byte constraint-record words per thread per round: a round = one colour of 2 * width *
                                block_threads free edges or of block_threads compounds.  1: a compound is one tet with its
                                attached edges; 2: a bi-tet, two tets that share a face with up to four attached edges
-                               (sb_get_tet_mates).  0 = auto: 2, except for one rank of a partition with ghosts (1) */
+                               (sb_get_tet_mates).  0 = auto: 1 (bi-tets halve the rounds but serialise two projections per
+                               thread: measured slower) */
   int32_t attach_edges;     /* 0 = auto, 1 = on, 2 = off: project each edge right after a tet that contains it, from the
                                registers holding the tet's vertices (the tet's vertex ROLES are then an even permutation
                                of the caller's order, see sb_get_tet_roles).  Auto: on */

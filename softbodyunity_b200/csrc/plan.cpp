@@ -1861,7 +1861,8 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   lap("edges, masses");
   // round_width 2 (the default for a mesh that is not one rank of a partition): tets in face-sharing pairs
   if (opt.round_width < 0 || opt.round_width > 2) return "round_width must be 1 or 2";
-  const bool bitets = !P.n_ghost && (opt.round_width == 2 || (opt.round_width == 0 && opt.compounds != 0));
+  static const int auto_width = getenv("SB_ROUND_WIDTH") ? atoi(getenv("SB_ROUND_WIDTH")) : 1; // (A/B switch for benches)
+  const bool bitets = !P.n_ghost && (opt.round_width == 2 || (opt.round_width == 0 && auto_width == 2 && opt.compounds != 0));
   if (bitets) pair_and_attach(P, threads, opt.compounds != 0);
   else attach_edges(P, opt.compounds != 0);
   lap("attach edges");

@@ -262,6 +262,7 @@ struct sb_solver {
       CK(cudaMemset(nrm.p, 0, (ns ? ns : 1) * sizeof(float4)));
     }
     // tile passes
+    static const uint32_t l2_prefetch = getenv("SB_L2_PREFETCH") ? (uint32_t)atoi(getenv("SB_L2_PREFETCH")) : 0u; // (0: A/B switch for benches)
     passes.resize(plan.passes.size());
     for (size_t k = 0; k < plan.passes.size(); k++) {
       const TilePass &tp = plan.passes[k];
@@ -276,10 +277,7 @@ struct sb_solver {
       pb.stream.upload(tp.stream, &dev_bytes);
       pb.aux.upload(tp.aux, &dev_bytes);
       const uint32_t pos_bytes = (tp.max_tile_verts * 16u + 127u) & ~127u;
-      // positions + the mbarrier their bulk copies complete on + the ring of constraint records (16-byte words) and
-      // aux floats the asynchronous copies fill, SB_PREFETCH rounds deep (kernels.cuh)
-      const uint32_t ring_depth = tp.width == 2 ? 2u : 4u;
-      pb.smem = pos_bytes + 16u + ring_depth * tp.bt * tp.width * 20u;
+      pb.smem = pos_bytes + 16u; // positions + the mbarrier their bulk copies complete on
       if (pb.smem > (uint32_t)prop.sharedMemPerBlockOptin) throw std::string("tile_cap exceeds the shared memory of this device");
       // bulk copies per run pay off when runs are long; else threads gather vertex by vertex
       const bool use_runs = !tp.contiguous && !tp.tile_verts.empty() &&
@@ -291,7 +289,7 @@ struct sb_solver {
       pb.order.upload(tp.launch_order, &dev_bytes);
       pb.dev = PassDev{pb.order.p, pb.vert_off.p, tp.contiguous ? nullptr : pb.tile_verts.p, use_runs ? pb.run_off.p : nullptr,
                        use_runs ? pb.runs.p : nullptr, pb.rounds.p, reinterpret_cast<const uint4 *>(pb.stream.p),
-                       pb.aux.p, tp.n_tiles(), pos_bytes, nullptr, nullptr, 1u, 1u, 0u, 0u, nullptr, nullptr, 0u};
+                       pb.aux.p, tp.n_tiles(), pos_bytes, nullptr, nullptr, 1u, 1u, 0u, 0u, nullptr, nullptr, 0u, l2_prefetch, 0u};
       pb.grid = tp.n_tiles();
       pb.bt = tp.bt;
       pb.width = tp.width;
