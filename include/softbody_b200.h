@@ -101,7 +101,7 @@ typedef struct sb_mesh_desc {
   int32_t device;           /* CUDA device ordinal */
   int32_t tile_cap;         /* max vertices per shared-memory tile; 0 = auto */
   int32_t max_tile_passes;  /* -1 = auto; 0 = global colour batches only */
-  int32_t block_threads;    /* threads per tile CTA (32, 64, 128 or 256); 0 = auto per pass */
+  int32_t block_threads;    /* threads per tile CTA (32, 64, 128, 160, 192 or 256); 0 = auto per pass */
   int32_t later_tile_cap;   /* max vertices per tile in passes after the first; 0 = auto */
   int32_t host_threads;     /* threads for the host-side build; 0 = auto */
   int32_t round_width;      /* 16-byte constraint-record words per thread per round: a round = one colour of 2 * width *

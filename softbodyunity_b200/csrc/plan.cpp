@@ -835,10 +835,10 @@ bool grid_tilings(const Plan &P, uint32_t cap, int n_tilings, std::vector<Tiling
       // within the cap: a union of boxes of one tiling keeps every element that was interior to one of them (and
       // gains those that crossed the plane between them).
       static const int merge_rims = getenv("SB_MERGE_RIMS") ? atoi(getenv("SB_MERGE_RIMS")) : 1;
-      static const int merge_pct = getenv("SB_MERGE_PCT") ? atoi(getenv("SB_MERGE_PCT")) : 100;
+      static const int merge_pct = getenv("SB_MERGE_PCT") ? atoi(getenv("SB_MERGE_PCT")) : 130;
       uint32_t biggest = 0;
       for (uint32_t c : count) biggest = std::max(biggest, c);
-      const uint32_t limit = (uint32_t)((uint64_t)std::min(cap, biggest) * (uint32_t)merge_pct / 100);
+      const uint32_t limit = (uint32_t)std::min<uint64_t>(cap, (uint64_t)std::min(cap, biggest) * (uint32_t)merge_pct / 100);
       std::vector<uint32_t> root(count.size());
       std::iota(root.begin(), root.end(), 0u);
       if (ok && s > 0 && merge_rims) {
@@ -941,7 +941,7 @@ inline int ent_verts(const DevTopo &D, int32_t ent, int32_t *vs, bool with_mate 
 std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_t> &part, uint32_t n_tiles,
                        const std::vector<uint32_t> *contig_off, const std::vector<int32_t> &in,
                        std::vector<int32_t> &out, TilePass &TP, int threads, uint32_t bt_opt, uint32_t width, int n_sm,
-                       const std::vector<int32_t> *box0 = nullptr) {
+                       const std::vector<int32_t> *box0 = nullptr, bool wide = false) {
   // 1. classify and bucket by tile (stable)
   std::vector<uint64_t> toff((size_t)n_tiles + 1, 0);
   std::vector<int32_t> owner(in.size());
@@ -978,7 +978,10 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
       for (uint64_t i = toff[t]; i < toff[t + 1]; i++) w += (tent[i] < 0 && !D.apex.empty() && D.apex[tent[i] & 0x7fffffff] >= 0) ? 2 : 1;
       per_tile = std::max<uint64_t>(per_tile, w);
     }
-    bt = per_tile < 1600 ? 64u : per_tile < 6400 ? 128u : 256u;
+    // `wide`: every pass fits the SMs in one wave even at six 160-thread CTAs each -- five warps per tile then beat
+    // four (more warps in flight per SM, a round or two fewer per tile; measured 6.16 -> 5.87 ms per frame at 1 M
+    // vertices); with several waves per pass four fuller warps are better (4 M vertices: 20.1 against 20.7 ms)
+    bt = per_tile < 1600 ? 64u : per_tile < 6400 ? (wide ? 160u : 128u) : 256u;
   }
   // a round: 2 * width * bt free edges, or bt compounds (width 1: a tet with its attached edges in one 16-byte
   // word; width 2: a bi-tet -- or a single tet -- with its attached edges in two words)
@@ -1463,6 +1466,13 @@ std::string build_pass(const Plan &P, const DevTopo &D, const std::vector<int32_
           const uint32_t qnan = 0x7fc00000u;
           r[0] = local(vs[0]) | (local(vs[1]) << 16);
           r[1] = local(vs[2]) | (local(vs[3]) << 16);
+          // TIMING EXPERIMENT ONLY (results are garbage): every lane's role k reads slot thr + k * bt, so that the eight
+          // lanes of a quarter-warp never share a 16-byte bank group -- what a conflict-free layout would cost
+          static const int debug_noconflict = getenv("SB_DEBUG_NOCONFLICT") ? atoi(getenv("SB_DEBUG_NOCONFLICT")) : 0;
+          if (debug_noconflict && O.n_verts >= 4 * bt) {
+            r[0] = thr | ((thr + bt) << 16);
+            r[1] = (thr + 2 * bt) | ((thr + 3 * bt) << 16);
+          }
           r[2] = f2u(P.rest_vol6[id]);
           r[3] = e01 >= 0 ? f2u(P.rest_len[e01]) : qnan;
           O.aux[(size_t)(c - O.n_ecol) * width * bt + (size_t)thr * width] =
@@ -1878,7 +1888,8 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   cap = std::min(cap, 65536u);
   P.tile_cap = cap;
   const uint32_t bt_opt = opt.block_threads > 0 ? (uint32_t)opt.block_threads : 0u;
-  if (bt_opt && bt_opt != 32 && bt_opt != 64 && bt_opt != 128 && bt_opt != 256) return "block_threads must be 32, 64, 128 or 256";
+  if (bt_opt && bt_opt != 32 && bt_opt != 64 && bt_opt != 128 && bt_opt != 160 && bt_opt != 192 && bt_opt != 256)
+    return "block_threads must be 32, 64, 128, 160, 192 or 256";
   const uint32_t width = bitets ? 2u : 1u;
   P.round_width = width;
   int max_passes = opt.max_tile_passes < 0 ? 6 : std::min(opt.max_tile_passes, 8);
@@ -2134,11 +2145,16 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
     deg.clear();
     mask.clear();
     mask.shrink_to_fit();
+    bool wide = width == 1;
+    for (int s = 0; s < n_tilings; s++) { // (a mesh spread over several GPUs: a rank runs its share of the tiles, a few more on some ranks)
+      const uint64_t per_rank = opt.dist_ranks >= 2 ? ((uint64_t)tilings[s].n_tiles * 27 / 25 + opt.dist_ranks - 1) / opt.dist_ranks : tilings[s].n_tiles;
+      wide = wide && per_rank <= 6ull * (uint64_t)std::max(1, opt.n_sm);
+    }
     for (int s = 0; s < n_tilings; s++) {
       TilePass TP;
       // every tiling runs with the CTA width chosen for the unshifted one (whole boxes only)
       err = build_pass(P, D, dpart[s], tilings[s].n_tiles, s == 0 ? &tile_off : nullptr, assigned[s], next, TP, threads,
-                       s == 0 ? bt_opt : P.passes[P.passes.size() - (size_t)s].bt, width, opt.n_sm, s == 0 ? nullptr : &dpart[0]);
+                       s == 0 ? bt_opt : P.passes[P.passes.size() - (size_t)s].bt, width, opt.n_sm, s == 0 ? nullptr : &dpart[0], wide);
       if (!err.empty()) return err;
       work.insert(work.end(), next.begin(), next.end()); // empty by construction
       P.passes.push_back(std::move(TP));

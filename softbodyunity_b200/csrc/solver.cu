@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <new>
 #include <string>
@@ -63,7 +64,7 @@ struct DevBuf {
 struct PassBufs {
   DevBuf<uint32_t> vert_off, tile_verts, stream, run_off, order;
   DevBuf<uint2> runs;
-  DevBuf<uint4> rounds;
+  DevBuf<uint4> rounds, desc;
   DevBuf<float> aux;
   PassDev dev{};
   uint32_t smem = 0;
@@ -262,7 +263,6 @@ struct sb_solver {
       CK(cudaMemset(nrm.p, 0, (ns ? ns : 1) * sizeof(float4)));
     }
     // tile passes
-    static const uint32_t l2_prefetch = getenv("SB_L2_PREFETCH") ? (uint32_t)atoi(getenv("SB_L2_PREFETCH")) : 0u; // (0: A/B switch for benches)
     passes.resize(plan.passes.size());
     for (size_t k = 0; k < plan.passes.size(); k++) {
       const TilePass &tp = plan.passes[k];
@@ -288,9 +288,10 @@ struct sb_solver {
       }
       pb.order.upload(tp.launch_order, &dev_bytes);
       pb.dev = PassDev{pb.order.p, pb.vert_off.p, tp.contiguous ? nullptr : pb.tile_verts.p, use_runs ? pb.run_off.p : nullptr,
-                       use_runs ? pb.runs.p : nullptr, pb.rounds.p, reinterpret_cast<const uint4 *>(pb.stream.p),
-                       pb.aux.p, tp.n_tiles(), pos_bytes, nullptr, nullptr, 1u, 1u, 0u, 0u, nullptr, nullptr, 0u, l2_prefetch, 0u};
+                       use_runs ? pb.runs.p : nullptr, pb.rounds.p, nullptr, {nullptr}, 0u, reinterpret_cast<const uint4 *>(pb.stream.p),
+                       pb.aux.p, tp.n_tiles(), pos_bytes, nullptr, nullptr, 1u, 1u, 0u, 0u, nullptr, nullptr, 0u, 0u};
       pb.grid = tp.n_tiles();
+      build_desc(k, tp.launch_order);
       pb.bt = tp.bt;
       pb.width = tp.width;
       pb.empty = tp.n_edges + tp.n_tets == 0;
@@ -308,6 +309,57 @@ struct sb_solver {
     CK(cudaDeviceSynchronize());
   }
 
+  // One record per CTA of pass k, in launch order (k_tile_rounds reads nothing else about its tile).
+  // One record per CTA of pass k, in launch order (k_tile_rounds reads nothing else about its tile).
+  // Distributed (`tuple` = runner ranks per device vertex, dist_layout): every tile -- of a contiguous pass too -- gets a
+  // run list whose runs are cut where the tuple changes, with the tuple above the local offset (kernels.cuh: a tile
+  // stores each run into the array of the rank that touches it next).
+  void build_desc(size_t k, const std::vector<uint32_t> &order, const std::vector<uint32_t> *tuple = nullptr) {
+    const TilePass &tp = plan.passes[k];
+    PassBufs &pb = passes[k];
+    std::vector<uint32_t> roff;
+    if (tuple) {
+      if (!tp.contiguous && tp.run_off.empty()) throw std::string("a distributed mesh needs run lists for its shifted tilings");
+      std::vector<uint2> ro;
+      roff.assign((size_t)tp.n_tiles() + 1, 0);
+      auto emit = [&](uint32_t first, uint32_t len, uint32_t local) { // [first, first + len) at local offset `local`
+        uint32_t a = 0;
+        while (a < len) {
+          uint32_t b = a + 1;
+          while (b < len && (*tuple)[first + b] == (*tuple)[first + a]) b++;
+          ro.push_back(make_uint2(first + a, (local + a) | ((*tuple)[first + a] << 17)));
+          a = b;
+        }
+      };
+      for (uint32_t t = 0; t < tp.n_tiles(); t++) {
+        roff[t] = (uint32_t)ro.size();
+        const uint32_t nv_t = tp.vert_off[t + 1] - tp.vert_off[t];
+        if (nv_t > 0x1ffffu) throw std::string("tile too large for a distributed mesh");
+        if (tp.contiguous) {
+          emit(tp.vert_off[t], nv_t, 0);
+        } else {
+          for (uint32_t r = tp.run_off[t]; r + 1 < tp.run_off[t + 1]; r++) emit(tp.runs[r].x, tp.runs[r + 1].y - tp.runs[r].y, tp.runs[r].y);
+        }
+        ro.push_back(make_uint2(0, nv_t)); // closes the tile's list
+      }
+      roff[tp.n_tiles()] = (uint32_t)ro.size();
+      pb.runs.upload(ro, &dev_bytes);
+      pb.run_off.upload(roff, &dev_bytes);
+      pb.dev.runs = pb.runs.p;
+      pb.dev.run_off = pb.run_off.p;
+    }
+    const bool runs = pb.dev.run_off != nullptr;
+    const std::vector<uint32_t> &ro_off = tuple ? roff : tp.run_off;
+    std::vector<uint4> d(2 * order.size() + 2, make_uint4(0, 0, 0, 0));
+    for (size_t j = 0; j < order.size(); j++) {
+      const uint32_t t = order[j];
+      d[2 * j] = make_uint4(tp.vert_off[t], tp.vert_off[t + 1] - tp.vert_off[t], runs ? ro_off[t] : 0u, runs ? ro_off[t + 1] - ro_off[t] - 1u : 0u);
+      d[2 * j + 1] = make_uint4(tp.rounds[t].x, tp.rounds[t].y, tp.rounds[t].z, tp.rounds[t].w);
+    }
+    pb.desc.upload(d, &dev_bytes);
+    pb.dev.desc = pb.desc.p;
+  }
+
   template <bool FAST, int BT, int W16>
   static void set_attr_one(uint32_t smem) {
     CK(cudaFuncSetAttribute(k_tile_rounds<FAST, BT, W16, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -317,6 +369,7 @@ struct sb_solver {
   template <bool FAST>
   static void set_attr_math(uint32_t smem) {
     set_attr_one<FAST, 32, 1>(smem); set_attr_one<FAST, 64, 1>(smem); set_attr_one<FAST, 128, 1>(smem); set_attr_one<FAST, 256, 1>(smem);
+    set_attr_one<FAST, 160, 1>(smem); set_attr_one<FAST, 192, 1>(smem); set_attr_one<FAST, 160, 2>(smem); set_attr_one<FAST, 192, 2>(smem);
     set_attr_one<FAST, 32, 2>(smem); set_attr_one<FAST, 64, 2>(smem); set_attr_one<FAST, 128, 2>(smem); set_attr_one<FAST, 256, 2>(smem);
   }
   void set_smem_attr(uint32_t smem) {
@@ -397,13 +450,15 @@ struct sb_solver {
       case 32: launch_tile_cfg<FAST, 32, W16>(pb, dev, s); break;
       case 64: launch_tile_cfg<FAST, 64, W16>(pb, dev, s); break;
       case 128: launch_tile_cfg<FAST, 128, W16>(pb, dev, s); break;
+      case 160: launch_tile_cfg<FAST, 160, W16>(pb, dev, s); break;
+      case 192: launch_tile_cfg<FAST, 192, W16>(pb, dev, s); break;
       default: launch_tile_cfg<FAST, 256, W16>(pb, dev, s); break;
     }
   }
   // One launch of tile pass `pb`: n_seg segments (substeps) of `reps` repetitions of every tile's rounds, with the
   // substep boundaries between segments -- and predict before / finish after, if asked -- done on the tiles.
   template <bool FAST>
-  void launch_tile(const PassBufs &pb, cudaStream_t s, uint32_t n_seg = 1, uint32_t reps = 1, bool pre = false, bool post = false) {
+  void launch_tile(const PassBufs &pb, cudaStream_t s, uint32_t n_seg = 1, uint32_t reps = 1, bool pre = false, bool post = false, uint32_t next_pass = 0) {
     if (pb.empty && !(pre || post || n_seg > 1)) return;
     if (!pb.grid) {
       // distributed: this rank has no tile in the pass, but its epoch moves with every launch of the sequence
@@ -411,7 +466,9 @@ struct sb_solver {
       return;
     }
     PassDev dev = pb.dev;
-    dev.n_seg = n_seg; dev.reps = reps; dev.pre = pre; dev.post = post;
+    dev.n_seg = n_seg; dev.reps = reps; dev.pre = pre; dev.post = post; dev.next_pass = next_pass;
+    if (dist_on) for (uint32_t r = 0; r < dist.n_ranks; r++) dev.xs[r] = dist.x_of[r];
+    else dev.xs[0] = x.p;
     dev.v = v.p; dev.xp = xp.p;
     if (pb.width == 2) launch_tile_w<FAST, 2>(pb, dev, s);
     else launch_tile_w<FAST, 1>(pb, dev, s);
@@ -513,7 +570,8 @@ struct sb_solver {
   // ---- one mesh over several GPUs ------------------------------------------------------
   // Host-only part: the slab of the device numbering a rank owns, the tiles of every pass it runs (zone tiles first)
   // and how many of them are zone tiles.
-  void dist_layout(int rank, int n_ranks, DistDev &D, std::vector<std::vector<uint32_t>> &tiles, std::vector<uint32_t> &n_zone) const {
+  void dist_layout(int rank, int n_ranks, DistDev &D, std::vector<std::vector<uint32_t>> &tiles, std::vector<uint32_t> &n_zone,
+                   std::vector<uint32_t> *runner_tuple = nullptr) const {
     if (n_ranks < 2 || n_ranks > SB_MAX_RANKS || rank < 0 || rank >= n_ranks) throw std::string("rank / n_ranks out of range (2..8 ranks)");
     if (!plan.dag_ok) throw std::string("a distributed mesh must be planned as balanced shifted tilings (one big component, no ghosts, nothing left over)");
     const TilePass &t0 = plan.passes[0];
@@ -596,6 +654,16 @@ struct sb_solver {
       }
     }
     D.nbr_mask = nbr & ~(1u << rank);
+    if (runner_tuple) { // per device vertex: the rank that runs its tile in pass k, three bits per pass (pass 0 = its slab's rank)
+      if (np > 5) throw std::string("a distributed mesh has at most five tile passes");
+      runner_tuple->assign(plan.V, 0u);
+      for (uint32_t d = 0; d < plan.V; d++) {
+        uint32_t tup = 0;
+        for (size_t k = 0; k < np; k++) tup |= (tile_of[k][d] != 0xffffffffu ? (uint32_t)runner[k][tile_of[k][d]] : owner_of(d)) << (3 * k);
+        if ((tup & 7u) != owner_of(d)) throw std::string("the unshifted tiling's tiles must lie within one slab each");
+        (*runner_tuple)[d] = tup;
+      }
+    }
     // this rank's tiles of every pass: zone tiles first, each part heaviest first and dealt to the SMs in a snake
     // like the single-GPU launch order
     tiles.assign(np, {});
@@ -624,10 +692,12 @@ struct sb_solver {
     if (halo_active()) throw std::string("halo lists and the peer-memory distribution are alternatives");
     std::vector<std::vector<uint32_t>> tiles;
     std::vector<uint32_t> n_zone;
-    dist_layout(rank, n_ranks, dist, tiles, n_zone);
+    std::vector<uint32_t> tuple;
+    dist_layout(rank, n_ranks, dist, tiles, n_zone, &tuple);
     for (size_t k = 0; k < plan.passes.size(); k++) {
       passes[k].order.upload(tiles[k], &dev_bytes);
       passes[k].dev.order = passes[k].order.p;
+      build_desc(k, tiles[k], &tuple);
       passes[k].dev.n_zone = n_zone[k];
       passes[k].grid = (uint32_t)tiles[k].size();
     }
@@ -669,9 +739,9 @@ struct sb_solver {
     }
   }
 
-  void launch_pass(size_t k, cudaStream_t s, uint32_t n_seg = 1, uint32_t reps = 1, bool pre = false, bool post = false) {
-    if (fast()) launch_tile<true>(passes[k], s, n_seg, reps, pre, post);
-    else launch_tile<false>(passes[k], s, n_seg, reps, pre, post);
+  void launch_pass(size_t k, cudaStream_t s, uint32_t n_seg = 1, uint32_t reps = 1, bool pre = false, bool post = false, uint32_t next_pass = 0) {
+    if (fast()) launch_tile<true>(passes[k], s, n_seg, reps, pre, post, next_pass);
+    else launch_tile<false>(passes[k], s, n_seg, reps, pre, post, next_pass);
   }
   void launch_global(cudaStream_t s, int group = -1) {
     for (const GlobalBatch &b : plan.gbatches) {
@@ -754,6 +824,7 @@ struct sb_solver {
     int arg = 0;                  // pass index / constraint group / exchange phase
     uint32_t n_seg = 1, reps = 1; // PASS
     bool pre = false, post = false;
+    uint32_t next_pass = 0;       // PASS: the pass of the next launch that touches positions (0 also stands for the vertices' home)
   };
   // every constraint sits in a tile pass of group 0: any pass order is a Gauss-Seidel order, and passes can be fused
   bool pure() const {
@@ -846,6 +917,10 @@ struct sb_solver {
       else { flush(false); simple(Launch::FINISH); }
     }
     if (want_normals) simple(Launch::NORMALS);
+    // distributed meshes: a tile launch hands its vertices to the ranks that run the next launch's tiles; a per-vertex
+    // kernel, the normals and the next frame (which starts with pass 0 or a per-vertex kernel) find them at home
+    for (size_t i = 0; i < L.size(); i++)
+      if (L[i].kind == Launch::PASS) L[i].next_pass = (i + 1 < L.size() && L[i + 1].kind == Launch::PASS) ? (uint32_t)L[i + 1].arg : 0u;
     return L;
   }
 
@@ -853,7 +928,7 @@ struct sb_solver {
     switch (l.kind) {
       case Launch::PREDICT: launch_predict(s); break;
       case Launch::FINISH: launch_finish(s); break;
-      case Launch::PASS: launch_pass((size_t)l.arg, s, l.n_seg, l.reps, l.pre, l.post); break;
+      case Launch::PASS: launch_pass((size_t)l.arg, s, l.n_seg, l.reps, l.pre, l.post, l.next_pass); break;
       case Launch::GLOBAL: launch_global(s, l.arg); break;
       case Launch::GROUP: launch_group(l.arg, s); break;
       case Launch::EXCHANGE: exchange(l.arg, s); break;

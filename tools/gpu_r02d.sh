@@ -1,20 +1,18 @@
 #!/bin/bash
-# 2-GPU session: real-GPU bit-identity tests, the driver's N=2 bench line, strong scaling on a 2 M mesh with A/B switches
-out=gpurun_out; mkdir -p $out
+# 2-GPU session: real-GPU bit-identity tests, strong scaling of a 2 M mesh (1 vs 2 GPUs), the driver's N=2 bench line (8 M mesh)
+out=gpurun_out; mkdir -p $out; tag=${1:-r02g}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-timeout 900 python -m pytest tests/test_multigpu.py tests/test_partition.py -m gpu -x -q 2>&1 | tail -6
-python bench.py --workload dist --n 126 --steps 10 --no-bodies --no-cpu-baseline > $out/bench_r02d_2M_n1.json 2> $out/bench_r02d.err || tail -3 $out/bench_r02d.err
-for v in "" "--slabs" "--no-fuse" "--no-pdl"; do
-  $TR --master-port 29600 bench.py --gpus 2 --workload dist --n 126 --steps 10 --no-bodies $v > $out/bench_r02d_2M_n2$(echo $v | tr -d " ").json 2>> $out/bench_r02d.err || tail -3 $out/bench_r02d.err
-done
-$TR --master-port 29601 bench.py --gpus 2 --steps 10 --warmup 3 > $out/bench_r02d_8M_n2.json 2>> $out/bench_r02d.err || tail -3 $out/bench_r02d.err
-python - <<'PY'
-import json, glob
-for f in sorted(glob.glob("gpurun_out/bench_r02d_*.json")):
+timeout 900 python -m pytest tests/test_multigpu.py -m gpu -x -q > $out/pytest_multigpu_${tag}.log 2>&1; tail -3 $out/pytest_multigpu_${tag}.log
+python bench.py --workload dist --size 126 --steps 10 --no-bodies --no-cpu-baseline > $out/bench_${tag}_2M_n1.json 2> $out/bench_${tag}.err || tail -3 $out/bench_${tag}.err
+$TR --master-port 29600 bench.py --gpus 2 --workload dist --size 126 --steps 10 --no-bodies > $out/bench_${tag}_2M_n2.json 2>> $out/bench_${tag}.err || tail -3 $out/bench_${tag}.err
+$TR --master-port 29601 bench.py --gpus 2 --workload dist --size 126 --steps 10 --no-bodies --no-pdl > $out/bench_${tag}_2M_n2_nopdl.json 2>> $out/bench_${tag}.err || tail -3 $out/bench_${tag}.err
+python - $tag <<'PY'
+import json, glob, sys
+for f in sorted(glob.glob("gpurun_out/bench_%s_*.json" % sys.argv[1])):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         print(f, "ms/step %.3f" % d["ms_per_step"], "value %.4g" % d["value"], "e2e", (d.get("e2e") or {}).get("ms_per_step"), "chk", (d.get("state_checksum") or {}).get("x4_words_hi_lo"),
-              "tiles0", d["config"].get("tiles_rank0"), "bodies", (d.get("bodies") or {}).get("value"))
+              "tiles0", d["config"].get("tiles_rank0"), "bodies", (d.get("bodies") or {}).get("value"), "build_s", d["config"].get("build_seconds"))
     except Exception as e:
         print(f, "ERR", e)
 PY
