@@ -286,14 +286,20 @@ def main():
         shared = PartitionedBody(part, device=local, **kw)
         connect_peers(shared, local)     # CUDA IPC handles travel over torch.distributed once; the data path is P2P stores
         sb = shared.sb
-    elif args.workload == "dist" and world > 1:
-        from softbodyunity_b200.dist import DistBody
-        V_global, T_global = len(pos), len(tets)
-        if args.slabs:
-            kw["dist_ranks"] = 0
-        shared = DistBody(pos, tets, tris, device=local, **kw)
+    elif args.workload == "dist":
+        # ONE plan for every N: the box grid and the block numbering are those of an 8-way split (2 and 4 ranks take
+        # unions of its blocks), the CTA width is pinned -- so the Gauss-Seidel order, and with it the state checksum,
+        # is the same on 1, 2, 4 and 8 GPUs
+        kw["dist_ranks"] = 0 if args.slabs else 8
+        kw["block_threads"] = args.block_threads or 160
+        if world > 1:
+            from softbodyunity_b200.dist import DistBody
+            V_global, T_global = len(pos), len(tets)
+            shared = DistBody(pos, tets, tris, device=local, **kw)
+            sb = shared.sb
+        else:
+            sb = SoftBody(pos, tets, tris, device=local, **kw)
         kw.pop("dist_ranks", None)
-        sb = shared.sb
     else:
         sb = SoftBody(pos, tets, tris, device=local, **kw)
     info = sb.info()

@@ -760,7 +760,7 @@ struct Tiling {
 // `atom_key` (per caller vertex) orders vertices inside a box of tiling 0 by the 1/N_T-box
 // sub-box ("atom") they fall in, z-major, so that every box of every shifted tiling is a
 // union of a few contiguous runs of the device numbering.
-bool grid_tilings(const Plan &P, uint32_t cap, int n_tilings, std::vector<Tiling> &out, std::vector<uint32_t> &atom_key) {
+bool grid_tilings(const Plan &P, uint32_t cap, int n_tilings, std::vector<Tiling> &out, std::vector<uint32_t> &atom_key, int dist_ranks = 0) {
   const uint32_t V = P.V;
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (uint32_t v = 0; v < V; v++)
@@ -785,8 +785,25 @@ bool grid_tilings(const Plan &P, uint32_t cap, int n_tilings, std::vector<Tiling
     double wa[3];
     for (int k = 0; k < 3; k++) {
       n[k] = ext[k] > 0 ? std::max(1, (int)std::ceil(ext[k] / w - 1e-9)) : 1;
-      wa[k] = ext[k] > 0 ? ext[k] / n[k] : 1.0;
     }
+    // One mesh over 2 / 4 / 8 GPUs: the boxes are later cut into compact blocks by recursive bisection along the
+    // longest axis (make_plan).  An odd number of boxes along a cut axis would leave one side a whole layer of
+    // boxes heavier (17 boxes: 8 | 9, i.e. 9^3 against an average of 8.5^3 boxes per rank at 8 ranks: +19 % on the
+    // slowest rank), so the count along every axis is rounded up to a multiple of the cuts it will take.
+    if (dist_ranks >= 2 && (dist_ranks & (dist_ranks - 1)) == 0) {
+      double e[3] = {ext[0], ext[1], ext[2]};
+      int mult[3] = {1, 1, 1};
+      for (int r = dist_ranks; r > 1; r /= 2) {
+        int ax = 2; // ties: z first, like the bisection
+        for (int k = 1; k >= 0; k--)
+          if (e[k] > e[ax]) ax = k;
+        mult[ax] *= 2;
+        e[ax] /= 2;
+      }
+      for (int k = 0; k < 3; k++)
+        if (ext[k] > 0) n[k] = (n[k] + mult[k] - 1) / mult[k] * mult[k];
+    }
+    for (int k = 0; k < 3; k++) wa[k] = ext[k] > 0 ? ext[k] / n[k] : 1.0;
     if ((double)(n[0] + 1) * (n[1] + 1) * (n[2] + 1) > 64e6) return false;
     out.assign(n_tilings, Tiling());
     bool ok = true;
@@ -1918,7 +1935,7 @@ std::string build_plan(const MeshInput &in, const PlanOptions &opt, Plan &P) {
   }
   n_tilings = std::min(n_tilings, 8);
   std::vector<uint32_t> atom_key;
-  if (n_tilings >= 2 && !grid_tilings(P, cap, n_tilings, tilings, atom_key)) n_tilings = 1;
+  if (n_tilings >= 2 && !grid_tilings(P, cap, n_tilings, tilings, atom_key, opt.dist_ranks)) n_tilings = 1;
   P.n_tilings = (uint32_t)n_tilings;
 
   std::vector<uint32_t> tile_off;

@@ -5,7 +5,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 
 timeout 900 python -m pytest tests/test_multigpu.py -m gpu -x -q > $out/pytest_multigpu_${tag}.log 2>&1; tail -3 $out/pytest_multigpu_${tag}.log
 python bench.py --workload dist --size 126 --steps 10 --no-bodies --no-cpu-baseline > $out/bench_${tag}_2M_n1.json 2> $out/bench_${tag}.err || tail -3 $out/bench_${tag}.err
 $TR --master-port 29600 bench.py --gpus 2 --workload dist --size 126 --steps 10 --no-bodies > $out/bench_${tag}_2M_n2.json 2>> $out/bench_${tag}.err || tail -3 $out/bench_${tag}.err
-$TR --master-port 29601 bench.py --gpus 2 --workload dist --size 126 --steps 10 --no-bodies --no-pdl > $out/bench_${tag}_2M_n2_nopdl.json 2>> $out/bench_${tag}.err || tail -3 $out/bench_${tag}.err
+$TR --master-port 29601 bench.py --gpus 2 --workload dist --size 126 --steps 10 --no-bodies --slabs > $out/bench_${tag}_2M_n2_slabs.json 2>> $out/bench_${tag}.err || tail -3 $out/bench_${tag}.err
 python - $tag <<'PY'
 import json, glob, sys
 for f in sorted(glob.glob("gpurun_out/bench_%s_*.json" % sys.argv[1])):
