@@ -43,7 +43,7 @@ typedef enum sb_status {
   SB_E_CUDA = -2,  /* CUDA runtime error (message via sb_last_error) */
   SB_E_NCCL = -3,  /* reserved for the multi-GPU halo exchange */
   SB_E_NAN = -4,   /* non-finite state detected */
-  SB_E_STATE = -5, /* call not valid in the current state (e.g. destroyed handle) */
+  SB_E_STATE = -5, /* call not valid in the current state (e.g. a device call on a host-only handle, a peer wait that timed out) */
   SB_E_NOMEM = -6
 } sb_status;
 
@@ -162,6 +162,8 @@ int sb_create(const sb_mesh_desc *mesh, const sb_params *params, sb_handle *out)
  * queries work on it; everything that needs the device returns SB_E_STATE.
  */
 int sb_plan(const sb_mesh_desc *mesh, const sb_params *params, sb_handle *out);
+/* Releases the handle and everything it owns (synchronises its stream first).  The handle is INVALID afterwards: like
+ * free(), a second sb_destroy or any other call on it is undefined.  The managed mirrors null their copy. */
 int sb_destroy(sb_handle h);
 
 int sb_set_params(sb_handle h, const sb_params *params);

@@ -687,7 +687,7 @@ int load_msh(const std::string &path, sb_tetmesh &m) {
         if (!std::getline(in, line)) return fail(SB_E_ARG, ".msh: fewer elements than the header says");
         std::istringstream s(line);
         long long id, type, ntags, tag;
-        if (!(s >> id >> type >> ntags)) return fail(SB_E_ARG, ".msh: malformed element");
+        if (!(s >> id >> type >> ntags) || ntags < 0 || ntags > 64) return fail(SB_E_ARG, ".msh: malformed element");
         for (long long k = 0; k < ntags; k++) s >> tag;
         const int nn = type == 4 ? 4 : type == 2 ? 3 : 0;
         if (!nn) continue;

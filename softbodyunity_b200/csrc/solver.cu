@@ -112,7 +112,6 @@ struct sb_solver {
   Plan plan;
   sb_params prm{};
   bool on_device = false;
-  bool destroyed = false;
   int device = 0;
   int n_sm = 148;
   cudaStream_t stream = nullptr;
@@ -1256,9 +1255,8 @@ static int guarded(sb_handle h, F fn) {
   }
 }
 
-#define NEED_HANDLE(h)          \
-  if (!(h)) return SB_E_ARG;    \
-  if ((h)->destroyed) return SB_E_STATE
+#define NEED_HANDLE(h) \
+  if (!(h)) return SB_E_ARG
 #define NEED_DEVICE(h)                                   \
   NEED_HANDLE(h);                                        \
   if (!(h)->on_device) {                                 \
@@ -1939,6 +1937,10 @@ int sb_halo_set(sb_handle h, int32_t list_id, const int32_t *vertex_ids, uint32_
       if (vertex_ids[k] < 0 || (uint32_t)vertex_ids[k] >= h->plan.V) throw std::string("halo vertex id out of range");
       slots[k] = h->plan.inv[vertex_ids[k]];
     }
+    if (h->links.count(list_id)) throw std::string("this halo list is linked to a peer already (sb_halo_alloc / sb_halo_connect): its size is fixed");
+    CK(cudaStreamSynchronize(h->stream));
+    for (auto &g : h->graphs) cudaGraphExecDestroy(g.second); // a captured frame holds the old index buffer and count
+    h->graphs.clear();
     h->halo[list_id].upload(slots, &h->dev_bytes);
     return SB_OK;
   });

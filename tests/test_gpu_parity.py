@@ -8,6 +8,7 @@ full-size runs: max position error <= 1e-4 of the body's bounding-box diagonal a
 in the mount): the oracle is the in-repo XPBD restatement.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -195,6 +196,43 @@ def test_energy_and_volume_drift_track_the_oracle():
     assert abs(r[2] - 1.0) < 0.05
 
 
+def test_sphere_100k_hundred_substeps_both_modes():
+    # BASELINE.json configs[1]: the 100 k-vertex tet-mesh sphere, 10 substeps x 10 iterations; 100 substeps (10 frames):
+    # exact mode bit-identical to the oracle, fast math within 1e-4 of the bounding-box diagonal
+    pos, tets, tris = meshgen.sphere(58, spacing=0.01)
+    assert 95_000 < len(pos) < 110_000
+    for flags, exact in ((0, True), (FLAG_FAST_MATH, False)):
+        sb, m, x4, v4 = run_pair(pos, tets, tris, n_frames=10, flags=flags)
+        assert m.x4[:, 1].min() == 0.0  # in ground contact
+        if exact:
+            assert ulp_diff_count(x4, m.x4) == 0 and bits_equal(v4, m.v4)
+        else:
+            assert rel_err(x4, m.x4) <= 1e-4, rel_err(x4, m.x4)
+
+
+def test_thousand_substeps_energy_and_volume_drift_track_the_oracle():
+    # BASELINE.json:5 "energy and volume drift must match over 1000 steps": the config-1 substitute (soft cube dropped on the
+    # ground plane, 60 Hz, 10 x 10), 100 frames = 1000 substeps, diagnostics sampled every 10 frames; the state itself stays
+    # bit-identical, so the curves agree to the rounding of the fp64 reductions
+    pos, tets, tris = meshgen.sample_cube(6, centre_height=0.55, jitter=0.05, seed=1234)
+    sb = SoftBody(pos, tets, tris, stiffness=2e5)
+    sched = sb.schedule_kw()
+    m = orc.Model(pos, tets, roles=sb.tet_roles())
+    p = oracle_params(sb)
+    e0 = None
+    for _ in range(10):
+        sb.step(frames=10)
+        m.simulate(p, n_frames=10, **sched)
+        d, r = sb.diagnostics()["raw"], m.diagnostics()
+        e_gpu, e_ref = d[0] + d[1], r[0] + r[1]
+        e0 = e_ref if e0 is None else e0
+        assert abs(e_gpu - e_ref) <= 1e-9 * max(1.0, abs(e_ref))
+        assert abs(d[2] - r[2]) <= 1e-12 + 1e-9 * abs(r[2])
+    x4, v4 = sb.get_state()
+    assert ulp_diff_count(x4, m.x4) == 0
+    assert sb.frames_done() == 100
+
+
 def test_many_bodies_batch():
     pos, tets, tris = meshgen.bodies(40, dims=(6, 5, 5), spacing=0.04, base_height=0.03)
     sb, m, x4, v4 = run_pair(pos, tets, tris, n_frames=10, tile_cap=512)
@@ -215,9 +253,14 @@ def test_large_mesh_properties():
     x4, v4 = sb.get_state()
     sched = sb.schedule_kw()
     m = orc.Model(pos, tets, roles=sb.tet_roles())
-    m.simulate(oracle_params(sb), n_frames=2, threads=16, **sched)
+    threads = os.cpu_count() or 16
+    m.simulate(oracle_params(sb), n_frames=2, threads=threads, **sched)
     assert ulp_diff_count(x4, m.x4) == 0
+    # BASELINE.json:5 "after 100 steps": 10 frames x 10 substeps x 10 iterations of the headline mesh, bit for bit
     sb.step(frames=8)
+    x4, v4 = sb.get_state()
+    m.simulate(oracle_params(sb), n_frames=8, threads=threads, **sched)
+    assert ulp_diff_count(x4, m.x4) == 0 and bits_equal(v4, m.v4)
     d1 = sb.diagnostics()
     assert d1["nonfinite"] == 0 and d1["min_y"] >= 0.0
     # 10 sweeps per substep do not converge a 100-layer stack: it compresses a few percent on impact
