@@ -318,7 +318,6 @@ struct sb_solver {
     PassBufs &pb = passes[k];
     std::vector<uint32_t> roff;
     if (tuple) {
-      if (!tp.contiguous && tp.run_off.empty()) throw std::string("a distributed mesh needs run lists for its shifted tilings");
       std::vector<uint2> ro;
       roff.assign((size_t)tp.n_tiles() + 1, 0);
       auto emit = [&](uint32_t first, uint32_t len, uint32_t local) { // [first, first + len) at local offset `local`
@@ -336,8 +335,14 @@ struct sb_solver {
         if (nv_t > 0x1ffffu) throw std::string("tile too large for a distributed mesh");
         if (tp.contiguous) {
           emit(tp.vert_off[t], nv_t, 0);
-        } else {
-          for (uint32_t r = tp.run_off[t]; r + 1 < tp.run_off[t + 1]; r++) emit(tp.runs[r].x, tp.runs[r + 1].y - tp.runs[r].y, tp.runs[r].y);
+        } else { // maximal ranges of consecutive device ids in the tile's (ascending) vertex list
+          const uint32_t *tv = tp.tile_verts.data() + tp.vert_off[t];
+          for (uint32_t a = 0; a < nv_t;) {
+            uint32_t b = a + 1;
+            while (b < nv_t && tv[b] == tv[b - 1] + 1) b++;
+            emit(tv[a], b - a, a);
+            a = b;
+          }
         }
         ro.push_back(make_uint2(0, nv_t)); // closes the tile's list
       }
@@ -572,7 +577,8 @@ struct sb_solver {
   void dist_layout(int rank, int n_ranks, DistDev &D, std::vector<std::vector<uint32_t>> &tiles, std::vector<uint32_t> &n_zone,
                    std::vector<uint32_t> *runner_tuple = nullptr) const {
     if (n_ranks < 2 || n_ranks > SB_MAX_RANKS || rank < 0 || rank >= n_ranks) throw std::string("rank / n_ranks out of range (2..8 ranks)");
-    if (!plan.dag_ok) throw std::string("a distributed mesh must be planned as balanced shifted tilings (one big component, no ghosts, nothing left over)");
+    if (plan.n_tilings < 2 || plan.n_ghost || !plan.gbatches.empty() || plan.passes.empty() || plan.passes.size() > 5)
+      throw std::string("a distributed mesh must be planned as balanced shifted tilings (one big component, no ghosts, no global colour batches, at most one leftover pass)");
     const TilePass &t0 = plan.passes[0];
     if (!t0.contiguous || t0.n_tiles() < (uint32_t)n_ranks) throw std::string("fewer tiles than ranks");
     D = DistDev{};
@@ -601,14 +607,6 @@ struct sb_solver {
       while (r + 1 < D.n_ranks && dev >= D.slab_lo[r + 1]) r++;
       return r;
     };
-    // a tile reads and writes each of its runs in the memory of the rank that owns the run's first vertex: no run
-    // may cross a slab boundary (the planner never lets a run cross a box of the unshifted tiling)
-    for (const TilePass &tp : plan.passes)
-      for (uint32_t t = 0; t < tp.n_tiles() && !tp.contiguous && !tp.run_off.empty(); t++)
-        for (uint32_t r = tp.run_off[t]; r + 1 < tp.run_off[t + 1]; r++) {
-          const uint32_t first = tp.runs[r].x, len = tp.runs[r + 1].y - tp.runs[r].y;
-          if (len && owner_of(first) != owner_of(first + len - 1)) throw std::string("a vertex run crosses a slab boundary");
-        }
     // Who runs a tile: the rank that owns most of its vertices (ties: the lower rank).  (Dealing a spanning tile
     // to the less loaded of its ranks instead was measured slower: more of its runs become remote.)
     const size_t np = plan.passes.size();

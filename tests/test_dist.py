@@ -18,9 +18,8 @@ def test_virtual_ranks_over_peer_memory_match_one_gpu_and_the_oracle(n_ranks, kw
     import torch
     pos, tets, tris = meshgen.block(14, 12, 26, spacing=0.05, origin=(0, 0.02, 0))
     kw = dict(dict(substeps=5, iterations=6, dist_ranks=n_ranks), **kw)
-    # one GPU, default numbering of the boxes: how the boxes of the unshifted tiling are numbered (block by block for
-    # the ranks, dist_ranks) changes neither the colouring nor the passes, so the results are the same bits
-    one = SoftBody(pos, tets, tris, **{k: v for k, v in kw.items() if k != "dist_ranks"})
+    # one GPU, the same plan (dist_ranks is a planner hint: box grid rounded to the cuts, boxes numbered block by block)
+    one = SoftBody(pos, tets, tris, **kw)
     one.step(frames=6)
     x1, v1 = one.get_state()
     stream = torch.cuda.Stream()
@@ -41,6 +40,36 @@ def test_virtual_ranks_over_peer_memory_match_one_gpu_and_the_oracle(n_ranks, kw
     assert m.x4[:, 1].min() == 0.0
     assert bits_equal(X, m.x4) and bits_equal(U[:, :3], m.v4[:, :3])
     ids = one.surface_vertices()
+    assert bits_equal(N[ids], m.normals(tris)[ids])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_ranks", [2, 3, 4])
+def test_an_ingested_body_is_cut_by_recursive_bisection_and_matches_the_oracle(n_ranks):
+    # not a lattice block: a torus surface -> tets (boundary snapped onto the surface), cut into n_ranks compact parts by
+    # recursive coordinate bisection of the boxes' centroids weighted by their vertex counts (the partitioner of this path)
+    import torch
+    from softbodyunity_b200 import ingest
+    from test_ingest import torus
+    sp, st = torus(0.5, 0.2, 48, 24)
+    sp = sp + np.float32([0.0, 0.25, 0.0])  # lying flat, 5 cm above the ground
+    pos, tets, tris = ingest.tetrahedralize_surface(sp, st, 0.035, snap=True)
+    assert len(pos) > 8000
+    kw = dict(substeps=4, iterations=5, tile_cap=400, dist_ranks=n_ranks, stiffness=3e5)  # (four tilings and one leftover pass)
+    stream = torch.cuda.Stream()
+    vr = VirtualRanks(pos, tets, tris, n_ranks, stream.cuda_stream, **kw)
+    owned = np.stack(vr.owned)
+    assert (owned.sum(0) == 1).all()
+    share = owned.sum(1) / len(pos)
+    assert share.min() > 0.6 / n_ranks and share.max() < 1.5 / n_ranks, share  # balanced by vertex count
+    vr.step(frames=5)
+    stream.synchronize()
+    X, U, N = vr.gather_state(with_surface=True)
+    assert not any(sb.dist_error() for sb in vr.ranks)
+    m = orc.Model(pos, tets, roles=vr.ranks[0].tet_roles())
+    m.simulate(oracle_params(vr.ranks[0]), n_frames=5, threads=8, **vr.ranks[0].schedule_kw())
+    assert bits_equal(X, m.x4) and bits_equal(U[:, :3], m.v4[:, :3])
+    ids = vr.ranks[0].surface_vertices()
     assert bits_equal(N[ids], m.normals(tris)[ids])
 
 
