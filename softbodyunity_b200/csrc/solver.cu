@@ -287,7 +287,7 @@ struct sb_solver {
       }
       pb.order.upload(tp.launch_order, &dev_bytes);
       pb.dev = PassDev{pb.order.p, pb.vert_off.p, tp.contiguous ? nullptr : pb.tile_verts.p, use_runs ? pb.run_off.p : nullptr,
-                       use_runs ? pb.runs.p : nullptr, pb.rounds.p, nullptr, {nullptr}, 0u, reinterpret_cast<const uint4 *>(pb.stream.p),
+                       use_runs ? pb.runs.p : nullptr, pb.rounds.p, nullptr, {nullptr}, 0u, 0u, reinterpret_cast<const uint4 *>(pb.stream.p),
                        pb.aux.p, tp.n_tiles(), pos_bytes, nullptr, nullptr, 1u, 1u, 0u, 0u, nullptr, nullptr, 0u, 0u};
       pb.grid = tp.n_tiles();
       build_desc(k, tp.launch_order);
@@ -325,14 +325,14 @@ struct sb_solver {
         while (a < len) {
           uint32_t b = a + 1;
           while (b < len && (*tuple)[first + b] == (*tuple)[first + a]) b++;
-          ro.push_back(make_uint2(first + a, (local + a) | ((*tuple)[first + a] << 17)));
+          ro.push_back(make_uint2(first + a, (local + a) | ((*tuple)[first + a] << 16)));
           a = b;
         }
       };
       for (uint32_t t = 0; t < tp.n_tiles(); t++) {
         roff[t] = (uint32_t)ro.size();
         const uint32_t nv_t = tp.vert_off[t + 1] - tp.vert_off[t];
-        if (nv_t > 0x1ffffu) throw std::string("tile too large for a distributed mesh");
+        if (nv_t > 0xffffu) throw std::string("tile too large for a distributed mesh");
         if (tp.contiguous) {
           emit(tp.vert_off[t], nv_t, 0);
         } else { // maximal ranges of consecutive device ids in the tile's (ascending) vertex list
@@ -462,7 +462,8 @@ struct sb_solver {
   // One launch of tile pass `pb`: n_seg segments (substeps) of `reps` repetitions of every tile's rounds, with the
   // substep boundaries between segments -- and predict before / finish after, if asked -- done on the tiles.
   template <bool FAST>
-  void launch_tile(const PassBufs &pb, cudaStream_t s, uint32_t n_seg = 1, uint32_t reps = 1, bool pre = false, bool post = false, uint32_t next_pass = 0) {
+  void launch_tile(const PassBufs &pb, cudaStream_t s, uint32_t n_seg = 1, uint32_t reps = 1, bool pre = false, bool post = false, uint32_t next_pass = 0,
+                   uint32_t next_full_pass = 0) {
     if (pb.empty && !(pre || post || n_seg > 1)) return;
     if (!pb.grid) {
       // distributed: this rank has no tile in the pass, but its epoch moves with every launch of the sequence
@@ -470,7 +471,7 @@ struct sb_solver {
       return;
     }
     PassDev dev = pb.dev;
-    dev.n_seg = n_seg; dev.reps = reps; dev.pre = pre; dev.post = post; dev.next_pass = next_pass;
+    dev.n_seg = n_seg; dev.reps = reps; dev.pre = pre; dev.post = post; dev.next_pass = next_pass; dev.next_full_pass = next_full_pass;
     if (dist_on) for (uint32_t r = 0; r < dist.n_ranks; r++) dev.xs[r] = dist.x_of[r];
     else dev.xs[0] = x.p;
     dev.v = v.p; dev.xp = xp.p;
@@ -653,10 +654,14 @@ struct sb_solver {
     D.nbr_mask = nbr & ~(1u << rank);
     if (runner_tuple) { // per device vertex: the rank that runs its tile in pass k, three bits per pass (pass 0 = its slab's rank)
       if (np > 5) throw std::string("a distributed mesh has at most five tile passes");
+      // (only the last pass may leave vertices out -- a leftover pass after the tilings; bit 15: this vertex is in it)
       runner_tuple->assign(plan.V, 0u);
       for (uint32_t d = 0; d < plan.V; d++) {
         uint32_t tup = 0;
-        for (size_t k = 0; k < np; k++) tup |= (tile_of[k][d] != 0xffffffffu ? (uint32_t)runner[k][tile_of[k][d]] : owner_of(d)) << (3 * k);
+        for (size_t k = 0; k < np; k++) {
+          if (tile_of[k][d] != 0xffffffffu) tup |= (uint32_t)runner[k][tile_of[k][d]] << (3 * k) | (k + 1 == np && np > plan.n_tilings ? 1u << 15 : 0u);
+          else if (k + 1 != np || np <= plan.n_tilings) throw std::string("a distributed mesh needs tilings that stage every vertex (SB_WHOLE_BOXES)");
+        }
         if ((tup & 7u) != owner_of(d)) throw std::string("the unshifted tiling's tiles must lie within one slab each");
         (*runner_tuple)[d] = tup;
       }
@@ -736,9 +741,10 @@ struct sb_solver {
     }
   }
 
-  void launch_pass(size_t k, cudaStream_t s, uint32_t n_seg = 1, uint32_t reps = 1, bool pre = false, bool post = false, uint32_t next_pass = 0) {
-    if (fast()) launch_tile<true>(passes[k], s, n_seg, reps, pre, post, next_pass);
-    else launch_tile<false>(passes[k], s, n_seg, reps, pre, post, next_pass);
+  void launch_pass(size_t k, cudaStream_t s, uint32_t n_seg = 1, uint32_t reps = 1, bool pre = false, bool post = false, uint32_t next_pass = 0,
+                   uint32_t next_full_pass = 0) {
+    if (fast()) launch_tile<true>(passes[k], s, n_seg, reps, pre, post, next_pass, next_full_pass);
+    else launch_tile<false>(passes[k], s, n_seg, reps, pre, post, next_pass, next_full_pass);
   }
   void launch_global(cudaStream_t s, int group = -1) {
     for (const GlobalBatch &b : plan.gbatches) {
@@ -821,7 +827,7 @@ struct sb_solver {
     int arg = 0;                  // pass index / constraint group / exchange phase
     uint32_t n_seg = 1, reps = 1; // PASS
     bool pre = false, post = false;
-    uint32_t next_pass = 0;       // PASS: the pass of the next launch that touches positions (0 also stands for the vertices' home)
+    uint32_t next_pass = 0, next_full_pass = 0; // PASS: the pass of the next launch that touches positions (0 also stands for the vertices' home)
   };
   // every constraint sits in a tile pass of group 0: any pass order is a Gauss-Seidel order, and passes can be fused
   bool pure() const {
@@ -916,8 +922,17 @@ struct sb_solver {
     if (want_normals) simple(Launch::NORMALS);
     // distributed meshes: a tile launch hands its vertices to the ranks that run the next launch's tiles; a per-vertex
     // kernel, the normals and the next frame (which starts with pass 0 or a per-vertex kernel) find them at home
-    for (size_t i = 0; i < L.size(); i++)
-      if (L[i].kind == Launch::PASS) L[i].next_pass = (i + 1 < L.size() && L[i + 1].kind == Launch::PASS) ? (uint32_t)L[i + 1].arg : 0u;
+    const int partial = plan.passes.size() > plan.n_tilings ? (int)plan.passes.size() - 1 : -1; // a leftover pass covers only some vertices
+    for (size_t i = 0; i < L.size(); i++) {
+      if (L[i].kind != Launch::PASS) continue;
+      L[i].next_pass = (i + 1 < L.size() && L[i + 1].kind == Launch::PASS) ? (uint32_t)L[i + 1].arg : 0u;
+      L[i].next_full_pass = L[i].next_pass;
+      if ((int)L[i].next_pass == partial) { // the vertices it leaves out go on to the first launch after it that is not that pass
+        size_t j = i + 1;
+        while (j < L.size() && L[j].kind == Launch::PASS && L[j].arg == partial) j++;
+        L[i].next_full_pass = (j < L.size() && L[j].kind == Launch::PASS) ? (uint32_t)L[j].arg : 0u;
+      }
+    }
     return L;
   }
 
@@ -925,7 +940,7 @@ struct sb_solver {
     switch (l.kind) {
       case Launch::PREDICT: launch_predict(s); break;
       case Launch::FINISH: launch_finish(s); break;
-      case Launch::PASS: launch_pass((size_t)l.arg, s, l.n_seg, l.reps, l.pre, l.post, l.next_pass); break;
+      case Launch::PASS: launch_pass((size_t)l.arg, s, l.n_seg, l.reps, l.pre, l.post, l.next_pass, l.next_full_pass); break;
       case Launch::GLOBAL: launch_global(s, l.arg); break;
       case Launch::GROUP: launch_group(l.arg, s); break;
       case Launch::EXCHANGE: exchange(l.arg, s); break;
