@@ -675,8 +675,9 @@ struct sb_solver {
       std::vector<uint32_t> part[2];
       for (uint32_t t = 0; t < tp.n_tiles(); t++) {
         if (runner[k][t] != (uint8_t)rank) continue;
-        const bool has_rounds = tp.rounds[t].y + tp.rounds[t].z != 0;
-        if (!has_rounds && !tp.contiguous) continue; // (a contiguous pass may carry the vertex stages: every tile runs)
+        // (a tile without constraints in this pass runs all the same: it hands its vertices on to the ranks that hold
+        // them in the next pass)
+        if (tp.vert_off[t + 1] == tp.vert_off[t]) continue;
         part[in_zone[k][t] ? 0 : 1].push_back(t);
       }
       auto work = [&](uint32_t t) { return ((uint64_t)(tp.rounds[t].y + tp.rounds[t].z) << 32) | (uint32_t)(tp.ent_off[t + 1] - tp.ent_off[t]); };
