@@ -230,7 +230,7 @@ def test_thousand_substeps_energy_and_volume_drift_track_the_oracle():
         assert abs(d[2] - r[2]) <= 1e-12 + 1e-9 * abs(r[2])
     x4, v4 = sb.get_state()
     assert ulp_diff_count(x4, m.x4) == 0
-    assert sb.frames_done() == 100
+    assert sb.frames_done == 100
 
 
 def test_many_bodies_batch():
