@@ -13,11 +13,12 @@ from softbodyunity_b200.dist import VirtualRanks
 @pytest.mark.gpu
 @pytest.mark.parametrize("n_ranks,kw", [(2, dict(tile_cap=256)), (3, dict(tile_cap=200, block_threads=32)),
                                          (4, dict(tile_cap=300, flags=16)), (8, dict(tile_cap=300, iterations=5)),
-                                         (2, dict(tile_cap=256, flags=128)), (4, dict(tile_cap=256, dist_ranks=0))])
+                                         (2, dict(tile_cap=256, flags=128)), (4, dict(tile_cap=256, dist_ranks=0)),
+                                         (2, dict(tile_cap=300, dist_ranks=8)), (4, dict(tile_cap=300, dist_ranks=8))])  # bench.py: the 8-way plan on 2 / 4 GPUs
 def test_virtual_ranks_over_peer_memory_match_one_gpu_and_the_oracle(n_ranks, kw):
     import torch
     # (eight ranks: a mesh with room for eight blocks of boxes -- four tilings and one leftover pass)
-    pos, tets, tris = meshgen.block(*((18, 18, 36) if n_ranks == 8 else (14, 12, 26)), spacing=0.05, origin=(0, 0.02, 0))
+    pos, tets, tris = meshgen.block(*((18, 18, 36) if 8 in (n_ranks, kw.get("dist_ranks")) else (14, 12, 26)), spacing=0.05, origin=(0, 0.02, 0))
     kw = dict(dict(substeps=5, iterations=6, dist_ranks=n_ranks), **kw)
     # one GPU, the same plan (dist_ranks is a planner hint: box grid rounded to the cuts, boxes numbered block by block)
     one = SoftBody(pos, tets, tris, **kw)
