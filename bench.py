@@ -15,8 +15,9 @@ the 1 M-vertex (100^3) tet block dropped on the ground plane, 10 substeps x 10 i
           not in the mount) on this box's host cores, bounded sample
 
 `--impl reference` times that CPU oracle alone (all host threads) on the same workload.
-N > 1 (torchrun): every rank steps its own body of the same size (independent bodies per
-GPU, no communication, BASELINE.json configs[3] sharding) -> weak scaling.
+N > 1 (torchrun): the path that shards -- ONE 200^3 = 8 M-vertex block spread over all the GPUs through
+NVLink peer memory (BASELINE.json configs[4], strong scaling; `--workload dist`), with the 4096-body batch
+of configs[3] sharded over the ranks as a secondary figure in the same line (`bodies`).
 """
 import argparse
 import json
@@ -176,7 +177,9 @@ def run_reference(args, rank, world):
         return
     from softbodyunity_b200 import SoftBody
     pos, tets, tris, name = workload(args)
-    plan = SoftBody(pos, tets, tris, host_only=True)  # only the Gauss-Seidel order (colour schedule) is taken from it
+    # only the Gauss-Seidel order (colour schedule) is taken from the plan; the same plan options as the native arm
+    pkw = dict(dist_ranks=0 if args.slabs else 8, block_threads=args.block_threads or 160) if args.workload == "dist" else dict(block_threads=args.block_threads)
+    plan = SoftBody(pos, tets, tris, host_only=True, tile_cap=args.tile_cap, **pkw)
     sched = plan.schedule_kw()
     info = plan.info()
     threads = os.cpu_count() or 1
