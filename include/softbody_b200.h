@@ -352,8 +352,9 @@ int sb_lumped_inv_mass(const float *pos_xyz, uint32_t n_verts, const int32_t *te
  *                    returns the device addresses of its position array and control block (export them with
  *                    sb_ipc_export, or pass them directly between handles of one process);
  *   sb_dist_connect  (once per peer) gives the peer's two addresses; when all peers are connected the handle is live.
- * sb_step then runs this rank's tiles; a tile reads and writes each of its vertex runs in the memory of the rank that
- * owns the run, and kernels of neighbouring ranks order themselves through an epoch word.  All ranks must issue the
+ * sb_step then runs this rank's tiles; a vertex's position lives with the rank that touches it next: a tile loads from
+ * its own GPU's array and stores every run of vertices into the array of the rank that holds it in the next launch (at the
+ * end of a frame: of the rank that owns it), and kernels of neighbouring ranks order themselves through an epoch word.  All ranks must issue the
  * same sequence of steps (and hold the same flags: the launch sequence must be the same everywhere).  Positions /
  * state read back from a rank are valid for the vertices sb_dist_owned marks; sb_read_packed carries exactly those.
  * Surface normals: each rank computes them for the surface vertices it owns (triangles that reach into a
@@ -366,6 +367,14 @@ int sb_dist_error(sb_handle h, int32_t *out); /* 1 if a wait for a peer ever tim
 /* Host only (works on an sb_plan handle): the vertices rank would own and, for one pass, which tiles it would run
    (tile_owner_pass[t] = 1 / 0; sb_get_tiles gives the tile count).  Either pointer may be NULL. */
 int sb_dist_layout(sb_handle h, int32_t rank, int32_t n_ranks, uint8_t *owned_V, int32_t *tile_owner_pass, uint32_t pass);
+/* Host only: replays the hand-over protocol of one frame symbolically for n_ranks ranks -- every tile launch of the frame
+   program, every tile of every rank -- and counts the vertices a tile would load while their current value sits in another
+   rank's array (n_stale), the vertices that are not back with their owner at a per-vertex kernel, the normals or the end
+   of the frame (n_not_home), and the vertices touched by a tile whose rank did not classify the tile as a zone tile although
+   the previous holder was another rank (n_unordered).  All three are 0 for a correct layout.  n_crossings: how many
+   vertex values changed rank during the frame (the NVLink stores of one frame, in vertices).  Any pointer may be NULL. */
+int sb_dist_verify(sb_handle h, int32_t n_ranks, uint64_t *n_stale, uint64_t *n_not_home, uint64_t *n_unordered,
+                   uint64_t *n_crossings);
 
 /* Debug aid: timestamps of one run of tile pass `pass` (see solver.cu); out holds 64 * 80 words. */
 int sb_debug_trace_pass(sb_handle h, uint32_t pass, unsigned long long *out, uint32_t n_words);

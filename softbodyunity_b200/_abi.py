@@ -25,7 +25,7 @@ EXPORTS = [
     "sb_time_frames", "sb_time_kernel", "sb_debug_trace_pass", "sb_debug_verify_streams", "sb_last_error",
     "sb_set_stream", "sb_prepare", "sb_enqueue", "sb_halo_set", "sb_halo_pack", "sb_halo_unpack", "sb_lumped_inv_mass",
     "sb_halo_alloc", "sb_halo_connect", "sb_halo_error", "sb_ipc_export", "sb_ipc_open",
-    "sb_dist_setup", "sb_dist_connect", "sb_dist_owned", "sb_dist_error", "sb_dist_layout",
+    "sb_dist_setup", "sb_dist_connect", "sb_dist_owned", "sb_dist_error", "sb_dist_layout", "sb_dist_verify",
     "sb_skin_bind", "sb_skin_get_binding", "sb_read_skinned", "sb_skin_compute",
     "sb_save_state", "sb_load_state", "sb_frames_done", "sb_state_write", "sb_state_read", "sb_topology_hash",
     "sb_tetmesh_from_surface", "sb_tetmesh_snap_to_surface", "sb_tetmesh_from_arrays", "sb_tetmesh_load", "sb_tetmesh_save", "sb_tetmesh_sizes",
@@ -149,6 +149,7 @@ def load():
         "sb_dist_owned": (C.c_int, [vp, vp, vp]),
         "sb_dist_error": (C.c_int, [vp, P(i32)]),
         "sb_dist_layout": (C.c_int, [vp, i32, i32, vp, vp, u32]),
+        "sb_dist_verify": (C.c_int, [vp, i32, vp, vp, vp, vp]),
         "sb_skin_bind": (C.c_int, [vp, vp, u32, vp, u32]),
         "sb_skin_get_binding": (C.c_int, [vp, vp, vp, u32]),
         "sb_read_skinned": (C.c_int, [vp, vp, vp, u32]),

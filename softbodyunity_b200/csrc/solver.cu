@@ -577,6 +577,7 @@ struct sb_solver {
   // and how many of them are zone tiles.
   void dist_layout(int rank, int n_ranks, DistDev &D, std::vector<std::vector<uint32_t>> &tiles, std::vector<uint32_t> &n_zone,
                    std::vector<uint32_t> *runner_tuple = nullptr) const {
+    // (tiles[k] = this rank's tiles of pass k, the first n_zone[k] of them zone tiles)
     if (n_ranks < 2 || n_ranks > SB_MAX_RANKS || rank < 0 || rank >= n_ranks) throw std::string("rank / n_ranks out of range (2..8 ranks)");
     if (plan.n_tilings < 2 || plan.n_ghost || !plan.gbatches.empty() || plan.passes.empty() || plan.passes.size() > 5)
       throw std::string("a distributed mesh must be planned as balanced shifted tilings (one big component, no ghosts, no global colour batches, at most one leftover pass)");
@@ -2058,6 +2059,94 @@ int sb_dist_owned(sb_handle h, uint8_t *owned_V, uint32_t *tiles_per_pass8) {
   if (tiles_per_pass8)
     for (size_t k = 0; k < 8; k++) tiles_per_pass8[k] = k < h->passes.size() ? h->passes[k].grid : 0u;
   return SB_OK;
+}
+
+/* Host only: symbolic replay of one frame's hand-overs (see the header). */
+int sb_dist_verify(sb_handle h, int32_t n_ranks, uint64_t *n_stale, uint64_t *n_not_home, uint64_t *n_unordered, uint64_t *n_crossings) {
+  NEED_HANDLE(h);
+  return guarded(h, [&]() -> int {
+    const Plan &P = h->plan;
+    const size_t np = P.passes.size();
+    std::vector<std::vector<std::vector<uint32_t>>> tiles(n_ranks); // [rank][pass] -> tiles, zone tiles first
+    std::vector<std::vector<uint32_t>> n_zone(n_ranks);
+    std::vector<uint32_t> tuple;
+    DistDev D{};
+    for (int r = 0; r < n_ranks; r++) {
+      std::vector<uint32_t> tup;
+      h->dist_layout(r, n_ranks, D, tiles[r], n_zone[r], &tup);
+      if (r == 0) tuple = tup;
+      else if (tup != tuple) throw std::string("the ranks disagree on who runs which tile");
+    }
+    auto owner_of = [&](uint32_t dev) {
+      uint32_t r = 0;
+      while (r + 1 < D.n_ranks && dev >= D.slab_lo[r + 1]) r++;
+      return r;
+    };
+    const int partial = np > P.n_tilings ? (int)np - 1 : -1;
+    std::vector<uint32_t> holder(P.V);   // the rank whose array holds the current value of a vertex
+    for (uint32_t d = 0; d < P.V; d++) holder[d] = owner_of(d);
+    uint64_t stale = 0, away = 0, unordered = 0, crossings = 0;
+    auto check_home = [&]() {
+      for (uint32_t d = 0; d < P.V; d++) away += holder[d] != owner_of(d);
+    };
+    for (const sb_solver::Launch &l : h->program()) {
+      if (l.kind != sb_solver::Launch::PASS) { // predict / finish / normals (and anything else) work on the owners' copies
+        check_home();
+        continue;
+      }
+      const TilePass &tp = P.passes[(size_t)l.arg];
+      std::vector<uint32_t> next(holder);
+      for (int r = 0; r < n_ranks; r++) {
+        const auto &mine = tiles[r][(size_t)l.arg];
+        for (size_t j = 0; j < mine.size(); j++) {
+          const uint32_t t = mine[j];
+          const bool zone = j < n_zone[r][(size_t)l.arg];
+          for (uint32_t i = tp.vert_off[t]; i < tp.vert_off[t + 1]; i++) {
+            const uint32_t d = tp.contiguous ? i : tp.tile_verts[i];
+            if (holder[d] != (uint32_t)r) stale++;
+            const uint32_t tup = tuple[d];
+            const bool covered = (int)l.next_pass != partial || (tup >> 15 & 1u);
+            const uint32_t dst = (tup >> (3 * (covered ? l.next_pass : l.next_full_pass))) & 7u;
+            // a vertex that came from, or goes to, another rank needs the epoch handshake: only zone tiles do it
+            if (!zone && dst != (uint32_t)r) unordered++;
+            crossings += dst != (uint32_t)r;
+            next[d] = dst;
+          }
+        }
+      }
+      // a vertex that arrived from another rank must be loaded by a zone tile of the NEXT launch: checked there through
+      // `stale` (wrong place) and here (right place, but would the loader wait for the sender?)
+      holder.swap(next);
+    }
+    check_home();
+    // the loader side of the handshake: replay once more and look at who loads what a foreign rank stored
+    {
+      std::vector<uint32_t> prev_writer(P.V, 0xffffffffu); // rank that stored the vertex last (0xffffffff: nobody yet this frame)
+      for (const sb_solver::Launch &l : h->program()) {
+        if (l.kind != sb_solver::Launch::PASS) continue;
+        const TilePass &tp = P.passes[(size_t)l.arg];
+        std::vector<uint32_t> writer(prev_writer);
+        for (int r = 0; r < n_ranks; r++) {
+          const auto &mine = tiles[r][(size_t)l.arg];
+          for (size_t j = 0; j < mine.size(); j++) {
+            const uint32_t t = mine[j];
+            const bool zone = j < n_zone[r][(size_t)l.arg];
+            for (uint32_t i = tp.vert_off[t]; i < tp.vert_off[t + 1]; i++) {
+              const uint32_t d = tp.contiguous ? i : tp.tile_verts[i];
+              if (!zone && prev_writer[d] != 0xffffffffu && prev_writer[d] != (uint32_t)r) unordered++;
+              writer[d] = (uint32_t)r;
+            }
+          }
+        }
+        prev_writer.swap(writer);
+      }
+    }
+    if (n_stale) *n_stale = stale;
+    if (n_not_home) *n_not_home = away;
+    if (n_unordered) *n_unordered = unordered;
+    if (n_crossings) *n_crossings = crossings;
+    return SB_OK;
+  });
 }
 
 /* Host only (works on an sb_plan handle): what sb_dist_setup(rank, n_ranks) would decide. */

@@ -260,6 +260,14 @@ class SoftBody:
         self._ck(self._lib.sb_dist_layout(self._h, rank, n_ranks, _ptr(own), _ptr(tiles), pass_index))
         return own.astype(bool), tiles.astype(bool)
 
+    def dist_verify(self, n_ranks: int):
+        """Host only: symbolic replay of one frame's hand-overs over `n_ranks` ranks -> (vertices loaded from the wrong
+        rank's array, vertices not home when a per-vertex kernel / the frame end needs them, hand-overs no epoch orders,
+        vertex values that changed rank during the frame); (0, 0, 0, > 0) for a correct layout of a mesh that is really cut."""
+        a, b, c, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.sb_dist_verify(self._h, n_ranks, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
     def dist_error(self) -> bool:
         out = C.c_int32()
         self._ck(self._lib.sb_dist_error(self._h, C.byref(out)))

@@ -379,6 +379,41 @@ def test_dist_layout_zones_and_compact_blocks():
         assert mixed.any() and not mixed.all()
 
 
+@pytest.mark.parametrize("n_ranks,dist_ranks,flags", [(2, 2, 0), (3, 3, 0), (4, 4, 0), (8, 8, 0), (2, 8, 0), (4, 8, 0), (3, 0, 0),
+                                                       (4, 4, 64), (8, 8, 128), (2, 2, 64 | 128), (8, 8, 2)])
+def test_the_hand_over_protocol_of_a_frame_replayed_symbolically(n_ranks, dist_ranks, flags):
+    # sb_dist_verify: every tile launch of the frame program, every tile of every rank.  A vertex is loaded from the
+    # array of the rank that runs the tile (the previous launch stored it there), is at home for the per-vertex work,
+    # the normals and the end of the frame, and every hand-over between two ranks is between zone tiles (the only
+    # ones that wait for / publish an epoch).  flags: 64 = no snake order, 128 = one launch per pass occurrence with
+    # separate predict / finish kernels, 2 = no normals.
+    pos, tets, tris = meshgen.block(18, 18, 36, spacing=0.05, origin=(0, 0.02, 0))
+    sb = SoftBody(pos, tets, tris, host_only=True, tile_cap=300, dist_ranks=dist_ranks, substeps=4, iterations=5, flags=flags)
+    stale, away, unordered, crossings = sb.dist_verify(n_ranks)
+    assert (stale, away, unordered) == (0, 0, 0)
+    assert crossings > 0  # the mesh is really cut: values do travel
+    # the cheaper cut travels less: compact blocks against slabs of the box order (same mesh, same rank count)
+    if dist_ranks == n_ranks == 8:
+        slabs = SoftBody(pos, tets, tris, host_only=True, tile_cap=300, dist_ranks=0, substeps=4, iterations=5, flags=flags)
+        assert slabs.dist_verify(8)[:3] == (0, 0, 0) and crossings < slabs.dist_verify(8)[3]
+
+
+def test_the_hand_over_protocol_on_an_ingested_body_and_a_leftover_pass():
+    from softbodyunity_b200 import ingest
+    from test_ingest import torus
+    sp, st_ = torus(0.5, 0.2, 48, 24)
+    pos, tets, tris = ingest.tetrahedralize_surface(sp + np.float32([0.0, 0.25, 0.0]), st_, 0.035, snap=True)
+    for n_ranks in (2, 3, 4):
+        sb = SoftBody(pos, tets, tris, host_only=True, tile_cap=400, dist_ranks=n_ranks, substeps=3, iterations=4)
+        assert sb.info()["n_tile_passes"] == 5  # four tilings and one leftover pass: vertices it leaves out skip it
+        r = sb.dist_verify(n_ranks)
+        assert r[:3] == (0, 0, 0) and r[3] > 0, r
+    # iterations = 1 and 0: the frame is predict / one sweep / finish, or the per-vertex kernels alone
+    for it in (1, 0):
+        sb = SoftBody(pos, tets, tris, host_only=True, tile_cap=400, dist_ranks=2, substeps=2, iterations=it)
+        assert sb.dist_verify(2)[:3] == (0, 0, 0)
+
+
 def test_bitets_pair_tets_across_a_face_on_fixed_registers():
     # round_width=2: tets in face-sharing pairs; the second tet (B) runs on the registers (4, 2, 1, 3) of the first (A)
     pos, tets, tris = meshgen.block(12, 11, 10, spacing=0.1, jitter=0.1, seed=3)
