@@ -7,10 +7,10 @@ the 1 M-vertex (100^3) tet block dropped on the ground plane, 10 substeps x 10 i
 
   value : V * substeps * steps / device time, state resident in HBM (CUDA events on the
           solver's stream around the K graph launches; max over ranks)
-  e2e   : the same frames through the C ABI with HOST buffers every step: sb_set_state from
-          pinned host memory (H2D), sb_step, sb_read_positions + sb_read_surface (D2H)
-  roofline : dominant kernel (first tile pass) timed alone with CUDA events, algorithmic
-          bytes per launch / time against MEASURED_PEAKS.json
+  e2e   : the same frames through the C ABI with HOST buffers every step: sb_write_packed (x4 | v4 from
+          pinned host memory, H2D), sb_step, sb_read_packed (x4 | v4 | surface positions | normals, D2H)
+  roofline : the tile launches (they carry the whole step: predict / finish run inside them): algorithmic
+          bytes per launch / mean launch time inside the device-timed step, against MEASURED_PEAKS.json
   cpu_baseline : the CPU oracle (oracle/, an XPBD restatement -- the reference C# solver is
           not in the mount) on this box's host cores, bounded sample
 
@@ -158,6 +158,50 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons)}
 
 
+def solver_flags(args):
+    from softbodyunity_b200 import FLAG_DAG, FLAG_FAST_MATH, FLAG_NO_FUSE, FLAG_NO_PDL, FLAG_NO_SNAKE
+    return ((FLAG_FAST_MATH if args.fast_math else 0) | (FLAG_NO_PDL if args.no_pdl else 0) | (FLAG_DAG if args.dag else 0) |
+            (FLAG_NO_SNAKE if args.no_snake else 0) | (FLAG_NO_FUSE if args.no_fuse else 0))
+
+
+def plan_options(args):
+    """Planner options of a run (the same for the native arm and for the plan the reference arm takes its order from)."""
+    kw = dict(tile_cap=args.tile_cap, later_tile_cap=args.later_tile_cap, block_threads=args.block_threads, round_width=args.round_width)
+    if args.workload == "dist":
+        # ONE plan for every N: the box grid and the block numbering are those of an 8-way split (2 and 4 ranks take
+        # unions of its blocks), the CTA width is pinned -- so the Gauss-Seidel order, and with it the state checksum,
+        # is the same on 1, 2, 4 and 8 GPUs
+        kw["dist_ranks"] = 0 if args.slabs else 8
+        kw["block_threads"] = args.block_threads or 160
+    return kw
+
+
+def describe_config(args, info, name, n_verts, world, replicas=False):
+    """`config` of the JSON line: the workload and the plan it runs on.  Both arms print the same object for the same
+    arguments (the reference arm replays the plan's Gauss-Seidel order on the host cores)."""
+    npass = info["n_tile_passes"]
+    cfg = {"workload": name + (" per GPU, independent bodies, no communication" if replicas and world > 1 else ""),
+           "n_verts": n_verts, "n_edges": info["n_edges"], "n_tets": info["n_tets"],
+           "math": "fast" if args.fast_math else "exact (bit-identical to CPU oracle)",
+           "tile_passes": npass, "tiles_in_pass": info["tiles_in_pass"][:npass],
+           "tile_cap": info["tile_cap"], "block_threads": info["block_threads"], "round_width": info["round_width"],
+           "edges_attached": info["edges_attached"], "rounds_per_sweep": sum(info["rounds_in_pass"][:npass]),
+           "runs_per_sweep": sum(info["runs_in_pass"][:npass]),
+           "order": "same pass order every iteration" if args.no_snake else "snake: odd iterations run the tile passes backwards",
+           "launches": "one per pass occurrence, separate predict / finish" if args.no_fuse else
+                       "consecutive occurrences of a pass fused; predict / finish inside the tile launches at substep boundaries",
+           "planner": {k: os.environ[k] for k in ("SB_RECOLOUR", "SB_ATTACH_AUGMENT", "SB_MERGE_RIMS", "SB_WHOLE_BOXES", "SB_ATOM_SNAKE") if k in os.environ} or "defaults",
+           "rounds_per_tile": [round(r / max(1, t), 1) for r, t in zip(info["rounds_in_pass"][:npass], info["tiles_in_pass"][:npass])],
+           "l2": "no flush: per-step working set (constraint streams + state) %.0f MB exceeds the 126 MB L2" %
+                 ((8.0 * info["n_edges"] + 16.0 * info["n_tets"] + 48.0 * n_verts) / 1e6)}
+    if world > 1 and args.workload in ("dist", "partitioned"):
+        cfg.update(comm="NVLink peer memory (CUDA IPC): tiles read / write their vertex runs in the owner's HBM; epoch words "
+                        "order the zone tiles of neighbouring ranks; no collective on the data path (NCCL: rendezvous, timing)"
+                        if args.workload == "dist" else "ghost vertices + P2P halo kernels twice per sweep",
+                   partition="slabs of the box order" if args.slabs else "compact blocks of boxes (recursive bisection)")
+    return cfg
+
+
 def cpu_oracle_rate(pos, tets, sched, substeps, iterations, threads, reps, roles=None):
     """vertex-substeps/s of the CPU oracle on `reps` steps of `substeps` substeps each."""
     from oracle import xpbd_oracle as orc
@@ -178,8 +222,8 @@ def run_reference(args, rank, world):
     from softbodyunity_b200 import SoftBody
     pos, tets, tris, name = workload(args)
     # only the Gauss-Seidel order (colour schedule) is taken from the plan; the same plan options as the native arm
-    pkw = dict(dist_ranks=0 if args.slabs else 8, block_threads=args.block_threads or 160) if args.workload == "dist" else dict(block_threads=args.block_threads)
-    plan = SoftBody(pos, tets, tris, host_only=True, tile_cap=args.tile_cap, **pkw)
+    plan = SoftBody(pos, tets, tris, host_only=True, substeps=args.substeps, iterations=args.iterations, flags=solver_flags(args),
+                    **plan_options(args))
     sched = plan.schedule_kw()
     info = plan.info()
     threads = os.cpu_count() or 1
@@ -197,13 +241,15 @@ def run_reference(args, rank, world):
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "vertex-substeps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "step": f"1 substep x {args.iterations} iterations per step (bounded sample of the frame)",
-                   "n_verts": info["n_verts"], "n_edges": info["n_edges"], "n_tets": info["n_tets"]},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": describe_config(args, info, name, info["n_verts"], world),
+        "step_sample": f"one step of this arm = 1 substep x {args.iterations} iterations of the workload (bounded sample of the frame; "
+                       "the unit, vertex-substeps/s, is the same)",
         "cpu_baseline": {"value": val, "unit": "vertex-substeps/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps of 1 substep x {args.iterations} iterations, OpenMP over colour batches; "
                                    "CPU oracle (C), not the reference C# solver (not in the mount)"},
         "e2e": {"value": val, "unit": "vertex-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "plan_build_seconds": info["build_seconds"],
     }
     print(json.dumps(out), flush=True)
 
@@ -218,7 +264,7 @@ def state_checksum(x4_owned, world, dist, torch):
     return "%x-%x" % (int(t[0].item()), int(t[1].item()))
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -243,9 +289,13 @@ def main():
     ap.add_argument("--no-bodies", action="store_true", help="skip the secondary 4096-body measurement (BASELINE.json configs[3])")
     ap.add_argument("--bodies-n", type=int, default=4096)
     ap.add_argument("--kernel-breakdown", action="store_true")
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     args.warmup = max(args.warmup, 3)
+    return args
 
+
+def main(argv=None):
+    args = parse_args(argv)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -274,12 +324,10 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()  # nvidia-smi takes a moment to come up; samples are windowed by timestamp
-    from softbodyunity_b200 import FLAG_FAST_MATH, SoftBody
+    from softbodyunity_b200 import SoftBody
     pos, tets, tris, name = workload(args, rank, world)
-    flags = ((FLAG_FAST_MATH if args.fast_math else 0) | (16 if args.no_pdl else 0) | (32 if args.dag else 0) |
-             (64 if args.no_snake else 0) | (128 if args.no_fuse else 0))
-    kw = dict(substeps=args.substeps, iterations=args.iterations, flags=flags, tile_cap=args.tile_cap,
-              later_tile_cap=args.later_tile_cap, block_threads=args.block_threads, round_width=args.round_width)
+    flags = solver_flags(args)
+    kw = dict(substeps=args.substeps, iterations=args.iterations, flags=flags, **plan_options(args))
     shared = None      # a body shared by all ranks (one mesh over the GPUs)
     if args.workload == "partitioned" and world > 1:
         from softbodyunity_b200.partition import PartitionedBody, connect_peers, slab_partition
@@ -290,11 +338,7 @@ def main():
         connect_peers(shared, local)     # CUDA IPC handles travel over torch.distributed once; the data path is P2P stores
         sb = shared.sb
     elif args.workload == "dist":
-        # ONE plan for every N: the box grid and the block numbering are those of an 8-way split (2 and 4 ranks take
-        # unions of its blocks), the CTA width is pinned -- so the Gauss-Seidel order, and with it the state checksum,
-        # is the same on 1, 2, 4 and 8 GPUs
-        kw["dist_ranks"] = 0 if args.slabs else 8
-        kw["block_threads"] = args.block_threads or 160
+        # (plan_options: ONE plan for every N)
         if world > 1:
             from softbodyunity_b200.dist import DistBody
             V_global, T_global = len(pos), len(tets)
@@ -302,7 +346,6 @@ def main():
             sb = shared.sb
         else:
             sb = SoftBody(pos, tets, tris, device=local, **kw)
-        kw.pop("dist_ranks", None)
     else:
         sb = SoftBody(pos, tets, tris, device=local, **kw)
     info = sb.info()
@@ -437,6 +480,7 @@ def main():
                 "pass0_alone_ms": alone_ms,
                 "step_achieved": V * args.substeps * args.steps / (ms * 1e-3) * B_sub / 1e9,
                 "step_frac": V * args.substeps * args.steps / (ms * 1e-3) * B_sub / 1e9 / hbm,
+                "step_frac_of_nominal_8000": V * args.substeps * args.steps / (ms * 1e-3) * B_sub / 1e9 / 8000.0,
                 "bytes_per_vertex_substep": B_sub}
         if args.kernel_breakdown:
             breakdown = {"predict_ms": t_pred, "finish_ms": t_fin, "normals_ms": t_nrm}
@@ -484,28 +528,7 @@ def main():
         del bsb
 
     if rank == 0:
-        cfg = {"workload": name + (" per GPU, independent bodies, no communication" if replicas and world > 1 else ""),
-               "n_verts": V_all if world > 1 and not replicas else V, "n_edges": E, "n_tets": T,
-               "math": "fast" if args.fast_math else "exact (bit-identical to CPU oracle)",
-               "tile_passes": info["n_tile_passes"], "tiles_in_pass": info["tiles_in_pass"][:info["n_tile_passes"]],
-               "tile_cap": info["tile_cap"], "block_threads": info["block_threads"], "round_width": info["round_width"],
-               "edges_attached": info["edges_attached"], "rounds_per_sweep": sum(info["rounds_in_pass"][:info["n_tile_passes"]]),
-               "runs_per_sweep": sum(info["runs_in_pass"][:info["n_tile_passes"]]),
-               "order": "same pass order every iteration" if args.no_snake else "snake: odd iterations run the tile passes backwards",
-               "launches": "one per pass occurrence, separate predict / finish" if args.no_fuse else
-                           "consecutive occurrences of a pass fused; predict / finish inside the tile launches at substep boundaries",
-               "planner": {k: os.environ[k] for k in ("SB_RECOLOUR", "SB_ATTACH_AUGMENT", "SB_MERGE_RIMS", "SB_WHOLE_BOXES", "SB_ATOM_SNAKE") if k in os.environ} or "defaults",
-               "rounds_per_tile": [round(r / max(1, t), 1) for r, t in zip(info["rounds_in_pass"][:info["n_tile_passes"]],
-                                                                          info["tiles_in_pass"][:info["n_tile_passes"]])],
-               "l2": "no flush: per-step working set (constraint streams + state) %.0f MB exceeds the 126 MB L2" %
-                     ((8.0 * E + 16.0 * T + 48.0 * (V_all if world > 1 and not replicas else V)) / 1e6),
-               "build_seconds": info["build_seconds"]}
-        if world > 1 and args.workload in ("dist", "partitioned"):
-            cfg.update(own_verts_rank0=own_rank0, tiles_rank0=tiles_rank0,
-                       comm="NVLink peer memory (CUDA IPC): tiles read / write their vertex runs in the owner's HBM; epoch words "
-                            "order the zone tiles of neighbouring ranks; no collective on the data path (NCCL: rendezvous, timing)"
-                            if args.workload == "dist" else "ghost vertices + P2P halo kernels twice per sweep",
-                       partition="slabs of the box order" if args.slabs else "compact blocks of boxes (recursive bisection)")
+        cfg = describe_config(args, info, name, V_all if world > 1 and not replicas else V, world, replicas)
         out = {
             "metric": METRIC, "value": value, "unit": "vertex-substeps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -514,6 +537,9 @@ def main():
             "e2e": e2e, "gpu_launches": launches * args.steps,
             "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }
+        out["plan_build_seconds"] = info["build_seconds"]
+        if world > 1 and args.workload in ("dist", "partitioned"):
+            out["distribution"] = {"own_verts_rank0": own_rank0, "tiles_rank0": tiles_rank0}
         if checksum is not None:
             out["state_checksum"] = {"after_frames": args.warmup + args.steps, "x4_words_hi_lo": checksum,
                                      "meaning": "sum of the 32-bit words of every vertex's (x, y, z, 1/m), high and low halves; the same for any "

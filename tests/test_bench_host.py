@@ -1,0 +1,71 @@
+"""bench.py on the host: the byte model of SURVEY.md 8(d), the reference arm's JSON line (it runs on the CPU by
+construction) and that both arms describe a run by the same `config` object.  The native arm needs a GPU; bench.py
+refuses to run without one."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def test_algorithmic_bytes_per_vertex_substep_at_the_headline_mesh():
+    # 64 + 10 * (12 E/V + 20 T/V + 32) + 64 = 2127.5 B at 100^3
+    assert bench.bytes_per_substep(1_000_000, 5_910_300, 4_851_495, 10) == pytest.approx(2127.535, abs=1e-3)
+    assert bench.bytes_per_substep(8_000_000, 47_640_600, 39_402_995, 10) == pytest.approx(2147.7, abs=0.1)
+
+
+def _run(*argv, env=None):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *argv], capture_output=True, text=True, timeout=600, cwd=ROOT,
+                       env=dict(os.environ, **(env or {})))
+    return r
+
+
+def test_reference_arm_prints_the_contract_line_and_the_native_arms_config():
+    r = _run("--impl", "reference", "--workload", "block", "--n", "14", "--steps", "2", "--warmup", "3", "--tile-cap", "256")
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "vertex-substeps/sec" and line["unit"] == "vertex-substeps/s"
+    assert line["higher_is_better"] is True and line["steps"] == 2 and line["warmup"] == 3 and line["n_gpus"] == 1
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["value"] == line["value"] and cb["cores"] == (os.cpu_count() or 1) and "sample" in cb
+    assert line["value"] == pytest.approx(14 ** 3 * 2 / (line["ms_per_step"] * 2e-3), rel=1e-6)
+    # the same object the native arm prints for these arguments (describe_config over the same plan)
+    from softbodyunity_b200 import SoftBody
+    args = bench.parse_args(["--workload", "block", "--n", "14", "--tile-cap", "256"])
+    pos, tets, tris, name = bench.workload(args)
+    plan = SoftBody(pos, tets, tris, host_only=True, substeps=args.substeps, iterations=args.iterations, flags=bench.solver_flags(args),
+                    **bench.plan_options(args))
+    assert line["config"] == json.loads(json.dumps(bench.describe_config(args, plan.info(), name, len(pos), 1)))
+    assert line["config"]["workload"].startswith("block14^3 (2744 verts)")
+
+
+def test_other_ranks_of_the_reference_arm_exit_without_work():
+    r = _run("--impl", "reference", "--gpus", "2", env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_native_arm_refuses_to_run_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = _run("--workload", "block", "--n", "8", "--steps", "1")
+    assert r.returncode != 0 and "no CUDA device" in (r.stdout + r.stderr)
+
+
+def test_the_plan_options_of_the_distributed_workload_do_not_depend_on_the_rank_count():
+    a = bench.parse_args(["--workload", "dist"])
+    assert bench.plan_options(a)["dist_ranks"] == 8 and bench.plan_options(a)["block_threads"] == 160
+    a = bench.parse_args(["--workload", "dist", "--slabs", "--block-threads", "128"])
+    assert bench.plan_options(a)["dist_ranks"] == 0 and bench.plan_options(a)["block_threads"] == 128
+
+
+def test_a_traffic_capture_of_another_plan_is_refused():
+    info = {"n_tile_passes": 2, "rounds_in_pass": [3, 4], "tiles_in_pass": [5, 6]}
+    t, why = bench.measured_traffic(info)
+    assert t is None and "another plan" in why

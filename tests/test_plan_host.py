@@ -380,13 +380,13 @@ def test_dist_layout_zones_and_compact_blocks():
 
 
 @pytest.mark.parametrize("n_ranks,dist_ranks,flags", [(2, 2, 0), (3, 3, 0), (4, 4, 0), (8, 8, 0), (2, 8, 0), (4, 8, 0), (3, 0, 0),
-                                                       (4, 4, 64), (8, 8, 128), (2, 2, 64 | 128), (8, 8, 2)])
+                                                       (4, 4, 64), (8, 8, 128), (2, 2, 64 | 128), (8, 8, 8)])
 def test_the_hand_over_protocol_of_a_frame_replayed_symbolically(n_ranks, dist_ranks, flags):
     # sb_dist_verify: every tile launch of the frame program, every tile of every rank.  A vertex is loaded from the
     # array of the rank that runs the tile (the previous launch stored it there), is at home for the per-vertex work,
     # the normals and the end of the frame, and every hand-over between two ranks is between zone tiles (the only
     # ones that wait for / publish an epoch).  flags: 64 = no snake order, 128 = one launch per pass occurrence with
-    # separate predict / finish kernels, 2 = no normals.
+    # separate predict / finish kernels, 8 = no normals.
     pos, tets, tris = meshgen.block(18, 18, 36, spacing=0.05, origin=(0, 0.02, 0))
     sb = SoftBody(pos, tets, tris, host_only=True, tile_cap=300, dist_ranks=dist_ranks, substeps=4, iterations=5, flags=flags)
     stale, away, unordered, crossings = sb.dist_verify(n_ranks)
