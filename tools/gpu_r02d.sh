@@ -12,7 +12,7 @@ for f in sorted(glob.glob("gpurun_out/bench_%s_*.json" % sys.argv[1])):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         print(f, "ms/step %.3f" % d["ms_per_step"], "value %.4g" % d["value"], "e2e", (d.get("e2e") or {}).get("ms_per_step"), "chk", (d.get("state_checksum") or {}).get("x4_words_hi_lo"),
-              "tiles0", d["config"].get("tiles_rank0"), "bodies", (d.get("bodies") or {}).get("value"), "build_s", d["config"].get("build_seconds"))
+              "tiles0", (d.get("distribution") or {}).get("tiles_rank0"), "bodies", (d.get("bodies") or {}).get("value"), "build_s", d.get("plan_build_seconds"))
     except Exception as e:
         print(f, "ERR", e)
 PY

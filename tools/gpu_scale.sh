@@ -8,5 +8,5 @@ python - $out/bench_${tag}_8M_n$n.json <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print(sys.argv[1], "ms/step %.3f" % d["ms_per_step"], "value %.4g" % d["value"], "e2e", (d.get("e2e") or {}).get("ms_per_step"), "chk", (d.get("state_checksum") or {}).get("x4_words_hi_lo"),
-      "tiles0", d["config"].get("tiles_rank0"), "bodies", (d.get("bodies") or {}).get("value"), "build_s", d["config"].get("build_seconds"))
+      "tiles0", (d.get("distribution") or {}).get("tiles_rank0"), "bodies", (d.get("bodies") or {}).get("value"), "build_s", d.get("plan_build_seconds"))
 PY
