@@ -255,6 +255,23 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
+def checksum_key(cfg, args):
+    """What a state checksum is a function of: mesh, stepping and the plan (the Gauss-Seidel order)."""
+    return "%s block%d^3 S=%d I=%d | tiles %s | rounds %d | bt %d | %s" % (
+        args.workload, args.n, args.substeps, args.iterations, cfg["tiles_in_pass"], cfg["rounds_per_sweep"], cfg["block_threads"],
+        "fast" if args.fast_math else "exact")
+
+
+def oracle_checksum(cfg, args, frames):
+    """The CPU oracle's checksum of this workload after `frames` frames from the committed fixture
+    (tests/golden/dist_checksum.json, made by tests/golden/make_dist_checksum.py), or None if it holds none."""
+    try:
+        doc = json.load(open(os.path.join(ROOT, "tests", "golden", "dist_checksum.json")))
+        return doc[checksum_key(cfg, args)]["after_frames"].get(str(frames))
+    except Exception:
+        return None
+
+
 def state_checksum(x4_owned, world, dist, torch):
     """Order-independent checksum of the positions (sum of the 32-bit words of x4, high and low halves apart),
     over all ranks: the same mesh stepped the same number of frames gives the same value on any number of GPUs."""
@@ -545,6 +562,9 @@ def main(argv=None):
             out["state_checksum"] = {"after_frames": args.warmup + args.steps, "x4_words_hi_lo": checksum,
                                      "meaning": "sum of the 32-bit words of every vertex's (x, y, z, 1/m), high and low halves; the same for any "
                                                 "number of GPUs (the execution order is the plan's), and for `--workload dist` on one GPU with the same plan"}
+            want = oracle_checksum(cfg, args, args.warmup + args.steps)
+            out["state_checksum"]["cpu_oracle"] = want  # None: the fixture holds no run of this workload / frame count
+            out["state_checksum"]["matches_cpu_oracle"] = None if want is None else (want == checksum)
         if bodies is not None:
             out["bodies"] = bodies
         if breakdown:
