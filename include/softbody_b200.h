@@ -358,7 +358,10 @@ int sb_lumped_inv_mass(const float *pos_xyz, uint32_t n_verts, const int32_t *te
  * same sequence of steps (and hold the same flags: the launch sequence must be the same everywhere).  Positions /
  * state read back from a rank are valid for the vertices sb_dist_owned marks; sb_read_packed carries exactly those.
  * Surface normals: each rank computes them for the surface vertices it owns (triangles that reach into a
- * neighbour's slab read the neighbour's positions over NVLink).  sb_time_kernel is refused on such a handle.
+ * neighbour's slab read the neighbour's positions over NVLink).  A frame always ends with a launch that waits for the
+ * neighbours' last stores (the normals launch; with SB_FLAG_NO_NORMALS or no surface, a one-CTA handshake), so a read-back
+ * after sb_step sees every owned vertex.  Writing state (sb_set_state, sb_write_packed) while a peer may still be inside
+ * its frame is the caller's race: synchronise the ranks first.  sb_time_kernel is refused on such a handle.
  */
 int sb_dist_setup(sb_handle h, int32_t rank, int32_t n_ranks, void **x_base_out, void **ctl_base_out);
 int sb_dist_connect(sb_handle h, int32_t peer, void *peer_x, void *peer_ctl);

@@ -800,7 +800,12 @@ struct sb_solver {
   }
   void launch_normals(cudaStream_t s) {
     const uint32_t ns = (uint32_t)plan.surf_ids.size();
-    if (!ns || (prm.flags & SB_FLAG_NO_NORMALS)) return;
+    if (!ns || (prm.flags & SB_FLAG_NO_NORMALS)) {
+      // distributed: the frame still ends with a launch of the epoch sequence -- one that waits for the neighbours'
+      // last tile launch, whose stores bring this rank's vertices home (a read-back after the frame needs them)
+      if (dist_on) k_dist_sync<<<1, 32, 0, s>>>(dist_dev.p);
+      return;
+    }
     if (dist_on) { // the surface vertices this rank owns; a launch of the epoch sequence on every rank
       if (n_own_surf) k_normals_dist<<<grid_for(n_own_surf, 256), 256, 0, s>>>(n_own_surf, own_surf.p, surf_tri_off.p, surf_tri_ids.p, tris_dev.p, nrm.p, dist_dev.p);
       else k_dist_bump<<<1, 32, 0, s>>>(dist_dev.p);
@@ -845,7 +850,8 @@ struct sb_solver {
     std::vector<Launch> L;
     const int S = prm.substeps, I = prm.iterations;
     auto simple = [&](Launch::Kind k, int arg = 0) { Launch l; l.kind = k; l.arg = arg; L.push_back(l); };
-    const bool want_normals = !plan.surf_ids.empty() && !(prm.flags & SB_FLAG_NO_NORMALS);
+    // (a distributed handle always ends its frame with the normals launch: without normals it is the closing handshake)
+    const bool want_normals = (!plan.surf_ids.empty() && !(prm.flags & SB_FLAG_NO_NORMALS)) || dist.ctl != nullptr;
     if (use_dag() || halo_active() || !pure()) {
       for (int ss = 0; ss < S; ss++) {
         simple(Launch::PREDICT);
