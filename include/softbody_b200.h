@@ -361,7 +361,9 @@ int sb_lumped_inv_mass(const float *pos_xyz, uint32_t n_verts, const int32_t *te
  * neighbour's slab read the neighbour's positions over NVLink).  A frame always ends with a launch that waits for the
  * neighbours' last stores (the normals launch; with SB_FLAG_NO_NORMALS or no surface, a one-CTA handshake), so a read-back
  * after sb_step sees every owned vertex.  Writing state (sb_set_state, sb_write_packed) while a peer may still be inside
- * its frame is the caller's race: synchronise the ranks first.  sb_time_kernel is refused on such a handle.
+ * its frame is the caller's race: synchronise the ranks first.  Refused on such a handle with SB_E_STATE: whole-mesh
+ * reads that would mix current and stale vertices (sb_read_surface, sb_read_normals, sb_diagnostics, sb_save_state /
+ * sb_load_state, sb_skin_bind) and stray launches the peers do not run (sb_time_kernel, sb_debug_trace_pass).
  */
 int sb_dist_setup(sb_handle h, int32_t rank, int32_t n_ranks, void **x_base_out, void **ctl_base_out);
 int sb_dist_connect(sb_handle h, int32_t peer, void *peer_x, void *peer_ctl);

@@ -1284,6 +1284,15 @@ static int guarded(sb_handle h, F fn) {
     (h)->err = "handle was created by sb_plan (host only)"; \
     return SB_E_STATE;                                   \
   }
+// whole-mesh reads / writes and stray launches make no sense on ONE rank of a distributed mesh (a rank holds current
+// values for the vertices it owns only, and a launch its peers do not run parts the epochs)
+#define NOT_DISTRIBUTED(h, what)                                                                         \
+  do {                                                                                                   \
+    if ((h)->dist.ctl) {                                                                                 \
+      (h)->err = what " is not available on one rank of a distributed mesh (use sb_read_packed / sb_write_packed per rank)"; \
+      return SB_E_STATE;                                                                                 \
+    }                                                                                                    \
+  } while (0)
 
 extern "C" {
 
@@ -1464,12 +1473,14 @@ int sb_surface_vertices(sb_handle h, int32_t *ids, uint32_t capacity, uint32_t *
 
 int sb_read_surface(sb_handle h, float *dpos, float *dnrm, uint32_t n_surface) {
   NEED_DEVICE(h);
+  NOT_DISTRIBUTED(h, "sb_read_surface");
   if (n_surface != h->plan.surf_ids.size()) { h->err = "n_surface mismatch"; return SB_E_ARG; }
   return guarded(h, [&]() -> int { h->read_surface(dpos, dnrm); return SB_OK; });
 }
 
 int sb_read_normals(sb_handle h, float *dst, uint32_t n) {
   NEED_DEVICE(h);
+  NOT_DISTRIBUTED(h, "sb_read_normals");
   if (!dst || n != h->plan.V) { h->err = "dst is NULL or n_verts mismatch"; return SB_E_ARG; }
   return guarded(h, [&]() -> int {
     const size_t ns = h->plan.surf_ids.size();
@@ -1527,6 +1538,7 @@ int sb_read_skinned(sb_handle h, float *dst_pos, float *dst_nrm, uint32_t n) {
 // ---- snapshots (file layout: ingest.cpp) ------------------------------------------------------------------
 int sb_save_state(sb_handle h, const char *path) {
   NEED_DEVICE(h);
+  NOT_DISTRIBUTED(h, "sb_save_state");
   if (!path) return SB_E_ARG;
   return guarded(h, [&]() -> int {
     const uint32_t V = h->plan.V;
@@ -1541,6 +1553,7 @@ int sb_save_state(sb_handle h, const char *path) {
 
 int sb_load_state(sb_handle h, const char *path, int32_t apply_params) {
   NEED_DEVICE(h);
+  NOT_DISTRIBUTED(h, "sb_load_state");
   if (!path) return SB_E_ARG;
   return guarded(h, [&]() -> int {
     const uint32_t V = h->plan.V;
@@ -1615,6 +1628,7 @@ int sb_write_packed(sb_handle h, const void *src, uint64_t bytes) {
 
 int sb_diagnostics(sb_handle h, double *out16) {
   NEED_DEVICE(h);
+  NOT_DISTRIBUTED(h, "sb_diagnostics");
   if (!out16) return SB_E_ARG;
   return guarded(h, [&]() -> int {
     h->diagnostics(out16);
@@ -2246,6 +2260,7 @@ int sb_lumped_inv_mass(const float *pos_xyz, uint32_t n_verts, const int32_t *te
    3 CTA end, 4 + i start of chunk i (globaltimer ns; first 64 CTAs). */
 int sb_debug_trace_pass(sb_handle h, uint32_t pass, unsigned long long *out, uint32_t n_words) {
   NEED_DEVICE(h);
+  NOT_DISTRIBUTED(h, "sb_debug_trace_pass");
   if (pass >= h->passes.size() || !out || n_words < 64u * 80u + 256u + 3u * 4096u) { h->err = "bad trace arguments"; return SB_E_ARG; }
   return guarded(h, [&]() -> int {
     CK(cudaSetDevice(h->device));
