@@ -69,3 +69,31 @@ def test_a_traffic_capture_of_another_plan_is_refused():
     info = {"n_tile_passes": 2, "rounds_in_pass": [3, 4], "tiles_in_pass": [5, 6]}
     t, why = bench.measured_traffic(info)
     assert t is None and "another plan" in why
+
+
+def test_the_oracle_checksum_fixture_is_found_by_the_key_bench_uses(tmp_path, monkeypatch):
+    # tests/golden/make_dist_checksum.py writes {key: {"after_frames": {frames: checksum}}}; bench.py looks the GPUs' run up
+    # by the same key (mesh, stepping, plan) and reports `matches_cpu_oracle`
+    out = tmp_path / "tests" / "golden"
+    out.mkdir(parents=True)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "make_dist_checksum.py"), "--n", "20", "--frames", "1", "2",
+                        "--out", str(out / "dist_checksum.json")], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    doc = json.load(open(out / "dist_checksum.json"))
+    (key, entry), = doc.items()
+    assert key.startswith("dist block20^3 S=10 I=10 | tiles [") and set(entry["after_frames"]) == {"1", "2"}
+    assert entry["after_frames"]["1"] != entry["after_frames"]["2"]
+    from softbodyunity_b200 import SoftBody
+    args = bench.parse_args(["--workload", "dist", "--n", "20"])
+    pos, tets, tris, name = bench.workload(args)
+    plan = SoftBody(pos, tets, tris, host_only=True, substeps=10, iterations=10, flags=0, **bench.plan_options(args))
+    cfg = bench.describe_config(args, plan.info(), name, len(pos), 2)   # any rank count: the key does not depend on it
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench.oracle_checksum(cfg, args, 2) == entry["after_frames"]["2"]
+    assert bench.oracle_checksum(cfg, args, 3) is None
+    # the committed fixture, if present, is well-formed
+    monkeypatch.undo()
+    path = os.path.join(ROOT, "tests", "golden", "dist_checksum.json")
+    if os.path.exists(path):
+        for k, e in json.load(open(path)).items():
+            assert " | tiles [" in k and all(len(v.split("-")) == 2 for v in e["after_frames"].values())
