@@ -1,9 +1,10 @@
-"""CPU oracle run of bench.py's distributed workload (`--workload dist`: ONE n^3 block, the plan of an 8-way split) ->
-the state checksum bench.py prints (`state_checksum.x4_words_hi_lo`) after given numbers of frames, written to
-tests/golden/dist_checksum.json.  bench.py compares what the GPUs computed with this file (it reads the JSON, never the
+"""CPU oracle run of a bench.py workload (default `--workload dist`: ONE n^3 block, the plan of an 8-way split; `block`:
+the single-GPU headline mesh) -> the state checksum bench.py prints (`state_checksum.x4_words_hi_lo`) after given numbers
+of frames, written to tests/golden/dist_checksum.json.  bench.py compares what the GPUs computed with this file (it reads the JSON, never the
 oracle).  TEST INFRASTRUCTURE: this is the only place outside tests/ proper that runs the oracle at this size.
 
-    python tests/golden/make_dist_checksum.py [--n 200] [--frames 13 25]      # 8 M vertices: about an hour on 8 cores
+    python tests/golden/make_dist_checksum.py [--n 200] [--frames 13 23 25]                 # 8 M vertices: 1.5 hours on 8 cores
+    python tests/golden/make_dist_checksum.py --workload block --n 100 --frames 23 25       # the 1 M headline mesh: 10 minutes
 """
 import argparse
 import json
@@ -30,11 +31,12 @@ def checksum(x4):
 
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="dist", choices=["dist", "block", "sphere"])
     ap.add_argument("--n", type=int, default=200)
     ap.add_argument("--frames", type=int, nargs="+", default=[13, 25])
     ap.add_argument("--out", default=os.path.join(HERE, "dist_checksum.json"))
     a = ap.parse_args()
-    args = bench.parse_args(["--workload", "dist", "--n", str(a.n)])
+    args = bench.parse_args(["--workload", a.workload, "--n", str(a.n)])
     pos, tets, tris, name = bench.workload(args)
     plan = SoftBody(pos, tets, tris, host_only=True, substeps=args.substeps, iterations=args.iterations, flags=bench.solver_flags(args),
                     **bench.plan_options(args))
