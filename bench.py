@@ -257,7 +257,7 @@ def run_reference(args, rank, world):
 
 def checksum_key(cfg, args):
     """What a state checksum is a function of: mesh, stepping and the plan (the Gauss-Seidel order)."""
-    return "%s block%d^3 S=%d I=%d | tiles %s | rounds %d | bt %d | %s" % (
+    return "%s n=%d S=%d I=%d | tiles %s | rounds %d | bt %d | %s" % (
         args.workload, args.n, args.substeps, args.iterations, cfg["tiles_in_pass"], cfg["rounds_per_sweep"], cfg["block_threads"],
         "fast" if args.fast_math else "exact")
 

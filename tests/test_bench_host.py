@@ -81,7 +81,7 @@ def test_the_oracle_checksum_fixture_is_found_by_the_key_bench_uses(tmp_path, mo
     assert r.returncode == 0, r.stderr[-2000:]
     doc = json.load(open(out / "dist_checksum.json"))
     (key, entry), = doc.items()
-    assert key.startswith("dist block20^3 S=10 I=10 | tiles [") and set(entry["after_frames"]) == {"1", "2"}
+    assert key.startswith("dist n=20 S=10 I=10 | tiles [") and set(entry["after_frames"]) == {"1", "2"}
     assert entry["after_frames"]["1"] != entry["after_frames"]["2"]
     from softbodyunity_b200 import SoftBody
     args = bench.parse_args(["--workload", "dist", "--n", "20"])
