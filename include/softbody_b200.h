@@ -370,7 +370,9 @@ int sb_dist_connect(sb_handle h, int32_t peer, void *peer_x, void *peer_ctl);
 int sb_dist_owned(sb_handle h, uint8_t *owned_V, uint32_t *tiles_per_pass8); /* either pointer may be NULL */
 int sb_dist_error(sb_handle h, int32_t *out); /* 1 if a wait for a peer ever timed out (results invalid) */
 /* Host only (works on an sb_plan handle): the vertices rank would own and, for one pass, which tiles it would run
-   (tile_owner_pass[t] = 1 / 0; sb_get_tiles gives the tile count).  Either pointer may be NULL. */
+   (tile_owner_pass[t] = 0: not this rank's; j + 1: CTA j of the rank's launch, an interior tile; -(j + 1): CTA j, a zone
+   tile -- one that waits for the neighbours' epoch and counts towards this rank's; sb_get_tiles gives the tile count).
+   Either pointer may be NULL. */
 int sb_dist_layout(sb_handle h, int32_t rank, int32_t n_ranks, uint8_t *owned_V, int32_t *tile_owner_pass, uint32_t pass);
 /* Host only: replays the hand-over protocol of one frame symbolically for n_ranks ranks -- every tile launch of the frame
    program, every tile of every rank -- and counts the vertices a tile would load while their current value sits in another

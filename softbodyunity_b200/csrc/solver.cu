@@ -652,6 +652,24 @@ struct sb_solver {
         if (ranks >> rank & 1u) nbr |= ranks;
       }
     }
+    // Surface normals read across a cut: the normals launch of the rank that owns a surface vertex reads the other
+    // vertices of its triangles where they live, in their owners' arrays (k_normals_dist).  The owner's last tile
+    // launch of the frame must have published such a vertex before the reader starts, and its first launch of the
+    // next frame must wait for the reader: the tiles of all three vertices of a triangle whose vertices have different
+    // owners are zone tiles, and those owners neighbours.  (With cuts along box faces the shifted tilings make these
+    // vertices two-rank vertices anyway -- nothing changes for a lattice block; this makes it so by construction.)
+    for (size_t f = 0; f + 2 < plan.tris.size(); f += 3) {
+      uint32_t d[3], own = 0;
+      for (int j = 0; j < 3; j++) {
+        d[j] = plan.inv[(size_t)plan.tris[f + j]];
+        own |= 1u << owner_of(d[j]);
+      }
+      if (!(own & (own - 1))) continue;
+      for (int j = 0; j < 3; j++)
+        for (size_t k = 0; k < np; k++)
+          if (tile_of[k][d[j]] != 0xffffffffu) in_zone[k][tile_of[k][d[j]]] = 1;
+      if (own >> rank & 1u) nbr |= own;
+    }
     D.nbr_mask = nbr & ~(1u << rank);
     if (runner_tuple) { // per device vertex: the rank that runs its tile in pass k, three bits per pass (pass 0 = its slab's rank)
       if (np > 5) throw std::string("a distributed mesh has at most five tile passes");
@@ -2181,10 +2199,11 @@ int sb_dist_layout(sb_handle h, int32_t rank, int32_t n_ranks, uint8_t *owned_V,
       std::memset(owned_V, 0, h->plan.V);
       for (uint32_t d = D.slab_lo[rank]; d < D.slab_lo[rank + 1]; d++) owned_V[h->plan.perm[d]] = 1;
     }
-    if (tile_owner_pass) { // tile_owner_pass[t] = 1 if this rank runs tile t of pass `pass`, else 0
+    if (tile_owner_pass) { // tile_owner_pass[t] = 0: another rank's tile; j + 1 > 0: CTA j of this rank's launch, an interior tile;
+                           // -(j + 1) < 0: CTA j, a zone tile (zone tiles come first)
       if (pass >= tiles.size()) throw std::string("no such pass");
       for (uint32_t t = 0; t < h->plan.passes[pass].n_tiles(); t++) tile_owner_pass[t] = 0;
-      for (uint32_t t : tiles[pass]) tile_owner_pass[t] = 1;
+      for (size_t j = 0; j < tiles[pass].size(); j++) tile_owner_pass[tiles[pass][j]] = j < n_zone[pass] ? -(int32_t)(j + 1) : (int32_t)(j + 1);
     }
     return SB_OK;
   });

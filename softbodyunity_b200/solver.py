@@ -260,6 +260,15 @@ class SoftBody:
         self._ck(self._lib.sb_dist_layout(self._h, rank, n_ranks, _ptr(own), _ptr(tiles), pass_index))
         return own.astype(bool), tiles.astype(bool)
 
+    def dist_launch_order(self, rank: int, n_ranks: int, pass_index: int = 0):
+        """Host only: (tiles of `pass_index` in the order `rank` launches them, how many of them -- the first -- are zone
+        tiles: they wait for the neighbours' epoch and count towards this rank's)."""
+        tiles = np.zeros(self.info()["tiles_in_pass"][pass_index], np.int32)
+        self._ck(self._lib.sb_dist_layout(self._h, rank, n_ranks, None, _ptr(tiles), pass_index))
+        mine = np.nonzero(tiles)[0]
+        order = mine[np.argsort(np.abs(tiles[mine]))]
+        return order, int((tiles < 0).sum())
+
     def dist_verify(self, n_ranks: int):
         """Host only: symbolic replay of one frame's hand-overs over `n_ranks` ranks -> (vertices loaded from the wrong
         rank's array, vertices not home when a per-vertex kernel / the frame end needs them, hand-overs no epoch orders,

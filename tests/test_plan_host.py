@@ -414,6 +414,34 @@ def test_the_hand_over_protocol_on_an_ingested_body_and_a_leftover_pass():
         assert sb.dist_verify(2)[:3] == (0, 0, 0)
 
 
+def test_vertices_a_neighbours_normals_launch_reads_sit_in_zone_tiles():
+    # k_normals_dist reads the vertices of a triangle where they live -- in their owners' arrays.  Every tile (of every
+    # pass) that holds a vertex of a surface triangle whose vertices have different owners must be a zone tile of the rank
+    # that runs it: the owner's last launch then publishes the vertex before the reader starts, and its next frame waits
+    # for the reader.  Cuts along box faces give that for free; a slab cut of an 8-way numbering over 3 ranks and a
+    # bisected torus do not (one and two pass-0 tiles were interior before the triangles were looked at).
+    from softbodyunity_b200 import ingest
+    from test_ingest import torus
+    sp, st_ = torus(0.5, 0.2, 48, 24)
+    cases = [(meshgen.block(18, 18, 36, spacing=0.05, origin=(0, 0.02, 0)), dict(tile_cap=300, dist_ranks=8), 3),
+             (ingest.tetrahedralize_surface(sp + np.float32([0.0, 0.25, 0.0]), st_, 0.035, snap=True), dict(tile_cap=400, dist_ranks=3), 3),
+             (meshgen.block(14, 12, 26, spacing=0.05), dict(tile_cap=256, dist_ranks=4), 4)]
+    for (pos, tets, tris), kw, n_ranks in cases:
+        sb = SoftBody(pos, tets, tris, host_only=True, **kw)
+        owner = np.argmax(np.stack([sb.dist_layout(r, n_ranks)[0] for r in range(n_ranks)]), axis=0)
+        cross = tris[(owner[tris] != owner[tris][:, :1]).any(axis=1)]
+        assert len(cross) > 0
+        verts = np.unique(cross)
+        for k in range(sb.info()["n_tile_passes"]):
+            zone = np.zeros(sb.info()["tiles_in_pass"][k], bool)
+            for r in range(n_ranks):
+                order, n_zone = sb.dist_launch_order(r, n_ranks, k)
+                zone[order[:n_zone]] = True
+            tile_of = sb.tiles(k)[0][verts]
+            assert zone[tile_of[tile_of >= 0]].all(), (n_ranks, k)
+        assert sb.dist_verify(n_ranks)[:3] == (0, 0, 0)
+
+
 def test_bitets_pair_tets_across_a_face_on_fixed_registers():
     # round_width=2: tets in face-sharing pairs; the second tet (B) runs on the registers (4, 2, 1, 3) of the first (A)
     pos, tets, tris = meshgen.block(12, 11, 10, spacing=0.1, jitter=0.1, seed=3)
