@@ -658,17 +658,21 @@ struct sb_solver {
     // next frame must wait for the reader: the tiles of all three vertices of a triangle whose vertices have different
     // owners are zone tiles, and those owners neighbours.  (With cuts along box faces the shifted tilings make these
     // vertices two-rank vertices anyway -- nothing changes for a lattice block; this makes it so by construction.)
+    // (Neighbours: every rank that touches one of the three vertices in any pass -- the last holder of a vertex, which
+    // stores it home, need not be its owner.)
     for (size_t f = 0; f + 2 < plan.tris.size(); f += 3) {
-      uint32_t d[3], own = 0;
+      uint32_t d[3], own = 0, touch = 0;
       for (int j = 0; j < 3; j++) {
         d[j] = plan.inv[(size_t)plan.tris[f + j]];
         own |= 1u << owner_of(d[j]);
+        for (size_t k = 0; k < np; k++)
+          if (tile_of[k][d[j]] != 0xffffffffu) touch |= 1u << runner[k][tile_of[k][d[j]]];
       }
       if (!(own & (own - 1))) continue;
       for (int j = 0; j < 3; j++)
         for (size_t k = 0; k < np; k++)
           if (tile_of[k][d[j]] != 0xffffffffu) in_zone[k][tile_of[k][d[j]]] = 1;
-      if (own >> rank & 1u) nbr |= own;
+      if (touch >> rank & 1u) nbr |= touch;
     }
     D.nbr_mask = nbr & ~(1u << rank);
     if (runner_tuple) { // per device vertex: the rank that runs its tile in pass k, three bits per pass (pass 0 = its slab's rank)
