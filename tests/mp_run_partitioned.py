@@ -1,6 +1,6 @@
 """torchrun entry: one rank per GPU steps its slab of one block; rank 0 checks the assembled state
 against the CPU oracle replaying the combined order (bitwise) and prints timings.
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/run_partitioned.py --dims 40 80 40 --frames 6
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mp_run_partitioned.py --dims 40 80 40 --frames 6
 """
 import argparse, os, sys, time
 import numpy as np
