@@ -221,7 +221,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from softbodyunity_b200 import SoftBody
-    pos, tets, tris, name = workload(args)
+    # (the mesh of the distributed workload does not depend on the rank count; its name does, and both arms print it)
+    pos, tets, tris, name = workload(args, 0, world if args.workload in ("dist", "partitioned") else 1)
     # only the Gauss-Seidel order (colour schedule) is taken from the plan; the same plan options as the native arm
     plan = SoftBody(pos, tets, tris, host_only=True, substeps=args.substeps, iterations=args.iterations, flags=solver_flags(args),
                     **plan_options(args))

@@ -97,3 +97,19 @@ def test_the_oracle_checksum_fixture_is_found_by_the_key_bench_uses(tmp_path, mo
     if os.path.exists(path):
         for k, e in json.load(open(path)).items():
             assert " | tiles [" in k and all(len(v.split("-")) == 2 for v in e["after_frames"].values())
+
+
+def test_reference_arm_on_rank_0_of_two_prints_the_distributed_workloads_config():
+    # N > 1: the default workload is the mesh that shards; rank 0 alone runs the CPU arm and names the run as the native arm does
+    r = _run("--impl", "reference", "--gpus", "2", "--size", "20", "--steps", "1", "--warmup", "3",
+             env={"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["n_gpus"] == 2 and line["scaling"] == "strong"
+    from softbodyunity_b200 import SoftBody
+    args = bench.parse_args(["--workload", "dist", "--size", "20"])
+    pos, tets, tris, name = bench.workload(args, 0, 2)
+    assert "over 2 rank(s)" in name and line["config"]["workload"] == name
+    plan = SoftBody(pos, tets, tris, host_only=True, substeps=10, iterations=10, flags=0, **bench.plan_options(args))
+    assert line["config"] == json.loads(json.dumps(bench.describe_config(args, plan.info(), name, len(pos), 2)))
+    assert "comm" in line["config"] and "partition" in line["config"]
