@@ -113,3 +113,42 @@ def test_reference_arm_on_rank_0_of_two_prints_the_distributed_workloads_config(
     plan = SoftBody(pos, tets, tris, host_only=True, substeps=10, iterations=10, flags=0, **bench.plan_options(args))
     assert line["config"] == json.loads(json.dumps(bench.describe_config(args, plan.info(), name, len(pos), 2)))
     assert "comm" in line["config"] and "partition" in line["config"]
+
+
+CONTRACT = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+            "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline")
+
+
+def test_native_arm_plumbing_on_one_rank_with_a_stand_in_solver():
+    # tests/bench_mock.py: no GPU, made-up timings -- only the shape of the line and the path through the script are checked
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_mock.py"), "--workload", "block", "--size", "20", "--steps", "3",
+                        "--tile-cap", "256", "--bodies-n", "4", "--kernel-breakdown"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert all(k in d for k in CONTRACT) and d["n_gpus"] == 1 and d["scaling"] == "strong"
+    assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "ms_per_step", "protocol"}
+    assert d["e2e"]["h2d_bytes_per_step"] == 32 * 8000 and d["e2e_component"]["h2d_bytes_per_step"] == 0
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic", "launch_ms", "step_frac", "step_frac_of_nominal_8000"}
+    assert d["roofline"]["traffic"] is None and "another plan" in d["roofline"]["traffic_source"]   # the capture is of the 1 M plan
+    assert d["cpu_baseline"]["kind"] == "port" and d["bodies"]["n_verts"] == 4 * 2028
+    assert d["state_checksum"]["after_frames"] == 6 and d["state_checksum"]["matches_cpu_oracle"] is None
+    assert "NOT A BENCH CONFIGURATION" in d["config"]["l2"] and "kernel_breakdown_ms" in d
+
+
+def test_native_arm_plumbing_on_two_gloo_ranks_with_a_stand_in_solver():
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29788", os.path.join(ROOT, "tests", "bench_mock.py"), "--gpus", "2", "--size", "24", "--steps", "3",
+                        "--bodies-n", "4"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1                                   # rank 0 alone prints
+    d = json.loads(lines[0])
+    assert all(k in d for k in CONTRACT) and d["n_gpus"] == 2 and d["scaling"] == "strong"
+    assert "single block24^3 (13824 verts) over 2 rank(s)" in d["config"]["workload"] and d["config"]["n_verts"] == 13824
+    assert "comm" in d["config"] and d["config"]["partition"].startswith("compact blocks")
+    assert d["value"] == pytest.approx(13824 * 10 / (d["ms_per_step"] * 1e-3))        # the WHOLE mesh over the max-over-ranks time
+    assert d["e2e"]["h2d_bytes_per_step"] == 32 * 13824                              # summed over the ranks: every vertex once
+    assert d["distribution"]["own_verts_rank0"] == 13824 // 2 and len(d["distribution"]["tiles_rank0"]) == d["config"]["tile_passes"]
+    assert d["roofline"]["peak"] == pytest.approx(2 * bench.peaks()[0]) and d["cpu_baseline"] is None
+    assert d["state_checksum"]["x4_words_hi_lo"] == "%x-%x" % (13824 * 4 * 0x3f80, 0)  # all-ones state of the stand-in, all ranks
+    assert d["bodies"]["n_verts"] == 4 * 2028 and d["bodies"]["bodies_rank0"] == 2
