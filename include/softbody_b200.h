@@ -378,7 +378,8 @@ int sb_dist_layout(sb_handle h, int32_t rank, int32_t n_ranks, uint8_t *owned_V,
    program, every tile of every rank -- and counts the vertices a tile would load while their current value sits in another
    rank's array (n_stale), the vertices that are not back with their owner at a per-vertex kernel, the normals or the end
    of the frame (n_not_home), and the vertices touched by a tile whose rank did not classify the tile as a zone tile although
-   the previous holder was another rank (n_unordered).  All three are 0 for a correct layout.  n_crossings: how many
+   the previous holder was another rank, or between ranks that do not poll each other, or read by a neighbour's normals launch
+   from a tile that is not a zone tile (n_unordered).  All three are 0 for a correct layout.  n_crossings: how many
    vertex values changed rank during the frame (the NVLink stores of one frame, in vertices).  Any pointer may be NULL. */
 int sb_dist_verify(sb_handle h, int32_t n_ranks, uint64_t *n_stale, uint64_t *n_not_home, uint64_t *n_unordered,
                    uint64_t *n_crossings);

@@ -660,6 +660,8 @@ struct sb_solver {
     // vertices two-rank vertices anyway -- nothing changes for a lattice block; this makes it so by construction.)
     // (Neighbours: every rank that touches one of the three vertices in any pass -- the last holder of a vertex, which
     // stores it home, need not be its owner.)
+    // TEST ONLY (reopens the race described above): lets the CPU test-suite show that sb_dist_verify reports it
+    const bool no_cut_zones = getenv("SB_DEBUG_NO_CUT_TRIANGLE_ZONES") != nullptr;
     for (size_t f = 0; f + 2 < plan.tris.size(); f += 3) {
       uint32_t d[3], own = 0, touch = 0;
       for (int j = 0; j < 3; j++) {
@@ -669,6 +671,7 @@ struct sb_solver {
           if (tile_of[k][d[j]] != 0xffffffffu) touch |= 1u << runner[k][tile_of[k][d[j]]];
       }
       if (!(own & (own - 1))) continue;
+      if (no_cut_zones) continue;
       for (int j = 0; j < 3; j++)
         for (size_t k = 0; k < np; k++)
           if (tile_of[k][d[j]] != 0xffffffffu) in_zone[k][tile_of[k][d[j]]] = 1;
@@ -2113,12 +2116,16 @@ int sb_dist_verify(sb_handle h, int32_t n_ranks, uint64_t *n_stale, uint64_t *n_
     std::vector<std::vector<uint32_t>> n_zone(n_ranks);
     std::vector<uint32_t> tuple;
     DistDev D{};
+    std::vector<uint32_t> nbr((size_t)n_ranks, 0u); // whose epoch a rank waits for, and to whom it publishes its own
     for (int r = 0; r < n_ranks; r++) {
       std::vector<uint32_t> tup;
       h->dist_layout(r, n_ranks, D, tiles[r], n_zone[r], &tup);
+      nbr[(size_t)r] = D.nbr_mask;
       if (r == 0) tuple = tup;
       else if (tup != tuple) throw std::string("the ranks disagree on who runs which tile");
     }
+    // two ranks between which a value travels (or whose launches read each other's arrays) must poll each other
+    auto linked = [&](uint32_t a, uint32_t b) { return a == b || ((nbr[a] >> b & 1u) && (nbr[b] >> a & 1u)); };
     auto owner_of = [&](uint32_t dev) {
       uint32_t r = 0;
       while (r + 1 < D.n_ranks && dev >= D.slab_lo[r + 1]) r++;
@@ -2150,7 +2157,7 @@ int sb_dist_verify(sb_handle h, int32_t n_ranks, uint64_t *n_stale, uint64_t *n_
             const bool covered = (int)l.next_pass != partial || (tup >> 15 & 1u);
             const uint32_t dst = (tup >> (3 * (covered ? l.next_pass : l.next_full_pass))) & 7u;
             // a vertex that came from, or goes to, another rank needs the epoch handshake: only zone tiles do it
-            if (!zone && dst != (uint32_t)r) unordered++;
+            if (dst != (uint32_t)r && (!zone || !linked((uint32_t)r, dst))) unordered++;
             crossings += dst != (uint32_t)r;
             next[d] = dst;
           }
@@ -2175,12 +2182,51 @@ int sb_dist_verify(sb_handle h, int32_t n_ranks, uint64_t *n_stale, uint64_t *n_
             const bool zone = j < n_zone[r][(size_t)l.arg];
             for (uint32_t i = tp.vert_off[t]; i < tp.vert_off[t + 1]; i++) {
               const uint32_t d = tp.contiguous ? i : tp.tile_verts[i];
-              if (!zone && prev_writer[d] != 0xffffffffu && prev_writer[d] != (uint32_t)r) unordered++;
+              if (prev_writer[d] != 0xffffffffu && prev_writer[d] != (uint32_t)r && (!zone || !linked(prev_writer[d], (uint32_t)r))) unordered++;
               writer[d] = (uint32_t)r;
             }
           }
         }
         prev_writer.swap(writer);
+      }
+    }
+    // the normals launch: the owner of a surface vertex reads the other vertices of its triangles in THEIR owners' arrays.
+    // Every tile that holds a vertex of a triangle cut between owners must be a zone tile of its runner (its last store
+    // is then published before the readers start, and its next load waits for them), and the readers must be linked
+    // with every rank that touches the vertex (the last holder stores it home, not necessarily the owner).
+    {
+      std::vector<std::vector<uint8_t>> zone_tile(np);
+      std::vector<std::vector<uint8_t>> runner(np);
+      for (size_t k = 0; k < np; k++) {
+        zone_tile[k].assign(P.passes[k].n_tiles(), 0);
+        runner[k].assign(P.passes[k].n_tiles(), 0xff);
+        for (int r = 0; r < n_ranks; r++)
+          for (size_t j = 0; j < tiles[(size_t)r][k].size(); j++) {
+            runner[k][tiles[(size_t)r][k][j]] = (uint8_t)r;
+            if (j < n_zone[(size_t)r][k]) zone_tile[k][tiles[(size_t)r][k][j]] = 1;
+          }
+      }
+      std::vector<std::vector<uint32_t>> tile_of(np, std::vector<uint32_t>(P.V, 0xffffffffu));
+      for (size_t k = 0; k < np; k++) {
+        const TilePass &tp = P.passes[k];
+        for (uint32_t t = 0; t < tp.n_tiles(); t++)
+          for (uint32_t i = tp.vert_off[t]; i < tp.vert_off[t + 1]; i++) tile_of[k][tp.contiguous ? i : tp.tile_verts[i]] = t;
+      }
+      for (size_t f = 0; f + 2 < P.tris.size(); f += 3) {
+        uint32_t d[3], own = 0;
+        for (int j = 0; j < 3; j++) {
+          d[j] = P.inv[(size_t)P.tris[f + j]];
+          own |= 1u << owner_of(d[j]);
+        }
+        if (!(own & (own - 1))) continue;
+        for (int j = 0; j < 3; j++)
+          for (size_t k = 0; k < np; k++) {
+            const uint32_t t = tile_of[k][d[j]];
+            if (t == 0xffffffffu || runner[k][t] == 0xff) continue;
+            if (!zone_tile[k][t]) unordered++;
+            for (uint32_t o = 0; o < (uint32_t)n_ranks; o++)
+              if ((own >> o & 1u) && !linked(o, runner[k][t])) unordered++;
+          }
       }
     }
     if (n_stale) *n_stale = stale;

@@ -442,6 +442,32 @@ def test_vertices_a_neighbours_normals_launch_reads_sit_in_zone_tiles():
         assert sb.dist_verify(n_ranks)[:3] == (0, 0, 0)
 
 
+def test_the_symbolic_replay_reports_a_layout_that_leaves_a_cut_triangle_unordered():
+    # negative control of sb_dist_verify: with the zone marking of cut triangles switched off (a debug switch that exists for
+    # this test) the two layouts that needed it show hand-overs no epoch orders; a lattice cut along box faces does not care
+    code = """
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from softbodyunity_b200 import SoftBody, meshgen, ingest
+from test_ingest import torus
+sp, st = torus(0.5, 0.2, 48, 24)
+pos, tets, tris = ingest.tetrahedralize_surface(sp + np.float32([0, 0.25, 0]), st, 0.035, snap=True)
+print(SoftBody(pos, tets, tris, host_only=True, tile_cap=400, dist_ranks=3, substeps=3, iterations=4).dist_verify(3)[2])
+pos, tets, tris = meshgen.block(18, 18, 36, spacing=0.05, origin=(0, 0.02, 0))
+print(SoftBody(pos, tets, tris, host_only=True, tile_cap=300, dist_ranks=8, substeps=3, iterations=4).dist_verify(3)[2])
+print(SoftBody(pos, tets, tris, host_only=True, tile_cap=300, dist_ranks=8, substeps=3, iterations=4).dist_verify(8)[2])
+""" % (ROOT, os.path.join(ROOT, "tests"))
+    import subprocess
+    import sys
+    def run(env):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr[-2000:]
+        return [int(x) for x in r.stdout.split()]
+    assert run({}) == [0, 0, 0]
+    off = run({"SB_DEBUG_NO_CUT_TRIANGLE_ZONES": "1"})
+    assert off[0] > 0 and off[1] > 0 and off[2] == 0
+
+
 def test_bitets_pair_tets_across_a_face_on_fixed_registers():
     # round_width=2: tets in face-sharing pairs; the second tet (B) runs on the registers (4, 2, 1, 3) of the first (A)
     pos, tets, tris = meshgen.block(12, 11, 10, spacing=0.1, jitter=0.1, seed=3)
