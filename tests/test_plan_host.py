@@ -83,6 +83,52 @@ def test_argument_errors():
     assert lib.sb_create(None, None, C.byref(h)) == _abi.SB_E_ARG and b"mesh" in lib.sb_last_error(None)
 
 
+def test_degenerate_and_ragged_meshes_plan_cleanly_or_are_refused():
+    # empty, single-element, ragged and degenerate inputs: either a clean SB_E_ARG or a plan whose device streams decode
+    # to a valid coloured order that the oracle runs to a finite state
+    from helpers import oracle_params
+    pos, tets, tris = meshgen.block(5, spacing=0.05, origin=(0, 0.02, 0))
+    unit = np.float32([[0, 0.1, 0], [0.1, 0.1, 0], [0, 0.2, 0], [0, 0.1, 0.1]])
+    ok = {
+        "no tets": (pos, np.zeros((0, 4), np.int32), None, {}),
+        "one tet": (unit, np.int32([[0, 1, 2, 3]]), None, {}),
+        "flat tet": (np.float32([[0, 0, 0], [1, 0, 0], [2, 0, 0], [3, 0, 0]]), np.int32([[0, 1, 2, 3]]), None, {}),
+        "inverted tet": (unit, np.int32([[0, 2, 1, 3]]), None, {}),
+        "vertices in no tet": (np.concatenate([pos, pos[:7] + np.float32([1, 0.5, 0])]), tets, tris, {}),
+        "duplicate tets": (pos, np.concatenate([tets, tets[:10]]), tris, {}),
+        "triangle with a repeated vertex": (pos, tets, np.concatenate([tris, np.int32([[0, 0, 1]])]), {}),
+        "one vertex per tile": (pos, tets, tris, dict(tile_cap=1)),
+        "tile cap beyond 16-bit local ids": (pos, tets, tris, dict(tile_cap=70000)),
+        "more tilings than the limit": (pos, tets, tris, dict(tilings=9)),
+        "eight rank blocks on a tiny mesh": (pos, tets, tris, dict(dist_ranks=8, tile_cap=30)),
+        "everything pinned": (pos, tets, tris, dict(inv_mass=np.zeros(len(pos), np.float32))),
+        "coincident vertices": (np.zeros_like(pos), tets, tris, {}),
+        "no projection sweeps": (pos, tets, tris, dict(substeps=3, iterations=0)),
+    }
+    for name, (p, t, f, kw) in ok.items():
+        sb = SoftBody(p, t, f, host_only=True, **kw)
+        assert sb.verify_streams() == 0, name
+        edges = sb.topology()[0]
+        if len(t):
+            check_schedule(sb, edges, sb.tet_roles())
+        m = orc.Model(p, t, inv_mass=kw.get("inv_mass"), roles=sb.tet_roles())
+        m.simulate(oracle_params(sb), n_frames=2, threads=2, **sb.schedule_kw())
+        assert np.isfinite(m.x4).all() and np.isfinite(m.v4).all(), name
+    nan_pos = pos.copy()
+    nan_pos[3, 1] = np.nan
+    bad_tri = tris.copy()
+    bad_tri[0, 0] = 100000
+    neg = tets.copy()
+    neg[1, 2] = -1
+    for name, (p, t, f, kw) in {"NaN position": (nan_pos, tets, tris, {}), "infinite position": (nan_pos * np.float32(np.inf), tets, tris, {}),
+                                "negative index": (pos, neg, tris, {}), "triangle index out of range": (pos, tets, bad_tri, {}),
+                                "block_threads 7": (pos, tets, tris, dict(block_threads=7)), "round_width 3": (pos, tets, tris, dict(round_width=3)),
+                                "dist_ranks 9": (pos, tets, tris, dict(dist_ranks=9))}.items():
+        with pytest.raises(SbError) as e:
+            SoftBody(p, t, f, host_only=True, **kw)
+        assert e.value.code == _abi.SB_E_ARG, name
+
+
 def check_schedule(sb: SoftBody, edges, tets):
     order, off = sb.schedule()
     E, T = len(edges), len(tets)
