@@ -77,6 +77,12 @@ int main(int argc, char **argv) {
   uint64_t bad = 1;
   CHECK(sb_debug_verify_streams(h, &bad, NULL, NULL) == SB_OK && bad == 0);
 
+  /* one mesh over several GPUs, host-only views: a mesh this small does not plan as balanced tilings and is refused cleanly */
+  uint64_t n_stale = 7, n_away = 7, n_unordered = 7;
+  CHECK(sb_dist_layout(h, 0, 2, NULL, NULL, 0) == SB_E_ARG && strstr(sb_last_error(h), "distributed mesh") != NULL);
+  CHECK(sb_dist_verify(h, 2, &n_stale, &n_away, &n_unordered, NULL) == SB_E_ARG);
+  CHECK(sb_dist_verify(h, 9, NULL, NULL, NULL, NULL) == SB_E_ARG && strstr(sb_last_error(h), "ranks") != NULL);
+
   /* colliders are validated on the host */
   sb_collider col[2];
   memset(col, 0, sizeof col);
