@@ -1319,6 +1319,12 @@ static int guarded(sb_handle h, F fn) {
     }                                                                                                    \
   } while (0)
 
+// copy of a vector into a caller's buffer; an empty vector's data() may be null, which memcpy must not be given
+template <class T>
+static inline void copy_out(T *dst, const std::vector<T> &src) {
+  if (dst && !src.empty()) std::memcpy(dst, src.data(), src.size() * sizeof(T));
+}
+
 extern "C" {
 
 int sb_abi_check(uint32_t *version, uint32_t *sizeof_params, uint32_t *sizeof_desc, uint32_t *sizeof_info) {
@@ -1491,7 +1497,7 @@ int sb_surface_vertices(sb_handle h, int32_t *ids, uint32_t capacity, uint32_t *
   if (n_surface) *n_surface = ns;
   if (ids) {
     if (capacity < ns) { h->err = "capacity too small"; return SB_E_ARG; }
-    std::memcpy(ids, h->plan.surf_ids.data(), ns * sizeof(int32_t));
+    copy_out(ids, h->plan.surf_ids);
   }
   return SB_OK;
 }
@@ -1711,9 +1717,9 @@ int sb_get_info(sb_handle h, sb_info *o) {
 int sb_get_tet_roles(sb_handle h, int32_t *tets_4T, int32_t *edge01_T, int32_t *edge23_T) {
   NEED_HANDLE(h);
   const Plan &P = h->plan;
-  if (tets_4T) std::memcpy(tets_4T, P.tet_roles.data(), P.tet_roles.size() * sizeof(int32_t));
-  if (edge01_T) std::memcpy(edge01_T, P.tet_e01.data(), P.tet_e01.size() * sizeof(int32_t));
-  if (edge23_T) std::memcpy(edge23_T, P.tet_e23.data(), P.tet_e23.size() * sizeof(int32_t));
+  copy_out(tets_4T, P.tet_roles);
+  copy_out(edge01_T, P.tet_e01);
+  copy_out(edge23_T, P.tet_e23);
   return SB_OK;
 }
 
@@ -1730,10 +1736,10 @@ int sb_get_tet_mates(sb_handle h, int32_t *mate_T, int32_t *lead_T) {
 int sb_get_topology(sb_handle h, int32_t *edges, float *rest_len, float *rest_vol6, float *inv_mass) {
   NEED_HANDLE(h);
   const Plan &P = h->plan;
-  if (edges) std::memcpy(edges, P.edges.data(), P.edges.size() * sizeof(int32_t));
-  if (rest_len) std::memcpy(rest_len, P.rest_len.data(), P.rest_len.size() * sizeof(float));
-  if (rest_vol6) std::memcpy(rest_vol6, P.rest_vol6.data(), P.rest_vol6.size() * sizeof(float));
-  if (inv_mass) std::memcpy(inv_mass, P.inv_mass.data(), P.inv_mass.size() * sizeof(float));
+  copy_out(edges, P.edges);
+  copy_out(rest_len, P.rest_len);
+  copy_out(rest_vol6, P.rest_vol6);
+  copy_out(inv_mass, P.inv_mass);
   return SB_OK;
 }
 
@@ -1745,8 +1751,8 @@ static int schedule_impl(sb_handle h, bool odd, int64_t *n_order, int32_t *order
     h->plan.export_schedule(ord, off, odd && h->snake());
     if (n_order) *n_order = (int64_t)ord.size();
     if (n_batches) *n_batches = (int32_t)off.size() - 1;
-    if (order) std::memcpy(order, ord.data(), ord.size() * sizeof(int32_t));
-    if (batch_off) std::memcpy(batch_off, off.data(), off.size() * sizeof(int64_t));
+    copy_out(order, ord);
+    copy_out(batch_off, off);
     return SB_OK;
   });
 }
