@@ -27,3 +27,23 @@ UBSAN_OPTIONS=print_stacktrace=1 SB_ASAN_LIB="$out" python "$drv" > /tmp/asan_ho
 rm -f "$drv"
 tail -2 /tmp/asan_host_library.log
 echo "sanitizer reports: $(grep -c 'runtime error\|AddressSanitizer' /tmp/asan_host_library.log)  (log: /tmp/asan_host_library.log)"
+
+# the CPU oracle (test infrastructure) under the same sanitizers: its known-answer tests, the golden fixtures and the planner tests that drive it
+orc=/tmp/liborc_asan.so
+gcc -O1 -g -std=c11 -fPIC -shared -fopenmp -ffp-contract=off -fno-fast-math -march=x86-64-v3 -fsanitize=address,undefined -fno-omit-frame-pointer \
+  -o "$orc" oracle/xpbd_oracle.c -lm
+drv=$(mktemp /tmp/asan_driver_XXXX.py)
+cat > "$drv" <<'PY'
+import os, sys
+sys.path.insert(0, os.getcwd())
+import oracle.xpbd_oracle as o
+o.LIB = "/tmp/liborc_asan.so"; o.build = lambda force=False: o.LIB
+if __name__ == "__main__":
+    import pytest
+    sys.exit(pytest.main(["tests/test_oracle_kat.py", "tests/test_golden.py", "tests/test_plan_host.py", "-q", "-m", "not gpu", "-p", "no:cacheprovider", "-s"]))
+PY
+LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0:abort_on_error=0 \
+UBSAN_OPTIONS=print_stacktrace=1 python "$drv" > /tmp/asan_oracle.log 2>&1 || true
+rm -f "$drv" "$orc"
+tail -1 /tmp/asan_oracle.log
+echo "oracle: sanitizer reports: $(grep -c 'runtime error\|AddressSanitizer' /tmp/asan_oracle.log)  (log: /tmp/asan_oracle.log)"
