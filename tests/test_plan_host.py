@@ -488,6 +488,37 @@ def test_vertices_a_neighbours_normals_launch_reads_sit_in_zone_tiles():
         assert sb.dist_verify(n_ranks)[:3] == (0, 0, 0)
 
 
+def test_random_meshes_rank_counts_and_programs_replay_cleanly_or_are_refused():
+    # seeded sweep over mesh shape (blocks, spheres, long blocks), tile size, rank count, planner hint and launch program:
+    # sb_dist_setup's layout is either refused with SB_E_ARG or replays with nothing stale, away from home or unordered
+    rng = np.random.default_rng(7)
+    ok = 0
+    for it in range(60):
+        dims = tuple(int(x) for x in rng.integers(6, 26, 3))
+        cap = int(rng.choice([64, 128, 200, 256, 300, 400, 512, 1024]))
+        n = int(rng.integers(2, 9))
+        dr = int(rng.choice([0, n, 8, 2, 4]))
+        flags = int(rng.choice([0, 8, 64, 128, 64 | 128, 16]))
+        S, I = int(rng.integers(1, 5)), int(rng.integers(0, 7))
+        kind = int(rng.integers(0, 3))
+        if kind == 0:
+            pos, tets, tris = meshgen.block(*dims, spacing=0.05, jitter=0.1, seed=it)
+        elif kind == 1:
+            pos, tets, tris = meshgen.sphere(int(max(dims)), spacing=0.05, seed=it)
+        else:
+            pos, tets, tris = meshgen.block(dims[0], dims[1], max(dims[2], 2 * dims[0]), spacing=0.05, seed=it)
+        try:
+            sb = SoftBody(pos, tets, tris, host_only=True, tile_cap=cap, dist_ranks=dr, substeps=S, iterations=I, flags=flags)
+            r = sb.dist_verify(n)
+        except SbError as e:
+            assert e.code == _abi.SB_E_ARG
+            continue
+        own = np.stack([sb.dist_layout(k, n)[0] for k in range(n)])
+        assert (own.sum(0) == 1).all() and r[:3] == (0, 0, 0), (dims, cap, n, dr, flags, S, I, kind, r)
+        ok += 1
+    assert ok >= 25  # most of the sweep is distributable
+
+
 def test_the_symbolic_replay_reports_a_layout_that_leaves_a_cut_triangle_unordered():
     # negative control of sb_dist_verify: with the zone marking of cut triangles switched off (a debug switch that exists for
     # this test) the two layouts that needed it show hand-overs no epoch orders; a lattice cut along box faces does not care
