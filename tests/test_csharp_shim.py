@@ -49,3 +49,45 @@ def test_managed_structs_have_the_c_sizes():
     assert _cs_struct_bytes("SbCollider") == 48
     # the version the shim insists on is the header's
     assert re.search(r"ver != (\d+)", CS).group(1) == re.search(r"#define SB_ABI_VERSION (\d+)u", HDR).group(1)
+
+
+def _c_params():
+    """name -> (return type, [parameter types]) from the header, comments stripped."""
+    text = re.sub(r"/\*.*?\*/", "", HDR, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(int|void|uint64_t|const char \*)\s*(\*?)\s*(sb_\w+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S):
+        args = m.group(4).strip()
+        types = []
+        if args not in ("", "void"):
+            for a in args.split(","):
+                a = " ".join(a.split())
+                types.append(re.sub(r"\s*\w+$", "", a) if not a.endswith("*") else a)  # drop the parameter name
+        out[m.group(3)] = ((m.group(1) + m.group(2)).strip(), types)
+    return out
+
+
+def test_every_dllimport_parameter_has_the_c_type():
+    # by position: scalars must be the same width and signedness, everything the C side takes by pointer (handles, arrays,
+    # structs, strings, out values) must be an IntPtr / ref / out / array / string on the managed side -- and vice versa
+    scalars = {"float": "float", "uint32_t": "uint", "int32_t": "int", "int": "int", "uint64_t": "ulong"}
+    protos = _c_params()
+    imports = re.findall(r"\[DllImport\(Lib\)\]\s*public static extern\s+(\w+)\s+(sb_\w+)\s*\(([^)]*)\)", CS)
+    checked = 0
+    for ret, name, args in imports:
+        c_ret, c_types = protos[name]
+        assert {"int": "int", "void": "void", "const char *": "IntPtr", "uint64_t": "ulong"}[c_ret] == ret, name
+        cs_types = [re.sub(r"\s*\w+$", "", " ".join(a.split())) for a in args.split(",")] if args.strip() else []
+        assert len(cs_types) == len(c_types), name
+        for ct, st in zip(c_types, cs_types):
+            by_pointer = "*" in ct or ct in ("sb_handle", "sb_tetmesh_handle")
+            if by_pointer:
+                assert st == "IntPtr" or st == "string" or st.startswith(("ref ", "out ", "[In] ")) or st.endswith("[]"), (name, ct, st)
+                if st == "string":
+                    assert ct.replace(" ", "") == "constchar*", (name, ct, st)
+                if st.startswith("out ") and st.split()[1] in ("uint", "int", "float", "ulong"):
+                    base = ct.replace("*", "").replace("const", "").strip()
+                    assert scalars[base] == st.split()[1], (name, ct, st)
+            else:
+                assert scalars[ct.replace("const", "").strip()] == st, (name, ct, st)
+            checked += 1
+    assert checked >= 50
