@@ -402,7 +402,7 @@ const char *sb_last_error(sb_handle h); /* h may be NULL: last sb_create failure
  *                            cells whose centre has non-zero winding number, five tets per cell
  *   sb_tetmesh_snap_to_surface  optional second step: the staircase boundary of that lattice pulled onto the surface
  *   sb_tetmesh_from_arrays   caller's arrays; orientation fixed, boundary extracted when n_tris == 0
- *   sb_tetmesh_load / save   TetGen <base>.node + .ele (+ .face) or Gmsh MSH 2.2 ASCII (.msh), by extension
+ *   sb_tetmesh_load / save   TetGen <base>.node + .ele (+ .face) or Gmsh MSH ASCII (.msh: 2.x and 4.1 are read, 2.2 is written), by extension
  */
 typedef struct sb_tetmesh *sb_tetmesh_handle;
 int sb_tetmesh_from_surface(const float *surf_pos_xyz, uint32_t n_verts, const int32_t *surf_tris, uint32_t n_tris,

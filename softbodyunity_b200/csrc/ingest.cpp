@@ -651,13 +651,32 @@ int load_tetgen(const std::string &base, sb_tetmesh &m) {
   return SB_OK;
 }
 
-// Gmsh MSH 2.2 ASCII: element type 4 = 4-node tet, type 2 = 3-node triangle; other types are skipped
+// Gmsh MSH ASCII, versions 2.x and 4.1: element type 4 = 4-node tet, type 2 = 3-node triangle; other types are skipped.
+// 2.x lists nodes as "id x y z" and elements as "id type ntags tags... nodes..."; 4.1 groups both into entity blocks
+// ("dim tag parametric n" + n node tags + n coordinate lines; "dim tag type n" + n lines "id nodes...").
 int load_msh(const std::string &path, sb_tetmesh &m) {
   std::ifstream in(path);
   if (!in) return fail(SB_E_ARG, "cannot open " + path);
+  const long long bytes = file_bytes(path);
   std::string line;
   std::map<long long, int32_t> id_of;
-  bool fmt = false;
+  int major = 0;
+  auto add_node = [&](long long id, size_t i, double x, double y, double z) {
+    if (!id_of.emplace(id, (int32_t)i).second) return false;
+    m.pos[3 * i] = (float)x; m.pos[3 * i + 1] = (float)y; m.pos[3 * i + 2] = (float)z;
+    return true;
+  };
+  // the node ids at the end of an element line -> tets / tris (nn = 0: an element type this library has no use for)
+  auto add_element = [&](std::istringstream &s, int nn) -> const char * {
+    for (int j = 0; j < nn; j++) {
+      long long v;
+      if (!(s >> v)) return ".msh: element with too few nodes";
+      auto it = id_of.find(v);
+      if (it == id_of.end()) return ".msh: element refers to an unknown node id";
+      (nn == 4 ? m.tets : m.tris).push_back(it->second);
+    }
+    return nullptr;
+  };
   while (std::getline(in, line)) {
     while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
     if (line == "$MeshFormat") {
@@ -665,20 +684,45 @@ int load_msh(const std::string &path, sb_tetmesh &m) {
       if (!std::getline(in, line)) break;
       std::istringstream s(line);
       s >> ver >> type;
-      if (!(ver >= 2.0 && ver < 3.0) || type != 0) return fail(SB_E_ARG, ".msh: only MSH 2.x ASCII is supported");
-      fmt = true;
-    } else if (line == "$Nodes") {
+      if (type != 0) return fail(SB_E_ARG, ".msh: binary files are not supported (save as ASCII)");
+      if (ver >= 2.0 && ver < 3.0) major = 2;
+      else if (ver > 4.05 && ver < 4.15) major = 4;
+      else return fail(SB_E_ARG, ".msh: only MSH 2.x and 4.1 ASCII are supported");
+    } else if (line == "$Nodes" && major == 2) {
       long long nn = 0;
       in >> nn;
-      if (nn <= 0 || nn > 0x7fffffffLL || nn > file_bytes(path)) return fail(SB_E_ARG, ".msh: no nodes");
+      if (nn <= 0 || nn > 0x7fffffffLL || nn > bytes) return fail(SB_E_ARG, ".msh: no nodes");
       m.pos.resize(3 * (size_t)nn);
       for (long long i = 0; i < nn; i++) {
         long long id; double x, y, z;
         if (!(in >> id >> x >> y >> z)) return fail(SB_E_ARG, ".msh: malformed node");
-        if (!id_of.emplace(id, (int32_t)i).second) return fail(SB_E_ARG, ".msh: duplicate node id");
-        m.pos[3 * (size_t)i] = (float)x; m.pos[3 * (size_t)i + 1] = (float)y; m.pos[3 * (size_t)i + 2] = (float)z;
+        if (!add_node(id, (size_t)i, x, y, z)) return fail(SB_E_ARG, ".msh: duplicate node id");
       }
-    } else if (line == "$Elements") {
+    } else if (line == "$Nodes" && major == 4) {
+      long long nblocks = 0, nn = 0, tmin = 0, tmax = 0;
+      in >> nblocks >> nn >> tmin >> tmax;
+      if (!in || nn <= 0 || nn > 0x7fffffffLL || nn > bytes || nblocks < 0 || nblocks > bytes) return fail(SB_E_ARG, ".msh: no nodes");
+      m.pos.resize(3 * (size_t)nn);
+      long long done = 0;
+      std::vector<long long> tags;
+      for (long long b = 0; b < nblocks; b++) {
+        long long dim = 0, tag = 0, parametric = 0, nb = 0;
+        if (!(in >> dim >> tag >> parametric >> nb) || nb < 0 || done + nb > nn || dim < 0 || dim > 3)
+          return fail(SB_E_ARG, ".msh: malformed node block");
+        tags.resize((size_t)nb);
+        for (long long i = 0; i < nb; i++)
+          if (!(in >> tags[(size_t)i])) return fail(SB_E_ARG, ".msh: malformed node block (tags)");
+        for (long long i = 0; i < nb; i++) {
+          double x, y, z, skip;
+          if (!(in >> x >> y >> z)) return fail(SB_E_ARG, ".msh: malformed node");
+          for (long long k = 0; parametric && k < dim; k++)
+            if (!(in >> skip)) return fail(SB_E_ARG, ".msh: malformed parametric node");
+          if (!add_node(tags[(size_t)i], (size_t)(done + i), x, y, z)) return fail(SB_E_ARG, ".msh: duplicate node id");
+        }
+        done += nb;
+      }
+      if (done != nn) return fail(SB_E_ARG, ".msh: fewer nodes than the header says");
+    } else if (line == "$Elements" && major == 2) {
       long long ne = 0;
       in >> ne;
       if (!in || ne < 0) return fail(SB_E_ARG, ".msh: bad element count");
@@ -689,19 +733,29 @@ int load_msh(const std::string &path, sb_tetmesh &m) {
         long long id, type, ntags, tag;
         if (!(s >> id >> type >> ntags) || ntags < 0 || ntags > 64) return fail(SB_E_ARG, ".msh: malformed element");
         for (long long k = 0; k < ntags; k++) s >> tag;
-        const int nn = type == 4 ? 4 : type == 2 ? 3 : 0;
-        if (!nn) continue;
-        for (int j = 0; j < nn; j++) {
-          long long v;
-          if (!(s >> v)) return fail(SB_E_ARG, ".msh: element with too few nodes");
-          auto it = id_of.find(v);
-          if (it == id_of.end()) return fail(SB_E_ARG, ".msh: element refers to an unknown node id");
-          (nn == 4 ? m.tets : m.tris).push_back(it->second);
+        if (const char *err = add_element(s, type == 4 ? 4 : type == 2 ? 3 : 0)) return fail(SB_E_ARG, err);
+      }
+    } else if (line == "$Elements" && major == 4) {
+      long long nblocks = 0, ne = 0, tmin = 0, tmax = 0;
+      in >> nblocks >> ne >> tmin >> tmax;
+      if (!in || ne < 0 || nblocks < 0 || nblocks > bytes) return fail(SB_E_ARG, ".msh: bad element count");
+      long long done = 0;
+      for (long long b = 0; b < nblocks; b++) {
+        long long dim = 0, tag = 0, type = 0, nb = 0;
+        if (!(in >> dim >> tag >> type >> nb) || nb < 0 || done + nb > ne) return fail(SB_E_ARG, ".msh: malformed element block");
+        std::getline(in, line);
+        for (long long e = 0; e < nb; e++) {
+          if (!std::getline(in, line)) return fail(SB_E_ARG, ".msh: fewer elements than the header says");
+          std::istringstream s(line);
+          long long id;
+          if (!(s >> id)) return fail(SB_E_ARG, ".msh: malformed element");
+          if (const char *err = add_element(s, type == 4 ? 4 : type == 2 ? 3 : 0)) return fail(SB_E_ARG, err);
         }
+        done += nb;
       }
     }
   }
-  if (!fmt) return fail(SB_E_ARG, ".msh: no $MeshFormat section");
+  if (!major) return fail(SB_E_ARG, ".msh: no $MeshFormat section");
   if (m.pos.empty() || m.tets.empty()) return fail(SB_E_ARG, ".msh: no nodes or no tetrahedra (element type 4)");
   return SB_OK;
 }

@@ -65,7 +65,7 @@ def from_arrays(pos, tets, tris=None):
 
 
 def load_mesh(path):
-    """TetGen (<base>.node/.ele[/.face], or the bare base path) or Gmsh MSH 2.2 ASCII (.msh)."""
+    """TetGen (<base>.node/.ele[/.face], or the bare base path) or Gmsh MSH ASCII (.msh; versions 2.x and 4.1)."""
     h = C.c_void_p()
     _ck(_abi.load().sb_tetmesh_load(str(path).encode(), C.byref(h)))
     return _take(h)

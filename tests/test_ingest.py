@@ -216,10 +216,36 @@ def test_hand_written_tetgen_and_gmsh_files(tmp_path):
         "$Elements\n3\n1 15 2 0 1 10\n2 2 2 0 1 10 30 20\n3 4 2 0 1 10 20 30 40\n$EndElements\n")
     p, t, f = ingest.load_mesh(tmp_path / "b.msh")
     assert np.array_equal(t, [[0, 1, 2, 3]]) and np.array_equal(f, [[0, 2, 1]])  # point element skipped, ids remapped
-    for text, msg in (("$MeshFormat\n4.1 0 8\n$EndMeshFormat\n", "MSH 2"), ("$Nodes\n1\n1 0 0 0\n$EndNodes\n", "MeshFormat")):
+    for text, msg in (("$MeshFormat\n4.0 0 8\n$EndMeshFormat\n", "2.x and 4.1"), ("$MeshFormat\n4.1 1 8\n$EndMeshFormat\n", "binary"),
+                      ("$MeshFormat\n4.1 0 8\n$EndMeshFormat\n", "no nodes"), ("$Nodes\n1\n1 0 0 0\n$EndNodes\n", "MeshFormat")):
         (tmp_path / "c.msh").write_text(text)
         with pytest.raises(SbError, match=msg):
             ingest.load_mesh(tmp_path / "c.msh")
+    # MSH 4.1 (what current Gmsh writes): entity blocks -- a point entity, a parametric curve block (one extra coordinate
+    # per node), a volume block; node tags first, coordinates after; point and line elements skipped; the same two tets as a.node
+    (tmp_path / "e.msh").write_text(
+        "$MeshFormat\n4.1 0 8\n$EndMeshFormat\n$Entities\n0 0 0 0\n$EndEntities\n"
+        "$Nodes\n3 5 10 50\n0 1 0 1\n10\n0 0 0\n1 7 1 2\n20\n30\n1 0 0 0.25\n0 1 0 0.75\n3 1 0 2\n40\n50\n0 0 1\n1 1 1\n$EndNodes\n"
+        "$Elements\n4 6 1 6\n0 1 15 1\n1 10\n1 7 1 1\n2 20 30\n2 3 2 2\n3 10 30 20\n4 20 30 40\n3 1 4 2\n5 10 20 30 40\n6 50 20 30 40\n$EndElements\n")
+    p4, t4, f4 = ingest.load_mesh(tmp_path / "e.msh")
+    assert p4.shape == (5, 3)
+    pa, ta, fa = ingest.load_mesh(tmp_path / "a.node")
+    assert np.array_equal(p4, pa) and np.array_equal(np.sort(t4, 1), np.sort(ta, 1)) and tet_volumes(p4, t4).min() > 0
+    assert np.array_equal(f4, [[0, 2, 1], [1, 2, 3]])           # the file's own triangles, ids remapped
+    # what the library writes (2.2) and this 4.1 file describe the same body
+    ingest.save_mesh(tmp_path / "e22.msh", p4, t4, f4)
+    p22, t22, f22 = ingest.load_mesh(tmp_path / "e22.msh")
+    assert np.array_equal(p22, p4) and np.array_equal(t22, t4) and np.array_equal(f22, f4)
+    for text, msg in (("$MeshFormat\n4.1 0 8\n$EndMeshFormat\n$Nodes\n1 2 1 2\n3 1 0 2\n1\n2\n0 0 0\n$EndNodes\n", "malformed node"),
+                      ("$MeshFormat\n4.1 0 8\n$EndMeshFormat\n$Nodes\n1 3 1 2\n3 1 0 2\n1\n2\n0 0 0\n1 0 0\n$EndNodes\n", "fewer nodes"),
+                      ("$MeshFormat\n4.1 0 8\n$EndMeshFormat\n$Nodes\n1 2 1 2\n3 1 0 2\n1\n1\n0 0 0\n1 0 0\n$EndNodes\n", "duplicate"),
+                      ("$MeshFormat\n4.1 0 8\n$EndMeshFormat\n$Nodes\n1 4 1 4\n3 1 0 4\n1\n2\n3\n4\n0 0 0\n1 0 0\n0 1 0\n0 0 1\n$EndNodes\n"
+                       "$Elements\n1 1 1 1\n3 1 4 1\n1 1 2 3 9\n$EndElements\n", "unknown node"),
+                      ("$MeshFormat\n4.1 0 8\n$EndMeshFormat\n$Nodes\n1 4 1 4\n3 1 0 4\n1\n2\n3\n4\n0 0 0\n1 0 0\n0 1 0\n0 0 1\n$EndNodes\n"
+                       "$Elements\n1 2 1 2\n3 1 4 2\n1 1 2 3 4\n", "fewer elements")):
+        (tmp_path / "g.msh").write_text(text)
+        with pytest.raises(SbError, match=msg):
+            ingest.load_mesh(tmp_path / "g.msh")
     (tmp_path / "d.node").write_text("2 3 0 0\n0 0 0 0\n1 1 0 0\n")
     (tmp_path / "d.ele").write_text("1 4 0\n0 0 1 2 3\n")
     with pytest.raises(SbError, match="unknown point"):
@@ -334,10 +360,23 @@ def test_parsers_survive_garbage(tmp_path):
         good[f] = (tmp_path / f).read_bytes()
     ingest.write_state(tmp_path / "g.sbs", np.zeros((64, 4), np.float32), np.zeros((64, 4), np.float32), default_params())
     good["g.sbs"] = (tmp_path / "g.sbs").read_bytes()
+    # the same mesh as Gmsh 4.1 writes it: two node blocks (the second parametric), a triangle block and a tet block
+    half = len(pos) // 2
+    lines = ["$MeshFormat", "4.1 0 8", "$EndMeshFormat", "$Nodes", f"2 {len(pos)} 1 {len(pos)}", f"3 1 0 {half}"]
+    lines += [str(i + 1) for i in range(half)] + ["%.9g %.9g %.9g" % tuple(q) for q in pos[:half]]
+    lines += [f"2 5 1 {len(pos) - half}"] + [str(i + 1) for i in range(half, len(pos))] + ["%.9g %.9g %.9g 0.5 0.25" % tuple(q) for q in pos[half:]]
+    lines += ["$EndNodes", "$Elements", f"2 {len(tris) + len(tets)} 1 {len(tris) + len(tets)}", f"2 5 2 {len(tris)}"]
+    lines += ["%d %d %d %d" % (i + 1, *(t + 1)) for i, t in enumerate(tris)] + [f"3 1 4 {len(tets)}"]
+    lines += ["%d %d %d %d %d" % (len(tris) + i + 1, *(t + 1)) for i, t in enumerate(tets)] + ["$EndElements", ""]
+    good["g41.msh"] = "\n".join(lines).encode()
+    (tmp_path / "g41.msh").write_bytes(good["g41.msh"])
+    p41, t41, f41 = ingest.load_mesh(tmp_path / "g41.msh")
+    p22, t22, f22 = ingest.load_mesh(tmp_path / "g.msh")
+    assert np.array_equal(p41, p22) and np.array_equal(t41, t22) and np.array_equal(f41, f22)
     rng = np.random.default_rng(11)
     outcomes = {"ok": 0, "error": 0}
-    for trial in range(120):
-        f = ("g.msh", "g.node", "g.ele", "g.sbs")[trial % 4]
+    for trial in range(150):
+        f = ("g.msh", "g.node", "g.ele", "g.sbs", "g41.msh")[trial % 5]
         raw = bytearray(good[f])
         kind = trial % 3
         if kind == 0:
@@ -361,7 +400,7 @@ def test_parsers_survive_garbage(tmp_path):
             outcomes["ok"] += 1
         except SbError:
             outcomes["error"] += 1
-    assert outcomes["error"] > 40 and outcomes["ok"] + outcomes["error"] == 120
+    assert outcomes["error"] > 50 and outcomes["ok"] + outcomes["error"] == 150
 
 
 def test_softbody_from_surface_and_from_file(tmp_path):
