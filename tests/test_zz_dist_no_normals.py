@@ -29,3 +29,16 @@ def test_a_distributed_frame_without_normals_ends_with_the_closing_handshake(n_r
     m = orc.Model(pos, tets, roles=vr.ranks[0].tet_roles())
     m.simulate(oracle_params(vr.ranks[0]), n_frames=5, threads=8, **vr.ranks[0].schedule_kw())
     assert bits_equal(X, m.x4) and bits_equal(U[:, :3], m.v4[:, :3])
+
+
+@pytest.mark.gpu
+def test_whole_mesh_reads_and_stray_launches_are_refused_on_one_rank_of_a_distributed_mesh():
+    # a rank holds current values for the vertices it owns only, and a launch its peers do not run would part the epochs:
+    # SB_E_STATE with a message, before any device work (sb_read_packed / sb_write_packed are the per-rank doors)
+    pos, tets, tris = meshgen.block(14, 12, 26, spacing=0.05)
+    sb = SoftBody(pos, tets, tris, tile_cap=256)
+    sb.dist_setup(0, 2)
+    for call in (sb.diagnostics, sb.read_surface, sb.normals, lambda: sb.save_state("/tmp/never_written.sbs"), lambda: sb.trace_pass(0),
+                 lambda: sb.time_kernel(16, 2)):
+        with pytest.raises(Exception, match="distributed"):
+            call()
